@@ -1,0 +1,153 @@
+/*
+ * uavsal_b200.h — C ABI of the B200 (sm_100a) UAVSal inference hot path.
+ *
+ * The reference (zhangkao/IIP_UAVSal_Saliency) has no FFI layer: its "operator API" for this path is the
+ * Python surface of model.py / model_feature.py / model_convlstm.py / utils_data.py / utils_score_torch.py,
+ * whose arithmetic runs in ATen/cuDNN/cuBLAS.  This header is the boundary the new build introduces
+ * underneath that surface.  Each entry point names the reference call site(s) whose
+ * arithmetic it replaces.  Conventions:
+ *
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative UAVSAL_E* argument error;
+ *     uavsal_last_error() returns a static description of the most recent failure on this thread;
+ *   - all pointers are DEVICE pointers unless named host_*; nothing is allocated, nothing synchronises;
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - "act" tensors are the arena format: NHWC rows (pixels) x channels, stored as TWO bf16 planes
+ *     (hi = bf16(x), lo = bf16(x - hi)) so that tensor-core GEMMs can run the error-compensated product
+ *     hi*hi + hi*lo + lo*hi with fp32 accumulation (DESIGN.md "Precision").  An act argument is the triple
+ *         (const uint16_t* p, int64_t plane, int ld)
+ *     p      = hi plane base (already offset to the first channel of a concat slot),
+ *     plane  = element offset from the hi plane to the lo plane (0 = no lo plane: bf16x1 "fast" mode),
+ *     ld     = row pitch in elements (multiple of 8; >= channel count for concat slots);
+ *   - BatchNorm (eval) is folded into weights/bias by the host (model.py:70,95; eps 1e-5).
+ */
+#ifndef UAVSAL_B200_H
+#define UAVSAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVSAL_EINVAL   (-1)   /* bad argument (shape, alignment, null pointer) */
+#define UAVSAL_ENOTSUP  (-2)   /* shape not supported by this kernel */
+#define UAVSAL_EDRIVER  (-3)   /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+/* epilogue flags for uavsal_pw_gemm* / uavsal_conv3x3* */
+#define UAVSAL_F_RELU6    1    /* clamp to [0,6]            (nn.ReLU6, model.py:71) */
+#define UAVSAL_F_RESIDUAL 2    /* out += res                (model.py:101, 247) */
+#define UAVSAL_F_SIGMOID  4    /* out = sigmoid(out)        (model.py:373) */
+#define UAVSAL_F_ADD2     8    /* out += res2 BEFORE the activation is NOT implied; res2 is a second addend */
+
+int         uavsal_version(void);                 /* ABI version, currently 1 */
+const char* uavsal_arch(void);                    /* "sm_100a" */
+const char* uavsal_last_error(void);
+int         uavsal_device_ok(int device);         /* 0 if `device` is compute capability 10.x */
+
+/* ---- layout conversion at the module boundary (torch NCHW fp32 <-> arena) ---------------------- */
+/* NCHW fp32 -> act NHWC with channels zero-padded to cpad (cb priors, Demo_Test.py:16,22; states).  */
+int uavsal_pack_nchw_f32(const float* src, int n, int c, int h, int w,
+                         uint16_t* dst, int64_t plane, int ld, int cpad, void* stream);
+/* act NHWC -> NCHW fp32 (returned maps and hidden state, model.py:370-375). */
+int uavsal_unpack_nchw_f32(const uint16_t* src, int64_t plane, int ld, int n, int c, int h, int w,
+                           float* dst, void* stream);
+
+/* ---- a1 + K1: normalize_data (utils_data.py:43-65) fused with the stem conv 3x3 s2 + BN + ReLU6
+ *      (torchvision features[0], used at model_feature.py:63).
+ *      x_kind: 0 = fp32 NCHW already normalised (UAVSal.forward input, model.py:341)
+ *              1 = uint8 NCHW raw RGB (Demo_Test.py:70,77: normalisation fused)
+ *              2 = uint8 NHWC raw RGB (preprocess_videos output, utils_data.py:255-287)
+ *      w: [3][3][3][32] (ky,kx,ci,co) fp32 BN-folded; bias[32]. */
+int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w,
+                          const float* wgt, const float* bias,
+                          uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K2: depthwise 3x3 + BN + ReLU6 (model.py:92 BasicConv2d(groups=hidden); torchvision InvertedResidual dw)
+ *      stride 1|2, dilation >= 1, padding = dilation.  wgt: [9][c] fp32 BN-folded, bias[c]. */
+int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c,
+                 int stride, int dilation, const float* wgt, const float* bias, int relu6,
+                 uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K3: pointwise 1x1 conv + BN (+ReLU6)(+residual)(+sigmoid) (model.py:89,94,120-128,181,184,230).
+ *      out[m][n0..] = act( sum_k A[m][k] * W[n][k] + bias[n] ) (+ res[m][n])
+ *      tcgen05 version: wgt = bf16 planes [2][n][kpad] (hi, lo), kpad % 8 == 0; terms = 1 (bf16x1) or 3.
+ *      SIMT version:    wgt_f32 = [k][n] fp32. */
+int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k,
+                   const uint16_t* wgt, int kpad, int n, const float* bias, int flags, int terms,
+                   const uint16_t* res, int64_t res_plane, int res_ld,
+                   uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+int uavsal_pw_gemm_simt(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k,
+                        const float* wgt_f32, int n, const float* bias, int flags,
+                        const uint16_t* res, int64_t res_plane, int res_ld,
+                        uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K4: dense 3x3 conv, pad 1, stride 1 + BN + ReLU6 (conv_last, model.py:131,156) as implicit GEMM.
+ *      in: act (n,h,w,c) with c % 64 == 0 for the tcgen05 version.
+ *      tcgen05: wgt = bf16 planes [2][cout][9*c], k = (ky*3+kx)*c + ci.   SIMT: wgt_f32 = [9*c][cout]. */
+int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c,
+                   const uint16_t* wgt, int cout, const float* bias, int flags, int terms,
+                   uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+int uavsal_conv3x3_simt(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c,
+                        const float* wgt_f32, int cout, const float* bias, int flags,
+                        uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K5: F.interpolate(bilinear, align_corners=True) written into a concat slot (model.py:152-153,360)
+ *      with the context prior's repeat(T,1,1,1) folded in: output frame i reads source frame i % n_src
+ *      (model.py:361, quirk Q3). */
+int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_src, int hs, int ws, int c,
+                       uint16_t* out, int64_t out_plane, int out_ld, int n_dst, int hd, int wd, void* stream);
+
+/* ---- K6: teConv_sub neighbour differences over the call batch (model.py:194-200): x1 (n,hw,c) -> (n,hw,2c) */
+int uavsal_tdiff_cat(const uint16_t* in, int64_t in_plane, int in_ld, int n, int hw, int c,
+                     uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K7: context prior T-sum: x.view(B,T,C,H,W).sum(1) (model.py:357-358): (b*t,hw,c) -> (b,hw,c) */
+int uavsal_ctx_sum(const uint16_t* in, int64_t in_plane, int in_ld, int b, int t, int hw, int c,
+                   uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* elementwise out = a + b (STBlock fu_type='sum', model.py:241) */
+int uavsal_add(const uint16_t* a, int64_t a_plane, int a_ld, const uint16_t* b, int64_t b_plane, int b_ld,
+               int64_t rows, int c, uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
+/* ---- K8: ConvTWA sequence, batch 1 (model_convlstm.py:276-292 cell, 364-377 loop):
+ *      for t: i = sigmoid(conv3x3([x_t, h])); h = i*x_t + (1-i)*h; seq_out[t] = h.
+ *      x: act (t_steps, h, w, c); h0: act (1,h,w,c); seq_out: act (t_steps,h,w,c) (last frame = h_last).
+ *      tcgen05: wgt = bf16 planes [2][c][9*2c] (input-channel order [x, h], model_convlstm.py:279). */
+int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
+                        const uint16_t* h0, int64_t h0_plane, int h0_ld,
+                        int t_steps, int h, int w, int c,
+                        const uint16_t* wgt, const float* wgt_f32, int terms,
+                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream);
+
+/* ---- K9: ConvLSTM sequence, one layer, batch_first (model_convlstm.py:111-126 cell, 199-212 loop).
+ *      x: act (b, t, h, w, cin) ; h state act (b,h,w,ch) updated in place through seq_out; c state fp32
+ *      (b,h,w,ch) updated in place.  Gate order i,f,o,g; packed weights interleave the four gates per channel:
+ *      packed row 4*ch_idx + g  <-  reference row g*ch + ch_idx.  bias (4*ch, same interleave) may be NULL.
+ *      seq_out: act (b, t, h, w, ch). */
+int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
+                             const uint16_t* h0, int64_t h0_plane, int h0_ld, float* c_state,
+                             int b, int t_steps, int h, int w, int cin, int ch,
+                             const uint16_t* wgt, const float* wgt_f32, const float* bias, int terms,
+                             uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream);
+
+/* ---- K10a: readout project conv 1536->1 + BN + sigmoid (conv_out_st.conv.2/.3 + model.py:373):
+ *      out_f32[row] = sigmoid( dot(A[row][:k], wgt[:k]) + bias ). */
+int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t rows, int k,
+                       const float* wgt, float bias, float* out_f32, void* stream);
+
+/* ---- K10b / a11: postprocess_predictions + np2mat (utils_data.py:289-303, 68-82):
+ *      letterbox-inverse bilinear resize (cv2.resize INTER_LINEAR semantics) of each (hs,ws) map to
+ *      (hd,wd), divide by the per-frame max, *255, round-half-even, uint8.  frame_max: scratch (n floats). */
+int uavsal_post_u8(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max,
+                   uint8_t* out_u8, void* stream);
+
+/* ---- K11: utils_score_torch.metric_cc / metric_nss / metric_kl / metric_sim (180-218, helpers 20-50).
+ *      pred (n,1,h,w), truth (n,2,h,w) (ch0 density, ch1 fixations), fp32 or uint8-valued (dtype 0=f32, 1=u8).
+ *      out (n,4) fp32 columns CC, NSS, KLD, SIM.  scratch: n*16 doubles. */
+int uavsal_metrics4(const void* pred, const void* truth, int dtype, int n, int h, int w,
+                    double* scratch, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVSAL_B200_H */

@@ -1,0 +1,16 @@
+"""TEST INFRASTRUCTURE ONLY — the parity oracle for uavsal-b200.
+
+Nothing under ``iip_uavsal_saliency_b200/`` imports this package.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may use it,
+and there only as the checker or the reported CPU baseline — never as the product path.
+
+Contents
+  shim.py        import the unmodified reference from /root/reference (authoring container only)
+  cpu_ref.py     functional CPU restatement of the reference hot path (torch CPU fp32 primitives)
+  synth.py       seeded synthetic clips, priors, weights ("stock" and "lively") and metric pairs
+  make_golden.py regenerates tests/golden/*.npz by running the real reference through shim.py
+
+Parity pin: the reference ships no tests or golden vectors, so cpu_ref.py is pinned
+against outputs of the reference itself executed in the authoring container (make_golden.py →
+tests/golden/), checked by tests/test_oracle_golden.py.
+"""

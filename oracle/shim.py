@@ -1,0 +1,75 @@
+"""Import the UNMODIFIED reference modules from /root/reference, offline.  TEST INFRASTRUCTURE ONLY.
+
+Two stubs are needed:
+  1. ``hdf5storage`` is imported at module top by utils_data.py:6 and utils_score_torch.py:9 but is not
+     installed; a stub module backed by ``iip_uavsal_saliency_b200.mat73`` is injected.
+  2. ``ReMobileNetV2.__init__`` calls ``mobilenet_v2(pretrained=True)`` (model_feature.py:59), which needs
+     the network; ``model_feature.feature_loader['mobilenet_v2']`` is replaced by a constructor that builds
+     the same torchvision architecture with ``weights=None``.
+
+The reference reads its prior ``.mat`` files relative to the CWD (utils_data.py:450-452, 554-557); use
+``reference_cwd()`` around calls to its prior loaders.  This module only works where /root/reference
+exists (the authoring container); GPU-box tests use the committed fixtures instead.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("UAVSAL_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model.py"))
+
+
+def _install_hdf5storage_stub():
+    if "hdf5storage" in sys.modules:
+        return
+    if _REPO_ROOT not in sys.path:
+        sys.path.insert(0, _REPO_ROOT)
+    from iip_uavsal_saliency_b200 import mat73
+
+    stub = types.ModuleType("hdf5storage")
+    stub.loadmat = lambda path, *a, **k: mat73.loadmat(path)
+    stub.savemat = lambda path, d, *a, **k: mat73.savemat(path, d)
+    sys.modules["hdf5storage"] = stub
+
+
+_REF_MODULE_NAMES = ("model", "model_feature", "model_convlstm", "utils_data", "utils_score_torch")
+
+
+def load():
+    """Return a namespace with the reference modules: .model .model_feature .model_convlstm .utils_data
+    .utils_score_torch.  They are imported under their own top-level names, as the reference expects."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    _install_hdf5storage_stub()
+    for name in _REF_MODULE_NAMES:
+        mod = sys.modules.get(name)
+        if mod is not None and not getattr(mod, "__file__", "").startswith(REFERENCE_ROOT):
+            raise RuntimeError("module name %r already taken by %s" % (name, mod.__file__))
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        mods = {n: importlib.import_module(n) for n in _REF_MODULE_NAMES}
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    import torchvision
+
+    mods["model_feature"].feature_loader["mobilenet_v2"] = (
+        lambda pretrained=True: torchvision.models.mobilenet_v2(weights=None))
+    return types.SimpleNamespace(**mods)
+
+
+@contextlib.contextmanager
+def reference_cwd():
+    old = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        yield
+    finally:
+        os.chdir(old)
