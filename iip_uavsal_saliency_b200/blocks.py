@@ -1,0 +1,159 @@
+"""BasicConv2d / dwBlock (model.py:65-103) with reference-identical parameters and kernel-plan emission."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ._kernel_module import KernelModule
+from .engine import F_RELU6, Buf, Plan, fold_bn, out_size, pack_dw
+
+__all__ = ["BasicConv2d", "dwBlock", "init_weights", "emit_stem"]
+
+_INIT = {
+    "uniform": nn.init.uniform_, "normal": nn.init.normal_, "constant": nn.init.constant_,
+    "xavier_uniform": nn.init.xavier_uniform_, "xavier_normal": nn.init.xavier_normal_,
+    "kaiming_uniform": nn.init.kaiming_uniform_, "kaiming_normal": nn.init.kaiming_normal_,
+    "orthogonal": nn.init.orthogonal_, "sparse": nn.init.sparse_, "ones": nn.init.ones_, "zeros": nn.init.zeros_,
+}
+init_func = _INIT
+
+
+def init_weights(model, funcname="kaiming_normal", **kwargs):
+    """model.py:49-60 — conv weights by ``funcname``, BN to (1, 0), Linear to N(0, 0.01)."""
+    fn = _INIT[funcname]
+    for m in model.modules():
+        if isinstance(m, (nn.Conv2d, nn.Conv3d)):
+            fn(m.weight, **kwargs)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Linear):
+            nn.init.normal_(m.weight, 0, 0.01)
+            nn.init.zeros_(m.bias)
+
+
+class BasicConv2d(nn.Sequential):
+    """conv (no bias) + BatchNorm2d + ReLU6, keys ``0.weight`` / ``1.*`` (model.py:65-72)."""
+
+    def __init__(self, in_planes, out_planes, kernel_size=3, stride=1, dilation=1, groups=1):
+        padding = dilation * (kernel_size - 1) // 2
+        super().__init__(
+            nn.Conv2d(in_planes, out_planes, kernel_size, stride, padding, dilation=dilation, groups=groups, bias=False),
+            nn.BatchNorm2d(out_planes),
+            nn.ReLU6(inplace=True),
+        )
+        self.spec = (in_planes, out_planes, kernel_size, stride, dilation, groups)
+
+    # ---- plan emission ----
+    def folded(self):
+        return fold_bn(self[0].weight, self[1])
+
+    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag=""):
+        cin, cout, k, stride, dil, groups = self.spec
+        wf, bf = self.folded()
+        if k == 1:
+            assert stride == 1 and groups == 1
+            out = out if out is not None else plan.alloc(n * h * w, cout)
+            plan.pw(x, n * h * w, wf.reshape(cout, cin), bf, F_RELU6, out, res=res, tag=tag)
+            return out, h, w
+        if groups == cin and groups == cout:
+            ho, wo = out_size(h, stride), out_size(w, stride)
+            out = out if out is not None else plan.alloc(n * ho * wo, cout)
+            plan.dw(x, n, h, w, cout, stride, dil, plan.hold(pack_dw(wf)), plan.hold(bf), True, out, tag=tag)
+            return out, ho, wo
+        if groups == 1 and stride == 1 and dil == 1 and k == 3:
+            out = out if out is not None else plan.alloc(n * h * w, cout)
+            plan.conv3x3(x, n, h, w, cin, wf, bf, F_RELU6, out, tag=tag)
+            return out, h, w
+        raise NotImplementedError("BasicConv2d%r has no sm_100a kernel on the UAVSal path" % (self.spec,))
+
+    def forward(self, x):
+        return _forward_single(self, x)
+
+
+def emit_stem(plan: Plan, stem: BasicConv2d, x_src: torch.Tensor, kind: int, n, h, w):
+    """features[0]: (normalise +) conv3x3 s2 (3->32) + BN + ReLU6 straight from the NCHW/NHWC input tensor."""
+    wf, bf = stem.folded()
+    ho, wo = out_size(h, 2), out_size(w, 2)
+    out = plan.alloc(n * ho * wo, 32)
+    plan.stem(x_src, kind, n, h, w, plan.hold(wf.permute(2, 3, 1, 0).contiguous()), plan.hold(bf), out, tag="features.0")
+    return out, ho, wo
+
+
+class dwBlock(KernelModule):
+    """Inverted residual: 1x1 expand + BN + ReLU6 -> depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (+ x)
+    (model.py:74-103; identical key layout to torchvision's InvertedResidual)."""
+
+    def __init__(self, inp, oup, kernel_size=3, stride=1, expand_ratio=6, dilation=1, res_connect=None):
+        super().__init__()
+        assert stride in [1, 2]
+        self.stride = stride
+        hidden = int(round(inp * expand_ratio))
+        self.use_res_connect = stride == 1 and inp == oup
+        if res_connect is not None:
+            self.use_res_connect = bool(res_connect and self.use_res_connect)
+        seq = []
+        if expand_ratio != 1:
+            seq.append(BasicConv2d(inp, hidden, kernel_size=1))
+        seq += [BasicConv2d(hidden, hidden, kernel_size, stride=stride, dilation=dilation, groups=hidden),
+                nn.Conv2d(hidden, oup, 1, 1, 0, bias=False), nn.BatchNorm2d(oup)]
+        self.conv = nn.Sequential(*seq)
+        self.geom = (inp, oup, hidden, stride, dilation, expand_ratio != 1)
+
+    def project_folded(self):
+        conv, bn = self.conv[-2], self.conv[-1]
+        wf, bf = fold_bn(conv.weight, bn)
+        return wf.reshape(wf.shape[0], wf.shape[1]), bf
+
+    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, extra_res: Buf = None, tag=""):
+        """``out`` lets the caller place the result in a concat slot.  Returns (Buf, h', w')."""
+        inp, oup, hidden, stride, dil, has_expand = self.geom
+        cur = x
+        i = 0
+        if has_expand:
+            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand")
+            i = 1
+        cur, ho, wo = self.conv[i]._emit(plan, cur, n, h, w, tag=tag + ".dw")
+        wf, bf = self.project_folded()
+        if oup % 8:
+            raise NotImplementedError("project conv with %d outputs is emitted by the readout path" % oup)
+        out = out if out is not None else plan.alloc(n * ho * wo, oup)
+        plan.pw(cur, n * ho * wo, wf, bf, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
+        return out, ho, wo
+
+    def forward(self, x):
+        return _forward_single(self, x)
+
+
+def _forward_single(mod, x):
+    """Stand-alone call of a block on an NCHW fp32 CUDA tensor (pack -> kernels -> unpack)."""
+    from ._kernel_module import KernelModule, require_cuda
+    require_cuda(x, type(mod).__name__)
+    if isinstance(mod, KernelModule):
+        return mod._forward_nchw(x)
+    # BasicConv2d is an nn.Sequential (key layout); borrow the machinery through a throw-away holder
+    holder = mod.__dict__.get("_holder")
+    if holder is None:
+        holder = _Holder(mod)
+        mod.__dict__["_holder"] = holder
+    return holder._forward_nchw(x)
+
+
+class _Holder(KernelModule):
+    def __init__(self, inner):
+        super().__init__()
+        self.__dict__["_inner"] = inner
+
+    def parameters(self, recurse=True):
+        return self.__dict__["_inner"].parameters(recurse)
+
+    def buffers(self, recurse=True):
+        return self.__dict__["_inner"].buffers(recurse)
+
+    def _emit(self, plan, x, n, h, w):
+        inner = self.__dict__["_inner"]
+        if inner.spec[2] == 3 and inner.spec[5] == 1 and inner.spec[0] == 3:
+            raise NotImplementedError("the 3-channel stem runs from the NCHW input (see ReMobileNetV2)")
+        return inner._emit(plan, x, n, h, w)

@@ -1,0 +1,138 @@
+// Shared helpers for the uavsal-b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/uavsal_b200.h"
+
+namespace uavsal {
+
+// ---- status / error reporting ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define UAVSAL_REQUIRE(cond, code, ...)                 \
+    do {                                                \
+        if (!(cond)) {                                  \
+            ::uavsal::set_error(__VA_ARGS__);           \
+            return (code);                              \
+        }                                               \
+    } while (0)
+
+static inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ---- the arena activation format: two bf16 planes (hi, lo) -----------------------------------------
+// x ~= float(hi) + float(lo) with hi = bf16_rn(x), lo = bf16_rn(x - hi)  (16 significant bits).
+struct Act {
+    const uint16_t* p;   // hi plane, offset to the first channel of the slot
+    int64_t plane;       // element offset hi -> lo (0: hi only)
+    int ld;              // row pitch in elements
+};
+struct ActW {
+    uint16_t* p;
+    int64_t plane;
+    int ld;
+};
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t b) { return __uint_as_float(b << 16); }
+
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float x) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+
+// split one fp32 into (hi, lo) bf16 bit patterns
+__device__ __forceinline__ void split1(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f32_to_bf16_bits(x);
+    lo = f32_to_bf16_bits(x - bf16_bits_to_f32(hi));
+}
+
+// unpack a 32-bit word holding two bf16 (little endian: element 0 in the low half)
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+}
+
+// load 8 consecutive channels (16-byte aligned) as fp32
+__device__ __forceinline__ void load8(const uint16_t* hi, int64_t plane, float v[8]) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi));
+    unpack2(h.x, v[0], v[1]);
+    unpack2(h.y, v[2], v[3]);
+    unpack2(h.z, v[4], v[5]);
+    unpack2(h.w, v[6], v[7]);
+    if (plane) {
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(hi + plane));
+        float t[8];
+        unpack2(l.x, t[0], t[1]);
+        unpack2(l.y, t[2], t[3]);
+        unpack2(l.z, t[4], t[5]);
+        unpack2(l.w, t[6], t[7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+}
+
+// load 4 consecutive channels (8-byte aligned) as fp32
+__device__ __forceinline__ void load4(const uint16_t* hi, int64_t plane, float v[4]) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi));
+    unpack2(h.x, v[0], v[1]);
+    unpack2(h.y, v[2], v[3]);
+    if (plane) {
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(hi + plane));
+        float t[4];
+        unpack2(l.x, t[0], t[1]);
+        unpack2(l.y, t[2], t[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += t[i];
+    }
+}
+
+__device__ __forceinline__ float load1(const uint16_t* hi, int64_t plane) {
+    float v = bf16_bits_to_f32(__ldg(hi));
+    if (plane) v += bf16_bits_to_f32(__ldg(hi + plane));
+    return v;
+}
+
+__device__ __forceinline__ void store8(uint16_t* hi, int64_t plane, const float v[8]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split1(v[i], h[i], l[i]);
+    uint4 H = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    *reinterpret_cast<uint4*>(hi) = H;
+    if (plane) {
+        uint4 L = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        *reinterpret_cast<uint4*>(hi + plane) = L;
+    }
+}
+
+__device__ __forceinline__ void store4(uint16_t* hi, int64_t plane, const float v[4]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split1(v[i], h[i], l[i]);
+    *reinterpret_cast<uint2*>(hi) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+    if (plane) *reinterpret_cast<uint2*>(hi + plane) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+
+__device__ __forceinline__ void store1(uint16_t* hi, int64_t plane, float v) {
+    uint32_t h, l;
+    split1(v, h, l);
+    *hi = (uint16_t)h;
+    if (plane) hi[plane] = (uint16_t)l;
+}
+
+__device__ __forceinline__ float relu6f(float x) { return fminf(fmaxf(x, 0.f), 6.f); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// accurate variants used where the reference's sigmoid/tanh feed a recurrence
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace uavsal

@@ -1,0 +1,575 @@
+// tcgen05 / TMA / TMEM GEMM and implicit-GEMM 3x3 for sm_100a.
+//
+//   D[128 x bn] (fp32, TMEM)  =  sum over k-blocks of  A[128 x 64] (smem, K-major, SW128) * B[bn x 64]^T
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> fused bias/ReLU6/residual/sigmoid | TWA blend | LSTM cell ->
+// split-bf16 stores).  Operands are the arena's bf16 hi/lo planes; TERMS=3 issues the error-compensated
+// product Ahi*Bhi + Ahi*Blo + Alo*Bhi into the same fp32 accumulator, TERMS=1 issues Ahi*Bhi only.
+//
+// MODE_PW  : A is a 2-D [M][K] matrix (NHWC rows x channels), tensor map (K, M, plane).
+// MODE_CONV: A is gathered by TMA from NHWC images with a (64ch, TW, TH) box per filter tap; padding comes
+//            from TMA out-of-bounds zero fill; two sources form the virtual concat [x, h] of the recurrences.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace uavsal {
+
+enum { MODE_PW = 0, MODE_CONV = 1 };
+enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2 };
+
+constexpr int kBM = 128;          // rows per tile = TMEM lanes
+constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KiB per plane per stage
+
+struct TcArgs {
+    int M, N;                 // rows (pw) / valid output channels
+    int bn;                   // N tile, multiple of 16, <= 256
+    int num_kb;               // k-blocks per tile
+    int stages;
+    int tmem_cols;            // power of two >= max(32, bn)
+    // conv geometry
+    int H, W, TW, TH, tiles_x, tiles_y;
+    int kb_per_tap, kb_src0;  // k-blocks per tap (both sources) and of source 0
+    int a0_mul, a0_off, a1_mul, a1_off, out_mul, out_off;   // image index = b*mul + off (b = batch index of the tile)
+    const float* bias;
+    int flags;
+    Act res;
+    ActW out;
+    Act x, hprev;             // TWA operands (indexed like out / a1)
+    float* c_state;           // LSTM cell state [b][H*W][N/4]
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+        if (it > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+template <int MODE, int EPI, int TERMS>
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                           const __grid_constant__ CUtensorMap tmA1,
+                                                           const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int NPL = TERMS == 3 ? 2 : 1;                 // planes staged per operand
+    const uint32_t b_bytes = (uint32_t)g.bn * kBK * 2;
+    const uint32_t stage_bytes = NPL * (kABytes + b_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+    uint64_t* empty = full + g.stages;
+    uint64_t* acc_full = empty + g.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, n0 = blockIdx.y * g.bn;
+
+    // tile -> image / origin (conv)
+    int bidx = 0, y0 = 0, x0 = 0;
+    if (MODE == MODE_CONV) {
+        const int per_img = g.tiles_x * g.tiles_y;
+        bidx = tile_m / per_img;
+        const int t = tile_m - bidx * per_img;
+        y0 = (t / g.tiles_x) * g.TH;
+        x0 = (t % g.tiles_x) * g.TW;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                const int s = kb % g.stages;
+                const uint32_t par = ((kb / g.stages) & 1) ^ 1;
+                mbar_wait(empty + s, par);
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                uint8_t* sb = sa + NPL * kABytes;
+                mbar_expect_tx(full + s, stage_bytes);
+                if (MODE == MODE_PW) {
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmA0, full + s, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
+                } else {
+                    const int tap = kb / g.kb_per_tap;
+                    const int r = kb - tap * g.kb_per_tap;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    const bool src0 = r < g.kb_src0;
+                    const CUtensorMap* tm = src0 ? &tmA0 : &tmA1;
+                    const int cch = (src0 ? r : r - g.kb_src0) * kBK;
+                    const int img = src0 ? bidx * g.a0_mul + g.a0_off : bidx * g.a1_mul + g.a1_off;
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
+                }
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, kb * kBK, n0, p);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc(g.bn);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+            const int s = kb % g.stages;
+            const uint32_t par = (kb / g.stages) & 1;
+            mbar_wait(full + s, par);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_hi = a_hi + NPL * kABytes;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t dah = umma_desc(a_hi + k * 32);
+                    const uint64_t dbh = umma_desc(b_hi + k * 32);
+                    umma_bf16(tmem_base, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+                    if (TERMS == 3) {
+                        const uint64_t dal = umma_desc(a_hi + kABytes + k * 32);
+                        const uint64_t dbl = umma_desc(b_hi + b_bytes + k * 32);
+                        umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                        umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(empty + s);                       // frees the smem stage when these MMAs retire
+                if (kb == g.num_kb - 1) umma_commit(acc_full); // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                          // row of the tile
+        int64_t orow, hrow = 0, crow = 0;
+        bool rvalid;
+        if (MODE == MODE_PW) {
+            orow = (int64_t)tile_m * kBM + r;
+            rvalid = orow < g.M;
+        } else {
+            const int y = y0 + r / g.TW, x = x0 + r % g.TW;
+            rvalid = y < g.H && x < g.W;
+            const int64_t pix = (int64_t)y * g.W + x;
+            const int64_t hw = (int64_t)g.H * g.W;
+            orow = (int64_t)(bidx * g.out_mul + g.out_off) * hw + pix;
+            hrow = (int64_t)(bidx * g.a1_mul + g.a1_off) * hw + pix;
+            crow = (int64_t)bidx * hw + pix;
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < g.bn; c0 += 16) {
+            uint32_t raw[16];
+            __syncwarp();
+            tmem_ld16(trow + c0, raw);                         // warp-collective: executed by all lanes
+            const int n = n0 + c0;
+            if (!rvalid || n >= g.N) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+            const bool second = n + 8 < g.N;                   // N is a multiple of 8
+            if (g.bias) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    if (j4 >= 2 && !second) break;
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
+                    v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+                }
+            }
+            if (EPI == EPI_STD) {
+                if (g.flags & UAVSAL_F_RELU6) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
+                }
+                if (g.flags & UAVSAL_F_RESIDUAL) {
+                    float rr[8];
+                    load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                    if (second) {
+                        load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 + j] += rr[j];
+                    }
+                }
+                if (g.flags & UAVSAL_F_SIGMOID) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = sigmoid_acc(v[j]);
+                }
+                store8(g.out.p + orow * g.out.ld + n, g.out.plane, v);
+                if (second) store8(g.out.p + orow * g.out.ld + n + 8, g.out.plane, v + 8);
+            } else if (EPI == EPI_TWA) {
+                // h = i*x_t + (1-i)*h_{t-1}, i = sigmoid(conv)      (model_convlstm.py:283,290)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1 && !second) break;
+                    float xv[8], hv[8];
+                    load8(g.x.p + orow * g.x.ld + n + half * 8, g.x.plane, xv);
+                    load8(g.hprev.p + hrow * g.hprev.ld + n + half * 8, g.hprev.plane, hv);
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float gi = sigmoid_acc(v[half * 8 + j]);
+                        o[j] = gi * xv[j] + (1.f - gi) * hv[j];
+                    }
+                    store8(g.out.p + orow * g.out.ld + n + half * 8, g.out.plane, o);
+                }
+            } else {
+                // interleaved gates (i,f,o,g) x 4 channels     (model_convlstm.py:117-124)
+                const int nch = g.N >> 2, ch = n >> 2;
+                float* cs = g.c_state + crow * nch + ch;
+                const int cnt = second ? 4 : 2;
+                float hout[4];
+                for (int j = 0; j < cnt; ++j) {
+                    const float gi = sigmoid_acc(v[4 * j + 0]), gf = sigmoid_acc(v[4 * j + 1]);
+                    const float go = sigmoid_acc(v[4 * j + 2]), gg = tanhf(v[4 * j + 3]);
+                    const float cn = gf * cs[j] + gi * gg;
+                    cs[j] = cn;
+                    hout[j] = go * tanhf(cn);
+                }
+                if (second) store4(g.out.p + orow * g.out.ld + ch, g.out.plane, hout);
+                else { store1(g.out.p + orow * g.out.ld + ch, g.out.plane, hout[0]); store1(g.out.p + orow * g.out.ld + ch + 1, g.out.plane, hout[1]); }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const char* what) {
+    EncodeTiledFn fn = get_encode();
+    UAVSAL_REQUIRE(fn != nullptr, UAVSAL_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                    reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAVSAL_REQUIRE(r == CUDA_SUCCESS, UAVSAL_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
+// 2-D activation matrix [rows][k] with hi/lo planes -> (k, rows, plane)
+static int map_pw(CUtensorMap* tm, Act a, int64_t rows, int k) {
+    const uint64_t dims[3] = {(uint64_t)k, (uint64_t)rows, a.plane ? 2u : 1u};
+    const uint64_t str[2] = {(uint64_t)a.ld * 2, a.plane ? (uint64_t)a.plane * 2 : (uint64_t)a.ld * 2 * (uint64_t)rows};
+    const uint32_t box[3] = {kBK, kBM, 1};
+    return encode(tm, a.p, 3, dims, str, box, "A(pw)");
+}
+// weights [n][kpad] with hi/lo planes -> (kpad, n, 2)
+static int map_w(CUtensorMap* tm, const uint16_t* w, int n, int kpad, int bn) {
+    const uint64_t dims[3] = {(uint64_t)kpad, (uint64_t)n, 2};
+    const uint64_t str[2] = {(uint64_t)kpad * 2, (uint64_t)kpad * 2 * (uint64_t)n};
+    const uint32_t box[3] = {kBK, (uint32_t)bn, 1};
+    return encode(tm, w, 3, dims, str, box, "B(weights)");
+}
+// NHWC images with hi/lo planes -> (c, w, h, nimg, plane)
+static int map_img(CUtensorMap* tm, Act a, int nimg, int h, int w, int c, int tw, int th) {
+    const uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)nimg, a.plane ? 2u : 1u};
+    const uint64_t row = (uint64_t)a.ld * 2;
+    const uint64_t str[4] = {row, row * w, row * w * h, a.plane ? (uint64_t)a.plane * 2 : row * w * h * (uint64_t)nimg};
+    const uint32_t box[5] = {kBK, (uint32_t)tw, (uint32_t)th, 1, 1};
+    return encode(tm, a.p, 5, dims, str, box, "A(conv)");
+}
+
+static int pick_bn(int n) {
+    // N tile: whole N when it fits one UMMA (<= 256), else 128/192/256 tiles chosen to minimise padding
+    const int n16 = (n + 15) / 16 * 16;
+    if (n16 <= 256) return n16;
+    int best = 256, waste = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 64) {
+        const int w = (n + bn - 1) / bn * bn - n;
+        if (w < waste) { waste = w; best = bn; }
+    }
+    return best;
+}
+
+static int tmem_cols_for(int bn) {
+    int c = 32;
+    while (c < bn) c <<= 1;
+    return c;
+}
+
+template <int MODE, int EPI>
+static int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcArgs& g, int terms, int tiles_m,
+                     cudaStream_t s, const char* what) {
+    const int npl = terms == 3 ? 2 : 1;
+    const uint32_t stage_bytes = npl * (kABytes + (uint32_t)g.bn * kBK * 2);
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > g.num_kb) stages = g.num_kb;
+    if (stages < 1) stages = 1;
+    g.stages = stages;
+    g.tmem_cols = tmem_cols_for(g.bn);
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    dim3 grid(tiles_m, div_up(g.N, g.bn));
+    cudaError_t e;
+    if (terms == 3) {
+        static bool attr3 = false;
+        if (!attr3) {
+            e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+            attr3 = true;
+        }
+        gemm_tc_kernel<MODE, EPI, 3><<<grid, kThreads, smem, s>>>(a0, a1, b, g);
+    } else {
+        static bool attr1 = false;
+        if (!attr1) {
+            e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+            attr1 = true;
+        }
+        gemm_tc_kernel<MODE, EPI, 1><<<grid, kThreads, smem, s>>>(a0, a1, b, g);
+    }
+    return check_launch(what);
+}
+
+// conv tiling: 128 pixels per tile as TW x TH with TW*TH = 128; pick the shape wasting the fewest pixels
+static void pick_tile(int H, int W, int& tw, int& th) {
+    int best = 1 << 30;
+    tw = 16; th = 8;
+    for (int cand = 8; cand <= 128; cand <<= 1) {
+        const int t_h = 128 / cand;
+        const int cover = div_up(W, cand) * cand * div_up(H, t_h) * t_h;
+        if (cover < best) { best = cover; tw = cand; th = t_h; }
+    }
+}
+
+int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img, int a1_mul, int a1_off, int c1,
+            int batch, int H, int W, const uint16_t* wgt, int cout, const float* bias, int flags, int terms, int epi,
+            Act x, Act hprev, float* c_state, ActW out, int out_mul, int out_off, cudaStream_t s, const char* what) {
+    UAVSAL_REQUIRE(c0 % kBK == 0 && c1 % kBK == 0 && c0 > 0, UAVSAL_ENOTSUP, "%s: channels must be multiples of 64", what);
+    UAVSAL_REQUIRE(cout % 8 == 0 && (terms == 1 || terms == 3), UAVSAL_EINVAL, "%s: bad cout/terms", what);
+    TcArgs g{};
+    int tw, th;
+    pick_tile(H, W, tw, th);
+    g.H = H; g.W = W; g.TW = tw; g.TH = th;
+    g.tiles_x = div_up(W, tw); g.tiles_y = div_up(H, th);
+    g.kb_src0 = c0 / kBK; g.kb_per_tap = (c0 + c1) / kBK; g.num_kb = 9 * g.kb_per_tap;
+    g.a0_mul = a0_mul; g.a0_off = a0_off; g.a1_mul = a1_mul; g.a1_off = a1_off; g.out_mul = out_mul; g.out_off = out_off;
+    g.M = batch * H * W; g.N = cout; g.bn = pick_bn(cout);
+    g.bias = bias; g.flags = flags; g.out = out; g.x = x; g.hprev = hprev; g.c_state = c_state;
+    const int kpad = 9 * (c0 + c1);
+    CUtensorMap tA0, tA1, tB;
+    int rc = map_img(&tA0, a0, n0img, H, W, c0, tw, th);
+    if (rc) return rc;
+    if (c1) rc = map_img(&tA1, a1, n1img, H, W, c1, tw, th); else tA1 = tA0;
+    if (rc) return rc;
+    rc = map_w(&tB, wgt, cout, kpad, g.bn);
+    if (rc) return rc;
+    const int tiles_m = batch * g.tiles_x * g.tiles_y;
+    if (epi == EPI_STD) return launch_tc<MODE_CONV, EPI_STD>(tA0, tA1, tB, g, terms, tiles_m, s, what);
+    if (epi == EPI_TWA) return launch_tc<MODE_CONV, EPI_TWA>(tA0, tA1, tB, g, terms, tiles_m, s, what);
+    return launch_tc<MODE_CONV, EPI_LSTM>(tA0, tA1, tB, g, terms, tiles_m, s, what);
+}
+
+// SIMT fall-backs for the recurrences live in gemm_simt.cu
+int twa_sequence_simt(Act x, Act h0, int t_steps, int H, int W, int c, const float* w, ActW seq, cudaStream_t s);
+int lstm_sequence_simt(Act x, Act h0, float* c_state, int b, int t_steps, int H, int W, int cin, int ch, const float* w,
+                       const float* bias, ActW seq, cudaStream_t s);
+
+}  // namespace uavsal
+
+using namespace uavsal;
+
+static inline bool act_ok16(const void* p, int64_t plane, int ld) {
+    return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 8) == 0 && (plane % 8) == 0 && plane >= 0;
+}
+
+extern "C" {
+
+int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, const uint16_t* wgt, int kpad, int n,
+                   const float* bias, int flags, int terms, const uint16_t* res, int64_t res_plane, int res_ld,
+                   uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && act_ok16(out, out_plane, out_ld) && wgt &&
+                       (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 && m > 0 && k > 0 && n > 0 && k % 8 == 0 &&
+                       kpad % 8 == 0 && kpad >= k && n % 8 == 0 && a_ld >= k && out_ld >= n,
+                   UAVSAL_EINVAL, "pw_gemm: bad arguments (m=%d k=%d kpad=%d n=%d)", m, k, kpad, n);
+    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && a_plane != 0), UAVSAL_EINVAL, "pw_gemm: terms must be 1, or 3 with a lo plane");
+    UAVSAL_REQUIRE(!(flags & UAVSAL_F_RESIDUAL) || act_ok16(res, res_plane, res_ld), UAVSAL_EINVAL,
+                   "pw_gemm: residual requested without a residual tensor");
+    UAVSAL_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, UAVSAL_EINVAL, "pw_gemm: bias must be 16-byte aligned");
+    TcArgs g{};
+    g.M = m; g.N = n; g.bn = pick_bn(n); g.num_kb = div_up(k, kBK);
+    g.bias = bias; g.flags = flags;
+    g.res = Act{res, res_plane, res_ld};
+    g.out = ActW{out, out_plane, out_ld};
+    CUtensorMap tA, tB;
+    int rc = map_pw(&tA, Act{a, a_plane, a_ld}, m, k);
+    if (rc) return rc;
+    rc = map_w(&tB, wgt, n, kpad, g.bn);
+    if (rc) return rc;
+    return launch_tc<MODE_PW, EPI_STD>(tA, tA, tB, g, terms, div_up(m, kBM), (cudaStream_t)stream, "pw_gemm");
+}
+
+int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, const uint16_t* wgt,
+                   int cout, const float* bias, int flags, int terms, uint16_t* out, int64_t out_plane, int out_ld,
+                   void* stream) {
+    UAVSAL_REQUIRE(act_ok16(in, in_plane, in_ld) && act_ok16(out, out_plane, out_ld) && wgt && n > 0 && h > 0 && w > 0 &&
+                       in_ld >= c && out_ld >= cout,
+                   UAVSAL_EINVAL, "conv3x3: bad arguments");
+    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && in_plane != 0), UAVSAL_EINVAL, "conv3x3: terms must be 1, or 3 with a lo plane");
+    Act a{in, in_plane, in_ld};
+    return conv_tc(a, n, 1, 0, c, a, n, 1, 0, 0, n, h, w, wgt, cout, bias, flags, terms, EPI_STD, Act{}, Act{}, nullptr,
+                   ActW{out, out_plane, out_ld}, 1, 0, (cudaStream_t)stream, "conv3x3");
+}
+
+int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
+                        int t_steps, int h, int w, int c, const uint16_t* wgt, const float* wgt_f32, int terms,
+                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
+                       t_steps > 0 && c % 8 == 0 && x_ld >= c && h0_ld >= c && seq_ld >= c,
+                   UAVSAL_EINVAL, "twa_sequence: bad arguments");
+    UAVSAL_REQUIRE((wgt != nullptr) != (wgt_f32 != nullptr), UAVSAL_EINVAL,
+                   "twa_sequence: pass exactly one of wgt (tcgen05) / wgt_f32 (SIMT)");
+    Act X{x, x_plane, x_ld}, H0{h0, h0_plane, h0_ld};
+    ActW S{seq_out, seq_plane, seq_ld};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (wgt_f32) return twa_sequence_simt(X, H0, t_steps, h, w, c, wgt_f32, S, s);
+    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
+                   "twa_sequence: terms=3 needs lo planes");
+    Act SA{seq_out, seq_plane, seq_ld};
+    for (int t = 0; t < t_steps; ++t) {
+        // step t: A = [x_t, h_{t-1}], out = seq[t]
+        int rc;
+        if (t == 0)
+            rc = conv_tc(X, t_steps, 0, 0, c, H0, 1, 0, 0, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S,
+                         0, 0, s, "twa_sequence");
+        else
+            rc = conv_tc(X, t_steps, 0, t, c, SA, t_steps, 0, t - 1, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, SA,
+                         nullptr, S, 0, t, s, "twa_sequence");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane,
+                             int h0_ld, float* c_state, int b, int t_steps, int h, int w, int cin, int ch,
+                             const uint16_t* wgt, const float* wgt_f32, const float* bias, int terms, uint16_t* seq_out,
+                             int64_t seq_plane, int seq_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
+                       c_state && b > 0 && t_steps > 0 && cin % 8 == 0 && ch % 8 == 0 && x_ld >= cin && h0_ld >= ch &&
+                       seq_ld >= ch,
+                   UAVSAL_EINVAL, "convlstm_sequence: bad arguments");
+    UAVSAL_REQUIRE((wgt != nullptr) != (wgt_f32 != nullptr), UAVSAL_EINVAL,
+                   "convlstm_sequence: pass exactly one of wgt (tcgen05) / wgt_f32 (SIMT)");
+    Act X{x, x_plane, x_ld}, H0{h0, h0_plane, h0_ld};
+    ActW S{seq_out, seq_plane, seq_ld};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (wgt_f32) return lstm_sequence_simt(X, H0, c_state, b, t_steps, h, w, cin, ch, wgt_f32, bias, S, s);
+    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
+                   "convlstm_sequence: terms=3 needs lo planes");
+    Act SA{seq_out, seq_plane, seq_ld};
+    for (int t = 0; t < t_steps; ++t) {
+        // image index of batch element bi: x -> bi*T + t ; h_{t-1} -> h0[bi] or seq[bi*T + t-1] ; out -> seq[bi*T + t]
+        int rc;
+        if (t == 0)
+            rc = conv_tc(X, b * t_steps, t_steps, 0, cin, H0, b, 1, 0, ch, b, h, w, wgt, 4 * ch, bias, 0, terms, EPI_LSTM,
+                         Act{}, Act{}, c_state, S, t_steps, 0, s, "convlstm_sequence");
+        else
+            rc = conv_tc(X, b * t_steps, t_steps, t, cin, SA, b * t_steps, t_steps, t - 1, ch, b, h, w, wgt, 4 * ch, bias, 0,
+                         terms, EPI_LSTM, Act{}, Act{}, c_state, S, t_steps, t, s, "convlstm_sequence");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

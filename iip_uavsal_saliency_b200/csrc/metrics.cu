@@ -1,0 +1,216 @@
+// CC / NSS / KLD / SIM of utils_score_torch.py:180-218 (helpers 20-50) as one fused kernel per map pair.
+//
+// One thread-block CLUSTER of 8 CTAs owns one (pred, density, fixation) triple: every CTA streams one eighth
+// of the pixels.  Pass 1 reduces the raw moments and extrema (warp shuffles -> shared memory -> distributed
+// shared memory across the cluster); pass 2 re-reads pred/density (L2 resident: one pair is 1.8 MB) for the
+// two quantities that need the pass-1 statistics element-wise (KLD terms, SIM min-sum).  Element-wise
+// arithmetic follows the reference's fp32 expressions; accumulation is fp64.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace uavsal {
+
+constexpr int kMetThreads = 512;
+constexpr int kCluster = 8;
+constexpr float kEpsF = 2.2204e-16f;     // utils_score_torch.py:13
+constexpr double kEps = 2.2204e-16;
+
+enum { S_P = 0, S_P2, S_T, S_T2, S_TP, S_F, S_FP, S_MINP, S_MAXP, S_MINT, S_MAXT, S_COUNT };
+
+template <typename T>
+__device__ __forceinline__ void load4v(const T* p, float v[4]);
+template <>
+__device__ __forceinline__ void load4v<float>(const float* p, float v[4]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void load4v<uint8_t>(const uint8_t* p, float v[4]) {
+    const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p));
+    v[0] = (float)(q & 0xFF); v[1] = (float)((q >> 8) & 0xFF); v[2] = (float)((q >> 16) & 0xFF); v[3] = (float)(q >> 24);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetThreads)
+metrics4_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, float* __restrict__ out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int pair = blockIdx.y;
+    const T* P = pred + (int64_t)pair * hw;
+    const T* D = truth + (int64_t)pair * 2 * hw;     // channel 0: density
+    const T* Fx = D + hw;                            // channel 1: fixations
+
+    __shared__ double wpart[kMetThreads / 32][S_COUNT];
+    __shared__ double part1[S_COUNT];                // this CTA's pass-1 partials (read by the whole cluster)
+    __shared__ double part2[2];                      // this CTA's pass-2 partials
+    __shared__ double tot[S_COUNT];
+
+    // slice of this CTA, in units of 4 pixels
+    const int n4 = hw >> 2;
+    const int per = (n4 + kCluster - 1) / kCluster;
+    const int q0 = rank * per, q1 = min(n4, q0 + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ------------------------------- pass 1 -------------------------------
+    double s[S_COUNT];
+#pragma unroll
+    for (int i = 0; i < S_COUNT; ++i) s[i] = 0.0;
+    s[S_MINP] = s[S_MINT] = 1e300;
+    s[S_MAXP] = s[S_MAXT] = -1e300;
+    auto acc1 = [&](float p, float t, float f) {
+        s[S_P] += p; s[S_P2] += (double)p * p; s[S_T] += t; s[S_T2] += (double)t * t;
+        s[S_TP] += (double)t * p; s[S_F] += f; s[S_FP] += (double)f * p;
+        s[S_MINP] = fmin(s[S_MINP], (double)p); s[S_MAXP] = fmax(s[S_MAXP], (double)p);
+        s[S_MINT] = fmin(s[S_MINT], (double)t); s[S_MAXT] = fmax(s[S_MAXT], (double)t);
+    };
+    for (int q = q0 + threadIdx.x; q < q1; q += kMetThreads) {
+        float p[4], t[4], f[4];
+        load4v<T>(P + 4 * q, p);
+        load4v<T>(D + 4 * q, t);
+        load4v<T>(Fx + 4 * q, f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc1(p[j], t[j], f[j]);
+    }
+    if (rank == kCluster - 1) {                       // pixel tail when hw % 4 != 0
+        for (int i = (n4 << 2) + threadIdx.x; i < hw; i += kMetThreads) acc1((float)P[i], (float)D[i], (float)Fx[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < S_COUNT; ++i) {
+        double v = s[i];
+        if (i == S_MINP || i == S_MINT) v = warp_min(v);
+        else if (i == S_MAXP || i == S_MAXT) v = warp_max(v);
+        else v = warp_sum(v);
+        if (lane == 0) wpart[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < S_COUNT) {
+        const int i = threadIdx.x;
+        double v = wpart[0][i];
+        for (int w = 1; w < kMetThreads / 32; ++w) {
+            if (i == S_MINP || i == S_MINT) v = fmin(v, wpart[w][i]);
+            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, wpart[w][i]);
+            else v += wpart[w][i];
+        }
+        part1[i] = v;
+    }
+    cluster.sync();
+    if (threadIdx.x < S_COUNT) {
+        const int i = threadIdx.x;
+        double v = 0.0;
+        for (int r = 0; r < kCluster; ++r) {
+            const double o = *cluster.map_shared_rank(&part1[i], r);
+            if (r == 0) v = o;
+            else if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+            else v += o;
+        }
+        tot[i] = v;
+    }
+    __syncthreads();
+
+    // statistics shared by pass 2 (fp32, as the reference holds them)
+    const double n = (double)hw;
+    const float sumP = (float)tot[S_P], sumT = (float)tot[S_T];
+    const float minP = (float)tot[S_MINP], minT = (float)tot[S_MINT];
+    const float rngP = ((float)tot[S_MAXP] - minP) + kEpsF, rngT = ((float)tot[S_MAXT] - minT) + kEpsF;
+    // sum of the min-max normalised maps, analytically from the raw sums
+    const float nsumP = (float)((tot[S_P] - n * tot[S_MINP]) / (double)rngP) + kEpsF;
+    const float nsumT = (float)((tot[S_T] - n * tot[S_MINT]) / (double)rngT) + kEpsF;
+    const float dP = sumP + kEpsF, dT = sumT + kEpsF;
+
+    // ------------------------------- pass 2 -------------------------------
+    double kld = 0.0, sim = 0.0;
+    auto acc2 = [&](float p, float t) {
+        const float th = __fdiv_rn(t, dT), ph = __fdiv_rn(p, dP);                      // utils_score_torch.py:182-183
+        kld += (double)(th * logf(__fdiv_rn(th, ph + kEpsF) + kEpsF));                 // :185
+        const float tn = __fdiv_rn(__fdiv_rn(t - minT, rngT), nsumT);                  // :209, :212
+        const float pn = __fdiv_rn(__fdiv_rn(p - minP, rngP), nsumP);                  // :210, :213
+        sim += (double)fminf(tn, pn);                                                  // :215-216
+    };
+    for (int q = q0 + threadIdx.x; q < q1; q += kMetThreads) {
+        float p[4], t[4];
+        load4v<T>(P + 4 * q, p);
+        load4v<T>(D + 4 * q, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc2(p[j], t[j]);
+    }
+    if (rank == kCluster - 1) {
+        for (int i = (n4 << 2) + threadIdx.x; i < hw; i += kMetThreads) acc2((float)P[i], (float)D[i]);
+    }
+    kld = warp_sum(kld);
+    sim = warp_sum(sim);
+    if (lane == 0) { wpart[warp][0] = kld; wpart[warp][1] = sim; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int w = 0; w < kMetThreads / 32; ++w) v += wpart[w][threadIdx.x];
+        part2[threadIdx.x] = v;
+    }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+        double k = 0.0, sm = 0.0;
+        for (int r = 0; r < kCluster; ++r) {
+            k += *cluster.map_shared_rank(&part2[0], r);
+            sm += *cluster.map_shared_rank(&part2[1], r);
+        }
+        // CC (:188-197) and NSS (:200-204) from the raw moments; std is unbiased (torch.std, :49)
+        const double mP = tot[S_P] / n, mT = tot[S_T] / n;
+        const double ssP = fmax(tot[S_P2] - tot[S_P] * mP, 0.0), ssT = fmax(tot[S_T2] - tot[S_T] * mT, 0.0);
+        const double sdP = sqrt(ssP / (n - 1.0)), sdT = sqrt(ssT / (n - 1.0));
+        const double cov = tot[S_TP] - tot[S_T] * mP;
+        const double zz = (sdP + kEps) * (sdT + kEps);
+        const double r1 = cov / zz;
+        const double r2 = sqrt((ssP / ((sdP + kEps) * (sdP + kEps))) * (ssT / ((sdT + kEps) * (sdT + kEps))));
+        const double cc = r1 / (r2 + kEps);
+        const double nss = ((tot[S_FP] - mP * tot[S_F]) / (sdP + kEps)) / (tot[S_F] + kEps);
+        out[pair * 4 + 0] = (float)cc;
+        out[pair * 4 + 1] = (float)nss;
+        out[pair * 4 + 2] = (float)k;
+        out[pair * 4 + 3] = (float)sm;
+    }
+    cluster.sync();     // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+}  // namespace uavsal
+
+using namespace uavsal;
+
+extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, int n, int h, int w, double* scratch,
+                               float* out, void* stream) {
+    (void)scratch;
+    UAVSAL_REQUIRE(pred && truth && out && n > 0 && h > 0 && w > 0 && (dtype == 0 || dtype == 1), UAVSAL_EINVAL,
+                   "metrics4: bad arguments");
+    UAVSAL_REQUIRE(n <= 65535, UAVSAL_ENOTSUP, "metrics4: at most 65535 pairs per call");
+    const int hw = h * w;
+    UAVSAL_REQUIRE(hw >= 2, UAVSAL_EINVAL, "metrics4: map must have at least 2 pixels (unbiased std)");
+    const bool al = dtype == 0 ? ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0 && hw % 4 == 0
+                               : ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 3) == 0 && hw % 4 == 0;
+    UAVSAL_REQUIRE(al, UAVSAL_ENOTSUP, "metrics4: h*w must be a multiple of 4 and the tensors 16-byte aligned");
+    dim3 grid(kCluster, n);
+    if (dtype == 0)
+        metrics4_kernel<float><<<grid, kMetThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out);
+    else
+        metrics4_kernel<uint8_t><<<grid, kMetThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint8_t*>(pred), reinterpret_cast<const uint8_t*>(truth), hw, out);
+    return check_launch("metrics4");
+}

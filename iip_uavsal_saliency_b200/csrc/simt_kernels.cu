@@ -1,0 +1,543 @@
+// HBM-bound kernels of the UAVSal path: layout conversion, stem conv, depthwise 3x3, bilinear (align_corners),
+// temporal differences, context-prior sum, readout dot+sigmoid, uint8 post-processing.
+// All activations are NHWC split-bf16 planes (common.cuh).  sm_100a only.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace uavsal {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int hw, ActW dst, int cpad) {
+    const int groups = cpad >> 3;
+    const int64_t total = (int64_t)n * hw * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % hw);
+        const int64_t r = i / hw;
+        const int g = (int)(r % groups);
+        const int img = (int)(r / groups);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = g * 8 + j;
+            v[j] = ch < c ? __ldg(src + ((int64_t)img * c + ch) * hw + p) : 0.f;
+        }
+        store8(dst.p + ((int64_t)img * hw + p) * dst.ld + g * 8, dst.plane, v);
+    }
+}
+
+__global__ void unpack_nchw_kernel(Act src, int n, int c, int hw, float* __restrict__ dst) {
+    const int64_t total = (int64_t)n * c * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % hw);
+        const int64_t r = i / hw;
+        const int ch = (int)(r % c);
+        const int img = (int)(r / c);
+        dst[i] = load1(src.p + ((int64_t)img * hw + p) * src.ld + ch, src.plane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stem: (normalise) + conv3x3 s2 p1 (3->32) + BN + ReLU6      [utils_data.py:43-65, torchvision features[0]]
+// one thread per output pixel, 32 accumulators, weights [27][32] in shared memory
+// ---------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float stem_fetch(const void* x, int img, int ch, int y, int xx, int h, int w) {
+    if (KIND == 0) {
+        return __ldg(reinterpret_cast<const float*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
+    } else {
+        uint8_t u;
+        if (KIND == 1) u = __ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
+        else           u = __ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch);
+        const float mean = ch == 0 ? 0.485f : (ch == 1 ? 0.456f : 0.406f);
+        const float sd = ch == 0 ? 0.229f : (ch == 1 ? 0.224f : 0.225f);
+        const float f = __fdiv_rn((float)u, 255.0f);
+        return __fdiv_rn(__fsub_rn(f, mean), sd);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, int n, int h, int w, int ho, int wo,
+                                                   const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                   ActW out) {
+    __shared__ float4 sw[27 * 8];
+    __shared__ float sb[32];
+    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int64_t total = (int64_t)n * ho * wo;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = (int)(i % wo);
+    const int oy = (int)((i / wo) % ho);
+    const int img = (int)(i / ((int64_t)wo * ho));
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = sb[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int y = oy * 2 - 1 + ky;
+        if (y < 0 || y >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = ox * 2 - 1 + kx;
+            if (xx < 0 || xx >= w) continue;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float v = stem_fetch<KIND>(x, img, ch, y, xx, h, w);
+                const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 ww = wr[q];
+                    acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+                    acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+                    acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+                    acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = relu6f(acc[j]);
+    uint16_t* o = out.p + i * out.ld;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) store8(o + q * 8, out.plane, acc + q * 8);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// depthwise 3x3 + BN + ReLU6, stride 1|2, dilation d, pad d     [model.py:92, torchvision InvertedResidual]
+// one thread per (output pixel, 8-channel group); taps falling in the padding are skipped
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw3x3_kernel(Act in, int n, int h, int w, int c, int ho, int wo, int stride,
+                                                    int dil, const float* __restrict__ wgt,
+                                                    const float* __restrict__ bias, int relu6, ActW out) {
+    const int groups = c >> 3;
+    const int64_t total = (int64_t)n * ho * wo * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int ox = (int)(pix % wo);
+    const int oy = (int)((pix / wo) % ho);
+    const int img = (int)(pix / ((int64_t)wo * ho));
+    const int c0 = g * 8;
+    float acc[8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int y = oy * stride + (ky - 1) * dil;
+        if (y < 0 || y >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = ox * stride + (kx - 1) * dil;
+            if (xx < 0 || xx >= w) continue;
+            float v[8];
+            load8(in.p + (((int64_t)img * h + y) * w + xx) * in.ld + c0, in.plane, v);
+            const float* wr = wgt + (ky * 3 + kx) * c + c0;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
+            acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+            acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+            acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+            acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+        }
+    }
+    if (relu6) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = relu6f(acc[j]);
+    }
+    store8(out.p + pix * out.ld + c0, out.plane, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bilinear, align_corners=True, into a concat slot; output frame i reads source frame i % n_src
+// [model.py:152-153, 360-361; ATen upsample_bilinear2d: ratio=(in-1)/(out-1), src=ratio*dst, l1=src-floor]
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int hs, int ws, int c, ActW out,
+                                                          int n_dst, int hd, int wd, float ry, float rx) {
+    const int groups = c >> 3;
+    const int64_t total = (int64_t)n_dst * hd * wd * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int ox = (int)(pix % wd);
+    const int oy = (int)((pix / wd) % hd);
+    const int img = (int)(pix / ((int64_t)wd * hd));
+    const int simg = img % n_src;
+    const float sy = __fmul_rn(ry, (float)oy);
+    const float sx = __fmul_rn(rx, (float)ox);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const uint16_t* base = in.p + (int64_t)simg * hs * ws * in.ld + g * 8;
+    float a[8], b[8], cc[8], d[8], r[8];
+    load8(base + ((int64_t)y0 * ws + x0) * in.ld, in.plane, a);
+    load8(base + ((int64_t)y0 * ws + x1) * in.ld, in.plane, b);
+    load8(base + ((int64_t)y1 * ws + x0) * in.ld, in.plane, cc);
+    load8(base + ((int64_t)y1 * ws + x1) * in.ld, in.plane, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        r[j] = ly0 * (lx0 * a[j] + lx1 * b[j]) + ly1 * (lx0 * cc[j] + lx1 * d[j]);
+    store8(out.p + pix * out.ld + g * 8, out.plane, r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// teConv_sub neighbour differences [model.py:194-200]
+//   first half : x[i]-x[i-1]   (i=0: x[1]-x[0])
+//   second half: x[i]-x[i+1]   (i=n-1: x[n-2]-x[n-1])
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, int c, ActW out) {
+    const int groups = c >> 3;
+    const int64_t total = (int64_t)n * hw * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;          // img*hw + p
+    const int img = (int)(pix / hw);
+    const int64_t fs = (int64_t)hw * in.ld;  // frame stride
+    const uint16_t* cur = in.p + pix * in.ld + g * 8;
+    float x[8], pv[8], nx[8], d0[8], d1[8];
+    load8(cur, in.plane, x);
+    if (img > 0) load8(cur - fs, in.plane, pv);
+    if (img < n - 1) load8(cur + fs, in.plane, nx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        d0[j] = img > 0 ? x[j] - pv[j] : nx[j] - x[j];
+        d1[j] = img < n - 1 ? x[j] - nx[j] : pv[j] - x[j];
+    }
+    uint16_t* o = out.p + pix * out.ld + g * 8;
+    store8(o, out.plane, d0);
+    store8(o + c, out.plane, d1);
+}
+
+// context prior: sum over the T frames of each chunk [model.py:357-358]
+__global__ void __launch_bounds__(256) ctx_sum_kernel(Act in, int b, int t, int hw, int c, ActW out) {
+    const int groups = c >> 3;
+    const int64_t total = (int64_t)b * hw * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;          // chunk*hw + p
+    const int chunk = (int)(pix / hw);
+    const int p = (int)(pix % hw);
+    float s[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int k = 0; k < t; ++k) {
+        load8(in.p + (((int64_t)chunk * t + k) * hw + p) * in.ld + g * 8, in.plane, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+    store8(out.p + pix * out.ld + g * 8, out.plane, s);
+}
+
+__global__ void __launch_bounds__(256) add_kernel(Act a, Act b, int64_t rows, int c, ActW out) {
+    const int groups = c >> 3;
+    const int64_t total = rows * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t r = i / groups;
+    float x[8], y[8];
+    load8(a.p + r * a.ld + g * 8, a.plane, x);
+    load8(b.p + r * b.ld + g * 8, b.plane, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    store8(out.p + r * out.ld + g * 8, out.plane, x);
+}
+
+// readout project (k -> 1) + BN + sigmoid: one warp per row [conv_out_st.conv.2/.3, model.py:373]
+__global__ void __launch_bounds__(256) dot_sigmoid_kernel(Act a, int64_t rows, int k, const float* __restrict__ wgt,
+                                                          float bias, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const uint16_t* ar = a.p + row * a.ld;
+    float s = 0.f;
+    for (int k0 = lane * 8; k0 < k; k0 += 256) {
+        float v[8];
+        load8(ar + k0, a.plane, v);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + k0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wgt + k0 + 4));
+        s += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = sigmoid_acc(s + bias);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// postprocess_predictions + np2mat [utils_data.py:289-303, 68-82]; cv2.resize INTER_LINEAR semantics
+// ---------------------------------------------------------------------------------------------------
+struct PostGeom {
+    int hs, ws;        // source map
+    int rh, rw;        // resized (before crop)
+    int oy, ox;        // crop offset
+    int hd, wd;        // output
+    double sy, sx;     // cv2 scale = src/dst
+};
+
+__device__ __forceinline__ void cv_tap(int d, double scale, int srcn, int& s0, int& s1, float& w1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= srcn - 1) { s = srcn - 1; f = 0.f; }
+    s0 = s;
+    s1 = min(s + 1, srcn - 1);
+    w1 = f;
+}
+
+__device__ __forceinline__ float post_value(const float* __restrict__ m, const PostGeom& g, int y, int x) {
+    int y0, y1, x0, x1;
+    float wy, wx;
+    cv_tap(y + g.oy, g.sy, g.hs, y0, y1, wy);
+    cv_tap(x + g.ox, g.sx, g.ws, x0, x1, wx);
+    const float ax = 1.f - wx, ay = 1.f - wy;
+    const float r0 = __fadd_rn(__fmul_rn(m[y0 * g.ws + x0], ax), __fmul_rn(m[y0 * g.ws + x1], wx));
+    const float r1 = __fadd_rn(__fmul_rn(m[y1 * g.ws + x0], ax), __fmul_rn(m[y1 * g.ws + x1], wx));
+    return __fadd_rn(__fmul_rn(r0, ay), __fmul_rn(r1, wy));
+}
+
+__global__ void __launch_bounds__(256) post_max_kernel(const float* __restrict__ maps, PostGeom g,
+                                                       float* __restrict__ frame_max) {
+    const int img = blockIdx.y;
+    const float* m = maps + (int64_t)img * g.hs * g.ws;
+    const int total = g.hd * g.wd;
+    float mx = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        mx = fmaxf(mx, post_value(m, g, i / g.wd, i % g.wd));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmaxf(mx, s[k]);
+        atomicMax(reinterpret_cast<int*>(frame_max) + img, __float_as_int(mx));   // maps are positive (sigmoid)
+    }
+}
+
+__global__ void __launch_bounds__(256) post_write_kernel(const float* __restrict__ maps, PostGeom g,
+                                                         const float* __restrict__ frame_max,
+                                                         uint8_t* __restrict__ out) {
+    const int img = blockIdx.y;
+    const float* m = maps + (int64_t)img * g.hs * g.ws;
+    const float mx = frame_max[img];
+    const int total4 = (g.hd * g.wd) >> 2;     // wd % 4 == 0 is required by the host wrapper
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (int64_t)img * g.hd * g.wd);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int p = i << 2;
+        const int y = p / g.wd, x = p % g.wd;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = __fmul_rn(__fdiv_rn(post_value(m, g, y, x + j), mx), 255.f);
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            pk |= ((uint32_t)__float2int_rn(v) & 0xFFu) << (8 * j);   // rint = round half to even
+        }
+        o[i] = pk;
+    }
+}
+
+__global__ void __launch_bounds__(256) post_write_f32_kernel(const float* __restrict__ maps, PostGeom g,
+                                                             const float* __restrict__ frame_max,
+                                                             float* __restrict__ out) {
+    const int img = blockIdx.y;
+    const float* m = maps + (int64_t)img * g.hs * g.ws;
+    const float mx = frame_max[img];
+    const int total = g.hd * g.wd;
+    float* o = out + (int64_t)img * total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        o[i] = __fmul_rn(__fdiv_rn(post_value(m, g, i / g.wd, i % g.wd), mx), 255.f);
+}
+
+}  // namespace uavsal
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+using namespace uavsal;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool act_ok(const void* p, int64_t plane, int ld) {
+    return p != nullptr && aligned16(p) && (ld % 8) == 0 && (plane % 8) == 0 && plane >= 0;
+}
+
+extern "C" {
+
+int uavsal_version(void) { return 1; }
+const char* uavsal_arch(void) { return "sm_100a"; }
+const char* uavsal_last_error(void) { return g_err; }
+
+int uavsal_device_ok(int device) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return (int)e; }
+    UAVSAL_REQUIRE(p.major == 10, UAVSAL_ENOTSUP, "device %d is sm_%d%d, this library is sm_100a only", device, p.major, p.minor);
+    return 0;
+}
+
+int uavsal_pack_nchw_f32(const float* src, int n, int c, int h, int w, uint16_t* dst, int64_t plane, int ld, int cpad,
+                         void* stream) {
+    UAVSAL_REQUIRE(src && act_ok(dst, plane, ld) && cpad % 8 == 0 && cpad >= c && ld >= cpad && n > 0, UAVSAL_EINVAL,
+                   "pack_nchw_f32: bad arguments");
+    const int64_t total = (int64_t)n * h * w * (cpad / 8);
+    pack_nchw_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h * w, ActW{dst, plane, ld}, cpad);
+    return check_launch("pack_nchw_f32");
+}
+
+int uavsal_unpack_nchw_f32(const uint16_t* src, int64_t plane, int ld, int n, int c, int h, int w, float* dst,
+                           void* stream) {
+    UAVSAL_REQUIRE(dst && src && ld >= c && n > 0, UAVSAL_EINVAL, "unpack_nchw_f32: bad arguments");
+    const int64_t total = (int64_t)n * c * h * w;
+    unpack_nchw_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{src, plane, ld}, n, c, h * w, dst);
+    return check_launch("unpack_nchw_f32");
+}
+
+int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const float* wgt, const float* bias,
+                          uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(x && wgt && bias && aligned16(wgt) && act_ok(out, out_plane, out_ld) && out_ld >= 32 && n > 0 &&
+                       h >= 2 && w >= 2 && x_kind >= 0 && x_kind <= 2,
+                   UAVSAL_EINVAL, "stem_conv3x3s2: bad arguments");
+    const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+    const int64_t total = (int64_t)n * ho * wo;
+    const dim3 grid(div_up(total, 128));
+    ActW o{out, out_plane, out_ld};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_kind == 0) stem_kernel<0><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
+    else if (x_kind == 1) stem_kernel<1><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
+    else stem_kernel<2><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
+    return check_launch("stem_conv3x3s2");
+}
+
+int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, int stride, int dilation,
+                 const float* wgt, const float* bias, int relu6, uint16_t* out, int64_t out_plane, int out_ld,
+                 void* stream) {
+    UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && wgt && bias && aligned16(wgt) &&
+                       aligned16(bias) && c % 8 == 0 && c > 0 && in_ld >= c && out_ld >= c && n > 0,
+                   UAVSAL_EINVAL, "dw3x3: bad arguments (c=%d)", c);
+    UAVSAL_REQUIRE((stride == 1 || stride == 2) && dilation >= 1 && (stride == 1 || dilation == 1), UAVSAL_ENOTSUP,
+                   "dw3x3: stride %d dilation %d unsupported", stride, dilation);   // model.py:78 assert stride in [1,2]
+    const int ho = stride == 1 ? h : (h - 1) / 2 + 1, wo = stride == 1 ? w : (w - 1) / 2 + 1;
+    const int64_t total = (int64_t)n * ho * wo * (c / 8);
+    dw3x3_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n, h, w, c, ho, wo,
+                                                                      stride, dilation, wgt, bias, relu6,
+                                                                      ActW{out, out_plane, out_ld});
+    return check_launch("dw3x3");
+}
+
+int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_src, int hs, int ws, int c, uint16_t* out,
+                       int64_t out_plane, int out_ld, int n_dst, int hd, int wd, void* stream) {
+    UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && n_src > 0 &&
+                       n_dst > 0 && hs > 0 && ws > 0 && hd > 0 && wd > 0,
+                   UAVSAL_EINVAL, "bilinear_ac: bad arguments");
+    const float ry = hd > 1 ? (float)(hs - 1) / (float)(hd - 1) : 0.f;
+    const float rx = wd > 1 ? (float)(ws - 1) / (float)(wd - 1) : 0.f;
+    const int64_t total = (int64_t)n_dst * hd * wd * (c / 8);
+    bilinear_ac_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n_src, hs, ws, c,
+                                                                            ActW{out, out_plane, out_ld}, n_dst, hd, wd,
+                                                                            ry, rx);
+    return check_launch("bilinear_ac");
+}
+
+int uavsal_tdiff_cat(const uint16_t* in, int64_t in_plane, int in_ld, int n, int hw, int c, uint16_t* out,
+                     int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && out_ld >= 2 * c,
+                   UAVSAL_EINVAL, "tdiff_cat: bad arguments");
+    UAVSAL_REQUIRE(n >= 2, UAVSAL_EINVAL, "tdiff_cat: needs at least 2 frames per call (model.py:194 indexes x1[1])");
+    const int64_t total = (int64_t)n * hw * (c / 8);
+    tdiff_cat_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n, hw, c,
+                                                                          ActW{out, out_plane, out_ld});
+    return check_launch("tdiff_cat");
+}
+
+int uavsal_ctx_sum(const uint16_t* in, int64_t in_plane, int in_ld, int b, int t, int hw, int c, uint16_t* out,
+                   int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && b > 0 && t > 0,
+                   UAVSAL_EINVAL, "ctx_sum: bad arguments");
+    const int64_t total = (int64_t)b * hw * (c / 8);
+    ctx_sum_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, b, t, hw, c,
+                                                                        ActW{out, out_plane, out_ld});
+    return check_launch("ctx_sum");
+}
+
+int uavsal_add(const uint16_t* a, int64_t a_plane, int a_ld, const uint16_t* b, int64_t b_plane, int b_ld, int64_t rows,
+               int c, uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(act_ok(a, a_plane, a_ld) && act_ok(b, b_plane, b_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 &&
+                       c > 0 && rows > 0,
+                   UAVSAL_EINVAL, "add: bad arguments");
+    add_kernel<<<div_up(rows * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(Act{a, a_plane, a_ld}, Act{b, b_plane, b_ld},
+                                                                             rows, c, ActW{out, out_plane, out_ld});
+    return check_launch("add");
+}
+
+int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t rows, int k, const float* wgt, float bias,
+                       float* out_f32, void* stream) {
+    UAVSAL_REQUIRE(act_ok(a, a_plane, a_ld) && wgt && aligned16(wgt) && out_f32 && k % 8 == 0 && k > 0 && rows > 0,
+                   UAVSAL_EINVAL, "dot_sigmoid: bad arguments");
+    dot_sigmoid_kernel<<<div_up(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(Act{a, a_plane, a_ld}, rows, k, wgt, bias,
+                                                                                out_f32);
+    return check_launch("dot_sigmoid");
+}
+
+static int post_common(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max, uint8_t* out_u8,
+                       float* out_f32, void* stream) {
+    UAVSAL_REQUIRE(maps && frame_max && (out_u8 || out_f32) && n > 0 && hs > 0 && ws > 0 && hd > 0 && wd > 0, UAVSAL_EINVAL,
+                   "post: bad arguments");
+    UAVSAL_REQUIRE(out_f32 || (wd % 4 == 0 && (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0), UAVSAL_ENOTSUP,
+                   "post_u8: output width must be a multiple of 4");
+    PostGeom g;
+    g.hs = hs; g.ws = ws; g.hd = hd; g.wd = wd;
+    // utils_data.py:291-301: compare rates, resize keeping aspect, centre-crop
+    const double rows_rate = (double)hd / hs, cols_rate = (double)wd / ws;
+    if (rows_rate > cols_rate) {
+        g.rh = hd; g.rw = (int)(((int64_t)ws * hd) / hs);
+        g.oy = 0; g.ox = (g.rw - wd) / 2;
+    } else {
+        g.rw = wd; g.rh = (int)(((int64_t)hs * wd) / ws);
+        g.ox = 0; g.oy = (g.rh - hd) / 2;
+    }
+    UAVSAL_REQUIRE(g.rh >= hd && g.rw >= wd, UAVSAL_ENOTSUP, "post_u8: letterbox geometry not supported");
+    g.sy = (double)hs / g.rh;
+    g.sx = (double)ws / g.rw;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(frame_max, 0, sizeof(float) * n, s);
+    if (e != cudaSuccess) { set_error("post_u8 memset: %s", cudaGetErrorString(e)); return (int)e; }
+    const int bpf = max(1, min(64, div_up((int64_t)hd * wd, 256 * 16)));
+    post_max_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max);
+    if (out_u8) post_write_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max, out_u8);
+    else        post_write_f32_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max, out_f32);
+    return check_launch("post");
+}
+
+int uavsal_post_u8(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max, uint8_t* out_u8,
+                   void* stream) {
+    return post_common(maps, n, hs, ws, hd, wd, frame_max, out_u8, nullptr, stream);
+}
+
+int uavsal_post_f32(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max, float* out_f32,
+                    void* stream) {
+    return post_common(maps, n, hs, ws, hd, wd, frame_max, nullptr, out_f32, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+"""Plan builder + executor: turns the module tree into a flat list of C-ABI kernel calls over a
+pre-allocated activation arena (NHWC, split-bf16 planes — see include/uavsal_b200.h).
+
+Nothing here computes on the CPU: a plan can be *built* on any device (the CPU test-suite checks shapes,
+packing and the op list that way) but ``Plan.run`` requires CUDA tensors and the sm_100a library.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _ext
+
+F_RELU6, F_RESIDUAL, F_SIGMOID = 1, 2, 4
+BN_EPS = 1e-5
+
+
+def _pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def out_size(n: int, stride: int) -> int:
+    """3x3, padding = dilation, stride 1|2 (model.py:67-69)."""
+    return n if stride == 1 else (n - 1) // 2 + 1
+
+
+class Buf:
+    """A (rows x c) activation living in a (2, rows, ld) bf16 tensor at channel offset ``off``."""
+
+    __slots__ = ("t", "rows", "c", "ld", "off")
+
+    def __init__(self, t: torch.Tensor, rows: int, c: int, ld: int, off: int = 0):
+        self.t, self.rows, self.c, self.ld, self.off = t, rows, c, ld, off
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 2 * self.off
+
+    @property
+    def plane(self) -> int:
+        return self.rows * self.ld
+
+    def act(self) -> Tuple[int, int, int]:
+        return (self.ptr, self.plane, self.ld)
+
+    def slot(self, off: int, c: int) -> "Buf":
+        assert off % 8 == 0 and off + c <= self.ld
+        return Buf(self.t, self.rows, c, self.ld, self.off + off)
+
+    def to_float(self) -> torch.Tensor:
+        """fp32 (rows, c) reconstruction hi + lo (debug / tests)."""
+        v = self.t[0].float() + self.t[1].float()
+        return v[:, self.off:self.off + self.c]
+
+
+NULL_ACT = (0, 0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# weight preparation (BN folding, hi/lo split, layouts)
+# ---------------------------------------------------------------------------------------------------
+def fold_bn(w: torch.Tensor, bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """conv(no bias) + BatchNorm2d(eval) -> (w', b') with w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)
+    (model.py:69-70, 94-95; eps = 1e-5)."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return w.detach().float() * scale.view(-1, 1, 1, 1), bias
+
+
+def split_bf16(w: torch.Tensor) -> torch.Tensor:
+    """fp32 (...)-> bf16 (2, ...) planes: hi = bf16(w), lo = bf16(w - hi)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
+def pack_pw_tc(w2d: torch.Tensor, kpad: int) -> torch.Tensor:
+    n, k = w2d.shape
+    full = torch.zeros((n, kpad), dtype=torch.float32, device=w2d.device)
+    full[:, :k] = w2d
+    return split_bf16(full)
+
+
+def pack_pw_simt(w2d: torch.Tensor, kpad: int) -> torch.Tensor:
+    n, k = w2d.shape
+    full = torch.zeros((kpad, n), dtype=torch.float32, device=w2d.device)
+    full[:k] = w2d.t()
+    return full.contiguous()
+
+
+def pack_dw(w: torch.Tensor) -> torch.Tensor:
+    c = w.shape[0]
+    return w.reshape(c, 9).t().contiguous()            # [9][C]
+
+
+def conv3x3_as_2d(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) -> (Cout, 9*Cin) with k = (ky*3+kx)*Cin + ci."""
+    cout, cin = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+
+
+def interleave_gates(w: torch.Tensor, ch: int) -> torch.Tensor:
+    """ConvLSTM rows g*ch + c (i,f,o,g blocks, model_convlstm.py:117) -> 4*c + g."""
+    return w.reshape(4, ch, *w.shape[1:]).transpose(0, 1).reshape(4 * ch, *w.shape[1:]).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# plan
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class Op:
+    name: str
+    fn: Callable
+    args: tuple
+    tag: str = ""
+
+
+class Plan:
+    def __init__(self, device: torch.device, terms: int = 3, engine: str = "tc"):
+        assert terms in (1, 3) and engine in ("tc", "simt")
+        self.device = torch.device(device)
+        self.terms = terms
+        self.engine = engine
+        self.ops: List[Op] = []
+        self.keep: List[torch.Tensor] = []       # packed weights / scratch kept alive with the plan
+        self.named: Dict[str, object] = {}       # name -> Buf / tensor (inputs, outputs, debug taps)
+        self.graph = None
+        self.arena_bytes = 0
+
+    # ---- allocation ----
+    def alloc(self, rows: int, c: int, ld: Optional[int] = None) -> Buf:
+        ld = _pad8(c) if ld is None else ld
+        t = torch.zeros((2, rows, ld), dtype=torch.bfloat16, device=self.device)
+        self.arena_bytes += t.numel() * 2
+        self.keep.append(t)
+        return Buf(t, rows, c, ld)
+
+    def tensor(self, shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.arena_bytes += t.numel() * t.element_size()
+        self.keep.append(t)
+        return t
+
+    def hold(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.to(self.device).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _add(self, name: str, args: Sequence, tag: str = ""):
+        fn = getattr(_ext.load(), name) if self.device.type == "cuda" else None
+        self.ops.append(Op(name, fn, tuple(args), tag))
+
+    # ---- ops ----
+    def pack_nchw(self, src: torch.Tensor, n, c, h, w, dst: Buf, tag=""):
+        self._add("uavsal_pack_nchw_f32", (src.data_ptr(), n, c, h, w, *dst.act(), _pad8(c)), tag)
+
+    def unpack_nchw(self, src: Buf, n, c, h, w, dst: torch.Tensor, tag=""):
+        self._add("uavsal_unpack_nchw_f32", (*src.act(), n, c, h, w, dst.data_ptr()), tag)
+
+    def stem(self, x: torch.Tensor, kind: int, n, h, w, wgt, bias, out: Buf, tag=""):
+        self._add("uavsal_stem_conv3x3s2", (x.data_ptr(), kind, n, h, w, wgt.data_ptr(), bias.data_ptr(), *out.act()), tag)
+
+    def dw(self, x: Buf, n, h, w, c, stride, dil, wgt, bias, relu6, out: Buf, tag=""):
+        self._add("uavsal_dw3x3", (*x.act(), n, h, w, c, stride, dil, wgt.data_ptr(), bias.data_ptr(), int(relu6), *out.act()), tag)
+
+    def pw(self, x: Buf, m: int, w2d: torch.Tensor, bias: Optional[torch.Tensor], flags: int, out: Buf,
+           res: Optional[Buf] = None, tag=""):
+        """Pointwise conv as GEMM.  w2d: folded fp32 (N, K_logical); x.c may be padded beyond K_logical."""
+        n, k = w2d.shape
+        kpad = _pad8(k)
+        assert x.c in (k, kpad) and out.c >= n and n % 8 == 0, (x.c, k, n)
+        b = self.hold(bias.float()) if bias is not None else None
+        bp = b.data_ptr() if b is not None else 0
+        r = res.act() if res is not None else NULL_ACT
+        if res is not None:
+            flags |= F_RESIDUAL
+        if self.engine == "tc":
+            wp = self.hold(pack_pw_tc(w2d, kpad))
+            self._add("uavsal_pw_gemm", (*x.act(), m, kpad, wp.data_ptr(), kpad, n, bp, flags, self.terms, *r, *out.act()), tag)
+        else:
+            wp = self.hold(pack_pw_simt(w2d, kpad))
+            self._add("uavsal_pw_gemm_simt", (*x.act(), m, kpad, wp.data_ptr(), n, bp, flags, *r, *out.act()), tag)
+
+    def conv3x3(self, x: Buf, n, h, w, c, w4d: torch.Tensor, bias, flags, out: Buf, tag=""):
+        cout = w4d.shape[0]
+        w2d = conv3x3_as_2d(w4d)
+        b = self.hold(bias.float()) if bias is not None else None
+        bp = b.data_ptr() if b is not None else 0
+        if self.engine == "tc":
+            wp = self.hold(split_bf16(w2d))
+            self._add("uavsal_conv3x3", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, self.terms, *out.act()), tag)
+        else:
+            wp = self.hold(w2d.t().contiguous())
+            self._add("uavsal_conv3x3_simt", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, *out.act()), tag)
+
+    def bilinear(self, x: Buf, n_src, hs, ws, c, out: Buf, n_dst, hd, wd, tag=""):
+        self._add("uavsal_bilinear_ac", (*x.act(), n_src, hs, ws, c, *out.act(), n_dst, hd, wd), tag)
+
+    def tdiff(self, x: Buf, n, hw, c, out: Buf, tag=""):
+        self._add("uavsal_tdiff_cat", (*x.act(), n, hw, c, *out.act()), tag)
+
+    def ctx_sum(self, x: Buf, b, t, hw, c, out: Buf, tag=""):
+        self._add("uavsal_ctx_sum", (*x.act(), b, t, hw, c, *out.act()), tag)
+
+    def twa(self, x: Buf, h0: Buf, t_steps, h, w, c, w4d: torch.Tensor, seq: Buf, tag=""):
+        w2d = conv3x3_as_2d(w4d.detach().float())
+        if self.engine == "tc":
+            wp = self.hold(split_bf16(w2d))
+            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, wp.data_ptr(), 0, self.terms, *seq.act()), tag)
+        else:
+            wp = self.hold(w2d.t().contiguous())
+            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, 0, wp.data_ptr(), self.terms, *seq.act()), tag)
+
+    def lstm(self, x: Buf, h0: Buf, c_state: torch.Tensor, b, t_steps, h, w, cin, ch, w4d, bias, seq: Buf, tag=""):
+        wi = interleave_gates(w4d.detach().float(), ch)
+        w2d = conv3x3_as_2d(wi)
+        bp = 0
+        if bias is not None:
+            bb = self.hold(interleave_gates(bias.detach().float(), ch))
+            bp = bb.data_ptr()
+        if self.engine == "tc":
+            wp = self.hold(split_bf16(w2d))
+            args = (*x.act(), *h0.act(), c_state.data_ptr(), b, t_steps, h, w, cin, ch, wp.data_ptr(), 0, bp, self.terms, *seq.act())
+        else:
+            wp = self.hold(w2d.t().contiguous())
+            args = (*x.act(), *h0.act(), c_state.data_ptr(), b, t_steps, h, w, cin, ch, 0, wp.data_ptr(), bp, self.terms, *seq.act())
+        self._add("uavsal_convlstm_sequence", args, tag)
+
+    def dot_sigmoid(self, x: Buf, rows, k, wgt: torch.Tensor, bias: float, out: torch.Tensor, tag=""):
+        wv = self.hold(wgt.float())
+        self._add("uavsal_dot_sigmoid", (*x.act(), rows, k, wv.data_ptr(), float(bias), out.data_ptr()), tag)
+
+    def post_u8(self, maps: torch.Tensor, n, hs, ws, hd, wd, out_u8: torch.Tensor, tag=""):
+        fm = self.tensor((n,), torch.float32)
+        self._add("uavsal_post_u8", (maps.data_ptr(), n, hs, ws, hd, wd, fm.data_ptr(), out_u8.data_ptr()), tag)
+
+    # ---- execution ----
+    def run(self, upto: Optional[int] = None):
+        if self.device.type != "cuda":
+            raise RuntimeError("uavsal-b200 kernels are CUDA (sm_100a) only; there is no CPU path")
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        ops = self.ops if upto is None else self.ops[:upto]
+        for op in ops:
+            rc = op.fn(*op.args, stream)
+            if rc:
+                _ext.check(rc, op.name + ("[" + op.tag + "]" if op.tag else ""))
+
+    def capture(self):
+        """Warm up once eagerly, then record the whole op list into a CUDA graph."""
+        self.run()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def launch(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run()
+
+    @property
+    def num_launches(self) -> int:
+        """Kernel launches per run (sequence ops launch one kernel per step; post_u8 launches two)."""
+        n = 0
+        for op in self.ops:
+            if op.name == "uavsal_twa_sequence":
+                n += op.args[6]
+            elif op.name == "uavsal_convlstm_sequence":
+                n += op.args[8] * (1 if self.engine == "tc" else op.args[7])
+            elif op.name == "uavsal_post_u8":
+                n += 2
+            else:
+                n += 1
+        return n

@@ -141,6 +141,10 @@ int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t row
 int uavsal_post_u8(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max,
                    uint8_t* out_u8, void* stream);
 
+/* postprocess_predictions alone (utils_data.py:289-303): same resize and /max*255, float output, no uint8 cast. */
+int uavsal_post_f32(const float* maps, int n, int hs, int ws, int hd, int wd, float* frame_max,
+                    float* out_f32, void* stream);
+
 /* ---- K11: utils_score_torch.metric_cc / metric_nss / metric_kl / metric_sim (180-218, helpers 20-50).
  *      pred (n,1,h,w), truth (n,2,h,w) (ch0 density, ch1 fixations), fp32 or uint8-valued (dtype 0=f32, 1=u8).
  *      out (n,4) fp32 columns CC, NSS, KLD, SIM.  scratch: n*16 doubles. */

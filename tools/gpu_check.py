@@ -1,0 +1,377 @@
+"""Bring-up diagnostics for a GPU box: runs groups of kernel checks against torch-CPU / oracle references and
+prints one line per check.  Each group runs in its own process (a faulting kernel cannot poison the others):
+
+    python tools/gpu_check.py            # all groups, each under `timeout`
+    python tools/gpu_check.py GROUP      # one group in-process
+
+Test infrastructure only (imports oracle/)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GROUPS = ["simt_units", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc", "runner"]
+
+
+def rel(a, b):
+    import torch
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+def report(name, a, b, tol=1e-3):
+    r, m = rel(a, b)
+    print("%-46s relL2 %.3e  maxabs %.3e  %s" % (name, r, m, "ok" if r < tol else "FAIL"), flush=True)
+    return r < tol
+
+
+def mk_plan(engine="tc", terms=3):
+    import torch
+    from iip_uavsal_saliency_b200.engine import Plan
+    return Plan(torch.device("cuda"), terms=terms, engine=engine)
+
+
+def act_from(plan, x_nchw):
+    """Upload an NCHW fp32 CPU tensor into a fresh arena buffer."""
+    import torch
+    n, c, h, w = x_nchw.shape
+    src = plan.hold(x_nchw.float())
+    buf = plan.alloc(n * h * w, (c + 7) // 8 * 8)
+    plan.pack_nchw(src, n, c, h, w, buf)
+    return buf
+
+
+def fetch(plan, buf, n, c, h, w):
+    import torch
+    out = plan.tensor((n, c, h, w))
+    plan.unpack_nchw(buf, n, c, h, w, out)
+    return out
+
+
+def g_simt_units():
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    # pack/unpack
+    p = mk_plan("simt")
+    x = torch.randn(2, 20, 9, 11)
+    b = act_from(p, x)
+    y = fetch(p, b, 2, 20, 9, 11)
+    p.run(); torch.cuda.synchronize()
+    report("pack/unpack roundtrip (split-bf16)", y, x, 1e-4)
+    # depthwise variants
+    for (c, s, d, h, w) in [(32, 1, 1, 20, 24), (96, 2, 1, 21, 23), (48, 1, 6, 12, 20), (1920, 1, 18, 12, 20), (144, 2, 1, 45, 80)]:
+        p = mk_plan("simt")
+        x = torch.randn(2, c, h, w)
+        wt = torch.randn(c, 1, 3, 3) * 0.3
+        bias = torch.randn(c) * 0.1
+        xb = act_from(p, x)
+        from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+        ho, wo = out_size(h, s), out_size(w, s)
+        ob = p.alloc(2 * ho * wo, c)
+        p.dw(xb, 2, h, w, c, s, d, p.hold(pack_dw(wt)), p.hold(bias), True, ob)
+        y = fetch(p, ob, 2, c, ho, wo)
+        p.run(); torch.cuda.synchronize()
+        ref = F.hardtanh(F.conv2d(x, wt, bias, s, d, d, c), 0, 6)
+        report("dw3x3 c=%d s=%d d=%d %dx%d" % (c, s, d, h, w), y, ref, 1e-4)
+    # stem (fp32 NCHW and uint8 kinds)
+    from oracle import cpu_ref
+    import numpy as np
+    wt = torch.randn(32, 3, 3, 3) * 0.3
+    bias = torch.randn(32) * 0.1
+    u8 = torch.randint(0, 256, (2, 3, 37, 50), dtype=torch.uint8)
+    xf = torch.from_numpy(cpu_ref.normalize_data(u8.numpy()))
+    ref = F.hardtanh(F.conv2d(xf, wt, bias, 2, 1), 0, 6)
+    for kind, src in ((0, xf), (1, u8), (2, u8.permute(0, 2, 3, 1).contiguous())):
+        p = mk_plan("simt")
+        s = p.hold(src)
+        ob = p.alloc(2 * 19 * 25, 32)
+        p.stem(s, kind, 2, 37, 50, p.hold(wt.permute(2, 3, 1, 0).contiguous()), p.hold(bias), ob)
+        y = fetch(p, ob, 2, 32, 19, 25)
+        p.run(); torch.cuda.synchronize()
+        report("stem kind=%d" % kind, y, ref, 1e-4)
+    # bilinear align_corners (+ modulo broadcast)
+    p = mk_plan("simt")
+    x = torch.randn(2, 64, 12, 20)
+    xb = act_from(p, x)
+    ob = p.alloc(6 * 45 * 80, 64)
+    p.bilinear(xb, 2, 12, 20, 64, ob, 6, 45, 80)
+    y = fetch(p, ob, 6, 64, 45, 80)
+    p.run(); torch.cuda.synchronize()
+    ref = F.interpolate(x, size=(45, 80), mode="bilinear", align_corners=True).repeat(3, 1, 1, 1)
+    report("bilinear_ac 12x20->45x80 repeat(3)", y, ref, 1e-4)
+    # tdiff, ctx_sum
+    p = mk_plan("simt")
+    x = torch.randn(5, 32, 6, 7)
+    xb = act_from(p, x)
+    ob = p.alloc(5 * 42, 64)
+    p.tdiff(xb, 5, 42, 32, ob)
+    y = fetch(p, ob, 5, 64, 6, 7)
+    sb = p.alloc(1 * 42, 32)
+    p.ctx_sum(xb, 1, 5, 42, 32, sb)
+    ys = fetch(p, sb, 1, 32, 6, 7)
+    p.run(); torch.cuda.synchronize()
+    prev = torch.cat([x[1:2], x[:-1]], 0); nxt = torch.cat([x[1:], x[-2:-1]], 0)
+    d = torch.cat([x - prev, x - nxt], 1)
+    d[0] = torch.cat([x[1] - x[0], x[0] - x[1]], 0); d[4] = torch.cat([x[4] - x[3], x[3] - x[4]], 0)
+    report("tdiff_cat", y, d, 1e-4)
+    report("ctx_sum", ys, x.sum(0, keepdim=True), 1e-4)
+    # SIMT gemm + conv
+    gemm_cases("simt")
+    conv_cases("simt")
+
+
+def gemm_cases(engine):
+    import torch
+    torch.manual_seed(1)
+    for (m, k, n, relu, res) in [(300, 32, 16, False, False), (1000, 16, 96, True, False), (777, 20, 120, True, False),
+                                 (3600, 256, 1536, True, False), (3600, 1536, 256, False, True), (130, 1024, 256, True, False),
+                                 (500, 8, 48, True, False), (260, 192, 1152, True, False), (128, 320, 1920, True, False),
+                                 (4000, 144, 24, False, True)]:
+        p = mk_plan(engine)
+        kp = (k + 7) // 8 * 8
+        a = torch.randn(m, k)
+        w = torch.randn(n, k) / (k ** 0.5)
+        bias = torch.randn(n) * 0.1
+        r = torch.randn(m, n)
+        ab = act_from(p, a.t().reshape(1, k, 1, m))          # (1,k,1,m) NCHW -> rows=m, channels=k
+        rb = act_from(p, r.t().reshape(1, n, 1, m)) if res else None
+        ob = p.alloc(m, n)
+        p.pw(ab, m, w, bias, 1 if relu else 0, ob, res=rb)
+        y = fetch(p, ob, 1, n, 1, m)
+        p.run(); torch.cuda.synchronize()
+        ref = a @ w.t() + bias
+        if relu:
+            ref = ref.clamp(0, 6)
+        if res:
+            ref = ref + r
+        report("pw_gemm[%s] m=%d k=%d n=%d relu=%d res=%d" % (engine, m, k, n, relu, res), y.reshape(n, m).t(), ref, 2e-4)
+
+
+def conv_cases(engine):
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(2)
+    for (nimg, c, co, h, w) in [(2, 64, 64, 10, 12), (1, 448, 256, 45, 80), (3, 128, 32, 36, 64)]:
+        p = mk_plan(engine)
+        x = torch.randn(nimg, c, h, w)
+        wt = torch.randn(co, c, 3, 3) / (3 * c ** 0.5)
+        bias = torch.randn(co) * 0.1
+        xb = act_from(p, x)
+        ob = p.alloc(nimg * h * w, co)
+        p.conv3x3(xb, nimg, h, w, c, wt, bias, 1, ob)
+        y = fetch(p, ob, nimg, co, h, w)
+        p.run(); torch.cuda.synchronize()
+        ref = F.hardtanh(F.conv2d(x, wt, bias, 1, 1), 0, 6)
+        report("conv3x3[%s] n=%d c=%d co=%d %dx%d" % (engine, nimg, c, co, h, w), y, ref, 2e-4)
+
+
+def g_tc_pw():
+    gemm_cases("tc")
+    # bf16x1 mode: looser tolerance
+    import torch
+    p = mk_plan("tc", terms=1)
+    a = torch.randn(512, 256); w = torch.randn(128, 256) / 16
+    ab = act_from(p, a.t().reshape(1, 256, 1, 512)); ob = p.alloc(512, 128)
+    p.pw(ab, 512, w, None, 0, ob)
+    y = fetch(p, ob, 1, 128, 1, 512)
+    p.run(); torch.cuda.synchronize()
+    report("pw_gemm[tc,bf16x1] 512x256x128", y.reshape(128, 512).t(), a @ w.t(), 1e-2)
+
+
+def g_tc_conv():
+    conv_cases("tc")
+
+
+def rnn_cases(engine):
+    import numpy as np
+    import torch
+    from oracle import cpu_ref
+    from iip_uavsal_saliency_b200.model_convlstm import ConvLSTM, ConvTWA
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rnn_small.npz"))
+    if engine == "simt":
+        for tag in ("lstm", "lstm_bias"):
+            net = ConvLSTM((10, 12), 8, 16, (3, 3), 1, batch_first=True, bias=(tag == "lstm_bias")).cuda().set_mode(engine="simt")
+            net.cell_list[0].rnn_conv.weight.data.copy_(torch.from_numpy(g[tag + "_w"]))
+            if tag == "lstm_bias":
+                net.cell_list[0].rnn_conv.bias.data.copy_(torch.from_numpy(g["lstm_b"]))
+            y, (h, c) = net(torch.from_numpy(g[tag + "_x"]).cuda(), [[torch.from_numpy(g[tag + "_h0"]).cuda(), torch.from_numpy(g[tag + "_c0"]).cuda()]])
+            report("ConvLSTM[simt] %s y vs reference golden" % tag, y, torch.from_numpy(g[tag + "_y"]), 2e-4)
+            report("ConvLSTM[simt] %s c vs reference golden" % tag, c, torch.from_numpy(g[tag + "_c"]), 2e-4)
+        net = ConvTWA((10, 12), 16, 16, (3, 3), 1, batch_first=True, bias=False).cuda().set_mode(engine="simt")
+        net.cell_list[0].rnn_conv.weight.data.copy_(torch.from_numpy(g["twa_w"]))
+        y, st = net(torch.from_numpy(g["twa_x"]).cuda(), [torch.from_numpy(g["twa_h0"]).cuda()])
+        report("ConvTWA[simt] y vs reference golden", y, torch.from_numpy(g["twa_y"]), 2e-4)
+        report("ConvTWA[simt] h vs reference golden", st[0], torch.from_numpy(g["twa_h"]), 2e-4)
+    # mid-size cases both engines vs oracle
+    torch.manual_seed(3)
+    for (b, t, cin, ch, h, w) in [(2, 3, 64, 64, 12, 20), (1, 2, 128, 64, 45, 80)]:
+        net = ConvLSTM((h, w), cin, ch, (3, 3), 1, batch_first=True, bias=True).cuda().set_mode(engine=engine)
+        x = torch.randn(b, t, cin, h, w); h0 = torch.randn(b, ch, h, w) * 0.5; c0 = torch.randn(b, ch, h, w) * 0.5
+        y, (hh, cc) = net(x.cuda(), [[h0.cuda(), c0.cuda()]])
+        ry, (rh, rc) = cpu_ref.lstm_sequence(net.cell_list[0].rnn_conv.weight.detach().cpu(), net.cell_list[0].rnn_conv.bias.detach().cpu(), x, h0, c0)
+        report("ConvLSTM[%s] b=%d t=%d cin=%d ch=%d y vs oracle" % (engine, b, t, cin, ch), y, ry, 2e-4)
+        report("ConvLSTM[%s] c vs oracle" % engine, cc, rc, 2e-4)
+    for (t, c, h, w) in [(3, 64, 12, 20), (4, 256, 45, 80)]:
+        net = ConvTWA((h, w), c, c, (3, 3), 1, batch_first=True, bias=False).cuda().set_mode(engine=engine)
+        x = torch.randn(1, t, c, h, w); h0 = torch.randn(1, c, h, w)
+        y, st = net(x.cuda(), [h0.cuda()])
+        ry, rh = cpu_ref.twa_sequence(net.cell_list[0].rnn_conv.weight.detach().cpu(), x[0], h0)
+        report("ConvTWA[%s] t=%d c=%d y vs oracle" % (engine, t, c), y[0], ry, 2e-4)
+
+
+def g_rnn_simt():
+    rnn_cases("simt")
+
+
+def g_rnn_tc():
+    rnn_cases("tc")
+
+
+def g_post_metrics():
+    import numpy as np
+    import torch
+    from oracle import cpu_ref, synth
+    from iip_uavsal_saliency_b200 import utils_data as ud, utils_score_torch as us
+    g = np.load(os.path.join(ROOT, "tests", "golden", "post_u8.npz"))
+    for m, u, shape, nm in ((g["m1"], g["u1"], (360, 640), "45x80->360x640"), (g["m1"], g["u2"], (720, 1280), "->720x1280"),
+                            (g["m3"], g["u3"], (300, 500), "36x64->300x500 crop cols"), (g["m3"], g["u4"], (270, 512), "->270x512 crop rows")):
+        mine = ud.postprocess_to_uint8(torch.from_numpy(m).cuda(), *shape)[0].cpu().numpy()
+        d = np.abs(mine.astype(int) - u.astype(int))
+        print("%-46s maxdiff %d  frac>0 %.2e  %s" % ("post_u8 " + nm + " vs cv2 golden", d.max(), (d > 0).mean(), "ok" if d.max() <= 1 else "FAIL"), flush=True)
+        orc = cpu_ref.im2uint8(cpu_ref.postprocess_predictions(m.copy(), *shape))
+        d = np.abs(mine.astype(int) - orc.astype(int))
+        print("%-46s maxdiff %d  frac>0 %.2e" % ("post_u8 " + nm + " vs oracle", d.max(), (d > 0).mean()), flush=True)
+    gm = np.load(os.path.join(ROOT, "tests", "golden", "metrics_pairs.npz"))
+    pred, true = synth.make_metric_pairs(8, 360, 640, seed=0)
+    mine = us.metrics4(torch.from_numpy(pred).cuda(), torch.from_numpy(true).cuda()).cpu().numpy()
+    relerr = np.abs(mine - gm["values"]) / np.abs(gm["values"])
+    print("metrics4 fp32 vs reference golden: max rel err per metric (CC,NSS,KLD,SIM) =", relerr.max(0), "ok" if relerr.max() < 1e-4 else "FAIL", flush=True)
+    mine8 = us.metrics4(torch.from_numpy(pred).cuda().to(torch.uint8), torch.from_numpy(true).cuda().to(torch.uint8)).cpu().numpy()
+    relerr = np.abs(mine8 - gm["values"]) / np.abs(gm["values"])
+    print("metrics4 uint8 vs reference golden: max rel err =", relerr.max(0), "ok" if relerr.max() < 1e-4 else "FAIL", flush=True)
+    tt = torch.from_numpy(gm["ka_true"])
+    same = tt[:, 0:1].clone()
+    print("known answers same:", us.metrics4(same.cuda(), tt.cuda()).cpu().numpy()[0], "ref", gm["ka_same"][0], flush=True)
+    print("known answers zero:", us.metrics4(torch.zeros(2, 1, 8, 8).cuda(), tt.cuda()).cpu().numpy()[0], "ref", gm["ka_zero"][0], flush=True)
+
+
+def e2e(engine):
+    import numpy as np
+    import torch
+    from oracle import cpu_ref, synth
+    from oracle.make_golden import sample_idx
+    from iip_uavsal_saliency_b200.model import UAVSal
+    g = np.load(os.path.join(ROOT, "tests", "golden", "call20_trace.npz"))
+    pr = np.load(os.path.join(ROOT, "tests", "golden", "priors.npz"))
+    gauss, ob = pr["gauss"], pr["uav2_u8"].astype(np.float32) / 255
+    clip = synth.make_clip(1, 20, 360, 640)
+    sd = synth.make_state_dict("lively", 0)
+    m = UAVSal().eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().set_mode(engine=engine)
+    x = torch.from_numpy(cpu_ref.normalize_data(clip.transpose(0, 3, 1, 2))).cuda()
+    cb = [torch.from_numpy(np.repeat(gauss.transpose(2, 0, 1)[None], 20, 0).copy()).cuda(),
+          torch.from_numpy(np.repeat(ob.transpose(2, 0, 1)[None], 20, 0).copy()).cuda()]
+    h0 = torch.from_numpy(np.random.RandomState(7).randn(1, 256, 45, 80).astype(np.float32) * 0.5).cuda()
+    plan = m.get_plan(x.device, 20, 360, 640, 0, None, True, False)
+    nm = plan.named
+    nm["x_in"].copy_(x); nm["cb_gauss_in"].copy_(cb[0]); nm["cb_ob_in"].copy_(cb[1]); nm["h_in"].copy_(h0)
+    t0 = time.time()
+    plan.run(); torch.cuda.synchronize()
+    print("first run %.3fs, launches %d, arena %.2f GiB" % (time.time() - t0, plan.num_launches, plan.arena_bytes / 2 ** 30), flush=True)
+    for name in ("c3", "c4", "c5", "sfnet", "st_layer.0", "st_layer.1", "fust", "cb_gauss", "cb_ob", "fucb", "fucbst"):
+        buf, hh, ww = nm["taps"][name]
+        v = buf.to_float().reshape(20, hh, ww, buf.c).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+        assert tuple(g["shape_" + name]) == v.shape, (name, v.shape)
+        ref = g["trace_" + name]
+        mine = v.ravel()[sample_idx(v.size, name)]
+        r = np.linalg.norm(mine - ref) / (np.linalg.norm(ref) + 1e-12)
+        print("%-46s relL2 %.3e  maxabs %.3e  %s" % ("stage[%s] %s vs reference golden" % (engine, name), r, np.abs(mine - ref).max(), "ok" if r < 1e-3 else "FAIL"), flush=True)
+    out = nm["out"].cpu().numpy()
+    d = np.abs(out - g["out"])
+    cc = cpu_ref.metric_cc(torch.from_numpy(out), torch.cat([torch.from_numpy(g["out"])] * 2, 1)).min().item()
+    print("OUT[%s] max-abs %.3e (tol 2e-3)  min CC %.7f (>=0.999)  %s" % (engine, d.max(), cc, "ok" if d.max() < 2e-3 and cc >= 0.999 else "FAIL"), flush=True)
+    hs = nm["h_out"].cpu().numpy().ravel()[sample_idx(256 * 3600, "h_last")]
+    print("h_last max-abs %.3e" % np.abs(hs - g["h_last_sample"]).max(), flush=True)
+    # timing (eager then graph)
+    for label in ("eager", "graph"):
+        if label == "graph":
+            plan.capture()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            plan.launch()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print("TIME[%s,%s] %.2f ms per 20-frame call -> %.1f frames/s" % (engine, label, ms, 20e3 / ms), flush=True)
+
+
+def g_e2e_simt():
+    e2e("simt")
+
+
+def g_e2e_tc():
+    e2e("tc")
+
+
+def g_runner():
+    import numpy as np
+    import torch
+    from oracle import synth
+    from iip_uavsal_saliency_b200.model import UAVSal
+    from iip_uavsal_saliency_b200.runner import ClipRunner
+    g = np.load(os.path.join(ROOT, "tests", "golden", "clip64_360.npz"))
+    pr = np.load(os.path.join(ROOT, "tests", "golden", "priors.npz"))
+    gauss, ob = pr["gauss"], pr["uav2_u8"].astype(np.float32) / 255
+    m = UAVSal().eval()
+    m.load_state_dict(synth.make_state_dict("lively", 0), strict=True)
+    m = m.cuda()
+    r = ClipRunner(m, gauss, ob, batch_size=4)
+    clip = torch.from_numpy(synth.make_clip(2, 64, 360, 640)).cuda()
+    maps, u8 = r.run_clip(clip)
+    torch.cuda.synchronize()
+    maps, u8 = maps.cpu().numpy(), u8.cpu().numpy()
+    print("runner maps", maps.shape, "u8", u8.shape, flush=True)
+    d = np.abs(maps - g["maps"])
+    print("RUNNER config#2 max-abs %.3e (tol 2e-3) %s" % (d.max(), "ok" if d.max() < 2e-3 else "FAIL"), flush=True)
+    du = np.abs(u8[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int))
+    print("RUNNER uint8 maxdiff %d (tol 1), frac>0 %.3e %s" % (du.max(), (du > 0).mean(), "ok" if du.max() <= 1 else "FAIL"), flush=True)
+    t0 = time.time()
+    for _ in range(3):
+        r.run_clip(clip, want_maps=False)
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / 3
+    print("RUNNER 64-frame clip %.1f ms -> %.1f frames/s (60 outputs)" % (dt * 1e3, 60 / dt), flush=True)
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] != "all":
+        name = sys.argv[1]
+        try:
+            globals()["g_" + name]()
+        except Exception:
+            traceback.print_exc()
+            print("GROUP %s: EXCEPTION" % name, flush=True)
+            sys.exit(1)
+        return
+    groups = sys.argv[2:] if len(sys.argv) > 2 else GROUPS
+    for name in groups:
+        print("=" * 20, name, "=" * 20, flush=True)
+        t0 = time.time()
+        try:
+            rc = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=420).returncode
+        except subprocess.TimeoutExpired:
+            rc = "TIMEOUT"
+        print("-- group %s rc=%s %.1fs" % (name, rc, time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    main()
