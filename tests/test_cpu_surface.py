@@ -1,0 +1,171 @@
+"""CPU-side tests: C-ABI exports, drop-in surface (signatures, state dict, errors), plan structure, packing
+arithmetic, MAT v7.3 I/O, prior loaders, sharding logic.  No GPU, no compute calls into the library."""
+import inspect
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from iip_uavsal_saliency_b200 import _ext, engine, mat73
+from iip_uavsal_saliency_b200 import model as M
+from iip_uavsal_saliency_b200 import model_convlstm as MC
+from iip_uavsal_saliency_b200 import model_feature as MF
+from iip_uavsal_saliency_b200 import utils_data as UD
+from iip_uavsal_saliency_b200 import utils_score_torch as US
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "uavsal_b200.h")).read()
+    declared = set(re.findall(r"\b(uavsal_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _ext.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.uavsal_version() == 1 and lib.uavsal_arch() == b"sm_100a"
+    assert declared == set(_ext.EXPORTS) | {"uavsal_version", "uavsal_arch", "uavsal_last_error"}
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    m = M.UAVSal()
+    sd = m.state_dict()
+    assert list(sorted(sd)) == sorted(k for k, _, _ in keys) and len(sd) == 685
+    for k, shape, dtype in keys:
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+    # a reference-shaped state dict loads strictly, buffers round-trip (quirk Q6: unused features.18, int64 counters)
+    new = synth.make_state_dict("lively", 3)
+    new["sfnet.features.features.18.1.num_batches_tracked"] = torch.tensor(7)
+    m.load_state_dict(new, strict=True)
+    back = m.state_dict()
+    assert back["sfnet.features.features.18.1.num_batches_tracked"].item() == 7
+    assert torch.equal(back["rnn.cell_list.0.rnn_conv.weight"], new["rnn.cell_list.0.rnn_conv.weight"])
+    assert sum(v.numel() for v in back.values() if v.dtype == torch.float32) == 13407338 + 117332 - 114
+
+
+def test_constructor_signatures_and_defaults():
+    def defaults(fn):
+        return {k: v.default for k, v in inspect.signature(fn).parameters.items() if v.default is not inspect._empty}
+    assert defaults(M.UAVSal.__init__) == dict(cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1],
+                                               iosize=[360, 640, 45, 80], planes=256, pre_model_path="")
+    assert defaults(M.dwBlock.__init__) == dict(kernel_size=3, stride=1, expand_ratio=6, dilation=1, res_connect=None)
+    assert defaults(M.BasicConv2d.__init__) == dict(kernel_size=3, stride=1, dilation=1, groups=1)
+    assert defaults(M.teConv_sub.__init__) == dict(planes=256, time_dims=8, reduction=8, res_connect=False)
+    assert defaults(M.STBlock.__init__) == dict(planes=256, time_dims=8, fu_type="sum", res_connect=True)
+    assert defaults(M.uavsal_srfnet_aspp.__init__) == dict(cnn_type="mobilenet_v2", planes=[64, 64, 128, 256], last_channel=256)
+    assert defaults(MC.ConvLSTM.__init__) == dict(batch_first=False, bias=True, return_all_layers=False)
+    assert defaults(MC.ConvTWA.__init__) == dict(batch_first=False, bias=True, return_all_layers=False)
+    assert list(inspect.signature(M.UAVSal.forward).parameters) == ["self", "x", "cb", "in_state"]
+    assert list(inspect.signature(MC.ConvTWA.forward).parameters) == ["self", "input_tensor", "hidden_state"]
+    assert list(inspect.signature(MC.ConvLSTMCell.forward).parameters) == ["self", "input_tensor", "cur_state"]
+    for name in ("metric_cc", "metric_nss", "metric_kl", "metric_sim"):
+        assert list(inspect.signature(getattr(US, name)).parameters) == ["y_pred", "y_true"]
+    assert US.EPS == 2.2204e-16 and set(US.metrics) == {"NSS", "CC", "SIM", "KLD"}
+
+
+def test_error_behaviour_follows_reference():
+    with pytest.raises(ValueError):
+        MF.ReMobileNetV2("resnet50")                                   # model_feature.py:54-55
+    with pytest.raises(ValueError):
+        MC.ConvLSTM((4, 4), 8, 8, 3, 1)                                # kernel_size must be tuple (:227-230)
+    with pytest.raises(ValueError):
+        MC.ConvTWA((4, 4), 8, [8, 8], (3, 3), 1)                       # inconsistent list length (:143-144)
+    with pytest.raises(AssertionError):
+        M.dwBlock(8, 8, stride=3)                                      # model.py:78
+    m = M.dwBlock(16, 16)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 16, 8, 8))                                    # product path never falls back to CPU
+    with pytest.raises(RuntimeError, match="no CPU"):
+        US.metric_cc(torch.zeros(1, 1, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.UAVSal().forward(torch.zeros(5, 3, 64, 64), [torch.zeros(5, 8, 8, 8), torch.zeros(5, 20, 8, 8)], None)
+
+
+def test_plan_structure_of_one_call():
+    m = M.UAVSal().eval()
+    plan = engine.Plan("cpu", 3, "tc")
+    m.build_plan(plan, 20, 360, 640, x_kind=1, post_hw=(360, 640))
+    names = [o.name for o in plan.ops]
+    assert names.count("uavsal_pw_gemm") == 76                         # 77 used pointwise convs, the 1536->1 one is the dot
+    assert names.count("uavsal_dw3x3") == 34
+    assert names.count("uavsal_conv3x3") == 1 and names.count("uavsal_twa_sequence") == 1
+    assert names.count("uavsal_bilinear_ac") == 3 and names.count("uavsal_tdiff_cat") == 2
+    assert plan.named["out"].shape == (20, 1, 45, 80) and plan.named["out_u8"].shape == (20, 360, 640)
+    assert plan.named["h_out"].shape == (1, 256, 45, 80)
+    with pytest.raises(ValueError):
+        m.build_plan(engine.Plan("cpu"), 7, 360, 640)                  # n must be a multiple of time_dims
+    p2 = engine.Plan("cpu", 3, "tc")
+    m.build_plan(p2, 5, 288, 512)
+    assert p2.named["out"].shape == (5, 1, 36, 64)
+
+
+def test_weight_packing_arithmetic():
+    torch.manual_seed(0)
+    w = torch.randn(24, 20)
+    pk = engine.pack_pw_tc(w, 24)
+    assert pk.shape == (2, 24, 24) and pk.dtype == torch.bfloat16
+    rec = pk[0].float() + pk[1].float()
+    assert torch.all(rec[:, 20:] == 0)
+    assert (rec[:, :20] - w).abs().max() <= w.abs().max() * 2 ** -16
+    assert torch.equal(engine.pack_pw_simt(w, 24)[:20], w.t())
+    # BN folding == conv followed by eval-mode batch norm
+    blk = M.BasicConv2d(6, 10, 1)
+    blk[1].running_mean.normal_(); blk[1].running_var.uniform_(0.5, 2); blk[1].weight.data.normal_(); blk[1].bias.data.normal_()
+    blk.eval()
+    x = torch.randn(2, 6, 5, 5)
+    wf, bf = blk.folded()
+    ref = blk[1](blk[0](x))
+    mine = F.conv2d(x, wf, bf)
+    assert (ref - mine).abs().max() < 1e-5
+    # implicit-GEMM K ordering: k = (ky*3+kx)*Cin + ci
+    w4 = torch.randn(7, 5, 3, 3)
+    x = torch.randn(1, 5, 6, 6)
+    cols = F.unfold(x, 3, padding=1).reshape(5, 9, 36).permute(1, 0, 2).reshape(45, 36)      # (tap, ci) major
+    assert (engine.conv3x3_as_2d(w4) @ cols - F.conv2d(x, w4, padding=1).reshape(7, 36)).abs().max() < 1e-5
+    # LSTM gate interleave: packed row 4*c+g <- reference row g*ch+c
+    ch = 3
+    wl = torch.arange(4 * ch).float().reshape(4 * ch, 1)
+    il = engine.interleave_gates(wl, ch).reshape(-1)
+    for c in range(ch):
+        for g in range(4):
+            assert il[4 * c + g].item() == g * ch + c
+    assert torch.equal(engine.pack_dw(torch.arange(18.).reshape(2, 1, 3, 3))[:, 1], torch.arange(9., 18.))
+
+
+def test_mat73_reads_reference_prior_format_and_roundtrips(tmp_path, gold_dir):
+    pri = np.load(os.path.join(gold_dir, "priors.npz"))
+    path = str(tmp_path / "gauss_priors.mat")
+    mat73.savemat(path, {"PriorMaps": pri["gauss"]})
+    back = mat73.loadmat(path)["PriorMaps"]
+    assert back.dtype == np.float32 and np.array_equal(back, pri["gauss"])
+    sal = np.random.RandomState(0).randint(0, 256, (36, 64, 1, 7)).astype(np.uint8)
+    mat73.savemat(str(tmp_path / "s.mat"), {"salmap": sal})
+    assert np.array_equal(mat73.loadmat(str(tmp_path / "s.mat"))["salmap"], sal)
+    ref = "/root/reference/gauss_priors.mat"
+    if os.path.exists(ref):       # authoring container only: the real file (chunked + shuffle + deflate + fletcher32)
+        assert np.array_equal(mat73.loadmat(ref)["PriorMaps"], pri["gauss"])
+
+
+def test_prior_loaders_and_host_helpers(tmp_path, gold_dir, monkeypatch):
+    pri = np.load(os.path.join(gold_dir, "priors.npz"))
+    monkeypatch.chdir(tmp_path)
+    g = UD.get_guasspriors(3, 45, 80, 8)                               # no .mat in CWD -> closed form (utils_data.py:453-457)
+    assert g.shape == (3, 45, 80, 8) and np.array_equal(g[1], pri["gauss"])
+    mat73.savemat("gauss_priors.mat", {"PriorMaps": pri["gauss"]})
+    mat73.savemat("UAV2_ob_priors_train.mat", {"PriorMaps": pri["uav2_u8"].astype(np.float32) / 255})
+    assert np.array_equal(UD.get_guasspriors(2)[0], pri["gauss"])
+    assert UD.get_ob_priors("", "UAV2", "train", 2).shape == (2, 45, 80, 20)
+    assert UD.get_guasspriors(1, 36, 64).max() == 0 and UD.get_ob_priors("", "UAV2", "train", 1, 36, 64).dtype == np.uint8   # quirk Q4
+    with pytest.raises(NotImplementedError):
+        UD.read_ob_priors("", "UAV2", "test")
+    post = np.load(os.path.join(gold_dir, "post_u8.npz"))
+    assert np.array_equal(UD.normalize_data(post["x8"]), post["nd"])
+    with pytest.raises(ValueError):
+        UD.normalize_data(np.zeros((4, 4), np.uint8))
+    assert np.array_equal(UD.np2mat(np.array([0.5, 1.5, 2.5, 300., -3.])), np.array([0, 2, 2, 255, 0], np.uint8))   # rint = half-to-even
