@@ -127,7 +127,7 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # product arm
 # ---------------------------------------------------------------------------------------------------
-def time_op_classes(plan, torch):
+def time_op_classes(plan, torch, detail=None):
     """Per-op CUDA-event timing of one plan (eager, after warm-up) -> {class: [ms, flops, bytes, launches]}."""
     import ctypes
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -164,6 +164,9 @@ def time_op_classes(plan, torch):
             by = 4.0 * nimg * c * (hh * ww + ho * wo)
         r = res.setdefault(op.name, [0.0, 0.0, 0.0, 0])
         r[0] += ms; r[1] += fl; r[2] += by; r[3] += 1
+        if detail is not None:
+            detail.append("%-26s %-22s %8.1f us %8.1f TF/s %8.1f GB/s  %s" % (op.name, op.tag, ms * 1e3, fl / ms / 1e9 if ms else 0,
+                                                                          by / ms / 1e6 if ms else 0, str(op.args[3:9])))
     return res
 
 
@@ -250,7 +253,11 @@ def run_product_arm(args):
     plan20 = model.get_plan(dev, 20, H, W, x_kind=2, post_hw=(H, W), cb_shared=True)
     plan20.named["x_in"].copy_(dev_clips[0][:20])
     cls = time_op_classes(plan20, torch)
-    cls = time_op_classes(plan20, torch)
+    detail = []
+    cls = time_op_classes(plan20, torch, detail)
+    if args.dump_ops:
+        with open(args.dump_ops, "w") as fh:
+            fh.write("\n".join(detail) + "\n")
     tot_ms = sum(v[0] for v in cls.values())
     breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot_ms, 3), "launches": v[3],
                      "tflops": round(v[1] / v[0] / 1e9, 1) if v[0] and v[1] else None,
@@ -295,6 +302,7 @@ def main():
     ap.add_argument("--clips", type=int, default=1, help="clips per step per GPU")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write per-op CUDA-event timings of one 20-frame call to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
