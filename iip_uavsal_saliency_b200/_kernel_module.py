@@ -52,7 +52,7 @@ class KernelModule(nn.Module):
         if precision is not None:
             self.__dict__["_terms"] = {"exact": 3, "fast": 1}[precision]
         if engine is not None:
-            assert engine in ("tc", "simt")
+            assert engine in ("tc", "tc1", "simt")
             self.__dict__["_engine"] = engine
         self._plan_cache().clear()
         return self

@@ -10,109 +10,10 @@
 // MODE_PW  : A is a 2-D [M][K] matrix (NHWC rows x channels), tensor map (K, M, plane).
 // MODE_CONV: A is gathered by TMA from NHWC images with a (64ch, TW, TH) box per filter tap; padding comes
 //            from TMA out-of-bounds zero fill; two sources form the virtual concat [x, h] of the recurrences.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
+#include "gemm_tc2.cuh"
 
 namespace uavsal {
-
-enum { MODE_PW = 0, MODE_CONV = 1 };
-enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2 };
-
-constexpr int kBM = 128;          // rows per tile = TMEM lanes
-constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kThreads = 192;
-constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KiB per plane per stage
-
-struct TcArgs {
-    int M, N;                 // rows (pw) / valid output channels
-    int bn;                   // N tile, multiple of 16, <= 256
-    int num_kb;               // k-blocks per tile
-    int stages;
-    int tmem_cols;            // power of two >= max(32, bn)
-    // conv geometry
-    int H, W, TW, TH, tiles_x, tiles_y;
-    int kb_per_tap, kb_src0;  // k-blocks per tap (both sources) and of source 0
-    int a0_mul, a0_off, a1_mul, a1_off, out_mul, out_off;   // image index = b*mul + off (b = batch index of the tile)
-    const float* bias;
-    int flags;
-    Act res;
-    ActW out;
-    Act x, hprev;             // TWA operands (indexed like out / a1)
-    float* c_state;           // LSTM cell state [b][H*W][N/4]
-};
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-        if (it > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-
-// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
-__device__ __forceinline__ uint32_t umma_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
 
 // ---- kernel ---------------------------------------------------------------------------------------
 template <int MODE, int EPI, int TERMS>
@@ -422,6 +323,70 @@ static int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     return check_launch(what);
 }
 
+// ---- version 2: persistent kernel (gemm_tc2.cuh) ------------------------------------------------------
+static int g_tc_version = 2;
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int MODE, int EPI>
+static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o, TcArgs& g,
+                      int terms, int tiles_m, cudaStream_t s, const char* what) {
+    const int npl = terms == 3 ? 2 : 1;
+    const uint32_t stage_bytes = npl * (kABytes + (uint32_t)g.bn * kBK * 2);
+    const uint32_t budget = 227u * 1024u - 1024u - kOutStageBytes - 512u;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 8) stages = 8;
+    UAVSAL_REQUIRE(stages >= 2, UAVSAL_ENOTSUP, "%s: tile does not fit shared memory", what);
+    g.stages = stages;
+    g.tiles_n = div_up(g.N, g.bn);
+    g.num_tiles = tiles_m * g.tiles_n;
+    int cols = 32;
+    while (cols < 2 * g.bn) cols <<= 1;
+    g.tmem_cols = cols;
+    const size_t smem = (size_t)stages * stage_bytes + kOutStageBytes + 1024 + 512;
+    const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+    cudaError_t e;
+    if (terms == 3) {
+        static bool attr3 = false;
+        if (!attr3) {
+            e = cudaFuncSetAttribute(gemm_tc2_kernel<MODE, EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+            attr3 = true;
+        }
+        gemm_tc2_kernel<MODE, EPI, 3><<<grid, kThreads, smem, s>>>(a0, a1, b, o, g);
+    } else {
+        static bool attr1 = false;
+        if (!attr1) {
+            e = cudaFuncSetAttribute(gemm_tc2_kernel<MODE, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+            attr1 = true;
+        }
+        gemm_tc2_kernel<MODE, EPI, 1><<<grid, kThreads, smem, s>>>(a0, a1, b, o, g);
+    }
+    return check_launch(what);
+}
+
+// output maps: same geometry as the loads, 64-column boxes, extent = VALID channels so stores clip at N and never touch
+// the neighbouring slot of a concat buffer
+static int map_out_pw(CUtensorMap* tm, ActW o, int64_t rows, int n) {
+    const uint64_t dims[3] = {(uint64_t)n, (uint64_t)rows, o.plane ? 2u : 1u};
+    const uint64_t str[2] = {(uint64_t)o.ld * 2, o.plane ? (uint64_t)o.plane * 2 : (uint64_t)o.ld * 2 * (uint64_t)rows};
+    const uint32_t box[3] = {64, kBM, 1};
+    return encode(tm, o.p, 3, dims, str, box, "O(pw)");
+}
+static int map_out_img(CUtensorMap* tm, ActW o, int nimg, int h, int w, int c, int tw, int th) {
+    return map_img(tm, Act{o.p, o.plane, o.ld}, nimg, h, w, c, tw, th);
+}
+
 // conv tiling: 128 pixels per tile as TW x TH with TW*TH = 128; pick the shape wasting the fewest pixels
 static void pick_tile(int H, int W, int& tw, int& th) {
     int best = 1 << 30;
@@ -435,7 +400,7 @@ static void pick_tile(int H, int W, int& tw, int& th) {
 
 int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img, int a1_mul, int a1_off, int c1,
             int batch, int H, int W, const uint16_t* wgt, int cout, const float* bias, int flags, int terms, int epi,
-            Act x, Act hprev, float* c_state, ActW out, int out_mul, int out_off, cudaStream_t s, const char* what) {
+            Act x, Act hprev, float* c_state, ActW out, int out_nimg, int out_mul, int out_off, cudaStream_t s, const char* what) {
     UAVSAL_REQUIRE(c0 % kBK == 0 && c1 % kBK == 0 && c0 > 0, UAVSAL_ENOTSUP, "%s: channels must be multiples of 64", what);
     UAVSAL_REQUIRE(cout % 8 == 0 && (terms == 1 || terms == 3), UAVSAL_EINVAL, "%s: bad cout/terms", what);
     TcArgs g{};
@@ -446,6 +411,11 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     g.kb_src0 = c0 / kBK; g.kb_per_tap = (c0 + c1) / kBK; g.num_kb = 9 * g.kb_per_tap;
     g.a0_mul = a0_mul; g.a0_off = a0_off; g.a1_mul = a1_mul; g.a1_off = a1_off; g.out_mul = out_mul; g.out_off = out_off;
     g.M = batch * H * W; g.N = cout; g.bn = pick_bn(cout);
+    const int tiles_m_ = batch * g.tiles_x * g.tiles_y;
+    const bool v2 = g_tc_version == 2 && epi != EPI_LSTM;
+    if (v2) {   // small problems (one image per step in the recurrence): narrower N tiles so that more SMs get a tile
+        while (g.bn > 64 && g.bn % 128 == 0 && tiles_m_ * div_up(cout, g.bn) < 100) g.bn /= 2;
+    }
     g.bias = bias; g.flags = flags; g.out = out; g.x = x; g.hprev = hprev; g.c_state = c_state;
     const int kpad = 9 * (c0 + c1);
     CUtensorMap tA0, tA1, tB;
@@ -456,6 +426,13 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     rc = map_w(&tB, wgt, cout, kpad, g.bn);
     if (rc) return rc;
     const int tiles_m = batch * g.tiles_x * g.tiles_y;
+    if (v2) {
+        CUtensorMap tO;
+        rc = map_out_img(&tO, out, out_nimg, H, W, cout, tw, th);
+        if (rc) return rc;
+        if (epi == EPI_STD) return launch_tc2<MODE_CONV, EPI_STD>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
+        return launch_tc2<MODE_CONV, EPI_TWA>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
+    }
     if (epi == EPI_STD) return launch_tc<MODE_CONV, EPI_STD>(tA0, tA1, tB, g, terms, tiles_m, s, what);
     if (epi == EPI_TWA) return launch_tc<MODE_CONV, EPI_TWA>(tA0, tA1, tB, g, terms, tiles_m, s, what);
     return launch_tc<MODE_CONV, EPI_LSTM>(tA0, tA1, tB, g, terms, tiles_m, s, what);
@@ -474,7 +451,16 @@ static inline bool act_ok16(const void* p, int64_t plane, int ld) {
     return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 8) == 0 && (plane % 8) == 0 && plane >= 0;
 }
 
+extern int g_dw_fast;
+
 extern "C" {
+
+int uavsal_set_option(int key, int value) {
+    if (key == 1 && (value == 1 || value == 2)) { g_tc_version = value; return 0; }
+    if (key == 2 && (value == 0 || value == 1)) { g_dw_fast = value; return 0; }
+    set_error("set_option: unknown key %d / value %d", key, value);
+    return UAVSAL_EINVAL;
+}
 
 int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, const uint16_t* wgt, int kpad, int n,
                    const float* bias, int flags, int terms, const uint16_t* res, int64_t res_plane, int res_ld,
@@ -497,6 +483,12 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
     if (rc) return rc;
     rc = map_w(&tB, wgt, n, kpad, g.bn);
     if (rc) return rc;
+    if (g_tc_version == 2) {
+        CUtensorMap tO;
+        rc = map_out_pw(&tO, g.out, m, n);
+        if (rc) return rc;
+        return launch_tc2<MODE_PW, EPI_STD>(tA, tA, tB, tO, g, terms, div_up(m, kBM), (cudaStream_t)stream, "pw_gemm");
+    }
     return launch_tc<MODE_PW, EPI_STD>(tA, tA, tB, g, terms, div_up(m, kBM), (cudaStream_t)stream, "pw_gemm");
 }
 
@@ -509,7 +501,7 @@ int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h
     UAVSAL_REQUIRE(terms == 1 || (terms == 3 && in_plane != 0), UAVSAL_EINVAL, "conv3x3: terms must be 1, or 3 with a lo plane");
     Act a{in, in_plane, in_ld};
     return conv_tc(a, n, 1, 0, c, a, n, 1, 0, 0, n, h, w, wgt, cout, bias, flags, terms, EPI_STD, Act{}, Act{}, nullptr,
-                   ActW{out, out_plane, out_ld}, 1, 0, (cudaStream_t)stream, "conv3x3");
+                   ActW{out, out_plane, out_ld}, n, 1, 0, (cudaStream_t)stream, "conv3x3");
 }
 
 int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
@@ -532,10 +524,10 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
         int rc;
         if (t == 0)
             rc = conv_tc(X, t_steps, 0, 0, c, H0, 1, 0, 0, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S,
-                         0, 0, s, "twa_sequence");
+                         t_steps, 0, 0, s, "twa_sequence");
         else
             rc = conv_tc(X, t_steps, 0, t, c, SA, t_steps, 0, t - 1, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, SA,
-                         nullptr, S, 0, t, s, "twa_sequence");
+                         nullptr, S, t_steps, 0, t, s, "twa_sequence");
         if (rc) return rc;
     }
     return 0;
@@ -563,10 +555,10 @@ int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const
         int rc;
         if (t == 0)
             rc = conv_tc(X, b * t_steps, t_steps, 0, cin, H0, b, 1, 0, ch, b, h, w, wgt, 4 * ch, bias, 0, terms, EPI_LSTM,
-                         Act{}, Act{}, c_state, S, t_steps, 0, s, "convlstm_sequence");
+                         Act{}, Act{}, c_state, S, b * t_steps, t_steps, 0, s, "convlstm_sequence");
         else
             rc = conv_tc(X, b * t_steps, t_steps, t, cin, SA, b * t_steps, t_steps, t - 1, ch, b, h, w, wgt, 4 * ch, bias, 0,
-                         terms, EPI_LSTM, Act{}, Act{}, c_state, S, t_steps, t, s, "convlstm_sequence");
+                         terms, EPI_LSTM, Act{}, Act{}, c_state, S, b * t_steps, t_steps, t, s, "convlstm_sequence");
         if (rc) return rc;
     }
     return 0;

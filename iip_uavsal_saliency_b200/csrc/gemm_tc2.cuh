@@ -1,0 +1,266 @@
+// Persistent tcgen05 GEMM / implicit-GEMM 3x3 (version 2 of gemm_tc_kernel).
+//
+// One CTA per SM walks a static round-robin list of output tiles (n fastest, so CTAs running at the same time
+// share A tiles in L2).  Three asynchronous pipelines overlap across tiles:
+//   TMA producer  -> smem ring (full/empty mbarriers, runs ahead into the next tile's k-blocks)
+//   MMA issuer    -> TWO TMEM accumulators (acc_full/acc_empty mbarriers): tile i+1 accumulates while
+//   epilogue      -> tile i is drained: tcgen05.ld -> bias/ReLU6/residual/sigmoid | TWA blend -> hi/lo split ->
+//                    128-byte-swizzled smem staging -> TMA tensor stores (coalesced, clipped at M/N/image edges).
+#pragma once
+#include "tc_common.cuh"
+
+namespace uavsal {
+
+constexpr uint32_t kOutPlaneBytes = kBM * 64 * 2;          // one 128 x 64 bf16 box
+constexpr uint32_t kOutStageBytes = 2 * kOutPlaneBytes;    // hi + lo
+
+template <int MODE, int EPI, int TERMS>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                               const __grid_constant__ CUtensorMap tmA1,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO, const TcArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int NPL = TERMS == 3 ? 2 : 1;
+    const uint32_t b_bytes = (uint32_t)g.bn * kBK * 2;
+    const uint32_t stage_bytes = NPL * (kABytes + b_bytes);
+    uint8_t* ostage = smem + (size_t)g.stages * stage_bytes;                  // 1024-aligned (stage_bytes % 1024 == 0)
+    uint64_t* full = reinterpret_cast<uint64_t*>(ostage + kOutStageBytes);
+    uint64_t* empty = full + g.stages;
+    uint64_t* acc_full = empty + g.stages;                                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile decomposition shared by all roles
+    auto tile_coords = [&](int t, int& tile_m, int& n0, int& bidx, int& y0, int& x0) {
+        tile_m = t / g.tiles_n;
+        n0 = (t - tile_m * g.tiles_n) * g.bn;
+        bidx = 0; y0 = 0; x0 = 0;
+        if (MODE == MODE_CONV) {
+            const int per_img = g.tiles_x * g.tiles_y;
+            bidx = tile_m / per_img;
+            const int r = tile_m - bidx * per_img;
+            y0 = (r / g.tiles_x) * g.TH;
+            x0 = (r % g.tiles_x) * g.TW;
+        }
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t kc = 0;                                                  // k-block counter across tiles
+            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+                int tile_m, n0, bidx, y0, x0;
+                tile_coords(t, tile_m, n0, bidx, y0, x0);
+                for (int kb = 0; kb < g.num_kb; ++kb, ++kc) {
+                    const int s = kc % g.stages;
+                    mbar_wait(empty + s, ((kc / g.stages) & 1) ^ 1);
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    uint8_t* sb = sa + NPL * kABytes;
+                    mbar_expect_tx(full + s, stage_bytes);
+                    if (MODE == MODE_PW) {
+#pragma unroll
+                        for (int p = 0; p < NPL; ++p) tma_load_3d(&tmA0, full + s, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
+                    } else {
+                        const int tap = kb / g.kb_per_tap;
+                        const int r = kb - tap * g.kb_per_tap;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const bool src0 = r < g.kb_src0;
+                        const CUtensorMap* tm = src0 ? &tmA0 : &tmA1;
+                        const int cch = (src0 ? r : r - g.kb_src0) * kBK;
+                        const int img = src0 ? bidx * g.a0_mul + g.a0_off : bidx * g.a1_mul + g.a1_off;
+#pragma unroll
+                        for (int p = 0; p < NPL; ++p) tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
+                    }
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, kb * kBK, n0, p);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc(g.bn);
+        uint32_t kc = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);                 // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.bn);
+            for (int kb = 0; kb < g.num_kb; ++kb, ++kc) {
+                const int s = kc % g.stages;
+                mbar_wait(full + s, (kc / g.stages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t b_hi = a_hi + NPL * kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t dah = umma_desc(a_hi + k * 32);
+                        const uint64_t dbh = umma_desc(b_hi + k * 32);
+                        umma_bf16(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+                        if (TERMS == 3) {
+                            const uint64_t dal = umma_desc(a_hi + kABytes + k * 32);
+                            const uint64_t dbl = umma_desc(b_hi + b_bytes + k * 32);
+                            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty + s);
+                    if (kb == g.num_kb - 1) umma_commit(acc_full + buf);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, 128 threads) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                                          // tile row = TMEM lane
+        const bool leader = threadIdx.x == 64;                                // first epilogue thread issues the stores
+        uint8_t* my_hi = ostage + r * 128;
+        uint8_t* my_lo = my_hi + kOutPlaneBytes;
+        const int sw = r & 7;
+        int it = 0;
+        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+            int tile_m, n0, bidx, y0, x0;
+            tile_coords(t, tile_m, n0, bidx, y0, x0);
+            const int buf = it & 1;
+            int64_t orow, hrow = 0;
+            bool rvalid;
+            int img_out = 0;
+            if (MODE == MODE_PW) {
+                orow = (int64_t)tile_m * kBM + r;
+                rvalid = orow < g.M;
+            } else {
+                const int y = y0 + r / g.TW, x = x0 + r % g.TW;
+                rvalid = y < g.H && x < g.W;
+                const int64_t pix = (int64_t)y * g.W + x, hw = (int64_t)g.H * g.W;
+                img_out = bidx * g.out_mul + g.out_off;
+                orow = (int64_t)img_out * hw + pix;
+                hrow = (int64_t)(bidx * g.a1_mul + g.a1_off) * hw + pix;
+            }
+            mbar_wait(acc_full + buf, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * g.bn);
+            const int nchunks = (g.bn + 63) >> 6;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
+                // staging buffer must have been read out by the previous TMA stores
+                if (leader) bulk_wait_read0();
+                named_bar_sync(1, 128);
+                for (int sub = 0; sub < ncols; sub += 16) {
+                    uint32_t raw[16];
+                    __syncwarp();
+                    tmem_ld16(trow + ch * 64 + sub, raw);
+                    const int n = n0 + ch * 64 + sub;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    const bool live = rvalid && n < g.N;
+                    const bool second = n + 8 < g.N;
+                    if (live) {
+                        if (g.bias) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                if (j4 >= 2 && !second) break;
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
+                                v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+                            }
+                        }
+                        if (EPI == EPI_STD) {
+                            if (g.flags & UAVSAL_F_RELU6) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
+                            }
+                            if (g.flags & UAVSAL_F_RESIDUAL) {
+                                float rr[8];
+                                load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                                if (second) {
+                                    load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[8 + j] += rr[j];
+                                }
+                            }
+                            if (g.flags & UAVSAL_F_SIGMOID) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = sigmoid_acc(v[j]);
+                            }
+                        } else {   // EPI_TWA: h = i*x_t + (1-i)*h_{t-1}  (model_convlstm.py:283,290)
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                if (half == 1 && !second) break;
+                                float xv[8], hv[8];
+                                load8(g.x.p + orow * g.x.ld + n + half * 8, g.x.plane, xv);
+                                load8(g.hprev.p + hrow * g.hprev.ld + n + half * 8, g.hprev.plane, hv);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float gi = sigmoid_acc(v[half * 8 + j]);
+                                    v[half * 8 + j] = gi * xv[j] + (1.f - gi) * hv[j];
+                                }
+                            }
+                        }
+                    }
+                    // hi/lo split, 128B-swizzled staging (16-byte chunk j of row r lives at chunk j ^ (r & 7))
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t h[8], l[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) split1(v[half * 8 + j], h[j], l[j]);
+                        const int cj = ((sub >> 3) + half) ^ sw;
+                        *reinterpret_cast<uint4*>(my_hi + cj * 16) =
+                            make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                        *reinterpret_cast<uint4*>(my_lo + cj * 16) =
+                            make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+                    }
+                }
+                if (ch == nchunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + buf);
+                }
+                fence_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    const int c0 = n0 + ch * 64;
+                    if (c0 < g.N) {
+                        if (MODE == MODE_PW) {
+                            tma_store_3d(&tmO, ostage, c0, tile_m * kBM, 0);
+                            if (g.out.plane) tma_store_3d(&tmO, ostage + kOutPlaneBytes, c0, tile_m * kBM, 1);
+                        } else {
+                            tma_store_5d(&tmO, ostage, c0, x0, y0, img_out, 0);
+                            if (g.out.plane) tma_store_5d(&tmO, ostage + kOutPlaneBytes, c0, x0, y0, img_out, 1);
+                        }
+                    }
+                    bulk_commit();
+                }
+            }
+        }
+        if (leader) bulk_wait0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace uavsal

@@ -167,6 +167,105 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(Act in, int n, int h, int w,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// depthwise 3x3 fast path (dilation 1, stride 1|2): sliding 3x3 register window down a strip of RB output rows.
+// thread = (8-channel group, output column); a block covers 64 channels x 32 columns x RB rows, so every warp-level
+// load is four full 128-byte lines per plane and each input row is fetched once per strip (3 loads per output instead
+// of 9); the two neighbouring columns come from L1.  BN-folded weights of the block's 64 channels sit in shared memory.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDwRB = 9;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256, 2) dw3x3_rows_kernel(Act in, int h, int w, int c, int ho, int wo,
+                                                         const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                         int relu6, ActW out, int strips) {
+    __shared__ float4 sw[9][8][2];      // [tap][group in block][half]
+    __shared__ float4 sb[8][2];
+    const int gl = threadIdx.x & 7;
+    const int cbase = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 9 * 16; i += 256) {
+        const int tap = i / 16, q = i % 16;       // q: float4 index within the 64 channels
+        const int ch = cbase + q * 4;
+        sw[tap][q >> 1][q & 1] = ch < c ? __ldg(reinterpret_cast<const float4*>(wgt + tap * c + ch)) : make_float4(0, 0, 0, 0);
+    }
+    if (threadIdx.x < 16) {
+        const int ch = cbase + threadIdx.x * 4;
+        sb[threadIdx.x >> 1][threadIdx.x & 1] = ch < c ? __ldg(reinterpret_cast<const float4*>(bias + ch)) : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int c0 = cbase + gl * 8;
+    const int ox = blockIdx.y * 32 + (threadIdx.x >> 3);
+    const int strip = blockIdx.z % strips, img = blockIdx.z / strips;
+    if (c0 >= c || ox >= wo) return;
+    const int oy0 = strip * kDwRB;
+    const int xc = ox * STRIDE;                   // centre input column
+    const bool xl = xc - 1 >= 0, xr = xc + 1 < w;
+    const uint16_t* ibase = in.p + (int64_t)img * h * w * in.ld + c0;
+
+    float win[3][3][8];                           // [row slot][dx][channel]
+    auto load_row = [&](int slot, int y) {
+        if (y < 0 || y >= h) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) win[slot][d][j] = 0.f;
+            return;
+        }
+        const uint16_t* rp = ibase + ((int64_t)y * w + xc) * in.ld;
+        if (xl) load8(rp - in.ld, in.plane, win[slot][0]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[slot][0][j] = 0.f;
+        }
+        load8(rp, in.plane, win[slot][1]);
+        if (xr) load8(rp + in.ld, in.plane, win[slot][2]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[slot][2][j] = 0.f;
+        }
+    };
+    // slots hold input rows: stride 1 -> rows (oy-1, oy, oy+1); stride 2 -> rows (2oy-1, 2oy, 2oy+1)
+    if (STRIDE == 1) { load_row(0, oy0 - 1); load_row(1, oy0); }
+    else             { load_row(0, 2 * oy0 - 1); }
+#pragma unroll
+    for (int i = 0; i < kDwRB; ++i) {
+        const int oy = oy0 + i;
+        if (oy >= ho) break;
+        // slot rotation is static because the loop is fully unrolled
+        int s0, s1, s2;
+        if (STRIDE == 1) {
+            s0 = i % 3; s1 = (i + 1) % 3; s2 = (i + 2) % 3;
+            load_row(s2, oy + 1);
+        } else {
+            s0 = (2 * i) % 3; s1 = (2 * i + 1) % 3; s2 = (2 * i + 2) % 3;
+            load_row(s1, 2 * oy);
+            load_row(s2, 2 * oy + 1);
+        }
+        float acc[8];
+        {
+            const float4 b0 = sb[gl][0], b1 = sb[gl][1];
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+        const int slots[3] = {s0, s1, s2};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 w0 = sw[ky * 3 + kx][gl][0], w1 = sw[ky * 3 + kx][gl][1];
+                const float* v = win[slots[ky]][kx];
+                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+            }
+        if (relu6) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = relu6f(acc[j]);
+        }
+        store8(out.p + (((int64_t)img * ho + oy) * wo + ox) * out.ld + c0, out.plane, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // bilinear, align_corners=True, into a concat slot; output frame i reads source frame i % n_src
 // [model.py:152-153, 360-361; ATen upsample_bilinear2d: ratio=(in-1)/(out-1), src=ratio*dst, l1=src-floor]
 // ---------------------------------------------------------------------------------------------------
@@ -378,6 +477,8 @@ __global__ void __launch_bounds__(256) post_write_f32_kernel(const float* __rest
 // ===================================================================================================
 using namespace uavsal;
 
+int g_dw_fast = 1;     // uavsal_set_option key 2: 1 = sliding-window depthwise kernel, 0 = generic one
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool act_ok(const void* p, int64_t plane, int ld) {
     return p != nullptr && aligned16(p) && (ld % 8) == 0 && (plane % 8) == 0 && plane >= 0;
@@ -439,6 +540,19 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
     UAVSAL_REQUIRE((stride == 1 || stride == 2) && dilation >= 1 && (stride == 1 || dilation == 1), UAVSAL_ENOTSUP,
                    "dw3x3: stride %d dilation %d unsupported", stride, dilation);   // model.py:78 assert stride in [1,2]
     const int ho = stride == 1 ? h : (h - 1) / 2 + 1, wo = stride == 1 ? w : (w - 1) / 2 + 1;
+    if (dilation == 1 && g_dw_fast) {
+        const int strips = div_up(ho, kDwRB);
+        const dim3 grid(div_up(c, 64), div_up(wo, 32), strips * n);
+        if (grid.y <= 65535 && grid.z <= 65535) {
+            if (stride == 1)
+                dw3x3_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, h, w, c, ho, wo, wgt, bias,
+                                                                           relu6, ActW{out, out_plane, out_ld}, strips);
+            else
+                dw3x3_rows_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, h, w, c, ho, wo, wgt, bias,
+                                                                           relu6, ActW{out, out_plane, out_ld}, strips);
+            return check_launch("dw3x3(rows)");
+        }
+    }
     const int64_t total = (int64_t)n * ho * wo * (c / 8);
     dw3x3_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n, h, w, c, ho, wo,
                                                                       stride, dilation, wgt, bias, relu6,

@@ -120,7 +120,7 @@ class Op:
 
 class Plan:
     def __init__(self, device: torch.device, terms: int = 3, engine: str = "tc"):
-        assert terms in (1, 3) and engine in ("tc", "simt")
+        assert terms in (1, 3) and engine in ("tc", "tc1", "simt")
         self.device = torch.device(device)
         self.terms = terms
         self.engine = engine
@@ -177,7 +177,7 @@ class Plan:
         r = res.act() if res is not None else NULL_ACT
         if res is not None:
             flags |= F_RESIDUAL
-        if self.engine == "tc":
+        if self.engine != "simt":
             wp = self.hold(pack_pw_tc(w2d, kpad))
             self._add("uavsal_pw_gemm", (*x.act(), m, kpad, wp.data_ptr(), kpad, n, bp, flags, self.terms, *r, *out.act()), tag)
         else:
@@ -189,7 +189,7 @@ class Plan:
         w2d = conv3x3_as_2d(w4d)
         b = self.hold(bias.float()) if bias is not None else None
         bp = b.data_ptr() if b is not None else 0
-        if self.engine == "tc":
+        if self.engine != "simt":
             wp = self.hold(split_bf16(w2d))
             self._add("uavsal_conv3x3", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, self.terms, *out.act()), tag)
         else:
@@ -207,7 +207,7 @@ class Plan:
 
     def twa(self, x: Buf, h0: Buf, t_steps, h, w, c, w4d: torch.Tensor, seq: Buf, tag=""):
         w2d = conv3x3_as_2d(w4d.detach().float())
-        if self.engine == "tc":
+        if self.engine != "simt":
             wp = self.hold(split_bf16(w2d))
             self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, wp.data_ptr(), 0, self.terms, *seq.act()), tag)
         else:
@@ -221,7 +221,7 @@ class Plan:
         if bias is not None:
             bb = self.hold(interleave_gates(bias.detach().float(), ch))
             bp = bb.data_ptr()
-        if self.engine == "tc":
+        if self.engine != "simt":
             wp = self.hold(split_bf16(w2d))
             args = (*x.act(), *h0.act(), c_state.data_ptr(), b, t_steps, h, w, cin, ch, wp.data_ptr(), 0, bp, self.terms, *seq.act())
         else:
@@ -242,6 +242,7 @@ class Plan:
         if self.device.type != "cuda":
             raise RuntimeError("uavsal-b200 kernels are CUDA (sm_100a) only; there is no CPU path")
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _ext.load().uavsal_set_option(1, 1 if self.engine == "tc1" else 2)      # tcgen05 kernel generation (process-global)
         ops = self.ops if upto is None else self.ops[:upto]
         for op in ops:
             rc = op.fn(*op.args, stream)
@@ -271,7 +272,7 @@ class Plan:
             if op.name == "uavsal_twa_sequence":
                 n += op.args[6]
             elif op.name == "uavsal_convlstm_sequence":
-                n += op.args[8] * (1 if self.engine == "tc" else op.args[7])
+                n += op.args[8] * (1 if self.engine != "simt" else op.args[7])
             elif op.name == "uavsal_post_u8":
                 n += 2
             else:

@@ -37,12 +37,12 @@ extern "C" {
 #define UAVSAL_F_RELU6    1    /* clamp to [0,6]            (nn.ReLU6, model.py:71) */
 #define UAVSAL_F_RESIDUAL 2    /* out += res                (model.py:101, 247) */
 #define UAVSAL_F_SIGMOID  4    /* out = sigmoid(out)        (model.py:373) */
-#define UAVSAL_F_ADD2     8    /* out += res2 BEFORE the activation is NOT implied; res2 is a second addend */
 
 int         uavsal_version(void);                 /* ABI version, currently 1 */
 const char* uavsal_arch(void);                    /* "sm_100a" */
 const char* uavsal_last_error(void);
 int         uavsal_device_ok(int device);         /* 0 if `device` is compute capability 10.x */
+int         uavsal_set_option(int key, int value);/* key 1: tcgen05 GEMM kernel version (2 = persistent, default; 1 = one tile per CTA) */
 
 /* ---- layout conversion at the module boundary (torch NCHW fp32 <-> arena) ---------------------- */
 /* NCHW fp32 -> act NHWC with channels zero-padded to cpad (cb priors, Demo_Test.py:16,22; states).  */

@@ -16,7 +16,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["simt_units", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc", "runner"]
+GROUPS = ["simt_units", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
 
 
 def rel(a, b):
@@ -320,6 +320,10 @@ def g_e2e_simt():
 
 def g_e2e_tc():
     e2e("tc")
+
+
+def g_e2e_tc1():
+    e2e("tc1")
 
 
 def g_runner():

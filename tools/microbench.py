@@ -1,0 +1,96 @@
+"""Kernel micro-benchmarks on one B200 (CUDA events, L2 flushed between repetitions).  Dev tool.
+    python tools/microbench.py [gemm|dw|conv|twa|all]"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from iip_uavsal_saliency_b200 import _ext
+from iip_uavsal_saliency_b200.engine import Plan, pack_dw
+
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(plan, reps=5):
+    plan.run(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); plan.run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm(engine, m, k, n, res=False, terms=3):
+    p = Plan(dev, terms, engine)
+    a = p.alloc(m, k); a.t.normal_()
+    o = p.alloc(m, n)
+    r = p.alloc(m, n) if res else None
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    p.pw(a, m, w, torch.zeros(n, device=dev), 1, o, res=r)
+    ms = timeit(p)
+    fl = 2.0 * m * k * n
+    by = 4.0 * m * (k + n * (2 if res else 1))
+    print("pw[%s,t%d] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
+
+
+def dw(fast, n, h, w, c, stride):
+    _ext.load().uavsal_set_option(2, fast)
+    p = Plan(dev, 3, "tc")
+    x = p.alloc(n * h * w, c); x.t.normal_()
+    ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
+    o = p.alloc(n * ho * wo, c)
+    p.dw(x, n, h, w, c, stride, 1, p.hold(pack_dw(torch.randn(c, 1, 3, 3))), p.hold(torch.zeros(c)), True, o)
+    ms = timeit(p)
+    by = 4.0 * n * c * (h * w + ho * wo)
+    print("dw[fast=%d] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
+    _ext.load().uavsal_set_option(2, 1)
+
+
+def conv(engine, n, h, w, c, co, terms=3):
+    p = Plan(dev, terms, engine)
+    x = p.alloc(n * h * w, c); x.t.normal_()
+    o = p.alloc(n * h * w, co)
+    p.conv3x3(x, n, h, w, c, torch.randn(co, c, 3, 3, device=dev) * 0.02, torch.zeros(co, device=dev), 1, o)
+    ms = timeit(p)
+    fl = 2.0 * n * h * w * 9 * c * co
+    print("conv3x3[%s,t%d] n=%d %dx%d c=%d co=%d: %.1f us  %.1f TF/s(alg)" % (engine, terms, n, h, w, c, co, ms * 1e3, fl / ms / 1e9), flush=True)
+
+
+def twa(engine, t, h, w, c):
+    p = Plan(dev, 3, engine)
+    x = p.alloc(t * h * w, c); x.t.normal_()
+    h0 = p.alloc(h * w, c)
+    seq = p.alloc(t * h * w, c)
+    p.twa(x, h0, t, h, w, c, torch.randn(c, 2 * c, 3, 3, device=dev) * 0.01, seq)
+    ms = timeit(p)
+    print("twa[%s] t=%d %dx%d c=%d: %.1f us total, %.1f us/step, %.1f TF/s(alg)" % (engine, t, h, w, c, ms * 1e3, ms * 1e3 / t, 2.0 * t * h * w * 9 * 2 * c * c / ms / 1e9), flush=True)
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    M = 72000
+    if what in ("gemm", "all"):
+        for eng in ("tc1", "tc"):
+            gemm(eng, M, 256, 1536); gemm(eng, M, 1536, 256, res=True); gemm(eng, M, 320, 1920); gemm(eng, M, 1920, 256)
+            gemm(eng, M, 256, 256); gemm(eng, M, 256, 32); gemm(eng, 20 * 180 * 320, 16, 96); gemm(eng, 20 * 90 * 160, 144, 24, res=True)
+            gemm(eng, 4800, 320, 1920); gemm(eng, M, 256, 1536, terms=1)
+    if what in ("dw", "all"):
+        for fast in (0, 1):
+            dw(fast, 20, 45, 80, 1536, 1); dw(fast, 20, 180, 320, 96, 2); dw(fast, 20, 180, 320, 32, 1); dw(fast, 20, 90, 160, 144, 1); dw(fast, 20, 23, 40, 384, 1)
+    if what in ("conv", "all"):
+        for eng in ("tc1", "tc"):
+            conv(eng, 20, 45, 80, 448, 256); conv(eng, 20, 45, 80, 448, 256, terms=1)
+    if what in ("twa", "all"):
+        for eng in ("tc1", "tc"):
+            twa(eng, 20, 45, 80, 256)
+
+
+if __name__ == "__main__":
+    main()
