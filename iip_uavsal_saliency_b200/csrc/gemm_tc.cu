@@ -81,8 +81,13 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
 #pragma unroll
                     for (int p = 0; p < NPL; ++p) tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
                 }
+                int bk = kb * kBK;
+                if (MODE == MODE_CONV) {
+                    const int tap = kb / g.kb_per_tap;
+                    bk = tap * g.bk_tap_stride + g.bk_off + (kb - tap * g.kb_per_tap) * kBK;
+                }
 #pragma unroll
-                for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, kb * kBK, n0, p);
+                for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
             }
         }
     } else if (warp == 1) {
@@ -362,7 +367,7 @@ static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
             if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
             attr3 = true;
         }
-        gemm_tc2_kernel<MODE, EPI, 3><<<grid, kThreads, smem, s>>>(a0, a1, b, o, g);
+        gemm_tc2_kernel<MODE, EPI, 3><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
     } else {
         static bool attr1 = false;
         if (!attr1) {
@@ -370,7 +375,7 @@ static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
             if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
             attr1 = true;
         }
-        gemm_tc2_kernel<MODE, EPI, 1><<<grid, kThreads, smem, s>>>(a0, a1, b, o, g);
+        gemm_tc2_kernel<MODE, EPI, 1><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
     }
     return check_launch(what);
 }
@@ -400,7 +405,8 @@ static void pick_tile(int H, int W, int& tw, int& th) {
 
 int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img, int a1_mul, int a1_off, int c1,
             int batch, int H, int W, const uint16_t* wgt, int cout, const float* bias, int flags, int terms, int epi,
-            Act x, Act hprev, float* c_state, ActW out, int out_nimg, int out_mul, int out_off, cudaStream_t s, const char* what) {
+            Act x, Act hprev, float* c_state, ActW out, int out_nimg, int out_mul, int out_off, cudaStream_t s, const char* what,
+            int wk_total = 0, int wk_off = 0, const float* gx = nullptr, float* raw_out = nullptr) {
     UAVSAL_REQUIRE(c0 % kBK == 0 && c1 % kBK == 0 && c0 > 0, UAVSAL_ENOTSUP, "%s: channels must be multiples of 64", what);
     UAVSAL_REQUIRE(cout % 8 == 0 && (terms == 1 || terms == 3), UAVSAL_EINVAL, "%s: bad cout/terms", what);
     TcArgs g{};
@@ -413,11 +419,15 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     g.M = batch * H * W; g.N = cout; g.bn = pick_bn(cout);
     const int tiles_m_ = batch * g.tiles_x * g.tiles_y;
     const bool v2 = g_tc_version == 2 && epi != EPI_LSTM;
+    UAVSAL_REQUIRE(v2 || epi != EPI_RAW, UAVSAL_ENOTSUP, "%s: raw output needs the persistent kernel", what);
     if (v2) {   // small problems (one image per step in the recurrence): narrower N tiles so that more SMs get a tile
         while (g.bn > 64 && g.bn % 128 == 0 && tiles_m_ * div_up(cout, g.bn) < 100) g.bn /= 2;
     }
     g.bias = bias; g.flags = flags; g.out = out; g.x = x; g.hprev = hprev; g.c_state = c_state;
-    const int kpad = 9 * (c0 + c1);
+    const int kpad = wk_total ? 9 * wk_total : 9 * (c0 + c1);        // weight rows may hold more input channels than this launch reads
+    g.bk_tap_stride = wk_total ? wk_total : c0 + c1;
+    g.bk_off = wk_off;
+    g.gx = gx; g.raw_out = raw_out;
     CUtensorMap tA0, tA1, tB;
     int rc = map_img(&tA0, a0, n0img, H, W, c0, tw, th);
     if (rc) return rc;
@@ -428,9 +438,11 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     const int tiles_m = batch * g.tiles_x * g.tiles_y;
     if (v2) {
         CUtensorMap tO;
-        rc = map_out_img(&tO, out, out_nimg, H, W, cout, tw, th);
+        if (epi == EPI_RAW) tO = tA0;
+        else rc = map_out_img(&tO, out, out_nimg, H, W, cout, tw, th);
         if (rc) return rc;
         if (epi == EPI_STD) return launch_tc2<MODE_CONV, EPI_STD>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
+        if (epi == EPI_RAW) return launch_tc2<MODE_CONV, EPI_RAW>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
         return launch_tc2<MODE_CONV, EPI_TWA>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
     }
     if (epi == EPI_STD) return launch_tc<MODE_CONV, EPI_STD>(tA0, tA1, tB, g, terms, tiles_m, s, what);
@@ -506,7 +518,7 @@ int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h
 
 int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
                         int t_steps, int h, int w, int c, const uint16_t* wgt, const float* wgt_f32, int terms,
-                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream) {
+                        float* gx_workspace, uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream) {
     UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
                        t_steps > 0 && c % 8 == 0 && x_ld >= c && h0_ld >= c && seq_ld >= c,
                    UAVSAL_EINVAL, "twa_sequence: bad arguments");
@@ -519,6 +531,25 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
     UAVSAL_REQUIRE(terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
                    "twa_sequence: terms=3 needs lo planes");
     Act SA{seq_out, seq_plane, seq_ld};
+    if (gx_workspace && g_tc_version == 2) {
+        // hoisted: G_x = W_x * x_t for ALL steps in one batched implicit GEMM (fp32 pre-activations), then per step only the
+        // recurrent half W_h * h_{t-1} (K = 9c instead of 18c) with G_x[t] added in the epilogue before the gate
+        int rc = conv_tc(X, t_steps, 1, 0, c, X, t_steps, 1, 0, 0, t_steps, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
+                         nullptr, ActW{}, t_steps, 1, 0, s, "twa_sequence(x half)", 2 * c, 0, nullptr, gx_workspace);
+        if (rc) return rc;
+        const int64_t fr = (int64_t)h * w * c;
+        for (int t = 0; t < t_steps; ++t) {
+            if (t == 0)
+                rc = conv_tc(H0, 1, 0, 0, c, H0, 1, 0, 0, 0, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S, t_steps, 0, 0,
+                             s, "twa_sequence(h half)", 2 * c, c, gx_workspace, nullptr);
+            else
+                rc = conv_tc(SA, t_steps, 0, t - 1, c, SA, t_steps, 0, t - 1, 0, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, SA, nullptr,
+                             S, t_steps, 0, t, s, "twa_sequence(h half)", 2 * c, c, gx_workspace, nullptr);
+            if (rc) return rc;
+        }
+        (void)fr;
+        return 0;
+    }
     for (int t = 0; t < t_steps; ++t) {
         // step t: A = [x_t, h_{t-1}], out = seq[t]
         int rc;

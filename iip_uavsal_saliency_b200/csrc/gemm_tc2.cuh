@@ -13,9 +13,21 @@ namespace uavsal {
 
 constexpr uint32_t kOutPlaneBytes = kBM * 64 * 2;          // one 128 x 64 bf16 box
 constexpr uint32_t kOutStageBytes = 2 * kOutPlaneBytes;    // hi + lo
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads2 = 64 + kEpiThreads;                // producer warp + MMA warp + epilogue warps
+
+// two fp32 -> packed (hi, lo) bf16x2 words; element 0 in the low half
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 template <int MODE, int EPI, int TERMS>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO, const TcArgs g) {
@@ -35,7 +47,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -88,8 +100,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 #pragma unroll
                         for (int p = 0; p < NPL; ++p) tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
                     }
+                    int bk = kb * kBK;
+                    if (MODE == MODE_CONV) {
+                        const int tap = kb / g.kb_per_tap;
+                        bk = tap * g.bk_tap_stride + g.bk_off + (kb - tap * g.kb_per_tap) * kBK;
+                    }
 #pragma unroll
-                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, kb * kBK, n0, p);
+                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
                 }
             }
         }
@@ -129,8 +146,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5, 128 threads) =====================
+        // ===================== epilogue (warps 2..17, 512 threads) =====================
+        // A warp may only touch TMEM lanes 32*(warp%4)..+31, so the four warps sharing a quadrant split every 64-column
+        // chunk into 16-column pieces: 16 warps drain one chunk together (4 warps per scheduler hide each other's latency).
         const int q = warp & 3;
+        const int sub = ((warp - 2) >> 2) * 16;                               // column offset inside a 64-column chunk
         const int r = q * 32 + lane;                                          // tile row = TMEM lane
         const bool leader = threadIdx.x == 64;                                // first epilogue thread issues the stores
         uint8_t* my_hi = ostage + r * 128;
@@ -162,9 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
                 // staging buffer must have been read out by the previous TMA stores
-                if (leader) bulk_wait_read0();
-                named_bar_sync(1, 128);
-                for (int sub = 0; sub < ncols; sub += 16) {
+                if (EPI != EPI_RAW) {
+                    if (leader) bulk_wait_read0();
+                    named_bar_sync(1, kEpiThreads);
+                }
+                if (sub < ncols) {
                     uint32_t raw[16];
                     __syncwarp();
                     tmem_ld16(trow + ch * 64 + sub, raw);
@@ -174,6 +196,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
                     const bool live = rvalid && n < g.N;
                     const bool second = n + 8 < g.N;
+                    if (EPI == EPI_RAW) {
+                        if (live) {
+                            float4* o = reinterpret_cast<float4*>(g.raw_out + orow * g.N + n);
+                            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            if (second) {
+                                o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                            }
+                        }
+                    } else {
                     if (live) {
                         if (g.bias) {
 #pragma unroll
@@ -204,6 +237,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                                 for (int j = 0; j < 16; ++j) v[j] = sigmoid_acc(v[j]);
                             }
                         } else {   // EPI_TWA: h = i*x_t + (1-i)*h_{t-1}  (model_convlstm.py:283,290)
+                            if (g.gx) {                                       // hoisted W_x * x_t half of the gate conv
+                                const float4* gp = reinterpret_cast<const float4*>(g.gx + orow * g.N + n);
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    if (j4 >= 2 && !second) break;
+                                    const float4 b4 = __ldg(gp + j4);
+                                    v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+                                }
+                            }
 #pragma unroll
                             for (int half = 0; half < 2; ++half) {
                                 if (half == 1 && !second) break;
@@ -218,26 +260,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                             }
                         }
                     }
-                    // hi/lo split, 128B-swizzled staging (16-byte chunk j of row r lives at chunk j ^ (r & 7))
+                    // hi/lo split (packed bf16x2 converts), 128B-swizzled staging: 16-byte chunk j of row r at j ^ (r & 7)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        uint32_t h[8], l[8];
+                        uint32_t h[4], l[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) split1(v[half * 8 + j], h[j], l[j]);
+                        for (int j = 0; j < 4; ++j) split2(v[half * 8 + 2 * j], v[half * 8 + 2 * j + 1], h[j], l[j]);
                         const int cj = ((sub >> 3) + half) ^ sw;
-                        *reinterpret_cast<uint4*>(my_hi + cj * 16) =
-                            make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-                        *reinterpret_cast<uint4*>(my_lo + cj * 16) =
-                            make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+                        *reinterpret_cast<uint4*>(my_hi + cj * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(my_lo + cj * 16) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
+                    }   // EPI != EPI_RAW
                 }
                 if (ch == nchunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + buf);
                 }
+                if (EPI == EPI_RAW) continue;
                 fence_async_smem();
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiThreads);
                 if (leader) {
                     const int c0 = n0 + ch * 64;
                     if (c0 < g.N) {

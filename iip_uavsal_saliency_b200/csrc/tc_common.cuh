@@ -7,7 +7,7 @@
 namespace uavsal {
 
 enum { MODE_PW = 0, MODE_CONV = 1 };
-enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2 };
+enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3 };
 
 constexpr int kBM = 128;          // rows per tile = TMEM lanes
 constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
@@ -31,6 +31,9 @@ struct TcArgs {
     Act x, hprev;             // TWA operands (indexed like out / a1)
     float* c_state;           // LSTM cell state [b][H*W][N/4]
     int num_tiles, tiles_n;   // persistent kernel: tile t -> (m_tile = t / tiles_n, n_tile = t % tiles_n)
+    int bk_tap_stride, bk_off; // conv: weight K coordinate of k-block (tap, r) = tap*bk_tap_stride + bk_off + r*64
+    const float* gx;          // TWA: hoisted input-half pre-activations [rows][N] fp32 added before the gate (or null)
+    float* raw_out;           // EPI_RAW: fp32 accumulators [rows][N]
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
