@@ -24,7 +24,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     files.append(os.path.join(os.path.dirname(PKG), "include", "uavsal_b200.h"))
     for f in files:
         with open(f, "rb") as fh:
