@@ -240,17 +240,22 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, const char* what) {
+int tc_encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, const char* what, int swizzle128) {
     EncodeTiledFn fn = get_encode();
     UAVSAL_REQUIRE(fn != nullptr, UAVSAL_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UAVSAL_REQUIRE(r == CUDA_SUCCESS, UAVSAL_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return 0;
+}
+static int encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const char* what) {
+    return tc_encode(tm, base, rank, dims, strides_bytes, box, what, 1);
 }
 
 // 2-D activation matrix [rows][k] with hi/lo planes -> (k, rows, plane)
@@ -469,7 +474,7 @@ extern "C" {
 
 int uavsal_set_option(int key, int value) {
     if (key == 1 && (value == 1 || value == 2)) { g_tc_version = value; return 0; }
-    if (key == 2 && (value == 0 || value == 1)) { g_dw_fast = value; return 0; }
+    if (key == 2 && value >= 0 && value <= 2) { g_dw_fast = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }

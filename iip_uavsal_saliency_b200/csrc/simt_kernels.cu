@@ -477,7 +477,11 @@ __global__ void __launch_bounds__(256) post_write_f32_kernel(const float* __rest
 // ===================================================================================================
 using namespace uavsal;
 
-int g_dw_fast = 1;     // uavsal_set_option key 2: 1 = sliding-window depthwise kernel, 0 = generic one
+int g_dw_fast = 2;     // uavsal_set_option key 2: 2 = TMA-staged depthwise kernel (default), 1 = sliding window, 0 = generic
+namespace uavsal {
+int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, const float* bias, int relu6, ActW out,
+              cudaStream_t s);
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool act_ok(const void* p, int64_t plane, int ld) {
@@ -540,7 +544,11 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
     UAVSAL_REQUIRE((stride == 1 || stride == 2) && dilation >= 1 && (stride == 1 || dilation == 1), UAVSAL_ENOTSUP,
                    "dw3x3: stride %d dilation %d unsupported", stride, dilation);   // model.py:78 assert stride in [1,2]
     const int ho = stride == 1 ? h : (h - 1) / 2 + 1, wo = stride == 1 ? w : (w - 1) / 2 + 1;
-    if (dilation == 1 && g_dw_fast) {
+    if (dilation == 1 && g_dw_fast == 2 && in_plane != 0 && out_plane != 0 && (int64_t)n * ho * wo >= 512) {
+        return dw3x3_tma(Act{in, in_plane, in_ld}, n, h, w, c, stride, wgt, bias, relu6, ActW{out, out_plane, out_ld},
+                         (cudaStream_t)stream);
+    }
+    if (dilation == 1 && g_dw_fast == 1) {
         const int strips = div_up(ho, kDwRB);
         const dim3 grid(div_up(c, 64), div_up(wo, 32), strips * n);
         if (grid.y <= 65535 && grid.z <= 65535) {

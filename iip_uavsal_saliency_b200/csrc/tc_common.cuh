@@ -109,6 +109,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 }
 
 
+// host: cuTensorMapEncodeTiled through the runtime's driver entry point (defined in gemm_tc.cu)
+int tc_encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, const char* what, int swizzle128);
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

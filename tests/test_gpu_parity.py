@@ -48,7 +48,8 @@ def _download(plan, buf, n, c, h, w):
     return out
 
 
-@pytest.mark.parametrize("c,s,d,h,w", [(32, 1, 1, 20, 24), (96, 2, 1, 21, 23), (48, 1, 6, 12, 20), (1920, 1, 18, 12, 20), (8, 1, 1, 1, 1)])
+@pytest.mark.parametrize("c,s,d,h,w", [(32, 1, 1, 20, 24), (96, 2, 1, 21, 23), (48, 1, 6, 12, 20), (1920, 1, 18, 12, 20), (8, 1, 1, 1, 1),
+                                       (192, 1, 1, 45, 80), (120, 1, 1, 23, 40), (1536, 2, 1, 45, 80), (24, 1, 1, 37, 41), (144, 2, 1, 90, 160)])
 def test_depthwise(cuda, c, s, d, h, w):
     from iip_uavsal_saliency_b200.engine import out_size, pack_dw
     torch.manual_seed(0)

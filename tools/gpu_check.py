@@ -66,7 +66,8 @@ def g_simt_units():
     p.run(); torch.cuda.synchronize()
     report("pack/unpack roundtrip (split-bf16)", y, x, 1e-4)
     # depthwise variants
-    for (c, s, d, h, w) in [(32, 1, 1, 20, 24), (96, 2, 1, 21, 23), (48, 1, 6, 12, 20), (1920, 1, 18, 12, 20), (144, 2, 1, 45, 80)]:
+    for (c, s, d, h, w) in [(32, 1, 1, 20, 24), (96, 2, 1, 21, 23), (48, 1, 6, 12, 20), (1920, 1, 18, 12, 20), (144, 2, 1, 45, 80),
+                            (192, 1, 1, 45, 80), (120, 1, 1, 23, 40), (1536, 2, 1, 45, 80), (24, 1, 1, 37, 41), (96, 2, 1, 180, 320)]:
         p = mk_plan("simt")
         x = torch.randn(2, c, h, w)
         wt = torch.randn(c, 1, 3, 3) * 0.3

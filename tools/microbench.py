@@ -82,7 +82,7 @@ def main():
             gemm(eng, M, 256, 256); gemm(eng, M, 256, 32); gemm(eng, 20 * 180 * 320, 16, 96); gemm(eng, 20 * 90 * 160, 144, 24, res=True)
             gemm(eng, 4800, 320, 1920); gemm(eng, M, 256, 1536, terms=1)
     if what in ("dw", "all"):
-        for fast in (0, 1):
+        for fast in (0, 2):
             dw(fast, 20, 45, 80, 1536, 1); dw(fast, 20, 180, 320, 96, 2); dw(fast, 20, 180, 320, 32, 1); dw(fast, 20, 90, 160, 144, 1); dw(fast, 20, 23, 40, 384, 1)
     if what in ("conv", "all"):
         for eng in ("tc1", "tc"):
