@@ -27,20 +27,24 @@ struct DwGeom {
     static constexpr int IW = (TW - 1) * STRIDE + 3;      // haloed input box
     static constexpr int IH = (TH - 1) * STRIDE + 3;
     static constexpr int PIX = IW * IH;
-    static constexpr int RPT = TW * TH * 8 / 256;         // output rows per thread (one column, RPT consecutive rows)
+    static constexpr int RPT = TW * TH * 16 / 256;        // output rows per thread: 8 (stride 1) or 4 (stride 2)
     static constexpr uint32_t PLANE_BYTES = PIX * 128;    // 64 channels x bf16
 };
 
-__device__ __forceinline__ void lds8(const uint8_t* hi, const uint8_t* lo, float v[8]) {
-    const uint4 a = *reinterpret_cast<const uint4*>(hi);
-    const uint4 b = *reinterpret_cast<const uint4*>(lo);
-    float t[8];
-    unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]); unpack2(a.z, v[4], v[5]); unpack2(a.w, v[6], v[7]);
-    unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]); unpack2(b.z, t[4], t[5]); unpack2(b.w, t[6], t[7]);
+// 4 channels (8 bytes per plane) from the staged tile -> fp32
+__device__ __forceinline__ void lds4(const uint8_t* hi, const uint8_t* lo, float v[4]) {
+    const uint2 a = *reinterpret_cast<const uint2*>(hi);
+    const uint2 b = *reinterpret_cast<const uint2*>(lo);
+    float t[4];
+    unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]);
+    unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    for (int i = 0; i < 4; ++i) v[i] += t[i];
 }
 
+// thread = (4-channel quad, output column); it keeps its 36 folded weights in registers for the whole tile and slides a
+// 3x3x4 register window down RPT output rows, so the shared-memory/LSU pipe (the measured limiter of the first version,
+// whose weights were re-read from smem for every row) only carries 3 narrow reads and one write per output.
 template <int STRIDE>
 __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs g) {
     using G = DwGeom<STRIDE>;
@@ -48,19 +52,18 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* s_hi = smem;
     uint8_t* s_lo = smem + G::PLANE_BYTES;
-    float4* sw = reinterpret_cast<float4*>(s_lo + G::PLANE_BYTES);            // [9][16]
-    float4* sb = sw + 9 * 16;                                                  // [16]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 16);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_lo + G::PLANE_BYTES);
 
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     __syncthreads();
 
-    const int gl = tid & 7;                                                    // 8-channel group inside the 64-channel block
-    const int col = (tid >> 3) % G::TW;
-    const int rgrp = (tid >> 3) / G::TW;                                       // which RPT-row slice of the tile
+    const int quad = tid & 15;                                                 // 4-channel quad inside the 64-channel block
+    const int col = (tid >> 4) % G::TW;
+    const int rgrp = (tid >> 4) / G::TW;
     int last_cblk = -1;
     uint32_t parity = 0;
+    float wr[9][4], br[4];
     for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
         int r = t;
         const int cblk = r % g.cblocks; r /= g.cblocks;
@@ -74,29 +77,32 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
             tma_load_5d(&tmIn, bar, s_hi, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 0);
             tma_load_5d(&tmIn, bar, s_lo, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 1);
         }
-        if (cblk != last_cblk) {                                               // block-uniform
-            for (int i = tid; i < 10 * 16; i += 256) {
-                const int row = i >> 4, q = i & 15, ch = cblk * 64 + q * 4;
-                const float* src = row < 9 ? g.wgt + row * g.c : g.bias;
-                sw[i] = ch < g.c ? __ldg(reinterpret_cast<const float4*>(src + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c0 = cblk * 64 + quad * 4;
+        if (cblk != last_cblk) {                                               // block-uniform; overlaps the TMA flight time
+            if (c0 < g.c) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wgt + k * g.c + c0));
+                    wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
+                }
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
+                br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
             }
             last_cblk = cblk;
         }
-        __syncthreads();
         mbar_wait(bar, parity);
         parity ^= 1;
 
-        const int c0 = cblk * 64 + gl * 8;
         const int ox = x0 + col;
         if (c0 < g.c && ox < g.wo) {
-            const uint8_t* bh = s_hi + gl * 16;
-            const uint8_t* bl = s_lo + gl * 16;
-            float win[3][3][8];
+            const uint8_t* bh = s_hi + quad * 8;
+            const uint8_t* bl = s_lo + quad * 8;
+            float win[3][3][4];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const int pix = iy * G::IW + col * STRIDE + d;
-                    lds8(bh + pix * 128, bl + pix * 128, win[slot][d]);
+                    lds4(bh + pix * 128, bl + pix * 128, win[slot][d]);
                 }
             };
             const int oyl0 = rgrp * G::RPT;
@@ -116,28 +122,21 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
                 }
                 const int oy = y0 + oyl;
                 if (oy >= g.ho) break;
-                float acc[8];
-                {
-                    const float4 b0 = sb[gl * 2], b1 = sb[gl * 2 + 1];
-                    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-                }
+                float acc[4] = {br[0], br[1], br[2], br[3]};
                 const int slots[3] = {s0, s1, s2};
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        const float4 w0 = sw[(ky * 3 + kx) * 16 + gl * 2], w1 = sw[(ky * 3 + kx) * 16 + gl * 2 + 1];
                         const float* v = win[slots[ky]][kx];
-                        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-                        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-                        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-                        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
                     }
                 if (g.relu6) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = relu6f(acc[j]);
+                    for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
                 }
-                store8(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
+                store4(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
             }
         }
         __syncthreads();                                                       // tile consumed: the next TMA may overwrite it
@@ -151,7 +150,7 @@ static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     g.tiles_y = div_up(g.ho, G::TH);
     g.cblocks = div_up(g.c, 64);
     g.num_tiles = g.n * g.tiles_x * g.tiles_y * g.cblocks;
-    const size_t smem = 2 * G::PLANE_BYTES + 10 * 16 * sizeof(float4) + 64 + 128;
+    const size_t smem = 2 * G::PLANE_BYTES + 64 + 128;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -182,10 +182,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
                 // staging buffer must have been read out by the previous TMA stores
-                if (EPI != EPI_RAW) {
-                    if (leader) bulk_wait_read0();
-                    named_bar_sync(1, kEpiThreads);
-                }
+                if (EPI != EPI_RAW) named_bar_sync(1, kEpiThreads);              // staging buffer free (previous chunk copied out)
                 if (sub < ncols) {
                     uint32_t raw[16];
                     __syncwarp();
@@ -278,24 +275,39 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(acc_empty + buf);
                 }
                 if (EPI == EPI_RAW) continue;
-                fence_async_smem();
-                named_bar_sync(1, kEpiThreads);
-                if (leader) {
-                    const int c0 = n0 + ch * 64;
+                named_bar_sync(1, kEpiThreads);                                   // chunk fully staged
+                // cooperative copy-out: 8 consecutive threads write one 128-byte row segment per plane, so every warp store
+                // covers four full lines (the LSU path is used on purpose: TMA stores queue behind the producer's loads)
+                {
+                    const int et = threadIdx.x - 64;                              // 0..511
+                    const int cj = et & 7;
+                    const int c0 = n0 + ch * 64 + cj * 8;
                     if (c0 < g.N) {
-                        if (MODE == MODE_PW) {
-                            tma_store_3d(&tmO, ostage, c0, tile_m * kBM, 0);
-                            if (g.out.plane) tma_store_3d(&tmO, ostage + kOutPlaneBytes, c0, tile_m * kBM, 1);
-                        } else {
-                            tma_store_5d(&tmO, ostage, c0, x0, y0, img_out, 0);
-                            if (g.out.plane) tma_store_5d(&tmO, ostage + kOutPlaneBytes, c0, x0, y0, img_out, 1);
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int rr = (et >> 3) + pass * 64;
+                            int64_t grow;
+                            bool ok;
+                            if (MODE == MODE_PW) {
+                                grow = (int64_t)tile_m * kBM + rr;
+                                ok = grow < g.M;
+                            } else {
+                                const int y = y0 + rr / g.TW, x = x0 + rr % g.TW;
+                                ok = y < g.H && x < g.W;
+                                grow = (int64_t)img_out * g.H * g.W + (int64_t)y * g.W + x;
+                            }
+                            if (ok) {
+                                const uint8_t* src = ostage + rr * 128 + ((cj ^ (rr & 7)) << 4);
+                                uint16_t* dst = g.out.p + grow * g.out.ld + c0;
+                                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                                if (g.out.plane)
+                                    *reinterpret_cast<uint4*>(dst + g.out.plane) = *reinterpret_cast<const uint4*>(src + kOutPlaneBytes);
+                            }
                         }
                     }
-                    bulk_commit();
                 }
             }
         }
-        if (leader) bulk_wait0();
     }
 
     tc_fence_before();

@@ -84,6 +84,10 @@ def main():
     if what in ("dw", "all"):
         for fast in (0, 2):
             dw(fast, 20, 45, 80, 1536, 1); dw(fast, 20, 180, 320, 96, 2); dw(fast, 20, 180, 320, 32, 1); dw(fast, 20, 90, 160, 144, 1); dw(fast, 20, 23, 40, 384, 1)
+    if what == "dwbig":
+        dw(int(sys.argv[2]) if len(sys.argv) > 2 else 2, 20, 45, 80, 1536, 1)
+    if what == "gemmbig":
+        gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True)
     if what in ("conv", "all"):
         for eng in ("tc1", "tc"):
             conv(eng, 20, 45, 80, 448, 256); conv(eng, 20, 45, 80, 448, 256, terms=1)
