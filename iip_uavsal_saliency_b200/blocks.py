@@ -50,12 +50,13 @@ class BasicConv2d(nn.Sequential):
     def folded(self):
         return fold_bn(self[0].weight, self[1])
 
-    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag=""):
+    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag="", f32_out: bool = False):
         cin, cout, k, stride, dil, groups = self.spec
         wf, bf = self.folded()
         if k == 1:
             assert stride == 1 and groups == 1
-            out = out if out is not None else plan.alloc(n * h * w, cout)
+            if out is None:
+                out = plan.alloc_f32(n * h * w, cout) if f32_out else plan.alloc(n * h * w, cout)
             plan.pw(x, n * h * w, wf.reshape(cout, cin), bf, F_RELU6, out, res=res, tag=tag)
             return out, h, w
         if groups == cin and groups == cout:
@@ -77,7 +78,7 @@ def emit_stem(plan: Plan, stem: BasicConv2d, x_src: torch.Tensor, kind: int, n, 
     """features[0]: (normalise +) conv3x3 s2 (3->32) + BN + ReLU6 straight from the NCHW/NHWC input tensor."""
     wf, bf = stem.folded()
     ho, wo = out_size(h, 2), out_size(w, 2)
-    out = plan.alloc(n * ho * wo, 32)
+    out = plan.alloc_f32(n * ho * wo, 32) if plan.f32_hidden else plan.alloc(n * ho * wo, 32)   # features.1 starts with its depthwise conv
     plan.stem(x_src, kind, n, h, w, plan.hold(wf.permute(2, 3, 1, 0).contiguous()), plan.hold(bf), out, tag="features.0")
     return out, ho, wo
 
@@ -113,7 +114,8 @@ class dwBlock(KernelModule):
         cur = x
         i = 0
         if has_expand:
-            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand")
+            # the 6x hidden tensor stays fp32 between the expand GEMM and the TMA depthwise kernel (dilation 1 only)
+            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", f32_out=plan.f32_hidden and dil == 1)
             i = 1
         cur, ho, wo = self.conv[i]._emit(plan, cur, n, h, w, tag=tag + ".dw")
         wf, bf = self.project_folded()

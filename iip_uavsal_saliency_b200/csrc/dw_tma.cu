@@ -1,12 +1,14 @@
-// Depthwise 3x3 + BN + ReLU6 (dilation 1, stride 1|2) with TMA-staged input tiles.
+// Depthwise 3x3 + BN + ReLU6 (dilation 1, stride 1|2) with TMA-staged, double-buffered input tiles.
 //
-// A CTA owns a tile of 16x8 (stride 1) or 8x8 (stride 2) output pixels x 64 channels.  One thread issues two
-// cp.async.bulk.tensor loads (hi and lo plane) of the haloed input box into shared memory; out-of-bounds zero fill
-// provides the convolution padding, so there is no per-thread address arithmetic or predication on the input side and
-// every input element is fetched from L2/HBM once per tile (1.4x halo factor) instead of nine times.  Threads then
-// slide a 3x3 register window down their column of the tile (3 shared-memory reads per output), apply the folded
-// BN bias + ReLU6 and write both bf16 planes with 128-byte-contiguous stores.  Several CTAs per SM overlap each other's
-// TMA latency and compute.
+// A CTA walks a static list of tiles of 16x8 (stride 1) or 8x4 (stride 2) output pixels x 64 channels.  One thread
+// issues the cp.async.bulk.tensor load of the haloed input box of tile i+1 while the CTA computes tile i from the other
+// buffer; out-of-bounds zero fill provides the convolution padding, so there is no per-thread address arithmetic or
+// predication on the input side and every input element crosses L2 -> SM once per tile (1.4x halo factor) instead of
+// nine times.  Threads slide a 3x3 register window down their column of the tile (3 shared-memory reads per output),
+// apply the folded BN bias + ReLU6 and write both bf16 planes of the output with 128-byte-contiguous stores.
+//
+// Input formats: the arena's split-bf16 planes (two boxes per tile) or plain fp32 rows (F32IN — the "hidden" tensor
+// between an expand GEMM and its depthwise conv is kept in fp32: same bytes, no unpack/re-split work on either side).
 #include "tc_common.cuh"
 
 namespace uavsal {
@@ -23,87 +25,100 @@ struct DwArgs {
 template <int STRIDE>
 struct DwGeom {
     static constexpr int TW = STRIDE == 1 ? 16 : 8;       // output tile
-    static constexpr int TH = 8;
+    static constexpr int TH = STRIDE == 1 ? 8 : 4;
     static constexpr int IW = (TW - 1) * STRIDE + 3;      // haloed input box
     static constexpr int IH = (TH - 1) * STRIDE + 3;
     static constexpr int PIX = IW * IH;
-    static constexpr int RPT = TW * TH * 16 / 256;        // output rows per thread: 8 (stride 1) or 4 (stride 2)
-    static constexpr uint32_t PLANE_BYTES = PIX * 128;    // 64 channels x bf16
+    static constexpr int RGRPS = 256 / (16 * TW);         // row groups: 1 (stride 1) or 2 (stride 2)
+    static constexpr int RPT = TH / RGRPS;                // output rows per thread: 8 (stride 1) or 2 (stride 2)
+    static constexpr uint32_t TILE_BYTES = PIX * 256;     // 64 channels x (2 bf16 planes | fp32)
 };
 
-// 4 channels (8 bytes per plane) from the staged tile -> fp32
-__device__ __forceinline__ void lds4(const uint8_t* hi, const uint8_t* lo, float v[4]) {
-    const uint2 a = *reinterpret_cast<const uint2*>(hi);
-    const uint2 b = *reinterpret_cast<const uint2*>(lo);
-    float t[4];
-    unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]);
-    unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]);
+// 4 channels from the staged tile -> fp32
+template <bool F32IN>
+__device__ __forceinline__ void lds4(const uint8_t* tile, uint32_t plane_bytes, int pix, int quad, float v[4]) {
+    if (F32IN) {
+        const float4 a = *reinterpret_cast<const float4*>(tile + pix * 256 + quad * 16);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(tile + pix * 128 + quad * 8);
+        const uint2 b = *reinterpret_cast<const uint2*>(tile + plane_bytes + pix * 128 + quad * 8);
+        float t[4];
+        unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]);
+        unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] += t[i];
+        for (int i = 0; i < 4; ++i) v[i] += t[i];
+    }
 }
 
-// thread = (4-channel quad, output column); it keeps its 36 folded weights in registers for the whole tile and slides a
-// 3x3x4 register window down RPT output rows, so the shared-memory/LSU pipe (the measured limiter of the first version,
-// whose weights were re-read from smem for every row) only carries 3 narrow reads and one write per output.
-template <int STRIDE>
+// thread = (4-channel quad, output column[, row group]); it keeps its 36 folded weights in registers for the tile and
+// slides a 3x3x4 register window down RPT output rows.
+template <int STRIDE, bool F32IN>
 __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs g) {
     using G = DwGeom<STRIDE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint8_t* s_hi = smem;
-    uint8_t* s_lo = smem + G::PLANE_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_lo + G::PLANE_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * G::TILE_BYTES);      // [2]
 
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
     __syncthreads();
+
+    auto decode = [&](int t, int& cblk, int& x0, int& y0, int& img) {
+        int r = t;
+        cblk = r % g.cblocks; r /= g.cblocks;
+        x0 = (r % g.tiles_x) * G::TW; r /= g.tiles_x;
+        y0 = (r % g.tiles_y) * G::TH;
+        img = r / g.tiles_y;
+    };
+    auto issue = [&](int t, int b) {                                           // one thread
+        int cblk, x0, y0, img;
+        decode(t, cblk, x0, y0, img);
+        uint8_t* dst = smem + b * G::TILE_BYTES;
+        fence_async_smem();                                                    // order the buffer's generic reads before the async overwrite
+        mbar_expect_tx(bar + b, G::TILE_BYTES);
+        if (F32IN) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(dst)), "l"(&tmIn), "r"(smem_u32(bar + b)), "r"(cblk * 64), "r"(x0 * STRIDE - 1), "r"(y0 * STRIDE - 1), "r"(img)
+                : "memory");
+        } else {
+            tma_load_5d(&tmIn, bar + b, dst, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 0);
+            tma_load_5d(&tmIn, bar + b, dst + G::TILE_BYTES / 2, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 1);
+        }
+    };
 
     const int quad = tid & 15;                                                 // 4-channel quad inside the 64-channel block
     const int col = (tid >> 4) % G::TW;
     const int rgrp = (tid >> 4) / G::TW;
-    int last_cblk = -1;
-    uint32_t parity = 0;
-    float wr[9][4], br[4];
-    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-        int r = t;
-        const int cblk = r % g.cblocks; r /= g.cblocks;
-        const int tx = r % g.tiles_x;   r /= g.tiles_x;
-        const int ty = r % g.tiles_y;
-        const int img = r / g.tiles_y;
-        const int x0 = tx * G::TW, y0 = ty * G::TH;
-        if (tid == 0) {
-            fence_async_smem();                                                // order the tile's generic reads before the async overwrite
-            mbar_expect_tx(bar, 2 * G::PLANE_BYTES);
-            tma_load_5d(&tmIn, bar, s_hi, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 0);
-            tma_load_5d(&tmIn, bar, s_lo, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 1);
-        }
+    if (tid == 0 && (int)blockIdx.x < g.num_tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < g.num_tiles) issue(t + gridDim.x, b ^ 1);   // prefetch the next tile
+        int cblk, x0, y0, img;
+        decode(t, cblk, x0, y0, img);
         const int c0 = cblk * 64 + quad * 4;
-        if (cblk != last_cblk) {                                               // block-uniform; overlaps the TMA flight time
-            if (c0 < g.c) {
+        const bool cvalid = c0 < g.c;
+        float wr[9][4], br[4];
+        if (cvalid) {                                                          // overlaps the TMA flight time (L1/L2 hits)
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wgt + k * g.c + c0));
-                    wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
-                }
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
-                br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
+            for (int k = 0; k < 9; ++k) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wgt + k * g.c + c0));
+                wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
             }
-            last_cblk = cblk;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
+            br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
         }
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        mbar_wait(bar + b, (it >> 1) & 1);
 
         const int ox = x0 + col;
-        if (c0 < g.c && ox < g.wo) {
-            const uint8_t* bh = s_hi + quad * 8;
-            const uint8_t* bl = s_lo + quad * 8;
+        if (cvalid && ox < g.wo) {
+            const uint8_t* tile = smem + b * G::TILE_BYTES;
             float win[3][3][4];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int pix = iy * G::IW + col * STRIDE + d;
-                    lds4(bh + pix * 128, bl + pix * 128, win[slot][d]);
-                }
+                for (int d = 0; d < 3; ++d) lds4<F32IN>(tile, G::TILE_BYTES / 2, iy * G::IW + col * STRIDE + d, quad, win[slot][d]);
             };
             const int oyl0 = rgrp * G::RPT;
             if (STRIDE == 1) { load_row(0, oyl0); load_row(1, oyl0 + 1); }
@@ -139,32 +154,32 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
                 store4(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
             }
         }
-        __syncthreads();                                                       // tile consumed: the next TMA may overwrite it
+        __syncthreads();                                                       // tile consumed: its buffer may be refilled
     }
 }
 
-template <int STRIDE>
+template <int STRIDE, bool F32IN>
 static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     using G = DwGeom<STRIDE>;
     g.tiles_x = div_up(g.wo, G::TW);
     g.tiles_y = div_up(g.ho, G::TH);
     g.cblocks = div_up(g.c, 64);
     g.num_tiles = g.n * g.tiles_x * g.tiles_y * g.cblocks;
-    const size_t smem = 2 * G::PLANE_BYTES + 64 + 128;
+    const size_t smem = 2 * G::TILE_BYTES + 64 + 128;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("dw3x3(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int per_sm = (int)((220u * 1024u) / smem) < 4 ? (int)((220u * 1024u) / smem) : 4;
-    const int grid = g.num_tiles < sms * per_sm ? g.num_tiles : sms * per_sm;
-    dw3x3_tma_kernel<STRIDE><<<grid, 256, smem, s>>>(tm, g);
+    const int grid = g.num_tiles < sms * 2 ? g.num_tiles : sms * 2;           // 2 resident CTAs per SM (registers, 2 x 92 KiB smem)
+    dw3x3_tma_kernel<STRIDE, F32IN><<<grid, 256, smem, s>>>(tm, g);
     return check_launch("dw3x3(tma)");
 }
 
+// in.plane == UAVSAL_PLANE_F32: `in.p` is a float* to fp32 rows [n*h*w][in.ld]
 int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, const float* bias, int relu6, ActW out,
               cudaStream_t s) {
     DwArgs g{};
@@ -172,21 +187,36 @@ int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, 
     g.ho = stride == 1 ? h : (h - 1) / 2 + 1;
     g.wo = stride == 1 ? w : (w - 1) / 2 + 1;
     g.wgt = wgt; g.bias = bias; g.relu6 = relu6; g.out = out;
+    CUtensorMap tm;
+    int rc;
+    if (in.plane == UAVSAL_PLANE_F32) {
+        const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t row = (uint64_t)in.ld * 4;
+        const uint64_t str[3] = {row, row * w, row * w * h};
+        if (stride == 1) {
+            const uint32_t box[4] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1};
+            rc = tc_encode(&tm, in.p, 4, dims, str, box, "dw input (f32)", 2);
+            if (rc) return rc;
+            return launch_dw_tma<1, true>(tm, g, s);
+        }
+        const uint32_t box[4] = {64, (uint32_t)DwGeom<2>::IW, (uint32_t)DwGeom<2>::IH, 1};
+        rc = tc_encode(&tm, in.p, 4, dims, str, box, "dw input (f32)", 2);
+        if (rc) return rc;
+        return launch_dw_tma<2, true>(tm, g, s);
+    }
     const uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n, in.plane ? 2u : 1u};
     const uint64_t row = (uint64_t)in.ld * 2;
     const uint64_t str[4] = {row, row * w, row * w * h, in.plane ? (uint64_t)in.plane * 2 : row * w * h * (uint64_t)n};
-    CUtensorMap tm;
-    int rc;
     if (stride == 1) {
         const uint32_t box[5] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1, 1};
         rc = tc_encode(&tm, in.p, 5, dims, str, box, "dw input", 0);
         if (rc) return rc;
-        return launch_dw_tma<1>(tm, g, s);
+        return launch_dw_tma<1, false>(tm, g, s);
     }
     const uint32_t box[5] = {64, (uint32_t)DwGeom<2>::IW, (uint32_t)DwGeom<2>::IH, 1, 1};
     rc = tc_encode(&tm, in.p, 5, dims, str, box, "dw input", 0);
     if (rc) return rc;
-    return launch_dw_tma<2>(tm, g, s);
+    return launch_dw_tma<2, false>(tm, g, s);
 }
 
 }  // namespace uavsal

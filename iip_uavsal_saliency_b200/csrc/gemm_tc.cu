@@ -245,10 +245,11 @@ int tc_encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
     EncodeTiledFn fn = get_encode();
     UAVSAL_REQUIRE(fn != nullptr, UAVSAL_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+    // swizzle128: bit 0 = 128-byte swizzle, bit 1 = fp32 elements (else bf16)
+    CUresult r = fn(tm, (swizzle128 & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    (swizzle128 & 1) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UAVSAL_REQUIRE(r == CUDA_SUCCESS, UAVSAL_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return 0;
@@ -335,6 +336,7 @@ static int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
 
 // ---- version 2: persistent kernel (gemm_tc2.cuh) ------------------------------------------------------
 static int g_tc_version = 2;
+static int g_tc_debug = 0;     // DBG_* ablation bits ORed into the kernel flags
 
 static int num_sms() {
     static int n = 0;
@@ -347,9 +349,51 @@ static int num_sms() {
     return n;
 }
 
+static int g_tc_cluster = 2;   // uavsal_set_option key 4: CTAs per cluster of the persistent GEMM (1 = no multicast)
+
+template <int MODE, int EPI, int TERMS, int CL>
+static int launch_tc2_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o, const TcArgs& g,
+                           int grid, size_t smem, cudaStream_t s, const char* what) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<MODE, EPI, TERMS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    if (CL == 1) {
+        gemm_tc2_kernel<MODE, EPI, TERMS, CL><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        // the persistent tile walk assumes every cluster is resident at once: clamp the grid to what the GPCs can co-schedule
+        static int max_clusters = 0;
+        if (!max_clusters) {
+            cudaLaunchConfig_t q = cfg;
+            q.gridDim = dim3((num_sms() / CL) * CL);
+            q.dynamicSmemBytes = 227 * 1024 - 1024;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<MODE, EPI, TERMS, CL>, &q) != cudaSuccess || n <= 0) { n = num_sms() / CL - 2; cudaGetLastError(); }
+            max_clusters = n;
+        }
+        if (grid > max_clusters * CL) cfg.gridDim = dim3(max_clusters * CL);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<MODE, EPI, TERMS, CL>, a0, a1, b, o, g);
+        if (e != cudaSuccess) { set_error("%s: cudaLaunchKernelEx: %s", what, cudaGetErrorString(e)); return (int)e; }
+    }
+    return check_launch(what);
+}
+
+// the B tensor map of a cluster launch has a box of bn / CL rows (each CTA loads and multicasts its share)
+static bool want_cluster(const TcArgs& g, int tiles_m) {
+    return g_tc_cluster == 2 && tiles_m >= 2 && (int64_t)tiles_m * div_up(g.N, g.bn) >= num_sms() && g.bn % 32 == 0;
+}
+
 template <int MODE, int EPI>
 static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o, TcArgs& g,
-                      int terms, int tiles_m, cudaStream_t s, const char* what) {
+                      int terms, int tiles_m, bool cluster, cudaStream_t s, const char* what) {
     const int npl = terms == 3 ? 2 : 1;
     const uint32_t stage_bytes = npl * (kABytes + (uint32_t)g.bn * kBK * 2);
     const uint32_t budget = 227u * 1024u - 1024u - kOutStageBytes - 512u;
@@ -357,32 +401,23 @@ static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
     if (stages > 8) stages = 8;
     UAVSAL_REQUIRE(stages >= 2, UAVSAL_ENOTSUP, "%s: tile does not fit shared memory", what);
     g.stages = stages;
+    g.tiles_m = tiles_m;
     g.tiles_n = div_up(g.N, g.bn);
     g.num_tiles = tiles_m * g.tiles_n;
+    g.flags |= g_tc_debug;
     int cols = 32;
     while (cols < 2 * g.bn) cols <<= 1;
     g.tmem_cols = cols;
     const size_t smem = (size_t)stages * stage_bytes + kOutStageBytes + 1024 + 512;
-    const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
-    cudaError_t e;
-    if (terms == 3) {
-        static bool attr3 = false;
-        if (!attr3) {
-            e = cudaFuncSetAttribute(gemm_tc2_kernel<MODE, EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
-            attr3 = true;
-        }
-        gemm_tc2_kernel<MODE, EPI, 3><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
-    } else {
-        static bool attr1 = false;
-        if (!attr1) {
-            e = cudaFuncSetAttribute(gemm_tc2_kernel<MODE, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
-            attr1 = true;
-        }
-        gemm_tc2_kernel<MODE, EPI, 1><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
+    if (cluster) {
+        const int work = div_up(tiles_m, 2) * g.tiles_n;
+        int grid = 2 * work < num_sms() ? 2 * work : (num_sms() / 2) * 2;
+        if (terms == 3) return launch_tc2_inst<MODE, EPI, 3, 2>(a0, a1, b, o, g, grid, smem, s, what);
+        return launch_tc2_inst<MODE, EPI, 1, 2>(a0, a1, b, o, g, grid, smem, s, what);
     }
-    return check_launch(what);
+    const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+    if (terms == 3) return launch_tc2_inst<MODE, EPI, 3, 1>(a0, a1, b, o, g, grid, smem, s, what);
+    return launch_tc2_inst<MODE, EPI, 1, 1>(a0, a1, b, o, g, grid, smem, s, what);
 }
 
 // output maps: same geometry as the loads, 64-column boxes, extent = VALID channels so stores clip at N and never touch
@@ -438,17 +473,18 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     if (rc) return rc;
     if (c1) rc = map_img(&tA1, a1, n1img, H, W, c1, tw, th); else tA1 = tA0;
     if (rc) return rc;
-    rc = map_w(&tB, wgt, cout, kpad, g.bn);
-    if (rc) return rc;
     const int tiles_m = batch * g.tiles_x * g.tiles_y;
+    const bool cl = v2 && want_cluster(g, tiles_m);
+    rc = map_w(&tB, wgt, cout, kpad, cl ? g.bn / 2 : g.bn);
+    if (rc) return rc;
     if (v2) {
         CUtensorMap tO;
         if (epi == EPI_RAW) tO = tA0;
         else rc = map_out_img(&tO, out, out_nimg, H, W, cout, tw, th);
         if (rc) return rc;
-        if (epi == EPI_STD) return launch_tc2<MODE_CONV, EPI_STD>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
-        if (epi == EPI_RAW) return launch_tc2<MODE_CONV, EPI_RAW>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
-        return launch_tc2<MODE_CONV, EPI_TWA>(tA0, tA1, tB, tO, g, terms, tiles_m, s, what);
+        if (epi == EPI_STD) return launch_tc2<MODE_CONV, EPI_STD>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
+        if (epi == EPI_RAW) return launch_tc2<MODE_CONV, EPI_RAW>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
+        return launch_tc2<MODE_CONV, EPI_TWA>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
     }
     if (epi == EPI_STD) return launch_tc<MODE_CONV, EPI_STD>(tA0, tA1, tB, g, terms, tiles_m, s, what);
     if (epi == EPI_TWA) return launch_tc<MODE_CONV, EPI_TWA>(tA0, tA1, tB, g, terms, tiles_m, s, what);
@@ -475,6 +511,8 @@ extern "C" {
 int uavsal_set_option(int key, int value) {
     if (key == 1 && (value == 1 || value == 2)) { g_tc_version = value; return 0; }
     if (key == 2 && value >= 0 && value <= 2) { g_dw_fast = value; return 0; }
+    if (key == 3) { g_tc_debug = value & 0xF0000; return 0; }
+    if (key == 4 && (value == 1 || value == 2)) { g_tc_cluster = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }
@@ -482,7 +520,9 @@ int uavsal_set_option(int key, int value) {
 int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, const uint16_t* wgt, int kpad, int n,
                    const float* bias, int flags, int terms, const uint16_t* res, int64_t res_plane, int res_ld,
                    uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
-    UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && act_ok16(out, out_plane, out_ld) && wgt &&
+    const bool f32out = flags & UAVSAL_F_OUT_F32;
+    UAVSAL_REQUIRE(!f32out || (g_tc_version == 2 && !(flags & UAVSAL_F_SIGMOID)), UAVSAL_ENOTSUP, "pw_gemm: fp32 output needs the persistent kernel");
+    UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && (f32out ? (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_ld % 4 == 0) : act_ok16(out, out_plane, out_ld)) && wgt &&
                        (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 && m > 0 && k > 0 && n > 0 && k % 8 == 0 &&
                        kpad % 8 == 0 && kpad >= k && n % 8 == 0 && a_ld >= k && out_ld >= n,
                    UAVSAL_EINVAL, "pw_gemm: bad arguments (m=%d k=%d kpad=%d n=%d)", m, k, kpad, n);
@@ -498,13 +538,14 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
     CUtensorMap tA, tB;
     int rc = map_pw(&tA, Act{a, a_plane, a_ld}, m, k);
     if (rc) return rc;
-    rc = map_w(&tB, wgt, n, kpad, g.bn);
+    const bool cl = g_tc_version == 2 && want_cluster(g, div_up(m, kBM));
+    rc = map_w(&tB, wgt, n, kpad, cl ? g.bn / 2 : g.bn);
     if (rc) return rc;
     if (g_tc_version == 2) {
-        CUtensorMap tO;
-        rc = map_out_pw(&tO, g.out, m, n);
+        CUtensorMap tO = tA;                                   // (the copy-out uses the LSU path; the map is kept for TMA-store experiments)
+        if (!f32out) rc = map_out_pw(&tO, g.out, m, n);
         if (rc) return rc;
-        return launch_tc2<MODE_PW, EPI_STD>(tA, tA, tB, tO, g, terms, div_up(m, kBM), (cudaStream_t)stream, "pw_gemm");
+        return launch_tc2<MODE_PW, EPI_STD>(tA, tA, tB, tO, g, terms, div_up(m, kBM), cl, (cudaStream_t)stream, "pw_gemm");
     }
     return launch_tc<MODE_PW, EPI_STD>(tA, tA, tB, g, terms, div_up(m, kBM), (cudaStream_t)stream, "pw_gemm");
 }

@@ -14,6 +14,7 @@ namespace uavsal {
 constexpr uint32_t kOutPlaneBytes = kBM * 64 * 2;          // one 128 x 64 bf16 box
 constexpr uint32_t kOutStageBytes = 2 * kOutPlaneBytes;    // hi + lo
 constexpr int kEpiWarps = 16;
+constexpr int kPF = 6;                                     // L2 prefetch distance of the A operand, in k-blocks
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads2 = 64 + kEpiThreads;                // producer warp + MMA warp + epilogue warps
 
@@ -26,7 +27,11 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int MODE, int EPI, int TERMS>
+// CL = CTAs per cluster (1 | 2).  With CL = 2 the two CTAs of a cluster work on neighbouring 128-row tiles of the SAME
+// n-tile: each loads its own A tile and one half of the B tile, multicasting that half into both CTAs' shared memory,
+// so the weight traffic L2 -> SM (the measured limiter of the single-CTA kernel: 1.33 GB per 256<->1536 GEMM at the
+// ~7.4 TB/s fabric cap) is halved.  A stage is recycled only when BOTH MMA warps have retired it (multicast commit).
+template <int MODE, int EPI, int TERMS, int CL>
 __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
                                                                const __grid_constant__ CUtensorMap tmB,
@@ -44,9 +49,13 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const int cta_first = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;   // first (pair-)tile of this CTA
+    const int cta_step = (int)(gridDim.x / CL);
+    const int num_work = CL > 1 ? ((g.tiles_m + CL - 1) / CL) * g.tiles_n : g.num_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, kEpiWarps); }
         fence_barrier_init();
     }
@@ -56,13 +65,15 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                           // peers' barriers are initialised
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile decomposition shared by all roles
+    // tile decomposition shared by all roles (work item t -> 128-row tile of this CTA; may be == tiles_m for the odd one out)
     auto tile_coords = [&](int t, int& tile_m, int& n0, int& bidx, int& y0, int& x0) {
-        tile_m = t / g.tiles_n;
-        n0 = (t - tile_m * g.tiles_n) * g.bn;
+        const int wm = t / g.tiles_n;
+        tile_m = CL > 1 ? wm * CL + (int)crank : wm;
+        n0 = (t - wm * g.tiles_n) * g.bn;
         bidx = 0; y0 = 0; x0 = 0;
         if (MODE == MODE_CONV) {
             const int per_img = g.tiles_x * g.tiles_y;
@@ -77,16 +88,32 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t kc = 0;                                                  // k-block counter across tiles
-            for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+            for (int t = cta_first; t < num_work; t += cta_step) {
                 int tile_m, n0, bidx, y0, x0;
                 tile_coords(t, tile_m, n0, bidx, y0, x0);
                 for (int kb = 0; kb < g.num_kb; ++kb, ++kc) {
+                    if (MODE == MODE_PW && g.num_kb >= 8) {
+                        // long-K GEMMs stream A from HBM with only 2-3 smem stages in flight: pull the tile kPF k-blocks
+                        // ahead (this tile's, then the next tile's) into L2 so the staged loads see L2 latency
+                        int pk = kb + kPF, pt = tile_m;
+                        if (pk >= g.num_kb) {
+                            int nm, nn, nb, ny, nx;
+                            pk -= g.num_kb;
+                            if (t + cta_step < num_work) { tile_coords(t + cta_step, nm, nn, nb, ny, nx); pt = nm; } else pt = -1;
+                        }
+                        if (pt >= 0) {
+#pragma unroll
+                            for (int p = 0; p < NPL; ++p) tma_prefetch_3d(&tmA0, pk * kBK, pt * kBM, p);
+                        }
+                    }
                     const int s = kc % g.stages;
                     mbar_wait(empty + s, ((kc / g.stages) & 1) ^ 1);
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + NPL * kABytes;
-                    mbar_expect_tx(full + s, stage_bytes);
-                    if (MODE == MODE_PW) {
+                    const bool no_a = g.flags & DBG_NO_A, no_b = g.flags & DBG_NO_B;
+                    mbar_expect_tx(full + s, stage_bytes - (no_a ? NPL * kABytes : 0) - (no_b ? NPL * b_bytes : 0));
+                    if (no_a) {
+                    } else if (MODE == MODE_PW) {
 #pragma unroll
                         for (int p = 0; p < NPL; ++p) tma_load_3d(&tmA0, full + s, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
                     } else {
@@ -105,8 +132,16 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                         const int tap = kb / g.kb_per_tap;
                         bk = tap * g.bk_tap_stride + g.bk_off + (kb - tap * g.kb_per_tap) * kBK;
                     }
+                    if (no_b) {
+                    } else if (CL > 1) {                                      // my half of the B tile, into both CTAs
+                        const int half = g.bn / CL;
 #pragma unroll
-                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
+                        for (int p = 0; p < NPL; ++p)
+                            tma_load_3d_mc(&tmB, full + s, sb + p * b_bytes + crank * half * 128, bk, n0 + (int)crank * half, p, (uint16_t)((1u << CL) - 1));
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
+                    }
                 }
             }
         }
@@ -115,7 +150,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         const uint32_t idesc = umma_idesc(g.bn);
         uint32_t kc = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+        for (int t = cta_first; t < num_work; t += cta_step, ++it) {
             const int buf = it & 1;
             mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);                 // epilogue has drained this accumulator
             tc_fence_after();
@@ -129,6 +164,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                     const uint32_t b_hi = a_hi + NPL * kABytes;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
+                        if (g.flags & DBG_NO_MMA) break;
                         const uint64_t dah = umma_desc(a_hi + k * 32);
                         const uint64_t dbh = umma_desc(b_hi + k * 32);
                         umma_bf16(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
@@ -139,50 +175,56 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                             umma_bf16(d_tmem, dal, dbh, idesc, 1u);
                         }
                     }
-                    umma_commit(empty + s);
+                    if (CL > 1) umma_commit_mc(empty + s, (uint16_t)((1u << CL) - 1));
+                    else umma_commit(empty + s);
                     if (kb == g.num_kb - 1) umma_commit(acc_full + buf);
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===================== epilogue (warps 2..17, 512 threads) =====================
+        // ===================== epilogue (warps 2..17) =====================
         // A warp may only touch TMEM lanes 32*(warp%4)..+31, so the four warps sharing a quadrant split every 64-column
-        // chunk into 16-column pieces: 16 warps drain one chunk together (4 warps per scheduler hide each other's latency).
+        // chunk into 16-column pieces.  Each warp works on its own: tcgen05.ld -> bias/ReLU6/residual/sigmoid | TWA blend ->
+        // (hi/lo split) -> a PRIVATE 2 KiB transpose buffer -> coalesced global stores.  There is no block-wide barrier
+        // in the loop (the first version's two 512-thread barriers per chunk left the epilogue latency-bound: 80 us of a
+        // 180 us 256->1536 GEMM with MMA, loads and stores all disabled), so the warps of one scheduler hide each other's
+        // TMEM / shared-memory / store latency.
+        const int ew = warp - 2;
         const int q = warp & 3;
-        const int sub = ((warp - 2) >> 2) * 16;                               // column offset inside a 64-column chunk
+        const int sub = (ew >> 2) * 16;                                       // column offset inside a 64-column chunk
         const int r = q * 32 + lane;                                          // tile row = TMEM lane
-        const bool leader = threadIdx.x == 64;                                // first epilogue thread issues the stores
-        uint8_t* my_hi = ostage + r * 128;
-        uint8_t* my_lo = my_hi + kOutPlaneBytes;
-        const int sw = r & 7;
+        uint8_t* wst = ostage + ew * 2048;                                    // 32 rows x 16 columns: fp32, or hi | lo bf16
+        const bool f32out = EPI == EPI_STD && (g.flags & UAVSAL_F_OUT_F32);
+        const bool do_store = !(g.flags & DBG_NO_STORE);
         int it = 0;
-        for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+        for (int t = cta_first; t < num_work; t += cta_step, ++it) {
             int tile_m, n0, bidx, y0, x0;
             tile_coords(t, tile_m, n0, bidx, y0, x0);
             const int buf = it & 1;
-            int64_t orow, hrow = 0;
-            bool rvalid;
             int img_out = 0;
-            if (MODE == MODE_PW) {
-                orow = (int64_t)tile_m * kBM + r;
-                rvalid = orow < g.M;
-            } else {
-                const int y = y0 + r / g.TW, x = x0 + r % g.TW;
-                rvalid = y < g.H && x < g.W;
-                const int64_t pix = (int64_t)y * g.W + x, hw = (int64_t)g.H * g.W;
-                img_out = bidx * g.out_mul + g.out_off;
-                orow = (int64_t)img_out * hw + pix;
-                hrow = (int64_t)(bidx * g.a1_mul + g.a1_off) * hw + pix;
-            }
+            if (MODE == MODE_CONV) img_out = bidx * g.out_mul + g.out_off;
+            // global row of tile row rr (-1: outside the tensor)
+            auto grow_of = [&](int rr) -> int64_t {
+                if (MODE == MODE_PW) {
+                    const int64_t gr = (int64_t)tile_m * kBM + rr;
+                    return gr < g.M ? gr : -1;
+                }
+                const int y = y0 + rr / g.TW, x = x0 + rr % g.TW;
+                if (y >= g.H || x >= g.W || tile_m >= g.tiles_m) return -1;
+                return ((int64_t)img_out * g.H + y) * g.W + x;
+            };
+            const int64_t orow = grow_of(r);
+            const bool rvalid = orow >= 0;
+            int64_t hrow = 0;
+            if (MODE == MODE_CONV && rvalid)
+                hrow = orow + (int64_t)((bidx * g.a1_mul + g.a1_off) - img_out) * g.H * g.W;
             mbar_wait(acc_full + buf, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * g.bn);
             const int nchunks = (g.bn + 63) >> 6;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
-                // staging buffer must have been read out by the previous TMA stores
-                if (EPI != EPI_RAW) named_bar_sync(1, kEpiThreads);              // staging buffer free (previous chunk copied out)
                 if (sub < ncols) {
                     uint32_t raw[16];
                     __syncwarp();
@@ -204,107 +246,109 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                             }
                         }
                     } else {
-                    if (live) {
-                        if (g.bias) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                if (j4 >= 2 && !second) break;
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
-                                v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
-                            }
-                        }
-                        if (EPI == EPI_STD) {
-                            if (g.flags & UAVSAL_F_RELU6) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
-                            }
-                            if (g.flags & UAVSAL_F_RESIDUAL) {
-                                float rr[8];
-                                load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] += rr[j];
-                                if (second) {
-                                    load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[8 + j] += rr[j];
-                                }
-                            }
-                            if (g.flags & UAVSAL_F_SIGMOID) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = sigmoid_acc(v[j]);
-                            }
-                        } else {   // EPI_TWA: h = i*x_t + (1-i)*h_{t-1}  (model_convlstm.py:283,290)
-                            if (g.gx) {                                       // hoisted W_x * x_t half of the gate conv
-                                const float4* gp = reinterpret_cast<const float4*>(g.gx + orow * g.N + n);
+                        if (live) {
+                            if (g.bias) {
 #pragma unroll
                                 for (int j4 = 0; j4 < 4; ++j4) {
                                     if (j4 >= 2 && !second) break;
-                                    const float4 b4 = __ldg(gp + j4);
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
                                     v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
                                 }
                             }
+                            if (EPI == EPI_STD) {
+                                if (g.flags & UAVSAL_F_RELU6) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
+                                }
+                                if (g.flags & UAVSAL_F_RESIDUAL) {
+                                    float rr[8];
+                                    load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                                    if (second) {
+                                        load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[8 + j] += rr[j];
+                                    }
+                                }
+                                if (g.flags & UAVSAL_F_SIGMOID) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] = sigmoid_acc(v[j]);
+                                }
+                            } else {   // EPI_TWA: h = i*x_t + (1-i)*h_{t-1}  (model_convlstm.py:283,290)
+                                if (g.gx) {                                   // hoisted W_x * x_t half of the gate conv
+                                    const float4* gp = reinterpret_cast<const float4*>(g.gx + orow * g.N + n);
+#pragma unroll
+                                    for (int j4 = 0; j4 < 4; ++j4) {
+                                        if (j4 >= 2 && !second) break;
+                                        const float4 b4 = __ldg(gp + j4);
+                                        v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+                                    }
+                                }
+#pragma unroll
+                                for (int half = 0; half < 2; ++half) {
+                                    if (half == 1 && !second) break;
+                                    float xv[8], hv[8];
+                                    load8(g.x.p + orow * g.x.ld + n + half * 8, g.x.plane, xv);
+                                    load8(g.hprev.p + hrow * g.hprev.ld + n + half * 8, g.hprev.plane, hv);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float gi = sigmoid_acc(v[half * 8 + j]);
+                                        v[half * 8 + j] = gi * xv[j] + (1.f - gi) * hv[j];
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();                                         // the previous piece has been copied out of wst
+                        if (f32out) {
+                            // row = lane: 64 bytes = four 16-byte chunks, chunk j stored at j ^ ((lane >> 1) & 3) (conflict-free)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            __syncwarp();
+                            float* outf = reinterpret_cast<float*>(g.out.p);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {                     // 8 rows x 64 contiguous bytes per instruction
+                                const int row = 8 * i + (lane >> 2), c = lane & 3;
+                                const float4 val = *reinterpret_cast<const float4*>(wst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+                                const int64_t gr = grow_of(q * 32 + row);
+                                const int col = n + c * 4;
+                                if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<float4*>(outf + gr * g.out.ld + col) = val;
+                            }
+                        } else {
+                            // hi plane rows of 32 bytes at wst, lo plane at wst + 1024; chunk j of row at j ^ ((lane >> 2) & 1)
 #pragma unroll
                             for (int half = 0; half < 2; ++half) {
-                                if (half == 1 && !second) break;
-                                float xv[8], hv[8];
-                                load8(g.x.p + orow * g.x.ld + n + half * 8, g.x.plane, xv);
-                                load8(g.hprev.p + hrow * g.hprev.ld + n + half * 8, g.hprev.plane, hv);
+                                uint32_t h[4], l[4];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float gi = sigmoid_acc(v[half * 8 + j]);
-                                    v[half * 8 + j] = gi * xv[j] + (1.f - gi) * hv[j];
+                                for (int j = 0; j < 4; ++j) split2(v[half * 8 + 2 * j], v[half * 8 + 2 * j + 1], h[j], l[j]);
+                                const int off = lane * 32 + ((half ^ ((lane >> 2) & 1)) << 4);
+                                *reinterpret_cast<uint4*>(wst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<uint4*>(wst + 1024 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {                     // 16 rows x 32 contiguous bytes per plane per instruction
+                                const int row = 16 * i + (lane >> 1), c = lane & 1;
+                                const int off = row * 32 + ((c ^ ((row >> 2) & 1)) << 4);
+                                const uint4 hv4 = *reinterpret_cast<const uint4*>(wst + off);
+                                const uint4 lv4 = *reinterpret_cast<const uint4*>(wst + 1024 + off);
+                                const int64_t gr = grow_of(q * 32 + row);
+                                const int col = n + c * 8;
+                                if (gr >= 0 && col < g.N && do_store) {
+                                    uint16_t* dst = g.out.p + gr * g.out.ld + col;
+                                    *reinterpret_cast<uint4*>(dst) = hv4;
+                                    if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = lv4;
                                 }
                             }
                         }
                     }
-                    // hi/lo split (packed bf16x2 converts), 128B-swizzled staging: 16-byte chunk j of row r at j ^ (r & 7)
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) split2(v[half * 8 + 2 * j], v[half * 8 + 2 * j + 1], h[j], l[j]);
-                        const int cj = ((sub >> 3) + half) ^ sw;
-                        *reinterpret_cast<uint4*>(my_hi + cj * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(my_lo + cj * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
-                    }   // EPI != EPI_RAW
                 }
                 if (ch == nchunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + buf);
-                }
-                if (EPI == EPI_RAW) continue;
-                named_bar_sync(1, kEpiThreads);                                   // chunk fully staged
-                // cooperative copy-out: 8 consecutive threads write one 128-byte row segment per plane, so every warp store
-                // covers four full lines (the LSU path is used on purpose: TMA stores queue behind the producer's loads)
-                {
-                    const int et = threadIdx.x - 64;                              // 0..511
-                    const int cj = et & 7;
-                    const int c0 = n0 + ch * 64 + cj * 8;
-                    if (c0 < g.N) {
-#pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const int rr = (et >> 3) + pass * 64;
-                            int64_t grow;
-                            bool ok;
-                            if (MODE == MODE_PW) {
-                                grow = (int64_t)tile_m * kBM + rr;
-                                ok = grow < g.M;
-                            } else {
-                                const int y = y0 + rr / g.TW, x = x0 + rr % g.TW;
-                                ok = y < g.H && x < g.W;
-                                grow = (int64_t)img_out * g.H * g.W + (int64_t)y * g.W + x;
-                            }
-                            if (ok) {
-                                const uint8_t* src = ostage + rr * 128 + ((cj ^ (rr & 7)) << 4);
-                                uint16_t* dst = g.out.p + grow * g.out.ld + c0;
-                                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-                                if (g.out.plane)
-                                    *reinterpret_cast<uint4*>(dst + g.out.plane) = *reinterpret_cast<const uint4*>(src + kOutPlaneBytes);
-                            }
-                        }
-                    }
                 }
             }
         }
@@ -312,6 +356,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's smem / arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
     }

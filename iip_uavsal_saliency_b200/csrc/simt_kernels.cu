@@ -111,6 +111,12 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = relu6f(acc[j]);
+    if (out.plane == UAVSAL_PLANE_F32) {                                   // fp32 rows (input of features.1's depthwise conv)
+        float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.p) + i * out.ld);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) of[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        return;
+    }
     uint16_t* o = out.p + i * out.ld;
 #pragma unroll
     for (int q = 0; q < 4; ++q) store8(o + q * 8, out.plane, acc + q * 8);
@@ -521,7 +527,8 @@ int uavsal_unpack_nchw_f32(const uint16_t* src, int64_t plane, int ld, int n, in
 
 int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const float* wgt, const float* bias,
                           uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
-    UAVSAL_REQUIRE(x && wgt && bias && aligned16(wgt) && act_ok(out, out_plane, out_ld) && out_ld >= 32 && n > 0 &&
+    UAVSAL_REQUIRE(x && wgt && bias && aligned16(wgt) &&
+                       (out_plane == UAVSAL_PLANE_F32 ? (out && aligned16(out) && out_ld % 4 == 0) : act_ok(out, out_plane, out_ld)) && out_ld >= 32 && n > 0 &&
                        h >= 2 && w >= 2 && x_kind >= 0 && x_kind <= 2,
                    UAVSAL_EINVAL, "stem_conv3x3s2: bad arguments");
     const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
@@ -538,16 +545,18 @@ int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const 
 int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, int stride, int dilation,
                  const float* wgt, const float* bias, int relu6, uint16_t* out, int64_t out_plane, int out_ld,
                  void* stream) {
-    UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && wgt && bias && aligned16(wgt) &&
-                       aligned16(bias) && c % 8 == 0 && c > 0 && in_ld >= c && out_ld >= c && n > 0,
+    const bool f32in = in_plane == UAVSAL_PLANE_F32;
+    UAVSAL_REQUIRE((f32in ? (in && aligned16(in) && in_ld % 4 == 0) : act_ok(in, in_plane, in_ld)) && act_ok(out, out_plane, out_ld) &&
+                       wgt && bias && aligned16(wgt) && aligned16(bias) && c % 8 == 0 && c > 0 && in_ld >= c && out_ld >= c && n > 0,
                    UAVSAL_EINVAL, "dw3x3: bad arguments (c=%d)", c);
     UAVSAL_REQUIRE((stride == 1 || stride == 2) && dilation >= 1 && (stride == 1 || dilation == 1), UAVSAL_ENOTSUP,
                    "dw3x3: stride %d dilation %d unsupported", stride, dilation);   // model.py:78 assert stride in [1,2]
     const int ho = stride == 1 ? h : (h - 1) / 2 + 1, wo = stride == 1 ? w : (w - 1) / 2 + 1;
-    if (dilation == 1 && g_dw_fast == 2 && in_plane != 0 && out_plane != 0 && (int64_t)n * ho * wo >= 512) {
+    if (dilation == 1 && (g_dw_fast == 2 || f32in) && in_plane != 0 && out_plane != 0 && ((int64_t)n * ho * wo >= 512 || f32in)) {
         return dw3x3_tma(Act{in, in_plane, in_ld}, n, h, w, c, stride, wgt, bias, relu6, ActW{out, out_plane, out_ld},
                          (cudaStream_t)stream);
     }
+    UAVSAL_REQUIRE(!f32in, UAVSAL_ENOTSUP, "dw3x3: fp32 input is only implemented by the TMA kernel (dilation 1)");
     if (dilation == 1 && g_dw_fast == 1) {
         const int strips = div_up(ho, kDwRB);
         const dim3 grid(div_up(c, 64), div_up(wo, 32), strips * n);

@@ -8,6 +8,8 @@ namespace uavsal {
 
 enum { MODE_PW = 0, MODE_CONV = 1 };
 enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3 };
+// timing-ablation switches (uavsal_set_option key 3; results are garbage, never set on the product path)
+enum { DBG_NO_MMA = 1 << 16, DBG_NO_STORE = 1 << 17, DBG_NO_B = 1 << 18, DBG_NO_A = 1 << 19 };
 
 constexpr int kBM = 128;          // rows per tile = TMEM lanes
 constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
@@ -34,6 +36,7 @@ struct TcArgs {
     int bk_tap_stride, bk_off; // conv: weight K coordinate of k-block (tap, r) = tap*bk_tap_stride + bk_off + r*64
     const float* gx;          // TWA: hoisted input-half pre-activations [rows][N] fp32 added before the gate (or null)
     float* raw_out;           // EPI_RAW: fp32 accumulators [rows][N]
+    int tiles_m;              // number of 128-row tiles (cluster kernels may be handed one past the end)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -109,9 +112,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 }
 
 
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (defined in gemm_tc.cu)
 int tc_encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, const char* what, int swizzle128);
+
+// ---- thread-block-cluster variants (B operand multicast across a CTA pair) -------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one TMA load whose box lands at the same smem offset of every CTA in `mask`, completing tx bytes on each CTA's own barrier
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+// MMA completion arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -14,7 +14,8 @@ import torch
 
 from . import _ext
 
-F_RELU6, F_RESIDUAL, F_SIGMOID = 1, 2, 4
+F_RELU6, F_RESIDUAL, F_SIGMOID, F_OUT_F32 = 1, 2, 4, 8
+PLANE_F32 = -1            # UAVSAL_PLANE_F32: the activation is plain fp32 rows, not split-bf16 planes
 BN_EPS = 1e-5
 
 
@@ -28,31 +29,32 @@ def out_size(n: int, stride: int) -> int:
 
 
 class Buf:
-    """A (rows x c) activation living in a (2, rows, ld) bf16 tensor at channel offset ``off``."""
+    """A (rows x c) activation living in a (2, rows, ld) bf16 tensor at channel offset ``off`` — or, when ``f32``, in a
+    plain (rows, ld) fp32 tensor (the hidden tensor between an expand conv and its depthwise conv)."""
 
-    __slots__ = ("t", "rows", "c", "ld", "off")
+    __slots__ = ("t", "rows", "c", "ld", "off", "f32")
 
-    def __init__(self, t: torch.Tensor, rows: int, c: int, ld: int, off: int = 0):
-        self.t, self.rows, self.c, self.ld, self.off = t, rows, c, ld, off
+    def __init__(self, t: torch.Tensor, rows: int, c: int, ld: int, off: int = 0, f32: bool = False):
+        self.t, self.rows, self.c, self.ld, self.off, self.f32 = t, rows, c, ld, off, f32
 
     @property
     def ptr(self) -> int:
-        return self.t.data_ptr() + 2 * self.off
+        return self.t.data_ptr() + (4 if self.f32 else 2) * self.off
 
     @property
     def plane(self) -> int:
-        return self.rows * self.ld
+        return PLANE_F32 if self.f32 else self.rows * self.ld
 
     def act(self) -> Tuple[int, int, int]:
         return (self.ptr, self.plane, self.ld)
 
     def slot(self, off: int, c: int) -> "Buf":
         assert off % 8 == 0 and off + c <= self.ld
-        return Buf(self.t, self.rows, c, self.ld, self.off + off)
+        return Buf(self.t, self.rows, c, self.ld, self.off + off, self.f32)
 
     def to_float(self) -> torch.Tensor:
         """fp32 (rows, c) reconstruction hi + lo (debug / tests)."""
-        v = self.t[0].float() + self.t[1].float()
+        v = self.t if self.f32 else self.t[0].float() + self.t[1].float()
         return v[:, self.off:self.off + self.c]
 
 
@@ -138,6 +140,18 @@ class Plan:
         self.keep.append(t)
         return Buf(t, rows, c, ld)
 
+    def alloc_f32(self, rows: int, c: int) -> Buf:
+        """fp32 rows (only the persistent tcgen05 GEMM / the stem write them, only the TMA depthwise kernel reads them)."""
+        ld = _pad8(c)
+        t = torch.zeros((rows, ld), dtype=torch.float32, device=self.device)
+        self.arena_bytes += t.numel() * 4
+        self.keep.append(t)
+        return Buf(t, rows, c, ld, 0, True)
+
+    @property
+    def f32_hidden(self) -> bool:
+        return self.engine == "tc"
+
     def tensor(self, shape, dtype=torch.float32) -> torch.Tensor:
         t = torch.zeros(shape, dtype=dtype, device=self.device)
         self.arena_bytes += t.numel() * t.element_size()
@@ -177,6 +191,10 @@ class Plan:
         r = res.act() if res is not None else NULL_ACT
         if res is not None:
             flags |= F_RESIDUAL
+        assert not x.f32 and (res is None or not res.f32), "fp32 rows are only consumed by the depthwise kernel"
+        if out.f32:
+            assert self.engine == "tc"
+            flags |= F_OUT_F32
         if self.engine != "simt":
             wp = self.hold(pack_pw_tc(w2d, kpad))
             self._add("uavsal_pw_gemm", (*x.act(), m, kpad, wp.data_ptr(), kpad, n, bp, flags, self.terms, *r, *out.act()), tag)

@@ -280,7 +280,7 @@ class UAVSal(KernelModule):
         plan.unpack_nchw(last, 1, planes, mh, mw, h_out, tag="state.unpack")
         # readout: expand + dw (dwBlock 256->1), then the 1536->1 project + BN + sigmoid as a dot product (model.py:372-373)
         ro = self.conv_out_st
-        e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand")
+        e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", f32_out=plan.f32_hidden)
         d, _, _ = ro.conv[1]._emit(plan, e, n, mh, mw, tag="readout.dw")
         wf, bf = ro.project_folded()
         out = plan.tensor((n, 1, mh, mw))

@@ -37,12 +37,19 @@ extern "C" {
 #define UAVSAL_F_RELU6    1    /* clamp to [0,6]            (nn.ReLU6, model.py:71) */
 #define UAVSAL_F_RESIDUAL 2    /* out += res                (model.py:101, 247) */
 #define UAVSAL_F_SIGMOID  4    /* out = sigmoid(out)        (model.py:373) */
+#define UAVSAL_F_OUT_F32  8    /* uavsal_pw_gemm only: `out` is a float* to fp32 rows [m][out_ld] (out_plane ignored); used for the
+                                  hidden tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92) */
+/* plane value marking an activation argument as plain fp32 rows (uavsal_dw3x3 input) instead of split-bf16 planes */
+#define UAVSAL_PLANE_F32  (-1)
 
 int         uavsal_version(void);                 /* ABI version, currently 1 */
 const char* uavsal_arch(void);                    /* "sm_100a" */
 const char* uavsal_last_error(void);
 int         uavsal_device_ok(int device);         /* 0 if `device` is compute capability 10.x */
-int         uavsal_set_option(int key, int value);/* key 1: tcgen05 GEMM kernel version (2 = persistent, default; 1 = one tile per CTA) */
+int         uavsal_set_option(int key, int value);/* key 1: tcgen05 GEMM kernel version (2 = persistent, default; 1 = one tile per CTA);
+                                                     key 2: depthwise path (2 = TMA-staged, default; 1 = sliding rows; 0 = generic);
+                                                     key 3: timing-ablation bits (dev only; results invalid when non-zero);
+                                                     key 4: CTAs per cluster of the persistent GEMM (2 = weight-tile multicast, default; 1) */
 
 /* ---- layout conversion at the module boundary (torch NCHW fp32 <-> arena) ---------------------- */
 /* NCHW fp32 -> act NHWC with channels zero-padded to cpad (cb priors, Demo_Test.py:16,22; states).  */

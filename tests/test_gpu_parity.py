@@ -63,6 +63,28 @@ def test_depthwise(cuda, c, s, d, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(x, wt, b, s, d, d, c), 0, 6)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("cin,ch,s,n,h,w", [(32, 192, 1, 2, 45, 80), (16, 96, 2, 1, 90, 160), (24, 144, 2, 2, 45, 80), (8, 48, 1, 1, 45, 80),
+                                             (160, 960, 1, 3, 12, 20), (24, 120, 1, 1, 37, 41)])
+def test_fp32_hidden_expand_then_depthwise(cuda, cin, ch, s, n, h, w):
+    """dwBlock's hidden tensor (model.py:90-92): the expand GEMM writes fp32 rows, the TMA depthwise kernel reads them."""
+    from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+    torch.manual_seed(7)
+    p = _plan()
+    x = torch.randn(n, cin, h, w)
+    w1, b1 = torch.randn(ch, cin) / cin ** 0.5, torch.randn(ch) * 0.1
+    wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+    hid = p.alloc_f32(n * h * w, ch)
+    p.pw(_upload(p, x), n * h * w, w1.cuda(), b1.cuda(), 1, hid)
+    ho, wo = out_size(h, s), out_size(w, s)
+    ob = p.alloc(n * ho * wo, ch)
+    p.dw(hid, n, h, w, ch, s, 1, p.hold(pack_dw(wd)), p.hold(bd), True, ob)
+    y = _download(p, ob, n, ch, ho, wo)
+    p.run()
+    href = F.hardtanh(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1), 0, 6)
+    assert _rel(hid.to_float().reshape(n, h, w, ch).permute(0, 3, 1, 2), href) < KERNEL_TOL
+    assert _rel(y, F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 @pytest.mark.parametrize("m,k,n,relu,res", [(300, 32, 16, 0, 0), (777, 20, 120, 1, 0), (3600, 256, 1536, 1, 0), (3600, 1536, 256, 0, 1),
                                             (500, 8, 48, 1, 0), (129, 320, 1920, 1, 0), (4000, 144, 24, 0, 1), (1, 64, 64, 0, 0)])

@@ -16,7 +16,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["simt_units", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
+GROUPS = ["simt_units", "f32_hidden", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
 
 
 def rel(a, b):
@@ -171,6 +171,32 @@ def conv_cases(engine):
         p.run(); torch.cuda.synchronize()
         ref = F.hardtanh(F.conv2d(x, wt, bias, 1, 1), 0, 6)
         report("conv3x3[%s] n=%d c=%d co=%d %dx%d" % (engine, nimg, c, co, h, w), y, ref, 2e-4)
+
+
+def g_f32_hidden():
+    """expand GEMM writing fp32 rows -> TMA depthwise kernel reading them (the dwBlock hidden tensor)."""
+    import torch
+    import torch.nn.functional as F
+    from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+    torch.manual_seed(7)
+    for (cin, ch, s, n, h, w) in [(32, 192, 1, 2, 45, 80), (16, 96, 2, 1, 90, 160), (64, 384, 1, 2, 23, 40), (24, 144, 2, 2, 45, 80),
+                                  (256, 1536, 1, 1, 45, 80), (8, 48, 1, 1, 45, 80), (24, 120, 1, 1, 45, 80), (160, 960, 1, 3, 12, 20)]:
+        p = mk_plan("tc")
+        x = torch.randn(n, cin, h, w)
+        w1, b1 = torch.randn(ch, cin) / cin ** 0.5, torch.randn(ch) * 0.1
+        wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+        xb = act_from(p, x)
+        hid = p.alloc_f32(n * h * w, ch)
+        p.pw(xb, n * h * w, w1.cuda(), b1.cuda(), 1, hid)
+        ho, wo = out_size(h, s), out_size(w, s)
+        ob = p.alloc(n * ho * wo, ch)
+        p.dw(hid, n, h, w, ch, s, 1, p.hold(pack_dw(wd)), p.hold(bd), True, ob)
+        y = fetch(p, ob, n, ch, ho, wo)
+        p.run(); torch.cuda.synchronize()
+        href = F.hardtanh(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1), 0, 6)
+        report("expand(f32) %d->%d %dx%d hidden" % (cin, ch, h, w), hid.to_float().reshape(n, h, w, ch).permute(0, 3, 1, 2), href, 1e-4)
+        ref = F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)
+        report("  + dw(f32 in) s=%d" % s, y, ref, 1e-4)
 
 
 def g_tc_pw():

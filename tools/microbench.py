@@ -27,29 +27,29 @@ def timeit(plan, reps=5):
     return ts[len(ts) // 2]
 
 
-def gemm(engine, m, k, n, res=False, terms=3):
+def gemm(engine, m, k, n, res=False, terms=3, f32=False):
     p = Plan(dev, terms, engine)
     a = p.alloc(m, k); a.t.normal_()
-    o = p.alloc(m, n)
+    o = p.alloc_f32(m, n) if f32 else p.alloc(m, n)
     r = p.alloc(m, n) if res else None
     w = torch.randn(n, k, device=dev) / k ** 0.5
     p.pw(a, m, w, torch.zeros(n, device=dev), 1, o, res=r)
     ms = timeit(p)
     fl = 2.0 * m * k * n
     by = 4.0 * m * (k + n * (2 if res else 1))
-    print("pw[%s,t%d] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
+    print("pw[%s,t%d%s] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, ",f32out" if f32 else "", m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
 
 
-def dw(fast, n, h, w, c, stride):
+def dw(fast, n, h, w, c, stride, f32=False):
     _ext.load().uavsal_set_option(2, fast)
     p = Plan(dev, 3, "tc")
-    x = p.alloc(n * h * w, c); x.t.normal_()
+    x = p.alloc_f32(n * h * w, c) if f32 else p.alloc(n * h * w, c); x.t.normal_()
     ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
     o = p.alloc(n * ho * wo, c)
     p.dw(x, n, h, w, c, stride, 1, p.hold(pack_dw(torch.randn(c, 1, 3, 3))), p.hold(torch.zeros(c)), True, o)
     ms = timeit(p)
     by = 4.0 * n * c * (h * w + ho * wo)
-    print("dw[fast=%d] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
+    print("dw[fast=%d%s] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, ",f32in" if f32 else "", n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
     _ext.load().uavsal_set_option(2, 1)
 
 
@@ -86,6 +86,32 @@ def main():
             dw(fast, 20, 45, 80, 1536, 1); dw(fast, 20, 180, 320, 96, 2); dw(fast, 20, 180, 320, 32, 1); dw(fast, 20, 90, 160, 144, 1); dw(fast, 20, 23, 40, 384, 1)
     if what == "dwbig":
         dw(int(sys.argv[2]) if len(sys.argv) > 2 else 2, 20, 45, 80, 1536, 1)
+    if what == "r2":
+        gemm("tc", M, 256, 1536); gemm("tc", M, 256, 1536, f32=True); gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 320, 1920, f32=True)
+        gemm("tc", M, 1920, 256); gemm("tc", M, 256, 256); gemm("tc", M, 192, 1152, f32=True); gemm("tc", M, 1152, 64)
+        gemm("tc", M, 256, 1536, terms=1, f32=True); gemm("tc", 20 * 180 * 320, 16, 96, f32=True); gemm("tc", 20 * 90 * 160, 144, 24, res=True)
+        conv("tc", 20, 45, 80, 448, 256); twa("tc", 20, 45, 80, 256)
+        for f in (False, True):
+            dw(2, 20, 45, 80, 1536, 1, f); dw(2, 20, 180, 320, 96, 2, f); dw(2, 20, 180, 320, 32, 1, f); dw(2, 20, 90, 160, 144, 1, f); dw(2, 20, 23, 40, 384, 1, f)
+    if what == "cluster":
+        lib = _ext.load()
+        for cl in (1, 2):
+            lib.uavsal_set_option(4, cl)
+            print("--- cluster", cl)
+            gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 320, 1920); gemm("tc", M, 1920, 256)
+            gemm("tc", M, 256, 256); gemm("tc", M, 192, 1152); gemm("tc", M, 1152, 64); gemm("tc", M, 256, 1536, terms=1)
+            gemm("tc", 20 * 180 * 320, 16, 96); gemm("tc", 20 * 90 * 160, 144, 24, res=True)
+            conv("tc", 20, 45, 80, 448, 256)
+    if what == "ablate":
+        # timing ablations of the persistent GEMM: bit16 no MMA, bit17 no global stores, bit18 no B loads, bit19 no A loads
+        lib = _ext.load()
+        lib.uavsal_set_option(4, int(sys.argv[2]) if len(sys.argv) > 2 else 2)
+        for mask, name in ((0, "full"), (1 << 16, "no-mma"), (1 << 17, "no-store"), (1 << 18, "no-B"), (1 << 19, "no-A"),
+                           (3 << 18, "no-A no-B"), (3 << 16, "no-mma no-store"), (7 << 17, "no-store no-A no-B"), (0xF << 16, "nothing")):
+            lib.uavsal_set_option(3, mask)
+            print("---", name)
+            gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 256, 1536, terms=1)
+        lib.uavsal_set_option(3, 0)
     if what == "gemmbig":
         gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True)
     if what in ("conv", "all"):
