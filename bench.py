@@ -189,7 +189,8 @@ def run_product_arm(args):
     model.load_state_dict(synth.make_state_dict("lively", 0), strict=True)
     model = model.to(dev).set_mode(precision=args.precision)
     gauss, ob = load_priors()
-    runner = ClipRunner(model, gauss, ob, batch_size=BATCH, out_hw=(H, W), use_graph=not args.no_graph)
+    runner = ClipRunner(model, gauss, ob, batch_size=BATCH, out_hw=(H, W), use_graph=not args.no_graph, depth=args.depth)
+    runner.warm(FRAMES, H, W)
 
     # distinct clips rotated across steps so inputs (4 x 44 MB) exceed the 126 MB L2; the arena traffic of a step
     # (GBs) exceeds it by far anyway
@@ -197,20 +198,22 @@ def run_product_arm(args):
     host_clips = [torch.from_numpy(synth.make_clip(100 + rank * 16 + i, FRAMES, H, W)).pin_memory() for i in range(n_rot)]
     dev_clips = [c.to(dev) for c in host_clips]
     host_out = torch.empty((OUT_PER_CLIP, H, W), dtype=torch.uint8).pin_memory()
+    dev_out = torch.empty((OUT_PER_CLIP, H, W), dtype=torch.uint8, device=dev)
 
+    # the runner pipelines calls (and clips) over its own streams; finish() joins them into the timed stream
     def step_resident(i):
         for c in range(args.clips):
-            runner.run_clip(dev_clips[(i * args.clips + c) % n_rot], want_maps=False)
+            runner.run_clip(dev_clips[(i * args.clips + c) % n_rot], want_maps=False, out=dev_out, sync=False)
 
     def step_e2e(i):
         for c in range(args.clips):
-            _, u8 = runner.run_clip(host_clips[(i * args.clips + c) % n_rot], want_maps=False)   # H2D inside run_clip
-            host_out.copy_(u8, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            # H2D of the uint8 frames and D2H of the uint8 maps are queued by run_clip on its streams
+            runner.run_clip(host_clips[(i * args.clips + c) % n_rot], want_maps=False, out=host_out, sync=False)
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
+        runner.finish()
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
@@ -219,6 +222,7 @@ def run_product_arm(args):
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        runner.finish()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -283,7 +287,7 @@ def run_product_arm(args):
             "warmup": warm, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split (fp32 accumulate)" if args.precision == "exact" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": args.clips, "frames_in_per_clip": FRAMES, "maps_out_per_clip": OUT_PER_CLIP,
-                       "precision": args.precision, "cuda_graph": not args.no_graph,
+                       "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth,
                        "l2": "inputs larger than L2: %d distinct clips rotated (%.0f MB) and ~9.5 GB of arena traffic per call" % (n_rot, n_rot * 44.2)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.clips * OUT_PER_CLIP * H * W * 3,
                     "d2h_bytes_per_step": args.clips * OUT_PER_CLIP * H * W},
@@ -302,6 +306,7 @@ def main():
     ap.add_argument("--clips", type=int, default=1, help="clips per step per GPU")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, help="calls in flight per GPU (ClipRunner stream pipelining; 1 = serial)")
     ap.add_argument("--dump-ops", default="", help="write per-op CUDA-event timings of one 20-frame call to this file")
     args = ap.parse_args()
     if args.impl == "reference":

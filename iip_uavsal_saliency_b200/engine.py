@@ -258,31 +258,52 @@ class Plan:
         self._add("uavsal_post_u8", (maps.data_ptr(), n, hs, ws, hd, wd, fm.data_ptr(), out_u8.data_ptr()), tag)
 
     # ---- execution ----
-    def run(self, upto: Optional[int] = None):
+    def mark_split(self):
+        """Ops emitted after this point form the plan's "back" part (the recurrent tail of a UAVSal call, which depends on
+        the previous call's state); the ops before it form the "front", which a runner may overlap with another call."""
+        self.split = len(self.ops)
+
+    def _range(self, part: Optional[str]):
+        split = getattr(self, "split", None)
+        if part is None or split is None:
+            return 0, len(self.ops)
+        return (0, split) if part == "front" else (split, len(self.ops))
+
+    def run(self, upto: Optional[int] = None, part: Optional[str] = None):
         if self.device.type != "cuda":
             raise RuntimeError("uavsal-b200 kernels are CUDA (sm_100a) only; there is no CPU path")
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _ext.load().uavsal_set_option(1, 1 if self.engine == "tc1" else 2)      # tcgen05 kernel generation (process-global)
-        ops = self.ops if upto is None else self.ops[:upto]
+        lo, hi = self._range(part)
+        ops = self.ops[lo:hi] if upto is None else self.ops[:upto]
         for op in ops:
             rc = op.fn(*op.args, stream)
             if rc:
                 _ext.check(rc, op.name + ("[" + op.tag + "]" if op.tag else ""))
 
     def capture(self):
-        """Warm up once eagerly, then record the whole op list into a CUDA graph."""
+        """Warm up once eagerly, then record the op list into a CUDA graph (two graphs when the plan is split)."""
         self.run()
         torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run()
-        self.graph = g
+        self.graphs = {}
+        parts = ["front", "back"] if getattr(self, "split", None) is not None else [None]
+        for part in parts:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run(part=part)
+            self.graphs[part] = g
+        self.graph = self.graphs.get(None)
 
-    def launch(self):
-        if self.graph is not None:
-            self.graph.replay()
+    def launch(self, part: Optional[str] = None):
+        graphs = getattr(self, "graphs", None)
+        if graphs:
+            if part is None and None not in graphs:
+                graphs["front"].replay()
+                graphs["back"].replay()
+            else:
+                graphs[part].replay()
         else:
-            self.run()
+            self.run(part=part)
 
     @property
     def num_launches(self) -> int:

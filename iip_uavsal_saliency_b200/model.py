@@ -269,7 +269,9 @@ class UAVSal(KernelModule):
                 tp.update(fust=(cat2.slot(0, planes), mh, mw), fucb=(cat2.slot(planes, q), mh, mw), fucbst=(x, mh, mw))
         else:
             x, _, _ = self.fust_layer[0]._emit(plan, x, n, mh, mw, tag="fust")
-        # temporal weighted average over the call's frames, batch 1 (model.py:367-370)
+        # temporal weighted average over the call's frames, batch 1 (model.py:367-370).  Everything from here on depends on
+        # the previous call's hidden state: it is the plan's "back" part (runner.ClipRunner overlaps it with the next front)
+        plan.mark_split()
         h_in = plan.tensor((1, planes, mh, mw))
         hb = plan.alloc(mh * mw, planes)
         plan.pack_nchw(h_in, 1, planes, mh, mw, hb, tag="state.pack")
@@ -296,8 +298,9 @@ class UAVSal(KernelModule):
         plan.named.update(named)
         return plan
 
-    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False) -> Plan:
-        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared)
+    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0) -> Plan:
+        """``slot`` selects one of several independent plan instances (own arena) so that calls can be in flight together."""
+        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot)
         return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared))
 
     def forward(self, x, cb, in_state):

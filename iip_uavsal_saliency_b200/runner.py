@@ -6,6 +6,12 @@ uint8 frames in -> uint8 saliency maps out.
     prior see exactly that grouping, quirks Q2/Q3); a shorter last call gets its own plan;
   * the ConvTWA hidden state is handed from call to call (Demo_Test.py:75,85-86);
   * priors are one (h,w,C) map broadcast to every frame, as get_bias builds them (Demo_Test.py:14-27).
+
+Scheduling.  Only the recurrent tail of a call (ConvTWA -> readout -> post-process, the plan's "back" part) depends on
+the previous call; everything before it (the "front": backbone, SRF-Net, ST blocks, prior fusion) does not.  The runner
+therefore keeps ``depth`` plan instances (own arenas) and runs fronts on ``depth`` CUDA streams while one "back" stream
+walks the calls in order, so the latency-bound recurrence of call i overlaps the front of call i+1 - also across clip
+boundaries when the caller passes ``sync=False``.  Results are bit-identical to the serial order.
 """
 from __future__ import annotations
 
@@ -20,8 +26,9 @@ from .model import UAVSal
 
 class ClipRunner:
     def __init__(self, model: UAVSal, gauss: np.ndarray, ob: np.ndarray, batch_size: int = 4, out_hw: Optional[Tuple[int, int]] = None,
-                 use_graph: bool = True, frame_layout: str = "nhwc"):
-        """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw'."""
+                 use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2):
+        """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw';
+        depth = calls in flight (1 = strictly serial on the caller's stream order)."""
         self.model = model
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -31,13 +38,19 @@ class ClipRunner:
         self.kind = 2 if frame_layout == "nhwc" else 1
         self.out_hw = out_hw
         self.use_graph = use_graph
+        self.depth = max(1, int(depth))
         self.gauss = torch.from_numpy(np.ascontiguousarray(gauss.transpose(2, 0, 1)[None])).float().to(self.dev)
         self.ob = torch.from_numpy(np.ascontiguousarray(ob.transpose(2, 0, 1)[None])).float().to(self.dev)
+        self.front_streams = [torch.cuda.Stream(self.dev) for _ in range(self.depth)]
+        self.back_stream = torch.cuda.Stream(self.dev)
+        self._slot_free = [None] * self.depth          # event: the slot's previous call has left the back stream
+        self._calls = 0
 
-    def _plan(self, n, H, W):
+    def _plan(self, n, H, W, slot):
         post = self.out_hw or (H, W)
-        plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=post, cb_shared=True)
+        plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=post, cb_shared=True, slot=slot)
         if "ready" not in plan.named:
+            torch.cuda.synchronize(self.dev)
             if self.model.use_gauss_prior:
                 plan.named["cb_gauss_in"].copy_(self.gauss)
             if self.model.use_ob_prior:
@@ -45,29 +58,86 @@ class ClipRunner:
             plan.named["h_in"].zero_()
             if self.use_graph:
                 plan.capture()
+            torch.cuda.synchronize(self.dev)
             plan.named["ready"] = True
         return plan
 
-    def run_clip(self, frames: torch.Tensor, want_maps: bool = True):
+    def warm(self, n_frames: int, H: int, W: int):
+        """Build (and capture) the plans a clip of n_frames will use on every slot, outside any timed region."""
+        keep = (n_frames // self.T) * self.T
+        sizes = {min(self.per_call, keep - i * self.per_call) for i in range(math.ceil(keep / self.per_call))}
+        for slot in range(self.depth):
+            for n in sizes:
+                self._plan(n, H, W, slot)
+
+    def finish(self):
+        """Make the caller's stream wait for everything the runner has queued (needed after run_clip(sync=False))."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self.back_stream)
+        for s in self.front_streams:
+            cur.wait_stream(s)
+
+    def run_clip(self, frames: torch.Tensor, want_maps: bool = True, out: Optional[torch.Tensor] = None, sync: bool = True):
         """frames: uint8 (F,H,W,3) [nhwc] or (F,3,H,W) [nchw], on the device or in (pinned) host memory.
-        Returns (maps fp32 (F',1,h,w) or None, u8 (F',H_out,W_out)) on the device."""
+        Returns (maps fp32 (F',1,h,w) or None, u8 (F',H_out,W_out)); ``out`` (device or pinned host uint8 (>=F',H_out,W_out))
+        receives the maps instead of a fresh tensor.  With sync=False the call only queues work: call finish() before
+        touching the results from the caller's stream."""
         F_ = frames.shape[0]
         H, W = (frames.shape[1], frames.shape[2]) if self.kind == 2 else (frames.shape[2], frames.shape[3])
         keep = (F_ // self.T) * self.T
+        ncalls = math.ceil(keep / self.per_call)
+        plans = []
+        for i in range(ncalls):                                     # build before queueing (capture synchronises)
+            n = min(keep, (i + 1) * self.per_call) - i * self.per_call
+            plans.append(self._plan(n, H, W, (self._calls + i) % self.depth))
+        cur = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)                                           # inputs / `out` are ordered after the caller's stream
+        bs = self.back_stream
+        bs.wait_event(ready)
         maps, u8s = [], []
         state = None
-        for i in range(math.ceil(keep / self.per_call)):
-            chunk = frames[i * self.per_call:min(keep, (i + 1) * self.per_call)]
-            plan = self._plan(chunk.shape[0], H, W)
+        done = 0
+        for i in range(ncalls):
+            slot = self._calls % self.depth
+            self._calls += 1
+            plan = plans[i]
             nm = plan.named
-            nm["x_in"].copy_(chunk, non_blocking=True)
-            if state is None:
-                nm["h_in"].zero_()
-            else:
-                nm["h_in"].copy_(state)
-            plan.launch()
-            state = nm["h_out"].clone()
-            if want_maps:
-                maps.append(nm["out"].clone())
-            u8s.append(nm["out_u8"].clone())
-        return (torch.cat(maps, 0) if want_maps else None), torch.cat(u8s, 0)
+            chunk = frames[i * self.per_call:min(keep, (i + 1) * self.per_call)]
+            n = chunk.shape[0]
+            fs = self.front_streams[slot]
+            fs.wait_event(ready)
+            if self._slot_free[slot] is not None:
+                fs.wait_event(self._slot_free[slot])
+            with torch.cuda.stream(fs):
+                nm["x_in"].copy_(chunk, non_blocking=True)
+                plan.launch("front")
+                fdone = torch.cuda.Event()
+                fdone.record(fs)
+            bs.wait_event(fdone)
+            with torch.cuda.stream(bs):
+                if state is None:
+                    nm["h_in"].zero_()
+                else:
+                    nm["h_in"].copy_(state, non_blocking=True)
+                plan.launch("back")
+                state = nm["h_out"]                                 # read by the next call on this same stream
+                if want_maps:
+                    maps.append(nm["out"].clone())
+                if out is not None:
+                    out[done:done + n].copy_(nm["out_u8"], non_blocking=True)
+                else:
+                    u8s.append(nm["out_u8"].clone())
+                free = torch.cuda.Event()
+                free.record(bs)
+                self._slot_free[slot] = free
+            done += n
+        with torch.cuda.stream(bs):
+            m = torch.cat(maps, 0) if want_maps else None
+            u8 = out[:done] if out is not None else torch.cat(u8s, 0)
+        if sync:
+            cur.wait_stream(bs)
+            for t in (m, u8):
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
+        return m, u8

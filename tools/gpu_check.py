@@ -375,12 +375,30 @@ def g_runner():
     print("RUNNER config#2 max-abs %.3e (tol 2e-3) %s" % (d.max(), "ok" if d.max() < 2e-3 else "FAIL"), flush=True)
     du = np.abs(u8[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int))
     print("RUNNER uint8 maxdiff %d (tol 1), frac>0 %.3e %s" % (du.max(), (du > 0).mean(), "ok" if du.max() <= 1 else "FAIL"), flush=True)
-    t0 = time.time()
-    for _ in range(3):
-        r.run_clip(clip, want_maps=False)
-    torch.cuda.synchronize()
-    dt = (time.time() - t0) / 3
-    print("RUNNER 64-frame clip %.1f ms -> %.1f frames/s (60 outputs)" % (dt * 1e3, 60 / dt), flush=True)
+    # pipelining must not change a single bit: serial (depth 1) vs 3 calls in flight, clips queued back to back
+    clips = [clip] + [torch.from_numpy(synth.make_clip(20 + i, 64, 360, 640)).cuda() for i in range(2)]
+    outs = {}
+    for depth in (1, 3):
+        rr = ClipRunner(m, gauss, ob, batch_size=4, depth=depth)
+        rr.warm(64, 360, 640)
+        bufs = [torch.empty(60, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
+        for c, b in zip(clips, bufs):
+            rr.run_clip(c, want_maps=False, out=b, sync=False)
+        rr.finish()
+        torch.cuda.synchronize()
+        outs[depth] = [b.cpu() for b in bufs]
+        for reps in (1, 2):
+            t0 = time.time()
+            for _ in range(4):
+                for c, b in zip(clips, bufs):
+                    rr.run_clip(c, want_maps=False, out=b, sync=False)
+            rr.finish()
+            torch.cuda.synchronize()
+            dt = (time.time() - t0) / 12
+        print("RUNNER depth=%d: 64-frame clip %.2f ms -> %.1f frames/s (60 outputs)" % (depth, dt * 1e3, 60 / dt), flush=True)
+    same = all(torch.equal(a, b) for a, b in zip(outs[1], outs[3]))
+    same0 = torch.equal(outs[1][0], torch.from_numpy(u8))
+    print("RUNNER pipelined == serial: %s, == sync run: %s  %s" % (same, same0, "ok" if same and same0 else "FAIL"), flush=True)
 
 
 def main():

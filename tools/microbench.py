@@ -110,7 +110,7 @@ def main():
                            (3 << 18, "no-A no-B"), (3 << 16, "no-mma no-store"), (7 << 17, "no-store no-A no-B"), (0xF << 16, "nothing")):
             lib.uavsal_set_option(3, mask)
             print("---", name)
-            gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 256, 1536, terms=1)
+            gemm("tc", M, 256, 1536, f32=True); gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 256, 1536, terms=1, f32=True)
         lib.uavsal_set_option(3, 0)
     if what == "gemmbig":
         gemm("tc", M, 256, 1536); gemm("tc", M, 1536, 256, res=True)
