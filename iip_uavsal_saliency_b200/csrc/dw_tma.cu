@@ -34,15 +34,15 @@ struct DwGeom {
     static constexpr uint32_t TILE_BYTES = PIX * 256;     // 64 channels x (2 bf16 planes | fp32)
 };
 
-// 4 channels from the staged tile -> fp32
+// 4 channels from the staged tile -> fp32 (explicit shared-space loads: `tile` is a 32-bit shared address)
 template <bool F32IN>
-__device__ __forceinline__ void lds4(const uint8_t* tile, uint32_t plane_bytes, int pix, int quad, float v[4]) {
+__device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pix, int quad, float v[4]) {
     if (F32IN) {
-        const float4 a = *reinterpret_cast<const float4*>(tile + pix * 256 + quad * 16);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(tile + pix * 256 + quad * 16));
     } else {
-        const uint2 a = *reinterpret_cast<const uint2*>(tile + pix * 128 + quad * 8);
-        const uint2 b = *reinterpret_cast<const uint2*>(tile + plane_bytes + pix * 128 + quad * 8);
+        uint2 a, b;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(tile + pix * 128 + quad * 8));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(tile + plane_bytes + pix * 128 + quad * 8));
         float t[4];
         unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]);
         unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
 
         const int ox = x0 + col;
         if (cvalid && ox < g.wo) {
-            const uint8_t* tile = smem + b * G::TILE_BYTES;
+            const uint32_t tile = smem_u32(smem) + b * G::TILE_BYTES;
             float win[3][3][4];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
 #pragma unroll

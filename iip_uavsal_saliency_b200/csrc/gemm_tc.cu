@@ -349,6 +349,7 @@ static int num_sms() {
     return n;
 }
 
+static int g_tc_max_stages = 8;   // uavsal_set_option key 5 (dev): cap on the smem pipeline depth
 static int g_tc_cluster = 2;   // uavsal_set_option key 4: CTAs per cluster of the persistent GEMM (1 = no multicast)
 
 template <int MODE, int EPI, int TERMS, int CL>
@@ -388,18 +389,21 @@ static int launch_tc2_inst(const CUtensorMap& a0, const CUtensorMap& a1, const C
 
 // the B tensor map of a cluster launch has a box of bn / CL rows (each CTA loads and multicasts its share)
 static bool want_cluster(const TcArgs& g, int tiles_m) {
-    return g_tc_cluster == 2 && tiles_m >= 2 && (int64_t)tiles_m * div_up(g.N, g.bn) >= num_sms() && g.bn % 32 == 0;
+    // pair mode pays off when the tensor pipe / shared memory is the limiter (wide N tile, several k-blocks); the tiny-K
+    // high-resolution layers are HBM-bound and lose to the extra cross-CTA handshakes
+    return g_tc_cluster == 2 && tiles_m >= 2 && (int64_t)tiles_m * div_up(g.N, g.bn) >= num_sms() && g.bn % 32 == 0 && g.bn >= 128 &&
+           g.num_kb >= 3;
 }
 
 template <int MODE, int EPI>
 static int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o, TcArgs& g,
                       int terms, int tiles_m, bool cluster, cudaStream_t s, const char* what) {
     const int npl = terms == 3 ? 2 : 1;
-    const uint32_t stage_bytes = npl * (kABytes + (uint32_t)g.bn * kBK * 2);
+    const uint32_t stage_bytes = npl * (kABytes + (uint32_t)(cluster ? g.bn / 2 : g.bn) * kBK * 2);   // a pair CTA stages half of B
     const uint32_t budget = 227u * 1024u - 1024u - kOutStageBytes - 512u;
     int stages = (int)(budget / stage_bytes);
-    if (stages > 8) stages = 8;
-    UAVSAL_REQUIRE(stages >= 2, UAVSAL_ENOTSUP, "%s: tile does not fit shared memory", what);
+    if (stages > g_tc_max_stages) stages = g_tc_max_stages;
+    UAVSAL_REQUIRE(stages >= 1, UAVSAL_ENOTSUP, "%s: tile does not fit shared memory", what);
     g.stages = stages;
     g.tiles_m = tiles_m;
     g.tiles_n = div_up(g.N, g.bn);
@@ -513,6 +517,7 @@ int uavsal_set_option(int key, int value) {
     if (key == 2 && value >= 0 && value <= 2) { g_dw_fast = value; return 0; }
     if (key == 3) { g_tc_debug = value & 0xF0000; return 0; }
     if (key == 4 && (value == 1 || value == 2)) { g_tc_cluster = value; return 0; }
+    if (key == 5 && value >= 1 && value <= 8) { g_tc_max_stages = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }

@@ -27,10 +27,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// CL = CTAs per cluster (1 | 2).  With CL = 2 the two CTAs of a cluster work on neighbouring 128-row tiles of the SAME
-// n-tile: each loads its own A tile and one half of the B tile, multicasting that half into both CTAs' shared memory,
-// so the weight traffic L2 -> SM (the measured limiter of the single-CTA kernel: 1.33 GB per 256<->1536 GEMM at the
-// ~7.4 TB/s fabric cap) is halved.  A stage is recycled only when BOTH MMA warps have retired it (multicast commit).
+// CL = CTAs per cluster (1 | 2).  With CL = 2 the two CTAs of a cluster (the two SMs of a TPC) run cta_group::2 MMAs on
+// a 256-row tile: each CTA stages its own 128 rows of A and HALF of the B tile, keeps its 128 accumulator lanes in its own
+// TMEM and drains them with its own epilogue warps; the even CTA issues the MMAs and its commits arrive on both CTAs'
+// barriers.  Measured motivation: a single-CTA 128x256 tile with the 3-term split reads 36 KB of operands from shared
+// memory per k-step and fills 96 KB per k-block - more than the 128 B/clk/SM the shared memory delivers - and only two
+// 96 KB stages fit.  The pair reads 24 KB per k-step per SM, fills 64 KB per k-block and gets three stages.
 template <int MODE, int EPI, int TERMS, int CL>
 __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NPL = TERMS == 3 ? 2 : 1;
-    const uint32_t b_bytes = (uint32_t)g.bn * kBK * 2;
+    constexpr bool PAIR = CL == 2;
+    const uint32_t b_bytes = (uint32_t)(g.bn / CL) * kBK * 2;                 // B rows staged by THIS CTA
     const uint32_t stage_bytes = NPL * (kABytes + b_bytes);
     uint8_t* ostage = smem + (size_t)g.stages * stage_bytes;                  // 1024-aligned (stage_bytes % 1024 == 0)
     uint64_t* full = reinterpret_cast<uint64_t*>(ostage + kOutStageBytes);
@@ -55,13 +58,18 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     const int num_work = CL > 1 ? ((g.tiles_m + CL - 1) / CL) * g.tiles_n : g.num_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }
-        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, kEpiWarps); }
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, CL * kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -111,11 +119,22 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + NPL * kABytes;
                     const bool no_a = g.flags & DBG_NO_A, no_b = g.flags & DBG_NO_B;
-                    mbar_expect_tx(full + s, stage_bytes - (no_a ? NPL * kABytes : 0) - (no_b ? NPL * b_bytes : 0));
+                    const uint32_t tx = stage_bytes - (no_a ? NPL * kABytes : 0) - (no_b ? NPL * b_bytes : 0);
+                    // pair: all bytes of both CTAs complete on the even CTA's barrier, which alone is waited on (by the issuer)
+                    if (!PAIR || crank == 0) mbar_expect_tx(full + s, CL * tx);
+                    const uint32_t fbar = PAIR ? mapa_u32(smem_u32(full + s), 0) : 0;
+                    int bk = kb * kBK;
+                    if (MODE == MODE_CONV) {
+                        const int tap = kb / g.kb_per_tap;
+                        bk = tap * g.bk_tap_stride + g.bk_off + (kb - tap * g.kb_per_tap) * kBK;
+                    }
                     if (no_a) {
                     } else if (MODE == MODE_PW) {
 #pragma unroll
-                        for (int p = 0; p < NPL; ++p) tma_load_3d(&tmA0, full + s, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
+                        for (int p = 0; p < NPL; ++p) {
+                            if (PAIR) tma_load_3d_pair(&tmA0, fbar, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
+                            else tma_load_3d(&tmA0, full + s, sa + p * kABytes, kb * kBK, tile_m * kBM, p);
+                        }
                     } else {
                         const int tap = kb / g.kb_per_tap;
                         const int r = kb - tap * g.kb_per_tap;
@@ -125,34 +144,33 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                         const int cch = (src0 ? r : r - g.kb_src0) * kBK;
                         const int img = src0 ? bidx * g.a0_mul + g.a0_off : bidx * g.a1_mul + g.a1_off;
 #pragma unroll
-                        for (int p = 0; p < NPL; ++p) tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
+                        for (int p = 0; p < NPL; ++p) {
+                            if (PAIR) tma_load_5d_pair(tm, fbar, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
+                            else tma_load_5d(tm, full + s, sa + p * kABytes, cch, x0 + dx, y0 + dy, img, p);
+                        }
                     }
-                    int bk = kb * kBK;
-                    if (MODE == MODE_CONV) {
-                        const int tap = kb / g.kb_per_tap;
-                        bk = tap * g.bk_tap_stride + g.bk_off + (kb - tap * g.kb_per_tap) * kBK;
-                    }
-                    if (no_b) {
-                    } else if (CL > 1) {                                      // my half of the B tile, into both CTAs
-                        const int half = g.bn / CL;
+                    if (!no_b) {
 #pragma unroll
-                        for (int p = 0; p < NPL; ++p)
-                            tma_load_3d_mc(&tmB, full + s, sb + p * b_bytes + crank * half * 128, bk, n0 + (int)crank * half, p, (uint16_t)((1u << CL) - 1));
-                    } else {
-#pragma unroll
-                        for (int p = 0; p < NPL; ++p) tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
+                        for (int p = 0; p < NPL; ++p) {
+                            if (PAIR) tma_load_3d_pair(&tmB, fbar, sb + p * b_bytes, bk, n0 + (int)crank * (g.bn / CL), p);   // my half of the B tile
+                            else tma_load_3d(&tmB, full + s, sb + p * b_bytes, bk, n0, p);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc(g.bn);
+        // ===================== MMA issuer (pair: the even CTA only) =====================
+        if (!PAIR || crank == 0) {
+        const uint32_t idesc = PAIR ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24))
+                                    : umma_idesc(g.bn);
         uint32_t kc = 0;
         int it = 0;
         for (int t = cta_first; t < num_work; t += cta_step, ++it) {
             const int buf = it & 1;
-            mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);                 // epilogue has drained this accumulator
+            // the epilogue warps (of both CTAs) have drained this accumulator
+            if (PAIR) mbar_wait_cluster(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+            else mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.bn);
             for (int kb = 0; kb < g.num_kb; ++kb, ++kc) {
@@ -167,20 +185,21 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                         if (g.flags & DBG_NO_MMA) break;
                         const uint64_t dah = umma_desc(a_hi + k * 32);
                         const uint64_t dbh = umma_desc(b_hi + k * 32);
-                        umma_bf16(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+                        if (PAIR) umma_bf16_pair(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+                        else umma_bf16(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
                         if (TERMS == 3) {
                             const uint64_t dal = umma_desc(a_hi + kABytes + k * 32);
                             const uint64_t dbl = umma_desc(b_hi + b_bytes + k * 32);
-                            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-                            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+                            if (PAIR) { umma_bf16_pair(d_tmem, dah, dbl, idesc, 1u); umma_bf16_pair(d_tmem, dal, dbh, idesc, 1u); }
+                            else { umma_bf16(d_tmem, dah, dbl, idesc, 1u); umma_bf16(d_tmem, dal, dbh, idesc, 1u); }
                         }
                     }
-                    if (CL > 1) umma_commit_mc(empty + s, (uint16_t)((1u << CL) - 1));
-                    else umma_commit(empty + s);
-                    if (kb == g.num_kb - 1) umma_commit(acc_full + buf);
+                    if (PAIR) umma_commit_pair(empty + s); else umma_commit(empty + s);
+                    if (kb == g.num_kb - 1) { if (PAIR) umma_commit_pair(acc_full + buf); else umma_commit(acc_full + buf); }
                 }
                 __syncwarp();
             }
+        }
         }
     } else {
         // ===================== epilogue (warps 2..17) =====================
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         const int q = warp & 3;
         const int sub = (ew >> 2) * 16;                                       // column offset inside a 64-column chunk
         const int r = q * 32 + lane;                                          // tile row = TMEM lane
-        uint8_t* wst = ostage + ew * 2048;                                    // 32 rows x 16 columns: fp32, or hi | lo bf16
+        const uint32_t wst = smem_u32(ostage) + ew * 2048;                    // 32 rows x 16 columns: fp32, or hi | lo bf16
         const bool f32out = EPI == EPI_STD && (g.flags & UAVSAL_F_OUT_F32);
         const bool do_store = !(g.flags & DBG_NO_STORE);
         int it = 0;
@@ -304,17 +323,17 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                             // row = lane: 64 bytes = four 16-byte chunks, chunk j stored at j ^ ((lane >> 1) & 3) (conflict-free)
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<float4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                sts128(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                             __syncwarp();
                             float* outf = reinterpret_cast<float*>(g.out.p);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {                     // 8 rows x 64 contiguous bytes per instruction
                                 const int row = 8 * i + (lane >> 2), c = lane & 3;
-                                const float4 val = *reinterpret_cast<const float4*>(wst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+                                const uint4 val = lds128(wst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
                                 const int64_t gr = grow_of(q * 32 + row);
                                 const int col = n + c * 4;
-                                if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<float4*>(outf + gr * g.out.ld + col) = val;
+                                if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<uint4*>(outf + gr * g.out.ld + col) = val;
                             }
                         } else {
                             // hi plane rows of 32 bytes at wst, lo plane at wst + 1024; chunk j of row at j ^ ((lane >> 2) & 1)
@@ -324,16 +343,16 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) split2(v[half * 8 + 2 * j], v[half * 8 + 2 * j + 1], h[j], l[j]);
                                 const int off = lane * 32 + ((half ^ ((lane >> 2) & 1)) << 4);
-                                *reinterpret_cast<uint4*>(wst + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<uint4*>(wst + 1024 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                                sts128(wst + off, h[0], h[1], h[2], h[3]);
+                                sts128(wst + 1024 + off, l[0], l[1], l[2], l[3]);
                             }
                             __syncwarp();
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {                     // 16 rows x 32 contiguous bytes per plane per instruction
                                 const int row = 16 * i + (lane >> 1), c = lane & 1;
                                 const int off = row * 32 + ((c ^ ((row >> 2) & 1)) << 4);
-                                const uint4 hv4 = *reinterpret_cast<const uint4*>(wst + off);
-                                const uint4 lv4 = *reinterpret_cast<const uint4*>(wst + 1024 + off);
+                                const uint4 hv4 = lds128(wst + off);
+                                const uint4 lv4 = lds128(wst + 1024 + off);
                                 const int64_t gr = grow_of(q * 32 + row);
                                 const int col = n + c * 8;
                                 if (gr >= 0 && col < g.N && do_store) {
@@ -348,7 +367,10 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 if (ch == nchunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + buf);
+                    if (lane == 0) {
+                        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + buf), 0));
+                        else mbar_arrive(acc_empty + buf);
+                    }
                 }
             }
         }
@@ -358,7 +380,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's smem / arrive on its barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
     }
 }
 

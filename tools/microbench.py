@@ -93,6 +93,13 @@ def main():
         conv("tc", 20, 45, 80, 448, 256); twa("tc", 20, 45, 80, 256)
         for f in (False, True):
             dw(2, 20, 45, 80, 1536, 1, f); dw(2, 20, 180, 320, 96, 2, f); dw(2, 20, 180, 320, 32, 1, f); dw(2, 20, 90, 160, 144, 1, f); dw(2, 20, 23, 40, 384, 1, f)
+    if what == "stages":
+        lib = _ext.load()
+        for st in (1, 2, 3, 6):
+            lib.uavsal_set_option(5, st)
+            print("--- max stages", st)
+            gemm("tc", M, 1536, 256, res=True); gemm("tc", M, 1536, 256, terms=1); gemm("tc", M, 256, 1536, f32=True); conv("tc", 20, 45, 80, 448, 256)
+        lib.uavsal_set_option(5, 8)
     if what == "cluster":
         lib = _ext.load()
         for cl in (1, 2):
