@@ -266,12 +266,39 @@ def run_product_arm(args):
     breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot_ms, 3), "launches": v[3],
                      "tflops": round(v[1] / v[0] / 1e9, 1) if v[0] and v[1] else None,
                      "gbs": round(v[2] / v[0] / 1e6, 1) if v[0] and v[2] else None} for k, v in sorted(cls.items(), key=lambda kv: -kv[1][0])}
+    # measured DRAM traffic per kernel family from the committed ncu capture of the same 20-frame call (tools/profile_call.py)
+    traffic = {}
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r01_call20_summary.json")))
+        for k in summ["kernels"]:
+            fam = "uavsal_pw_gemm" if k["kernel"].startswith("gemm_tc2_kernel<0") else ("uavsal_dw3x3" if k["kernel"].startswith("dw3x3") else None)
+            if fam:
+                t = traffic.setdefault(fam, [0.0, 0])
+                t[0] += (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
+                t[1] += k["launches"]
+    except Exception:
+        pass
+
+    def per_launch_traffic(fam):
+        t = traffic.get(fam)
+        return round(t[0] / t[1]) if t and t[1] else None
+
+    terms = 3 if args.precision == "exact" else 1
     dom = "uavsal_pw_gemm"
     ach = cls[dom][1] / cls[dom][0] / 1e9
-    roofline = {"kernel": "gemm_tc_kernel<MODE_PW,EPI_STD,TERMS=%d> (%d launches per 20-frame call)" % (3 if args.precision == "exact" else 1, cls[dom][3]),
+    roofline = {"kernel": "gemm_tc2_kernel<MODE_PW,EPI_STD,TERMS=%d,CL=1|2> (tcgen05 pointwise-conv GEMM, %d launches per 20-frame call)" % (terms, cls[dom][3]),
                 "bound": "tensor", "achieved": round(ach, 2), "peak": tens_peak, "unit": "TFLOP/s", "frac": round(ach / tens_peak, 4),
-                "traffic": None, "peak_source": peak_src,
-                "note": "achieved = algorithmic 2*M*K*N flops (1x, not the 3x issued by the bf16x3 split) summed over the class / summed CUDA-event time"}
+                "traffic": per_launch_traffic(dom), "peak_source": peak_src,
+                "algorithmic_flops_per_launch": round(cls[dom][1] / cls[dom][3]), "avg_launch_us": round(1e3 * cls[dom][0] / cls[dom][3], 2),
+                "issued_frac": round(terms * ach / tens_peak, 4),
+                "note": "achieved = algorithmic 2*M*K*N flops (1x) summed over the class / summed CUDA-event time; the bf16x3 split issues "
+                        "3x that on the tensor pipe (issued_frac); traffic = ncu dram bytes per launch (profiles/r01_call20_summary.json)"}
+    hb = "uavsal_dw3x3"
+    ach_h = cls[hb][2] / cls[hb][0] / 1e6
+    roofline_hbm = {"kernel": "dw3x3_tma_kernel / dw3x3_kernel (depthwise 3x3 + BN + ReLU6, %d launches per 20-frame call)" % cls[hb][3],
+                    "bound": "hbm", "achieved": round(ach_h, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach_h / hbm_peak, 4),
+                    "traffic": per_launch_traffic(hb), "algorithmic_bytes_per_launch": round(cls[hb][2] / cls[hb][3]),
+                    "avg_launch_us": round(1e3 * cls[hb][0] / cls[hb][3], 2)}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cores = os.cpu_count() or 1
@@ -291,7 +318,7 @@ def run_product_arm(args):
                        "l2": "inputs larger than L2: %d distinct clips rotated (%.0f MB) and ~9.5 GB of arena traffic per call" % (n_rot, n_rot * 44.2)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.clips * OUT_PER_CLIP * H * W * 3,
                     "d2h_bytes_per_step": args.clips * OUT_PER_CLIP * H * W},
-            "gpu_launches": launches * args.clips * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches * args.clips * args.steps, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "breakdown_20_frame_call": breakdown, "hbm_peak_gbs": hbm_peak}
     print(json.dumps(line), flush=True)
     return 0

@@ -77,49 +77,68 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
+    __shared__ float st[128 * 33];                                         // output tile, row pitch 33 floats (conflict-free)
     const int64_t total = (int64_t)n * ho * wo;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int ox = (int)(i % wo);
-    const int oy = (int)((i / wo) % ho);
-    const int img = (int)(i / ((int64_t)wo * ho));
-    float acc[32];
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t i = i0 + threadIdx.x;
+    if (i < total) {
+        const int ox = (int)(i % wo);
+        const int oy = (int)((i / wo) % ho);
+        const int img = (int)(i / ((int64_t)wo * ho));
+        float acc[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = sb[j];
+        for (int j = 0; j < 32; ++j) acc[j] = sb[j];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int y = oy * 2 - 1 + ky;
-        if (y < 0 || y >= h) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int y = oy * 2 - 1 + ky;
+            if (y < 0 || y >= h) continue;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = ox * 2 - 1 + kx;
-            if (xx < 0 || xx >= w) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = ox * 2 - 1 + kx;
+                if (xx < 0 || xx >= w) continue;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float v = stem_fetch<KIND>(x, img, ch, y, xx, h, w);
-                const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float v = stem_fetch<KIND>(x, img, ch, y, xx, h, w);
+                    const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 ww = wr[q];
-                    acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
-                    acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
-                    acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
-                    acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 ww = wr[q];
+                        acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+                        acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+                        acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+                        acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[threadIdx.x * 33 + j] = relu6f(acc[j]);
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = relu6f(acc[j]);
+    __syncthreads();
+    // cooperative copy-out: consecutive threads write consecutive 16-byte pieces of the tile's pixels (the per-thread
+    // version wrote one 128-byte row per lane, 32 lines per store instruction)
     if (out.plane == UAVSAL_PLANE_F32) {                                   // fp32 rows (input of features.1's depthwise conv)
-        float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(out.p) + i * out.ld);
+        float* of = reinterpret_cast<float*>(out.p);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) of[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        for (int k = 0; k < 8; ++k) {
+            const int idx = k * 128 + threadIdx.x, px = idx >> 3, q = idx & 7;
+            if (i0 + px < total) {
+                const float* sp = st + px * 33 + q * 4;
+                *reinterpret_cast<float4*>(of + (i0 + px) * out.ld + q * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+        }
         return;
     }
-    uint16_t* o = out.p + i * out.ld;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) store8(o + q * 8, out.plane, acc + q * 8);
+    for (int k = 0; k < 4; ++k) {
+        const int idx = k * 128 + threadIdx.x, px = idx >> 2, q = idx & 3;
+        if (i0 + px < total) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = st[px * 33 + q * 8 + j];
+            store8(out.p + (i0 + px) * out.ld + q * 8, out.plane, v);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
