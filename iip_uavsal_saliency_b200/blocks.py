@@ -113,6 +113,22 @@ class dwBlock(KernelModule):
         inp, oup, hidden, stride, dil, has_expand = self.geom
         cur = x
         i = 0
+        fuse = getattr(plan, "fuse_expand_dw", "auto")
+        if fuse == "auto":       # measured (profiles/r01_microbench_expdw.txt): the fused kernel wins on the stride-2 high-resolution blocks
+            fuse = stride == 2 and n * h * w >= 200000
+        if has_expand and plan.engine == "tc" and dil == 1 and x.c <= 32 and not x.f32 and fuse:
+            # few input channels: expand + depthwise in one kernel, the 6x hidden tensor never reaches HBM
+            w1, b1 = self.conv[0].folded()
+            wdw, bdw = self.conv[1].folded()
+            ho, wo = out_size(h, stride), out_size(w, stride)
+            cur = plan.alloc(n * ho * wo, hidden)
+            plan.expdw(x, n, h, w, w1.reshape(hidden, inp), b1, stride, pack_dw(wdw), bdw, cur, tag=tag + ".expand+dw")
+            wf, bf = self.project_folded()
+            if oup % 8:
+                raise NotImplementedError("project conv with %d outputs is emitted by the readout path" % oup)
+            out = out if out is not None else plan.alloc(n * ho * wo, oup)
+            plan.pw(cur, n * ho * wo, wf, bf, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
+            return out, ho, wo
         if has_expand:
             # the 6x hidden tensor stays fp32 between the expand GEMM and the TMA depthwise kernel (dilation 1 only)
             cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", f32_out=plan.f32_hidden and dil == 1)

@@ -180,6 +180,21 @@ class Plan:
     def dw(self, x: Buf, n, h, w, c, stride, dil, wgt, bias, relu6, out: Buf, tag=""):
         self._add("uavsal_dw3x3", (*x.act(), n, h, w, c, stride, dil, wgt.data_ptr(), bias.data_ptr(), int(relu6), *out.act()), tag)
 
+    def expdw(self, x: Buf, n, h, w, w1: torch.Tensor, b1: torch.Tensor, stride: int, wd: torch.Tensor, bd: torch.Tensor, out: Buf, tag=""):
+        """Fused 1x1 expand + BN + ReLU6 -> depthwise 3x3 + BN + ReLU6 (cin <= 32).  w1: folded fp32 (hidden, cin_logical)."""
+        hidden, k = w1.shape
+        cin = x.c
+        assert not x.f32 and cin % 8 == 0 and k <= cin <= 32 and hidden % 8 == 0
+        kp = (cin + 15) // 16 * 16
+        hp = (hidden + 63) // 64 * 64
+        full = torch.zeros((hp, kp), dtype=torch.float32, device=w1.device)
+        full[:hidden, :k] = w1
+        bfull = torch.zeros((hp,), dtype=torch.float32, device=w1.device)
+        bfull[:hidden] = b1
+        wp, bp = self.hold(split_bf16(full)), self.hold(bfull)
+        self._add("uavsal_expand_dw3x3", (*x.act(), n, h, w, cin, wp.data_ptr(), kp, bp.data_ptr(), hidden, stride,
+                                          self.hold(wd).data_ptr(), self.hold(bd.float()).data_ptr(), *out.act()), tag)
+
     def pw(self, x: Buf, m: int, w2d: torch.Tensor, bias: Optional[torch.Tensor], flags: int, out: Buf,
            res: Optional[Buf] = None, tag=""):
         """Pointwise conv as GEMM.  w2d: folded fp32 (N, K_logical); x.c may be padded beyond K_logical."""

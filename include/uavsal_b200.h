@@ -75,6 +75,15 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
                  int stride, int dilation, const float* wgt, const float* bias, int relu6,
                  uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
+/* dwBlock conv[0] + conv[1] fused (model.py:90-92; torchvision InvertedResidual): 1x1 expand + BN + ReLU6 followed by the
+ * depthwise 3x3 (pad 1, stride 1|2) + BN + ReLU6, without materialising the expanded tensor.  cin <= 32.
+ * w1: bf16 planes [2][ceil(hidden/64)*64][kp] (K-major, kp = cin rounded up to 16, zero padded), b1: [ceil(hidden/64)*64]
+ * fp32; wd [9][hidden], bd [hidden] as uavsal_dw3x3.  out = (n, ho, wo, hidden) split-bf16. */
+int uavsal_expand_dw3x3(const uint16_t* x, int64_t x_plane, int x_ld, int n, int h, int w, int cin,
+                        const uint16_t* w1, int kp, const float* b1, int hidden, int stride,
+                        const float* wd, const float* bd,
+                        uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
 /* ---- K3: pointwise 1x1 conv + BN (+ReLU6)(+residual)(+sigmoid) (model.py:89,94,120-128,181,184,230).
  *      out[m][n0..] = act( sum_k A[m][k] * W[n][k] + bias[n] ) (+ res[m][n])
  *      tcgen05 version: wgt = bf16 planes [2][n][kpad] (hi, lo), kpad % 8 == 0; terms = 1 (bf16x1) or 3.

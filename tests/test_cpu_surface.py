@@ -92,8 +92,19 @@ def test_plan_structure_of_one_call():
     plan = engine.Plan("cpu", 3, "tc")
     m.build_plan(plan, 20, 360, 640, x_kind=1, post_hw=(360, 640))
     names = [o.name for o in plan.ops]
-    assert names.count("uavsal_pw_gemm") == 76                         # 77 used pointwise convs, the 1536->1 one is the dot
-    assert names.count("uavsal_dw3x3") == 34
+    # 77 used pointwise convs, the 1536->1 one is the dot; the two stride-2 high-resolution dwBlocks (features.2, features.4) run
+    # expand + depthwise fused by default, all eight dwBlocks with <= 32 input channels when asked to
+    assert names.count("uavsal_expand_dw3x3") == 2
+    assert names.count("uavsal_pw_gemm") == 76 - 2 and names.count("uavsal_dw3x3") == 34 - 2
+    pf = engine.Plan("cpu", 3, "tc")
+    pf.fuse_expand_dw = True
+    m.build_plan(pf, 20, 360, 640, x_kind=1, post_hw=(360, 640))
+    assert [o.name for o in pf.ops].count("uavsal_expand_dw3x3") == 8
+    ps = engine.Plan("cpu", 3, "simt")                                 # the SIMT cross-check engine keeps every conv separate
+    m.build_plan(ps, 20, 360, 640, x_kind=1, post_hw=(360, 640))
+    ns = [o.name for o in ps.ops]
+    assert ns.count("uavsal_pw_gemm_simt") == 76 and ns.count("uavsal_dw3x3") == 34 and ns.count("uavsal_expand_dw3x3") == 0
+    assert plan.split == names.index("uavsal_twa_sequence") - 1      # front | back boundary sits before the state pack
     assert names.count("uavsal_conv3x3") == 1 and names.count("uavsal_twa_sequence") == 1
     assert names.count("uavsal_bilinear_ac") == 3 and names.count("uavsal_tdiff_cat") == 2
     assert plan.named["out"].shape == (20, 1, 45, 80) and plan.named["out_u8"].shape == (20, 360, 640)

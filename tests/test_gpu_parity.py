@@ -85,6 +85,25 @@ def test_fp32_hidden_expand_then_depthwise(cuda, cin, ch, s, n, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("cin,ch,s,n,h,w", [(16, 96, 2, 1, 90, 160), (24, 144, 1, 2, 45, 80), (32, 192, 2, 1, 45, 80), (32, 384, 1, 2, 23, 40),
+                                             (20, 120, 1, 1, 45, 80), (16, 96, 1, 1, 7, 5), (24, 40, 1, 1, 17, 33)])
+def test_fused_expand_depthwise(cuda, cin, ch, s, n, h, w):
+    """dwBlock conv[0]+conv[1] in one kernel for cin <= 32 (model.py:90-92): edge tiles, stride 2, ragged channel blocks."""
+    from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+    torch.manual_seed(9)
+    p = _plan()
+    x = torch.randn(n, cin, h, w)
+    w1, b1 = torch.randn(ch, cin) / cin ** 0.5, torch.randn(ch) * 0.1
+    wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+    ho, wo = out_size(h, s), out_size(w, s)
+    ob = p.alloc(n * ho * wo, ch)
+    p.expdw(_upload(p, x), n, h, w, w1.cuda(), b1.cuda(), s, pack_dw(wd), bd, ob)
+    y = _download(p, ob, n, ch, ho, wo)
+    p.run()
+    href = F.hardtanh(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1), 0, 6)
+    assert _rel(y, F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 @pytest.mark.parametrize("m,k,n,relu,res", [(300, 32, 16, 0, 0), (777, 20, 120, 1, 0), (3600, 256, 1536, 1, 0), (3600, 1536, 256, 0, 1),
                                             (500, 8, 48, 1, 0), (129, 320, 1920, 1, 0), (4000, 144, 24, 0, 1), (1, 64, 64, 0, 0)])

@@ -16,7 +16,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["simt_units", "f32_hidden", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
+GROUPS = ["simt_units", "f32_hidden", "expdw", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
 
 
 def rel(a, b):
@@ -197,6 +197,30 @@ def g_f32_hidden():
         report("expand(f32) %d->%d %dx%d hidden" % (cin, ch, h, w), hid.to_float().reshape(n, h, w, ch).permute(0, 3, 1, 2), href, 1e-4)
         ref = F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)
         report("  + dw(f32 in) s=%d" % s, y, ref, 1e-4)
+
+
+def g_expdw():
+    """fused expand + depthwise kernel (cin <= 64) against torch."""
+    import torch
+    import torch.nn.functional as F
+    from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+    torch.manual_seed(9)
+    for (cin, ch, s, n, h, w) in [(16, 96, 2, 1, 90, 160), (24, 144, 1, 2, 45, 80), (24, 144, 2, 2, 45, 80), (32, 192, 1, 2, 45, 80),
+                                  (32, 192, 2, 1, 45, 80), (32, 384, 1, 2, 23, 40), (8, 48, 1, 1, 45, 80), (20, 120, 1, 1, 45, 80),
+                                  (32, 200, 2, 3, 23, 40), (16, 96, 1, 1, 7, 5), (24, 40, 1, 1, 17, 33)]:
+        p = mk_plan("tc")
+        x = torch.randn(n, cin, h, w)
+        w1, b1 = torch.randn(ch, cin) / cin ** 0.5, torch.randn(ch) * 0.1
+        wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+        xb = act_from(p, x)
+        ho, wo = out_size(h, s), out_size(w, s)
+        ob = p.alloc(n * ho * wo, ch)
+        p.expdw(xb, n, h, w, w1.cuda(), b1.cuda(), s, pack_dw(wd), bd, ob)
+        y = fetch(p, ob, n, ch, ho, wo)
+        p.run(); torch.cuda.synchronize()
+        href = F.hardtanh(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1), 0, 6)
+        ref = F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)
+        report("expand+dw %d->%d s=%d n=%d %dx%d" % (cin, ch, s, n, h, w), y, ref, 1e-4)
 
 
 def g_tc_pw():

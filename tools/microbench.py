@@ -53,6 +53,18 @@ def dw(fast, n, h, w, c, stride, f32=False):
     _ext.load().uavsal_set_option(2, 1)
 
 
+def expdw(n, h, w, cin, hidden, stride):
+    p = Plan(dev, 3, "tc")
+    x = p.alloc(n * h * w, cin); x.t.normal_()
+    ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
+    o = p.alloc(n * ho * wo, hidden)
+    p.expdw(x, n, h, w, torch.randn(hidden, cin, device=dev) / cin ** 0.5, torch.zeros(hidden, device=dev), stride,
+            pack_dw(torch.randn(hidden, 1, 3, 3)), torch.zeros(hidden), o)
+    ms = timeit(p)
+    by = 4.0 * n * (h * w * cin + ho * wo * hidden)
+    print("expand+dw n=%d %dx%d cin=%d hidden=%d s=%d: %.1f us  %.0f GB/s (in+out)" % (n, h, w, cin, hidden, stride, ms * 1e3, by / ms / 1e6), flush=True)
+
+
 def conv(engine, n, h, w, c, co, terms=3):
     p = Plan(dev, terms, engine)
     x = p.alloc(n * h * w, c); x.t.normal_()
@@ -93,6 +105,11 @@ def main():
         conv("tc", 20, 45, 80, 448, 256); twa("tc", 20, 45, 80, 256)
         for f in (False, True):
             dw(2, 20, 45, 80, 1536, 1, f); dw(2, 20, 180, 320, 96, 2, f); dw(2, 20, 180, 320, 32, 1, f); dw(2, 20, 90, 160, 144, 1, f); dw(2, 20, 23, 40, 384, 1, f)
+    if what == "expdw":
+        expdw(20, 180, 320, 16, 96, 2); expdw(20, 90, 160, 24, 144, 1); expdw(20, 90, 160, 24, 144, 2); expdw(20, 45, 80, 32, 192, 1)
+        expdw(20, 45, 80, 32, 192, 2)
+    if what == "expdw1":
+        expdw(20, 45, 80, 64, 384, 1)
     if what == "stages":
         lib = _ext.load()
         for st in (1, 2, 3, 6):
