@@ -462,7 +462,7 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     g.a0_mul = a0_mul; g.a0_off = a0_off; g.a1_mul = a1_mul; g.a1_off = a1_off; g.out_mul = out_mul; g.out_off = out_off;
     g.M = batch * H * W; g.N = cout; g.bn = pick_bn(cout);
     const int tiles_m_ = batch * g.tiles_x * g.tiles_y;
-    const bool v2 = g_tc_version == 2 && epi != EPI_LSTM;
+    const bool v2 = g_tc_version == 2;
     UAVSAL_REQUIRE(v2 || epi != EPI_RAW, UAVSAL_ENOTSUP, "%s: raw output needs the persistent kernel", what);
     if (v2) {   // small problems (one image per step in the recurrence): narrower N tiles so that more SMs get a tile
         while (g.bn > 64 && g.bn % 128 == 0 && tiles_m_ * div_up(cout, g.bn) < 100) g.bn /= 2;
@@ -483,11 +483,12 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     if (rc) return rc;
     if (v2) {
         CUtensorMap tO;
-        if (epi == EPI_RAW) tO = tA0;
+        if (epi == EPI_RAW || epi == EPI_LSTM) tO = tA0;          // (the output map is only kept for TMA-store experiments)
         else rc = map_out_img(&tO, out, out_nimg, H, W, cout, tw, th);
         if (rc) return rc;
         if (epi == EPI_STD) return launch_tc2<MODE_CONV, EPI_STD>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
         if (epi == EPI_RAW) return launch_tc2<MODE_CONV, EPI_RAW>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
+        if (epi == EPI_LSTM) return launch_tc2<MODE_CONV, EPI_LSTM>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
         return launch_tc2<MODE_CONV, EPI_TWA>(tA0, tA1, tB, tO, g, terms, tiles_m, cl, s, what);
     }
     if (epi == EPI_STD) return launch_tc<MODE_CONV, EPI_STD>(tA0, tA1, tB, g, terms, tiles_m, s, what);

@@ -264,6 +264,35 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                                 o[3] = make_float4(v[12], v[13], v[14], v[15]);
                             }
                         }
+                    } else if (EPI == EPI_LSTM) {
+                        // interleaved gates (i,f,o,g) x 4 channels per 16-column piece; c' = s(f)c + s(i)tanh(g); h' = s(o)tanh(c')
+                        // (model_convlstm.py:117-124).  c state fp32 in place; h goes straight to the output sequence.
+                        if (live) {
+                            if (g.bias) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    if (j4 >= 2 && !second) break;
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
+                                    v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+                                }
+                            }
+                            const int nch = g.N >> 2, chn = n >> 2;
+                            const int64_t crow = orow - (int64_t)(img_out - bidx) * g.H * g.W;
+                            float* cs = g.c_state + crow * nch + chn;
+                            const int cnt = second ? 4 : 2;
+                            float hout[4];
+                            for (int j = 0; j < cnt; ++j) {
+                                const float gi = sigmoid_acc(v[4 * j + 0]), gf = sigmoid_acc(v[4 * j + 1]);
+                                const float go = sigmoid_acc(v[4 * j + 2]), gg = tanhf(v[4 * j + 3]);
+                                const float cn = gf * cs[j] + gi * gg;
+                                cs[j] = cn;
+                                hout[j] = go * tanhf(cn);
+                            }
+                            if (do_store) {
+                                if (second) store4(g.out.p + orow * g.out.ld + chn, g.out.plane, hout);
+                                else { store1(g.out.p + orow * g.out.ld + chn, g.out.plane, hout[0]); store1(g.out.p + orow * g.out.ld + chn + 1, g.out.plane, hout[1]); }
+                            }
+                        }
                     } else {
                         if (live) {
                             if (g.bias) {

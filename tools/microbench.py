@@ -85,6 +85,26 @@ def twa(engine, t, h, w, c):
     print("twa[%s] t=%d %dx%d c=%d: %.1f us total, %.1f us/step, %.1f TF/s(alg)" % (engine, t, h, w, c, ms * 1e3, ms * 1e3 / t, 2.0 * t * h * w * 9 * 2 * c * c / ms / 1e9), flush=True)
 
 
+def lstm(b, t, h, w, c, terms=3):
+    """BASELINE config #3: ConvLSTM((h,w), c, c, (3,3), 1, batch_first=True, bias=False), x (b,t,c,h,w), h0 = c0 = 0."""
+    p = Plan(dev, terms, "tc")
+    x = p.alloc(b * t * h * w, c); x.t.normal_()
+    h0 = p.alloc(b * h * w, c)
+    cst = p.tensor((b, h * w, c))
+    seq = p.alloc(b * t * h * w, c)
+    wgt = torch.empty(4 * c, 2 * c, 3, 3, device=dev)
+    torch.nn.init.xavier_uniform_(wgt)
+    p.lstm(x, h0, cst, b, t, h, w, c, c, wgt, None, seq)
+    p.run(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    cst.zero_()
+    e0.record(); p.run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    fl = 2.0 * b * h * w * 4 * c * 9 * 2 * c * t
+    print("convlstm[tc,t%d] b=%d t=%d %dx%d c=%d: %.2f ms total, %.1f us/step, %.1f TF/s(alg), %.1f TF/s(issued)" %
+          (terms, b, t, h, w, c, ms, ms * 1e3 / t, fl / ms / 1e9, terms * fl / ms / 1e9), flush=True)
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     M = 72000
@@ -110,6 +130,8 @@ def main():
         expdw(20, 45, 80, 32, 192, 2)
     if what == "expdw1":
         expdw(20, 45, 80, 64, 384, 1)
+    if what == "lstm":
+        lstm(8, 64, 45, 80, 256); lstm(8, 64, 45, 80, 256, terms=1)
     if what == "stages":
         lib = _ext.load()
         for st in (1, 2, 3, 6):
