@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -243,6 +243,7 @@ def run_product_arm(args):
     launches = sum(model.get_plan(dev, n, H, W, x_kind=2, post_hw=(H, W), cb_shared=True).num_launches for n in calls)
 
     if rank != 0:
+        D.shutdown()
         return 0
 
     # ---- roofline of the dominant kernel class (the tcgen05 pointwise GEMM), timed per launch with CUDA events ----
@@ -321,6 +322,7 @@ def run_product_arm(args):
             "gpu_launches": launches * args.clips * args.steps, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "breakdown_20_frame_call": breakdown, "hbm_peak_gbs": hbm_peak}
     print(json.dumps(line), flush=True)
+    D.shutdown()
     return 0
 
 

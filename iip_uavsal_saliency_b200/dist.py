@@ -25,8 +25,16 @@ def init_process_group(backend: Optional[str] = None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
+
+
+def shutdown():
+    """Tear the process group down (quietens NCCL's leak warning at interpreter exit)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:

@@ -70,6 +70,7 @@ def main():
                           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4)},
                           "means": {k: float(v) for k, v in zip(("CC", "NSS", "KLD", "SIM"), means.tolist())},
                           "inputs": "%d pairs per rank (64 distinct, tiled) resident in HBM: %.1f GB > L2" % (mine, by * mine / 1e9)}), flush=True)
+    D.shutdown()
 
 
 if __name__ == "__main__":
