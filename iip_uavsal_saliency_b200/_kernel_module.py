@@ -63,7 +63,7 @@ class KernelModule(nn.Module):
         cache = self._plan_cache()
         plan = cache.get(full)
         if plan is None:
-            if len(cache) > 8:
+            if len(cache) > 32:
                 cache.clear()
             dev = key[0]
             plan = Plan(dev, terms=terms, engine=engine)

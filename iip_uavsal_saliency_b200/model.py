@@ -201,16 +201,30 @@ class UAVSal(KernelModule):
 
     # -----------------------------------------------------------------------------------------------
     def build_plan(self, plan: Plan, n: int, h: int, w: int, x_kind: int = 0, post_hw=None, taps: bool = False,
-                   cb_shared: bool = False):
+                   cb_shared: bool = False, stage: str = "all"):
         """Emit the whole forward for a call of n frames of (h, w) pixels.
         x_kind: 0 fp32 NCHW normalised, 1 uint8 NCHW raw, 2 uint8 NHWC raw.  post_hw=(H,W) adds the uint8 post-process.
-        cb_shared: cb tensors hold ONE frame that is broadcast to all n (Demo_Test's np.repeat'ed priors)."""
+        cb_shared: cb tensors hold ONE frame that is broadcast to all n (Demo_Test's np.repeat'ed priors).
+        stage: "all" (a reference call), "sfnet" (only the per-frame SRF-Net, any n: frames are independent there, so a
+        runner may batch a whole clip), "head" (everything after the SRF-Net, fed from the arena input ``sf_in``)."""
         planes, T = self._planes, self.time_dims
-        if n % T:
+        assert stage in ("all", "sfnet", "head")
+        if n % T and stage != "sfnet":
             raise ValueError("call batch %d is not a multiple of time_dims=%d (model.py:356-357)" % (n, T))
         tp = {} if taps else None
-        x_in = plan.tensor((n, 3, h, w) if x_kind < 2 else (n, h, w, 3), torch.float32 if x_kind == 0 else torch.uint8)
-        x, mh, mw = self.sfnet._emit_from_input(plan, x_in, x_kind, n, h, w, taps=tp)
+        if stage == "head":
+            mh, mw = self._iosize[2], self._iosize[3]
+            if (out_size(out_size(out_size(h, 2), 2), 2), out_size(out_size(out_size(w, 2), 2), 2)) != (mh, mw):
+                mh, mw = out_size(out_size(out_size(h, 2), 2), 2), out_size(out_size(out_size(w, 2), 2), 2)
+            x = plan.alloc(n * mh * mw, planes)
+            x_in = None
+            plan.named["sf_in"] = x
+        else:
+            x_in = plan.tensor((n, 3, h, w) if x_kind < 2 else (n, h, w, 3), torch.float32 if x_kind == 0 else torch.uint8)
+            x, mh, mw = self.sfnet._emit_from_input(plan, x_in, x_kind, n, h, w, taps=tp)
+            if stage == "sfnet":
+                plan.named.update(x_in=x_in, sf_out=x, map_hw=(mh, mw))
+                return plan
         for i, blk in enumerate(self.st_layer):
             x, _, _ = blk._emit(plan, x, n, mh, mw, tag="st%d" % i)
             if taps:
@@ -298,10 +312,10 @@ class UAVSal(KernelModule):
         plan.named.update(named)
         return plan
 
-    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0) -> Plan:
+    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0, stage="all") -> Plan:
         """``slot`` selects one of several independent plan instances (own arena) so that calls can be in flight together."""
-        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot)
-        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared))
+        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot, stage)
+        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared, stage))
 
     def forward(self, x, cb, in_state):
         require_cuda(x, "UAVSal")

@@ -7,6 +7,12 @@ uint8 frames in -> uint8 saliency maps out.
   * the ConvTWA hidden state is handed from call to call (Demo_Test.py:75,85-86);
   * priors are one (h,w,C) map broadcast to every frame, as get_bias builds them (Demo_Test.py:14-27).
 
+Batching.  The SRF-Net (backbone + ASPP + 3x3 fuse, model.py:139-158) treats every frame independently, so with
+``clip_backbone=True`` (default) it runs ONCE over all kept frames of a clip (stage "sfnet" plan) and the per-call plans
+(stage "head": ST blocks, prior fusion, ConvTWA, readout) read their 20-frame slices of its output.  The 12x20 / 23x40
+layers of MobileNetV2 are launch-latency-bound at 20 frames; at 60 they do three times the work in about the same time.
+Per-frame results are unchanged (eval-mode BN, no cross-frame op before the ST blocks).
+
 Scheduling.  Only the recurrent tail of a call (ConvTWA -> readout -> post-process, the plan's "back" part) depends on
 the previous call; everything before it (the "front": backbone, SRF-Net, ST blocks, prior fusion) does not.  The runner
 therefore keeps ``depth`` plan instances (own arenas) and runs fronts on ``depth`` CUDA streams while one "back" stream
@@ -26,9 +32,11 @@ from .model import UAVSal
 
 class ClipRunner:
     def __init__(self, model: UAVSal, gauss: np.ndarray, ob: np.ndarray, batch_size: int = 4, out_hw: Optional[Tuple[int, int]] = None,
-                 use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2):
+                 use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2, clip_backbone: bool = True,
+                 single_stream: bool = False):
         """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw';
-        depth = calls in flight (1 = strictly serial on the caller's stream order)."""
+        depth = calls in flight (1 = strictly serial on the caller's stream order); clip_backbone: run the SRF-Net once per
+        clip instead of once per call."""
         self.model = model
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -41,21 +49,30 @@ class ClipRunner:
         self.depth = max(1, int(depth))
         self.gauss = torch.from_numpy(np.ascontiguousarray(gauss.transpose(2, 0, 1)[None])).float().to(self.dev)
         self.ob = torch.from_numpy(np.ascontiguousarray(ob.transpose(2, 0, 1)[None])).float().to(self.dev)
-        self.front_streams = [torch.cuda.Stream(self.dev) for _ in range(self.depth)]
-        self.back_stream = torch.cuda.Stream(self.dev)
+        # single_stream: queue everything on ONE side stream in program order (no overlap between stages)
+        one = torch.cuda.Stream(self.dev) if single_stream else None
+        self.front_streams = [one or torch.cuda.Stream(self.dev) for _ in range(self.depth)]
+        self.back_stream = one or torch.cuda.Stream(self.dev)
         self._slot_free = [None] * self.depth          # event: the slot's previous call has left the back stream
         self._calls = 0
+        self.clip_backbone = bool(clip_backbone)
+        self.bb_stream = one or torch.cuda.Stream(self.dev)
+        self._sf_free = [[], []]                       # events: the heads of the previous clip on this slot have read its SRF-Net output
+        self._clips = 0
 
-    def _plan(self, n, H, W, slot):
+    def _plan(self, n, H, W, slot, stage=None):
         post = self.out_hw or (H, W)
-        plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=post, cb_shared=True, slot=slot)
+        stage = stage or ("head" if self.clip_backbone else "all")
+        plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=None if stage == "sfnet" else post, cb_shared=True,
+                                   slot=slot, stage=stage)
         if "ready" not in plan.named:
             torch.cuda.synchronize(self.dev)
-            if self.model.use_gauss_prior:
-                plan.named["cb_gauss_in"].copy_(self.gauss)
-            if self.model.use_ob_prior:
-                plan.named["cb_ob_in"].copy_(self.ob)
-            plan.named["h_in"].zero_()
+            if stage != "sfnet":
+                if self.model.use_gauss_prior:
+                    plan.named["cb_gauss_in"].copy_(self.gauss)
+                if self.model.use_ob_prior:
+                    plan.named["cb_ob_in"].copy_(self.ob)
+                plan.named["h_in"].zero_()
             if self.use_graph:
                 plan.capture()
             torch.cuda.synchronize(self.dev)
@@ -69,11 +86,15 @@ class ClipRunner:
         for slot in range(self.depth):
             for n in sizes:
                 self._plan(n, H, W, slot)
+        if self.clip_backbone:
+            for sslot in range(2):
+                self._plan(keep, H, W, sslot, "sfnet")
 
     def finish(self):
         """Make the caller's stream wait for everything the runner has queued (needed after run_clip(sync=False))."""
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_stream(self.back_stream)
+        cur.wait_stream(self.bb_stream)
         for s in self.front_streams:
             cur.wait_stream(s)
 
@@ -90,11 +111,29 @@ class ClipRunner:
         for i in range(ncalls):                                     # build before queueing (capture synchronises)
             n = min(keep, (i + 1) * self.per_call) - i * self.per_call
             plans.append(self._plan(n, H, W, (self._calls + i) % self.depth))
+        sf = sslot = None
+        if self.clip_backbone:
+            sslot = self._clips % 2
+            self._clips += 1
+            sf = self._plan(keep, H, W, sslot, "sfnet")
         cur = torch.cuda.current_stream(self.dev)
         ready = torch.cuda.Event()
         ready.record(cur)                                           # inputs / `out` are ordered after the caller's stream
         bs = self.back_stream
         bs.wait_event(ready)
+        sf_done = None
+        if sf is not None:                                          # SRF-Net over the whole clip, on its own stream
+            bbs = self.bb_stream
+            bbs.wait_event(ready)
+            for ev in self._sf_free[sslot]:
+                bbs.wait_event(ev)
+            self._sf_free[sslot] = []
+            with torch.cuda.stream(bbs):
+                sf.named["x_in"].copy_(frames[:keep], non_blocking=True)
+                sf.launch()
+                sf_done = torch.cuda.Event()
+                sf_done.record(bbs)
+            mh, mw = sf.named["map_hw"]
         maps, u8s = [], []
         state = None
         done = 0
@@ -110,7 +149,15 @@ class ClipRunner:
             if self._slot_free[slot] is not None:
                 fs.wait_event(self._slot_free[slot])
             with torch.cuda.stream(fs):
-                nm["x_in"].copy_(chunk, non_blocking=True)
+                if sf is not None:
+                    fs.wait_event(sf_done)
+                    r0 = i * self.per_call * mh * mw
+                    nm["sf_in"].t.copy_(sf.named["sf_out"].t[:, r0:r0 + n * mh * mw], non_blocking=True)
+                    rd = torch.cuda.Event()
+                    rd.record(fs)
+                    self._sf_free[sslot].append(rd)
+                else:
+                    nm["x_in"].copy_(chunk, non_blocking=True)
                 plan.launch("front")
                 fdone = torch.cuda.Event()
                 fdone.record(fs)

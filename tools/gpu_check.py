@@ -403,7 +403,7 @@ def g_runner():
     clips = [clip] + [torch.from_numpy(synth.make_clip(20 + i, 64, 360, 640)).cuda() for i in range(2)]
     outs = {}
     for depth in (1, 3):
-        rr = ClipRunner(m, gauss, ob, batch_size=4, depth=depth)
+        rr = ClipRunner(m, gauss, ob, batch_size=4, depth=depth, clip_backbone=(depth != 1))   # serial per-call reference vs batched + pipelined
         rr.warm(64, 360, 640)
         bufs = [torch.empty(60, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
         for c, b in zip(clips, bufs):
@@ -419,7 +419,7 @@ def g_runner():
             rr.finish()
             torch.cuda.synchronize()
             dt = (time.time() - t0) / 12
-        print("RUNNER depth=%d: 64-frame clip %.2f ms -> %.1f frames/s (60 outputs)" % (depth, dt * 1e3, 60 / dt), flush=True)
+        print("RUNNER depth=%d clip_backbone=%s: 64-frame clip %.2f ms -> %.1f frames/s (60 outputs)" % (depth, depth != 1, dt * 1e3, 60 / dt), flush=True)
     same = all(torch.equal(a, b) for a, b in zip(outs[1], outs[3]))
     same0 = torch.equal(outs[1][0], torch.from_numpy(u8))
     print("RUNNER pipelined == serial: %s, == sync run: %s  %s" % (same, same0, "ok" if same and same0 else "FAIL"), flush=True)
