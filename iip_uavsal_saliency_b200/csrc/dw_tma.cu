@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * G::TILE_BYTES);      // [2]
 
     const int tid = threadIdx.x;
+    pdl_trigger();
     if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
     __syncthreads();
+    pdl_wait();                                                                // the input tensor is the previous kernel's output
 
     auto decode = [&](int t, int& cblk, int& x0, int& y0, int& img) {
         int r = t;
@@ -175,7 +177,8 @@ static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = g.num_tiles < sms * 2 ? g.num_tiles : sms * 2;           // 2 resident CTAs per SM (registers, 2 x 92 KiB smem)
-    dw3x3_tma_kernel<STRIDE, F32IN><<<grid, 256, smem, s>>>(tm, g);
+    cudaError_t e = launch_k(dw3x3_tma_kernel<STRIDE, F32IN>, dim3(grid), dim3(256), smem, s, 1, tm, g);
+    if (e != cudaSuccess) { set_error("dw3x3(tma): launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("dw3x3(tma)");
 }
 

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
     const int kchunks = g.kp >> 3;
     // staging map: 16 consecutive threads serve one row (pixel / weight row): chunk lc of plane lp
     const int lrow = tid >> 4, lp = tid & 1, lc = (tid & 15) >> 1;
+    pdl_trigger();
     // zero the K padding columns once (they are multiplied by zero weights, but must not hold NaN bit patterns)
     if (lc >= cpp && lc < kchunks)
         for (int r = lrow; r < G::ROWS; r += 16) sts128((lp ? xs_lo : xs_hi) + r * kpitch + lc * 16, 0, 0, 0, 0);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
     const int quad = tid & 15;
     const int col = (tid >> 4) % G::TW;
     const int rgrp = (tid >> 4) / G::TW;
+    pdl_wait();
     for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
         int r = t;
         const int cg = r % g.cgroups; r /= g.cgroups;
@@ -264,7 +266,8 @@ static int launch_expdw(ExpDwArgs& g, cudaStream_t s) {
         attr = smem;
     }
     const int grid = g.num_tiles < sms * 2 ? g.num_tiles : sms * 2;
-    expdw_kernel<STRIDE><<<grid, 256, smem, s>>>(g);
+    cudaError_t e = launch_k(expdw_kernel<STRIDE>, dim3(grid), dim3(256), smem, s, 1, g);
+    if (e != cudaSuccess) { set_error("expand_dw3x3: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("expand_dw3x3");
 }
 

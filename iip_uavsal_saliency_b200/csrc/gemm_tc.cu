@@ -361,29 +361,25 @@ static int launch_tc2_inst(const CUtensorMap& a0, const CUtensorMap& a1, const C
         if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
-    if (CL == 1) {
-        gemm_tc2_kernel<MODE, EPI, TERMS, CL><<<grid, kThreads2, smem, s>>>(a0, a1, b, o, g);
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+    int grid_x = grid;
+    if (CL > 1) {
         // the persistent tile walk assumes every cluster is resident at once: clamp the grid to what the GPCs can co-schedule
         static int max_clusters = 0;
         if (!max_clusters) {
-            cudaLaunchConfig_t q = cfg;
-            q.gridDim = dim3((num_sms() / CL) * CL);
-            q.dynamicSmemBytes = 227 * 1024 - 1024;
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3((num_sms() / CL) * CL); q.blockDim = dim3(kThreads2); q.dynamicSmemBytes = 227 * 1024 - 1024; q.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
             int n = 0;
             if (cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<MODE, EPI, TERMS, CL>, &q) != cudaSuccess || n <= 0) { n = num_sms() / CL - 2; cudaGetLastError(); }
             max_clusters = n;
         }
-        if (grid > max_clusters * CL) cfg.gridDim = dim3(max_clusters * CL);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<MODE, EPI, TERMS, CL>, a0, a1, b, o, g);
-        if (e != cudaSuccess) { set_error("%s: cudaLaunchKernelEx: %s", what, cudaGetErrorString(e)); return (int)e; }
+        if (grid_x > max_clusters * CL) grid_x = max_clusters * CL;
     }
+    cudaError_t e = launch_k(gemm_tc2_kernel<MODE, EPI, TERMS, CL>, dim3(grid_x), dim3(kThreads2), smem, s, CL, a0, a1, b, o, g);
+    if (e != cudaSuccess) { set_error("%s: cudaLaunchKernelEx: %s", what, cudaGetErrorString(e)); return (int)e; }
     return check_launch(what);
 }
 
@@ -519,6 +515,7 @@ int uavsal_set_option(int key, int value) {
     if (key == 3) { g_tc_debug = value & 0xF0000; return 0; }
     if (key == 4 && (value == 1 || value == 2)) { g_tc_cluster = value; return 0; }
     if (key == 5 && value >= 1 && value <= 8) { g_tc_max_stages = value; return 0; }
+    if (key == 6 && (value == 0 || value == 1)) { g_pdl = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }

@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                                           // peers' barriers are initialised
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                               // everything above overlapped the previous kernel's tail; operands are its outputs
 
     // tile decomposition shared by all roles (work item t -> 128-row tile of this CTA; may be == tiles_m for the odd one out)
     auto tile_coords = [&](int t, int& tile_m, int& n0, int& bidx, int& y0, int& x0) {

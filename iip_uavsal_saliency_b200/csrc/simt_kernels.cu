@@ -21,6 +21,8 @@ void set_error(const char* fmt, ...) {
 // layout conversion
 // ---------------------------------------------------------------------------------------------------
 __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int hw, ActW dst, int cpad) {
+    pdl_trigger();
+    pdl_wait();
     const int groups = cpad >> 3;
     const int64_t total = (int64_t)n * hw * groups;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,6 +41,8 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
 }
 
 __global__ void unpack_nchw_kernel(Act src, int n, int c, int hw, float* __restrict__ dst) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)n * c * hw;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int p = (int)(i % hw);
@@ -72,6 +76,8 @@ template <int KIND>
 __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, int n, int h, int w, int ho, int wo,
                                                    const float* __restrict__ wgt, const float* __restrict__ bias,
                                                    ActW out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sw[27 * 8];
     __shared__ float sb[32];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
 __global__ void __launch_bounds__(256) dw3x3_kernel(Act in, int n, int h, int w, int c, int ho, int wo, int stride,
                                                     int dil, const float* __restrict__ wgt,
                                                     const float* __restrict__ bias, int relu6, ActW out) {
+    pdl_trigger();
+    pdl_wait();
     const int groups = c >> 3;
     const int64_t total = (int64_t)n * ho * wo * groups;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +304,8 @@ __global__ void __launch_bounds__(256, 2) dw3x3_rows_kernel(Act in, int h, int w
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int hs, int ws, int c, ActW out,
                                                           int n_dst, int hd, int wd, float ry, float rx) {
+    pdl_trigger();
+    pdl_wait();
     const int groups = c >> 3;
     const int64_t total = (int64_t)n_dst * hd * wd * groups;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,6 +340,8 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int
 //   second half: x[i]-x[i+1]   (i=n-1: x[n-2]-x[n-1])
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, int c, ActW out) {
+    pdl_trigger();
+    pdl_wait();
     const int groups = c >> 3;
     const int64_t total = (int64_t)n * hw * groups;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +367,8 @@ __global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, i
 
 // context prior: sum over the T frames of each chunk [model.py:357-358]
 __global__ void __launch_bounds__(256) ctx_sum_kernel(Act in, int b, int t, int hw, int c, ActW out) {
+    pdl_trigger();
+    pdl_wait();
     const int groups = c >> 3;
     const int64_t total = (int64_t)b * hw * groups;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,6 +406,8 @@ __global__ void __launch_bounds__(256) add_kernel(Act a, Act b, int64_t rows, in
 // readout project (k -> 1) + BN + sigmoid: one warp per row [conv_out_st.conv.2/.3, model.py:373]
 __global__ void __launch_bounds__(256) dot_sigmoid_kernel(Act a, int64_t rows, int k, const float* __restrict__ wgt,
                                                           float bias, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -444,6 +460,8 @@ __device__ __forceinline__ float post_value(const float* __restrict__ m, const P
 
 __global__ void __launch_bounds__(256) post_max_kernel(const float* __restrict__ maps, PostGeom g,
                                                        float* __restrict__ frame_max) {
+    pdl_trigger();
+    pdl_wait();
     const int img = blockIdx.y;
     const float* m = maps + (int64_t)img * g.hs * g.ws;
     const int total = g.hd * g.wd;
@@ -464,6 +482,8 @@ __global__ void __launch_bounds__(256) post_max_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) post_write_kernel(const float* __restrict__ maps, PostGeom g,
                                                          const float* __restrict__ frame_max,
                                                          uint8_t* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int img = blockIdx.y;
     const float* m = maps + (int64_t)img * g.hs * g.ws;
     const float mx = frame_max[img];
@@ -486,6 +506,8 @@ __global__ void __launch_bounds__(256) post_write_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) post_write_f32_kernel(const float* __restrict__ maps, PostGeom g,
                                                              const float* __restrict__ frame_max,
                                                              float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int img = blockIdx.y;
     const float* m = maps + (int64_t)img * g.hs * g.ws;
     const float mx = frame_max[img];
@@ -502,6 +524,7 @@ __global__ void __launch_bounds__(256) post_write_f32_kernel(const float* __rest
 // ===================================================================================================
 using namespace uavsal;
 
+namespace uavsal { int g_pdl = 1; }
 int g_dw_fast = 2;     // uavsal_set_option key 2: 2 = TMA-staged depthwise kernel (default), 1 = sliding window, 0 = generic
 namespace uavsal {
 int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, const float* bias, int relu6, ActW out,
@@ -532,7 +555,7 @@ int uavsal_pack_nchw_f32(const float* src, int n, int c, int h, int w, uint16_t*
     UAVSAL_REQUIRE(src && act_ok(dst, plane, ld) && cpad % 8 == 0 && cpad >= c && ld >= cpad && n > 0, UAVSAL_EINVAL,
                    "pack_nchw_f32: bad arguments");
     const int64_t total = (int64_t)n * h * w * (cpad / 8);
-    pack_nchw_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h * w, ActW{dst, plane, ld}, cpad);
+    launch_k(pack_nchw_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, src, n, c, h * w, ActW{dst, plane, ld}, cpad);
     return check_launch("pack_nchw_f32");
 }
 
@@ -540,7 +563,7 @@ int uavsal_unpack_nchw_f32(const uint16_t* src, int64_t plane, int ld, int n, in
                            void* stream) {
     UAVSAL_REQUIRE(dst && src && ld >= c && n > 0, UAVSAL_EINVAL, "unpack_nchw_f32: bad arguments");
     const int64_t total = (int64_t)n * c * h * w;
-    unpack_nchw_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{src, plane, ld}, n, c, h * w, dst);
+    launch_k(unpack_nchw_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{src, plane, ld}, n, c, h * w, dst);
     return check_launch("unpack_nchw_f32");
 }
 
@@ -555,9 +578,9 @@ int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const 
     const dim3 grid(div_up(total, 128));
     ActW o{out, out_plane, out_ld};
     cudaStream_t s = (cudaStream_t)stream;
-    if (x_kind == 0) stem_kernel<0><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
-    else if (x_kind == 1) stem_kernel<1><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
-    else stem_kernel<2><<<grid, 128, 0, s>>>(x, n, h, w, ho, wo, wgt, bias, o);
+    if (x_kind == 0) launch_k(stem_kernel<0>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
+    else if (x_kind == 1) launch_k(stem_kernel<1>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
+    else launch_k(stem_kernel<2>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
     return check_launch("stem_conv3x3s2");
 }
 
@@ -590,7 +613,7 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
         }
     }
     const int64_t total = (int64_t)n * ho * wo * (c / 8);
-    dw3x3_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n, h, w, c, ho, wo,
+    launch_k(dw3x3_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n, h, w, c, ho, wo,
                                                                       stride, dilation, wgt, bias, relu6,
                                                                       ActW{out, out_plane, out_ld});
     return check_launch("dw3x3");
@@ -604,7 +627,7 @@ int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_sr
     const float ry = hd > 1 ? (float)(hs - 1) / (float)(hd - 1) : 0.f;
     const float rx = wd > 1 ? (float)(ws - 1) / (float)(wd - 1) : 0.f;
     const int64_t total = (int64_t)n_dst * hd * wd * (c / 8);
-    bilinear_ac_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n_src, hs, ws, c,
+    launch_k(bilinear_ac_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n_src, hs, ws, c,
                                                                             ActW{out, out_plane, out_ld}, n_dst, hd, wd,
                                                                             ry, rx);
     return check_launch("bilinear_ac");
@@ -616,7 +639,7 @@ int uavsal_tdiff_cat(const uint16_t* in, int64_t in_plane, int in_ld, int n, int
                    UAVSAL_EINVAL, "tdiff_cat: bad arguments");
     UAVSAL_REQUIRE(n >= 2, UAVSAL_EINVAL, "tdiff_cat: needs at least 2 frames per call (model.py:194 indexes x1[1])");
     const int64_t total = (int64_t)n * hw * (c / 8);
-    tdiff_cat_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, n, hw, c,
+    launch_k(tdiff_cat_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n, hw, c,
                                                                           ActW{out, out_plane, out_ld});
     return check_launch("tdiff_cat");
 }
@@ -626,7 +649,7 @@ int uavsal_ctx_sum(const uint16_t* in, int64_t in_plane, int in_ld, int b, int t
     UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && b > 0 && t > 0,
                    UAVSAL_EINVAL, "ctx_sum: bad arguments");
     const int64_t total = (int64_t)b * hw * (c / 8);
-    ctx_sum_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(Act{in, in_plane, in_ld}, b, t, hw, c,
+    launch_k(ctx_sum_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, b, t, hw, c,
                                                                         ActW{out, out_plane, out_ld});
     return check_launch("ctx_sum");
 }
@@ -645,7 +668,7 @@ int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t row
                        float* out_f32, void* stream) {
     UAVSAL_REQUIRE(act_ok(a, a_plane, a_ld) && wgt && aligned16(wgt) && out_f32 && k % 8 == 0 && k > 0 && rows > 0,
                    UAVSAL_EINVAL, "dot_sigmoid: bad arguments");
-    dot_sigmoid_kernel<<<div_up(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(Act{a, a_plane, a_ld}, rows, k, wgt, bias,
+    launch_k(dot_sigmoid_kernel, dim3(div_up(rows * 32, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{a, a_plane, a_ld}, rows, k, wgt, bias,
                                                                                 out_f32);
     return check_launch("dot_sigmoid");
 }
@@ -674,9 +697,9 @@ static int post_common(const float* maps, int n, int hs, int ws, int hd, int wd,
     cudaError_t e = cudaMemsetAsync(frame_max, 0, sizeof(float) * n, s);
     if (e != cudaSuccess) { set_error("post_u8 memset: %s", cudaGetErrorString(e)); return (int)e; }
     const int bpf = max(1, min(64, div_up((int64_t)hd * wd, 256 * 16)));
-    post_max_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max);
-    if (out_u8) post_write_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max, out_u8);
-    else        post_write_f32_kernel<<<dim3(bpf, n), 256, 0, s>>>(maps, g, frame_max, out_f32);
+    launch_k(post_max_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max);
+    if (out_u8) launch_k(post_write_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max, out_u8);
+    else        launch_k(post_write_f32_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max, out_f32);
     return check_launch("post");
 }
 
