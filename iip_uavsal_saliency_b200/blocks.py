@@ -133,6 +133,16 @@ class dwBlock(KernelModule):
             # the 6x hidden tensor stays fp32 between the expand GEMM and the TMA depthwise kernel (dilation 1 only)
             cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", f32_out=plan.f32_hidden and dil == 1)
             i = 1
+        fuse_dp = getattr(plan, "fuse_dw_project", "auto")
+        if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
+            fuse_dp = n * h * w >= 32768
+        if (fuse_dp and has_expand and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and hidden % 64 == 0 and
+                oup % 64 == 0 and oup <= 256):
+            wdw, bdw = self.conv[1].folded()
+            wf, bf = self.project_folded()
+            out = out if out is not None else plan.alloc(n * h * w, oup)
+            plan.dwproj(cur, n, h, w, pack_dw(wdw), bdw, wf, bf, out, res=x if self.use_res_connect else None, tag=tag + ".dw+project")
+            return out, h, w
         cur, ho, wo = self.conv[i]._emit(plan, cur, n, h, w, tag=tag + ".dw")
         wf, bf = self.project_folded()
         if oup % 8:

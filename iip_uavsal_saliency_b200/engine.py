@@ -195,6 +195,18 @@ class Plan:
         self._add("uavsal_expand_dw3x3", (*x.act(), n, h, w, cin, wp.data_ptr(), kp, bp.data_ptr(), hidden, stride,
                                           self.hold(wd).data_ptr(), self.hold(bd.float()).data_ptr(), *out.act()), tag)
 
+    def dwproj(self, hid: Buf, n, h, w, wd: torch.Tensor, bd: torch.Tensor, w2d: torch.Tensor, bias: torch.Tensor, out: Buf,
+               res: Optional[Buf] = None, tag=""):
+        """Fused depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (+ residual) from the fp32 hidden tensor (stride 1)."""
+        cout, hidden = w2d.shape
+        assert hid.f32 and hid.c == hidden and hidden % 64 == 0 and cout % 64 == 0 and cout <= 256 and self.engine == "tc"
+        wp = self.hold(pack_pw_tc(w2d, hidden))
+        b = self.hold(bias.float())
+        r = res.act() if res is not None else NULL_ACT
+        self._add("uavsal_dw_project", (hid.ptr, hid.ld, n, h, w, hidden, self.hold(wd).data_ptr(), self.hold(bd.float()).data_ptr(),
+                                        wp.data_ptr(), hidden, cout, b.data_ptr(), F_RESIDUAL if res is not None else 0, self.terms,
+                                        *r, *out.act()), tag)
+
     def pw(self, x: Buf, m: int, w2d: torch.Tensor, bias: Optional[torch.Tensor], flags: int, out: Buf,
            res: Optional[Buf] = None, tag=""):
         """Pointwise conv as GEMM.  w2d: folded fp32 (N, K_logical); x.c may be padded beyond K_logical."""

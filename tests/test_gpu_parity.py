@@ -104,6 +104,28 @@ def test_fused_expand_depthwise(cuda, cin, ch, s, n, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (192, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
+                                              (64, 128, 1, 45, 80, False), (384, 256, 1, 9, 40, True)])
+def test_fused_depthwise_project(cuda, ch, co, n, h, w, res):
+    """dwBlock conv[1..3] in one kernel (model.py:92-101): depthwise tiles feed the tcgen05 project GEMM from shared memory;
+    single-tile, odd-tile-count and ragged-edge cases exercise the CTA-pair bookkeeping."""
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(11)
+    p = _plan()
+    hid = torch.rand(n, ch, h, w) * 6
+    wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+    w2, b2 = torch.randn(co, ch) / ch ** 0.5, torch.randn(co) * 0.1
+    r = torch.randn(n, co, h, w)
+    hb = p.alloc_f32(n * h * w, ch)
+    hb.t.copy_(hid.permute(0, 2, 3, 1).reshape(-1, ch))
+    ob = p.alloc(n * h * w, co)
+    p.dwproj(hb, n, h, w, pack_dw(wd), bd, w2.cuda(), b2.cuda(), ob, res=_upload(p, r) if res else None)
+    y = _download(p, ob, n, co, h, w)
+    p.run()
+    d = F.hardtanh(F.conv2d(hid, wd, bd, 1, 1, 1, ch), 0, 6)
+    assert _rel(y, F.conv2d(d, w2.reshape(co, ch, 1, 1), b2) + (r if res else 0)) < KERNEL_TOL
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 @pytest.mark.parametrize("m,k,n,relu,res", [(300, 32, 16, 0, 0), (777, 20, 120, 1, 0), (3600, 256, 1536, 1, 0), (3600, 1536, 256, 0, 1),
                                             (500, 8, 48, 1, 0), (129, 320, 1920, 1, 0), (4000, 144, 24, 0, 1), (1, 64, 64, 0, 0)])

@@ -16,7 +16,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["simt_units", "f32_hidden", "expdw", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
+GROUPS = ["simt_units", "f32_hidden", "expdw", "dwproj", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
 
 
 def rel(a, b):
@@ -221,6 +221,31 @@ def g_expdw():
         href = F.hardtanh(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1), 0, 6)
         ref = F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)
         report("expand+dw %d->%d s=%d n=%d %dx%d" % (cin, ch, s, n, h, w), y, ref, 1e-4)
+
+
+def g_dwproj():
+    """fused depthwise + project kernel (fp32 hidden in, split-bf16 out) against torch."""
+    import torch
+    import torch.nn.functional as F
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(11)
+    for (ch, co, n, h, w, res) in [(128, 64, 1, 8, 16, False), (192, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True), (64, 128, 1, 45, 80, False),
+                                   (384, 256, 1, 9, 40, True), (1152, 64, 1, 45, 80, False)]:
+        for terms in (3,):
+            p = mk_plan("tc", terms)
+            hid = torch.rand(n, ch, h, w) * 6
+            wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+            w2, b2 = torch.randn(co, ch) / ch ** 0.5, torch.randn(co) * 0.1
+            r = torch.randn(n, co, h, w)
+            hb = p.alloc_f32(n * h * w, ch)
+            hb.t.copy_(hid.permute(0, 2, 3, 1).reshape(-1, ch))
+            ob = p.alloc(n * h * w, co)
+            p.dwproj(hb, n, h, w, pack_dw(wd), bd, w2.cuda(), b2.cuda(), ob, res=act_from(p, r) if res else None)
+            y = fetch(p, ob, n, co, h, w)
+            p.run(); torch.cuda.synchronize()
+            d = F.hardtanh(F.conv2d(hid, wd, bd, 1, 1, 1, ch), 0, 6)
+            ref = F.conv2d(d, w2.reshape(co, ch, 1, 1), b2) + (r if res else 0)
+            report("dw+project %d->%d n=%d %dx%d res=%d" % (ch, co, n, h, w, res), y, ref, 1e-4)
 
 
 def g_tc_pw():

@@ -65,6 +65,18 @@ def expdw(n, h, w, cin, hidden, stride):
     print("expand+dw n=%d %dx%d cin=%d hidden=%d s=%d: %.1f us  %.0f GB/s (in+out)" % (n, h, w, cin, hidden, stride, ms * 1e3, by / ms / 1e6), flush=True)
 
 
+def dwproj(n, h, w, hidden, co, res=False, terms=3):
+    p = Plan(dev, terms, "tc")
+    hb = p.alloc_f32(n * h * w, hidden); hb.t.uniform_(0, 6)
+    o = p.alloc(n * h * w, co)
+    r = p.alloc(n * h * w, co) if res else None
+    p.dwproj(hb, n, h, w, pack_dw(torch.randn(hidden, 1, 3, 3)), torch.zeros(hidden), torch.randn(co, hidden, device=dev) / hidden ** 0.5,
+             torch.zeros(co, device=dev), o, res=r)
+    ms = timeit(p)
+    print("dw+project[t%d] n=%d %dx%d hidden=%d co=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s(hidden read)" %
+          (terms, n, h, w, hidden, co, ms * 1e3, 2.0 * n * h * w * hidden * co / ms / 1e9, 4.0 * n * h * w * hidden / ms / 1e6), flush=True)
+
+
 def conv(engine, n, h, w, c, co, terms=3):
     p = Plan(dev, terms, engine)
     x = p.alloc(n * h * w, c); x.t.normal_()
@@ -132,6 +144,11 @@ def main():
         expdw(20, 45, 80, 64, 384, 1)
     if what == "lstm":
         lstm(8, 64, 45, 80, 256); lstm(8, 64, 45, 80, 256, terms=1)
+    if what == "dwproj":
+        dwproj(20, 45, 80, 1536, 256); dwproj(20, 45, 80, 1536, 256, res=True); dwproj(20, 45, 80, 1920, 256); dwproj(20, 45, 80, 1152, 64)
+        dwproj(20, 45, 80, 1536, 256, terms=1); dw(2, 20, 45, 80, 1536, 1, True); gemm("tc", M, 1536, 256, res=True)
+    if what == "dwproj1":
+        dwproj(20, 45, 80, 1536, 256)
     if what == "stages":
         lib = _ext.load()
         for st in (1, 2, 3, 6):
