@@ -94,10 +94,13 @@ def test_plan_structure_of_one_call():
     names = [o.name for o in plan.ops]
     # 77 used pointwise convs, the 1536->1 one is the dot; the two stride-2 high-resolution dwBlocks (features.2, features.4) run
     # expand + depthwise fused by default, all eight dwBlocks with <= 32 input channels when asked to
-    assert names.count("uavsal_expand_dw3x3") == 2
-    assert names.count("uavsal_pw_gemm") == 76 - 2 and names.count("uavsal_dw3x3") == 34 - 2
+    # ... and the seven large stride-1 blocks whose project conv has 64..256 outputs (st0/st1.sp, fust, gauss1, ob1, fucb, fucbst)
+    # run depthwise + project fused
+    assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7
+    assert names.count("uavsal_pw_gemm") == 76 - 2 - 7 and names.count("uavsal_dw3x3") == 34 - 2 - 7
     pf = engine.Plan("cpu", 3, "tc")
     pf.fuse_expand_dw = True
+    pf.fuse_dw_project = False
     m.build_plan(pf, 20, 360, 640, x_kind=1, post_hw=(360, 640))
     assert [o.name for o in pf.ops].count("uavsal_expand_dw3x3") == 8
     ps = engine.Plan("cpu", 3, "simt")                                 # the SIMT cross-check engine keeps every conv separate
