@@ -136,7 +136,7 @@ class dwBlock(KernelModule):
         fuse_dp = getattr(plan, "fuse_dw_project", "auto")
         if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
             fuse_dp = n * h * w >= 32768
-        if (fuse_dp and has_expand and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and hidden % 64 == 0 and
+        if (fuse_dp and has_expand and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and hidden % 128 == 0 and
                 oup % 64 == 0 and oup <= 256):
             wdw, bdw = self.conv[1].folded()
             wf, bf = self.project_folded()

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(h_full + s, 1); mbar_init(h_empty + s, kEpiWarps);
-            mbar_init(a_full + s, 2 * kEpiWarps); mbar_init(b_full + s, 1); mbar_init(ab_empty + s, 1);
+            mbar_init(h_full + s, 1); mbar_init(h_empty + s, kEpiWarps / 2);
+            mbar_init(a_full + s, kEpiWarps); mbar_init(b_full + s, 1); mbar_init(ab_empty + s, 1);
         }
         mbar_init(acc_full, 1); mbar_init(acc_empty, 2 * kEpiWarps);
         fence_barrier_init();
@@ -154,22 +154,27 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
         }
     } else {
         // ===================== depthwise producer + epilogue (warps 2..17, 512 threads) =====================
+        // The 16 warps form two groups of 8; group gsel owns the k-blocks kb == gsel (mod 2) and therefore A/hidden buffer gsel
+        // (num_kb is even).  Inside a group a thread owns 4 channels x 2 adjacent columns x 4 rows: 24 LDS.128 and 40 weight
+        // floats per 8 output pixels (the 1-column x 4-row mapping of the first version needed 36 and 80 - the shared-memory
+        // / L1 data path, not the FMA pipe, limits this kernel).
         const int et = threadIdx.x - 64;
-        const int quad = et & 15;                                             // 4 channels of the 64-channel k-block
-        const int col = (et >> 4) & 15;                                       // output column of the 16x8 tile
-        const int rgrp = et >> 8;                                             // output rows rgrp*4 .. +3
+        const int gsel = et >> 8;
+        const int gt = et & 255;
+        const int quad = gt & 15;                                             // 4 channels of the 64-channel k-block
+        const int cp = (gt >> 4) & 7;                                         // output columns 2cp, 2cp+1 of the 16x8 tile
+        const int rgrp = gt >> 7;                                             // output rows rgrp*4 .. +3
         const int ew = warp - 2, q = warp & 3, sub = (ew >> 2) * 16;
         const uint32_t wst = smem_u32(abuf) + ew * 2048;                      // epilogue staging (A buffers are idle then)
         const uint32_t a_full_leader0 = mapa_u32(smem_u32(a_full), 0);
         const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
-        uint32_t kc = 0;
         int it = 0;
         for (int p = first; p < num_pairs; p += step, ++it) {
             int img, y0, x0;
             const bool tvalid = tile_coords(p, img, y0, x0);
-            for (int kb = 0; kb < g.num_kb; ++kb, ++kc) {
-                const int s = kc & 1;
-                const uint32_t par = (kc >> 1) & 1;
+            for (int kb = gsel; kb < g.num_kb; kb += 2) {
+                const int s = gsel;
+                const uint32_t par = (uint32_t)((it * (g.num_kb >> 1) + (kb >> 1)) & 1);   // use count of buffer s so far
                 const int c0 = kb * 64 + quad * 4;
                 float wr[9][4], br[4];
 #pragma unroll
@@ -185,13 +190,13 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
                 mbar_wait(ab_empty + s, par ^ 1);                             // the MMAs that read this A buffer two k-blocks ago retired
                 const uint32_t tile = smem_u32(hbuf + s * kDpHBytes);
                 const uint32_t a_hi = smem_u32(abuf + s * a_stage);
-                float win[3][3][4];
+                float win[3][4][4];                                           // [row slot][column 2cp-1 .. 2cp+2][channel]
                 auto load_row = [&](int slot, int iy) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
+                    for (int d = 0; d < 4; ++d) {
                         float* v = win[slot][d];
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-                                     : "r"(tile + (iy * kDpIW + col + d) * 256 + quad * 16));
+                                     : "r"(tile + (iy * kDpIW + 2 * cp + d) * 256 + quad * 16));
                     }
                 };
                 const int oyl0 = rgrp * 4;
@@ -200,26 +205,29 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
                 for (int i = 0; i < 4; ++i) {
                     const int s0 = i % 3, s1 = (i + 1) % 3, s2 = (i + 2) % 3;
                     load_row(s2, oyl0 + i + 2);
-                    float acc[4] = {br[0], br[1], br[2], br[3]};
                     const int slots[3] = {s0, s1, s2};
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                    for (int c = 0; c < 2; ++c) {
+                        float acc[4] = {br[0], br[1], br[2], br[3]};
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float* v = win[slots[ky]][kx];
+                        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
-                        }
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float* v = win[slots[ky]][c + kx];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
-                    // A row = pixel index inside the tile; 16-byte chunk (quad >> 1) of the 128-byte row sits at chunk ^ (row & 7)
-                    const int r = (oyl0 + i) * kDpTW + col;
-                    uint32_t h0, h1, l0, l1;
-                    split2(acc[0], acc[1], h0, l0);
-                    split2(acc[2], acc[3], h1, l1);
-                    const uint32_t off = r * 128 + ((((uint32_t)quad >> 1) ^ (r & 7)) << 4) + (quad & 1) * 8;
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
-                    if (TERMS == 3) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + kDpAPlane + off), "r"(l0), "r"(l1) : "memory");
+                                for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
+                            }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
+                        // A row = pixel index inside the tile; 16-byte chunk (quad >> 1) of the 128-byte row sits at chunk ^ (row & 7)
+                        const int r = (oyl0 + i) * kDpTW + 2 * cp + c;
+                        uint32_t h0, h1, l0, l1;
+                        split2(acc[0], acc[1], h0, l0);
+                        split2(acc[2], acc[3], h1, l1);
+                        const uint32_t off = r * 128 + ((((uint32_t)quad >> 1) ^ (r & 7)) << 4) + (quad & 1) * 8;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
+                        if (TERMS == 3) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + kDpAPlane + off), "r"(l0), "r"(l1) : "memory");
+                    }
                 }
                 fence_async_smem();                                           // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
@@ -350,8 +358,8 @@ extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int
                        hid_ld % 4 == 0 && hid_ld >= hidden && out_ld % 8 == 0 && out_ld >= cout && out_plane > 0 && out_plane % 8 == 0 &&
                        kpad >= hidden && kpad % 8 == 0,
                    UAVSAL_EINVAL, "dw_project: bad arguments");
-    UAVSAL_REQUIRE(hidden % 64 == 0 && cout % 64 == 0 && cout <= 256 && (terms == 1 || terms == 3), UAVSAL_ENOTSUP,
-                   "dw_project: hidden %d must be a multiple of 64, cout %d a multiple of 64 up to 256", hidden, cout);
+    UAVSAL_REQUIRE(hidden % 128 == 0 && cout % 64 == 0 && cout <= 256 && (terms == 1 || terms == 3), UAVSAL_ENOTSUP,
+                   "dw_project: hidden %d must be a multiple of 128, cout %d a multiple of 64 up to 256", hidden, cout);
     UAVSAL_REQUIRE(!(flags & UAVSAL_F_RESIDUAL) || (al16(res) && res_ld % 8 == 0 && res_plane % 8 == 0 && res_plane > 0), UAVSAL_EINVAL,
                    "dw_project: residual requested without a residual tensor");
     UAVSAL_REQUIRE(!(flags & ~UAVSAL_F_RESIDUAL), UAVSAL_ENOTSUP, "dw_project: only the residual flag is supported (the project conv is linear)");

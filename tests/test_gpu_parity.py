@@ -104,8 +104,8 @@ def test_fused_expand_depthwise(cuda, cin, ch, s, n, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(href, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
 
 
-@pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (192, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
-                                              (64, 128, 1, 45, 80, False), (384, 256, 1, 9, 40, True)])
+@pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
+                                              (128, 128, 1, 45, 80, False), (384, 256, 1, 9, 40, True)])
 def test_fused_depthwise_project(cuda, ch, co, n, h, w, res):
     """dwBlock conv[1..3] in one kernel (model.py:92-101): depthwise tiles feed the tcgen05 project GEMM from shared memory;
     single-tile, odd-tile-count and ragged-edge cases exercise the CTA-pair bookkeeping."""

@@ -229,7 +229,7 @@ def g_dwproj():
     import torch.nn.functional as F
     from iip_uavsal_saliency_b200.engine import pack_dw
     torch.manual_seed(11)
-    for (ch, co, n, h, w, res) in [(128, 64, 1, 8, 16, False), (192, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True), (64, 128, 1, 45, 80, False),
+    for (ch, co, n, h, w, res) in [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True), (128, 128, 1, 45, 80, False),
                                    (384, 256, 1, 9, 40, True), (1152, 64, 1, 45, 80, False)]:
         for terms in (3,):
             p = mk_plan("tc", terms)
