@@ -190,7 +190,7 @@ def run_product_arm(args):
     model = model.to(dev).set_mode(precision=args.precision)
     gauss, ob = load_priors()
     runner = ClipRunner(model, gauss, ob, batch_size=BATCH, out_hw=(H, W), use_graph=not args.no_graph, depth=args.depth,
-                        clip_backbone=not args.per_call_backbone, single_stream=args.single_stream)
+                        clip_backbone=not args.per_call_backbone, single_stream=args.single_stream, whole_clip=not args.per_call)
     runner.warm(FRAMES, H, W)
 
     # distinct clips rotated across steps so inputs (4 x 44 MB) exceed the 126 MB L2; the arena traffic of a step
@@ -241,7 +241,9 @@ def run_product_arm(args):
     value = frames_per_step * args.steps / t_res
     e2e = frames_per_step * args.steps / t_e2e
     calls = [20, 20, 20]
-    if args.per_call_backbone:
+    if not args.per_call:
+        launches = runner._plan(OUT_PER_CLIP, H, W, 0, "all", BATCH * T).num_launches
+    elif args.per_call_backbone:
         launches = sum(runner._plan(n, H, W, 0).num_launches for n in calls)
     else:           # one SRF-Net plan per clip + one head plan per call
         launches = runner._plan(OUT_PER_CLIP, H, W, 0, "sfnet").num_launches + sum(runner._plan(n, H, W, 0).num_launches for n in calls)
@@ -319,7 +321,7 @@ def run_product_arm(args):
             "warmup": warm, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split (fp32 accumulate)" if args.precision == "exact" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": args.clips, "frames_in_per_clip": FRAMES, "maps_out_per_clip": OUT_PER_CLIP,
-                       "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth, "srfnet_batch": "clip (60 frames)" if not args.per_call_backbone else "call (20 frames)",
+                       "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth, "plan": "one per clip (60 frames, call size 20 passed to the call-granular kernels)" if not args.per_call else "one per 20-frame call",
                        "l2": "inputs larger than L2: %d distinct clips rotated (%.0f MB) and ~9.5 GB of arena traffic per call" % (n_rot, n_rot * 44.2)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.clips * OUT_PER_CLIP * H * W * 3,
                     "d2h_bytes_per_step": args.clips * OUT_PER_CLIP * H * W},
@@ -339,6 +341,7 @@ def main():
     ap.add_argument("--clips", type=int, default=1, help="clips per step per GPU")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--per-call", action="store_true", help="keep Demo_Test's loop of 20-frame calls instead of one plan per clip")
     ap.add_argument("--single-stream", action="store_true", help="queue all stages of all calls on one stream (no overlap)")
     ap.add_argument("--per-call-backbone", action="store_true", help="run the SRF-Net per 20-frame call (as Demo_Test does) instead of once per clip")
     ap.add_argument("--depth", type=int, default=2, help="calls in flight per GPU (ClipRunner stream pipelining; 1 = serial)")

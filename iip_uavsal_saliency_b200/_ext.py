@@ -33,8 +33,8 @@ _SIGNATURES = {
     "uavsal_pw_gemm_simt": ACT + [I, I, P, I, P, I] + ACT + ACT + [P],
     "uavsal_conv3x3": ACT + [I, I, I, I, P, I, P, I, I] + ACT + [P],
     "uavsal_conv3x3_simt": ACT + [I, I, I, I, P, I, P, I] + ACT + [P],
-    "uavsal_bilinear_ac": ACT + [I, I, I, I] + ACT + [I, I, I, P],
-    "uavsal_tdiff_cat": ACT + [I, I, I] + ACT + [P],
+    "uavsal_bilinear_ac": ACT + [I, I, I, I] + ACT + [I, I, I, I, I, P],
+    "uavsal_tdiff_cat": ACT + [I, I, I] + ACT + [I, P],
     "uavsal_ctx_sum": ACT + [I, I, I, I] + ACT + [P],
     "uavsal_add": ACT + ACT + [L, I] + ACT + [P],
     "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [P],

@@ -115,7 +115,7 @@ class dwBlock(KernelModule):
         i = 0
         fuse = getattr(plan, "fuse_expand_dw", "auto")
         if fuse == "auto":       # measured (profiles/r01_microbench_expdw.txt): the fused kernel wins on the stride-2 high-resolution blocks
-            fuse = stride == 2 and n * h * w >= 200000
+            fuse = stride == 2 and h * w >= 10000       # per-frame size: the choice must not depend on how many frames are batched
         if has_expand and plan.engine == "tc" and dil == 1 and x.c <= 32 and not x.f32 and fuse:
             # few input channels: expand + depthwise in one kernel, the 6x hidden tensor never reaches HBM
             w1, b1 = self.conv[0].folded()
@@ -135,7 +135,7 @@ class dwBlock(KernelModule):
             i = 1
         fuse_dp = getattr(plan, "fuse_dw_project", "auto")
         if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
-            fuse_dp = n * h * w >= 32768
+            fuse_dp = h * w >= 3600 and n * h * w >= 32768
         if (fuse_dp and has_expand and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and hidden % 128 == 0 and
                 oup % 64 == 0 and oup <= 256):
             wdw, bdw = self.conv[1].folded()

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_rows_kernel(Act in, int h, int w
 // [model.py:152-153, 360-361; ATen upsample_bilinear2d: ratio=(in-1)/(out-1), src=ratio*dst, l1=src-floor]
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int hs, int ws, int c, ActW out,
-                                                          int n_dst, int hd, int wd, float ry, float rx) {
+                                                          int n_dst, int hd, int wd, float ry, float rx, int src_group, int dst_group) {
     pdl_trigger();
     pdl_wait();
     const int groups = c >> 3;
@@ -315,7 +315,11 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int
     const int ox = (int)(pix % wd);
     const int oy = (int)((pix / wd) % hd);
     const int img = (int)(pix / ((int64_t)wd * hd));
-    const int simg = img % n_src;
+    // output frame i = (call g, local j) reads source frame g*src_group + j % (sources of call g): with one group this is the
+    // reference's repeat(T) interleave i % n_src (quirk Q3); several groups = several reference calls batched in one launch
+    const int grp = img / dst_group, j = img - grp * dst_group;
+    const int nsg = min(src_group, n_src - grp * src_group);
+    const int simg = grp * src_group + j % nsg;
     const float sy = __fmul_rn(ry, (float)oy);
     const float sx = __fmul_rn(rx, (float)ox);
     const int y0 = (int)sy, x0 = (int)sx;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int
 //   first half : x[i]-x[i-1]   (i=0: x[1]-x[0])
 //   second half: x[i]-x[i+1]   (i=n-1: x[n-2]-x[n-1])
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, int c, ActW out) {
+__global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, int c, ActW out, int group) {
     pdl_trigger();
     pdl_wait();
     const int groups = c >> 3;
@@ -353,12 +357,15 @@ __global__ void __launch_bounds__(256) tdiff_cat_kernel(Act in, int n, int hw, i
     const uint16_t* cur = in.p + pix * in.ld + g * 8;
     float x[8], pv[8], nx[8], d0[8], d1[8];
     load8(cur, in.plane, x);
-    if (img > 0) load8(cur - fs, in.plane, pv);
-    if (img < n - 1) load8(cur + fs, in.plane, nx);
+    // the mirrored edges sit at the boundaries of each reference call (`group` frames; the last group may be shorter)
+    const int g0 = (img / group) * group, g1 = min(n, g0 + group);
+    const bool has_prev = img > g0, has_next = img < g1 - 1;
+    if (has_prev) load8(cur - fs, in.plane, pv);
+    if (has_next) load8(cur + fs, in.plane, nx);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        d0[j] = img > 0 ? x[j] - pv[j] : nx[j] - x[j];
-        d1[j] = img < n - 1 ? x[j] - nx[j] : pv[j] - x[j];
+        d0[j] = has_prev ? x[j] - pv[j] : nx[j] - x[j];
+        d1[j] = has_next ? x[j] - nx[j] : pv[j] - x[j];
     }
     uint16_t* o = out.p + pix * out.ld + g * 8;
     store8(o, out.plane, d0);
@@ -620,27 +627,32 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
 }
 
 int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_src, int hs, int ws, int c, uint16_t* out,
-                       int64_t out_plane, int out_ld, int n_dst, int hd, int wd, void* stream) {
+                       int64_t out_plane, int out_ld, int n_dst, int hd, int wd, int src_group, int dst_group, void* stream) {
     UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && n_src > 0 &&
                        n_dst > 0 && hs > 0 && ws > 0 && hd > 0 && wd > 0,
                    UAVSAL_EINVAL, "bilinear_ac: bad arguments");
     const float ry = hd > 1 ? (float)(hs - 1) / (float)(hd - 1) : 0.f;
     const float rx = wd > 1 ? (float)(ws - 1) / (float)(wd - 1) : 0.f;
     const int64_t total = (int64_t)n_dst * hd * wd * (c / 8);
+    if (src_group <= 0 || dst_group <= 0) { src_group = n_src; dst_group = n_dst; }
+    UAVSAL_REQUIRE((int64_t)div_up(n_dst, dst_group) * src_group >= n_src && div_up(n_dst, dst_group) == div_up(n_src, src_group), UAVSAL_EINVAL,
+                   "bilinear_ac: %d sources in groups of %d do not match %d outputs in groups of %d", n_src, src_group, n_dst, dst_group);
     launch_k(bilinear_ac_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n_src, hs, ws, c,
                                                                             ActW{out, out_plane, out_ld}, n_dst, hd, wd,
-                                                                            ry, rx);
+                                                                            ry, rx, src_group, dst_group);
     return check_launch("bilinear_ac");
 }
 
 int uavsal_tdiff_cat(const uint16_t* in, int64_t in_plane, int in_ld, int n, int hw, int c, uint16_t* out,
-                     int64_t out_plane, int out_ld, void* stream) {
+                     int64_t out_plane, int out_ld, int group, void* stream) {
     UAVSAL_REQUIRE(act_ok(in, in_plane, in_ld) && act_ok(out, out_plane, out_ld) && c % 8 == 0 && c > 0 && out_ld >= 2 * c,
                    UAVSAL_EINVAL, "tdiff_cat: bad arguments");
-    UAVSAL_REQUIRE(n >= 2, UAVSAL_EINVAL, "tdiff_cat: needs at least 2 frames per call (model.py:194 indexes x1[1])");
+    if (group <= 0 || group > n) group = n;
+    UAVSAL_REQUIRE(n >= 2 && group >= 2 && (n % group == 0 || n % group >= 2), UAVSAL_EINVAL,
+                   "tdiff_cat: needs at least 2 frames per call (model.py:194 indexes x1[1])");
     const int64_t total = (int64_t)n * hw * (c / 8);
     launch_k(tdiff_cat_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n, hw, c,
-                                                                          ActW{out, out_plane, out_ld});
+                                                                          ActW{out, out_plane, out_ld}, group);
     return check_launch("tdiff_cat");
 }
 

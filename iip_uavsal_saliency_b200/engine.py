@@ -241,11 +241,12 @@ class Plan:
             wp = self.hold(w2d.t().contiguous())
             self._add("uavsal_conv3x3_simt", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, *out.act()), tag)
 
-    def bilinear(self, x: Buf, n_src, hs, ws, c, out: Buf, n_dst, hd, wd, tag=""):
-        self._add("uavsal_bilinear_ac", (*x.act(), n_src, hs, ws, c, *out.act(), n_dst, hd, wd), tag)
+    def bilinear(self, x: Buf, n_src, hs, ws, c, out: Buf, n_dst, hd, wd, tag="", src_group=0, dst_group=0):
+        self._add("uavsal_bilinear_ac", (*x.act(), n_src, hs, ws, c, *out.act(), n_dst, hd, wd, src_group, dst_group), tag)
 
     def tdiff(self, x: Buf, n, hw, c, out: Buf, tag=""):
-        self._add("uavsal_tdiff_cat", (*x.act(), n, hw, c, *out.act()), tag)
+        """``self.call_group`` (frames per reference call, 0 = the whole batch is one call) places the mirrored edges."""
+        self._add("uavsal_tdiff_cat", (*x.act(), n, hw, c, *out.act(), int(getattr(self, "call_group", 0))), tag)
 
     def ctx_sum(self, x: Buf, b, t, hw, c, out: Buf, tag=""):
         self._add("uavsal_ctx_sum", (*x.act(), b, t, hw, c, *out.act()), tag)

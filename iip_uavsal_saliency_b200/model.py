@@ -201,14 +201,21 @@ class UAVSal(KernelModule):
 
     # -----------------------------------------------------------------------------------------------
     def build_plan(self, plan: Plan, n: int, h: int, w: int, x_kind: int = 0, post_hw=None, taps: bool = False,
-                   cb_shared: bool = False, stage: str = "all"):
+                   cb_shared: bool = False, stage: str = "all", group: int = 0):
         """Emit the whole forward for a call of n frames of (h, w) pixels.
         x_kind: 0 fp32 NCHW normalised, 1 uint8 NCHW raw, 2 uint8 NHWC raw.  post_hw=(H,W) adds the uint8 post-process.
         cb_shared: cb tensors hold ONE frame that is broadcast to all n (Demo_Test's np.repeat'ed priors).
         stage: "all" (a reference call), "sfnet" (only the per-frame SRF-Net, any n: frames are independent there, so a
-        runner may batch a whole clip), "head" (everything after the SRF-Net, fed from the arena input ``sf_in``)."""
+        runner may batch a whole clip), "head" (everything after the SRF-Net, fed from the arena input ``sf_in``).
+        group: > 0 = the n frames are CONSECUTIVE reference calls of `group` frames each (the last may be shorter) emitted as
+        one plan: the only call-granular operations - the temporal differences' mirrored edges (model.py:194-198) and the
+        context prior's repeat interleave (model.py:361) - are told the call size; the ConvTWA state simply runs through."""
         planes, T = self._planes, self.time_dims
         assert stage in ("all", "sfnet", "head")
+        if group:
+            if group % T or (n % group) % T:
+                raise ValueError("call size %d / batch %d must be multiples of time_dims=%d" % (group, n, T))
+            plan.call_group = group
         if n % T and stage != "sfnet":
             raise ValueError("call batch %d is not a multiple of time_dims=%d (model.py:356-357)" % (n, T))
         tp = {} if taps else None
@@ -275,7 +282,8 @@ class UAVSal(KernelModule):
                 y, h1, w1 = self.cxt_cb_prior[0]._emit(plan, s, b, mh, mw, tag="cxt0")
                 y, h2, w2 = self.cxt_cb_prior[1]._emit(plan, y, b, h1, w1, tag="cxt1")
                 # upsample (align_corners) + repeat(T): frame i reads chunk i % b (model.py:360-361, quirk Q3)
-                plan.bilinear(y, b, h2, w2, 64, cat1.slot(off, 64), n, mh, mw, tag="cxt.up")
+                plan.bilinear(y, b, h2, w2, 64, cat1.slot(off, 64), n, mh, mw, tag="cxt.up",
+                              src_group=(group // T) if group else 0, dst_group=group)
                 off += 64
             self.fucb_layer[0]._emit(plan, cat1, n, mh, mw, out=cat2.slot(planes, q), tag="fucb")
             x, _, _ = self.fucbst_layer[0]._emit(plan, cat2, n, mh, mw, tag="fucbst")
@@ -312,10 +320,10 @@ class UAVSal(KernelModule):
         plan.named.update(named)
         return plan
 
-    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0, stage="all") -> Plan:
+    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0, stage="all", group=0) -> Plan:
         """``slot`` selects one of several independent plan instances (own arena) so that calls can be in flight together."""
-        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot, stage)
-        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared, stage))
+        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot, stage, group)
+        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared, stage, group))
 
     def forward(self, x, cb, in_state):
         require_cuda(x, "UAVSal")

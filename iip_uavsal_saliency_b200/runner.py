@@ -7,7 +7,14 @@ uint8 frames in -> uint8 saliency maps out.
   * the ConvTWA hidden state is handed from call to call (Demo_Test.py:75,85-86);
   * priors are one (h,w,C) map broadcast to every frame, as get_bias builds them (Demo_Test.py:14-27).
 
-Batching.  The SRF-Net (backbone + ASPP + 3x3 fuse, model.py:139-158) treats every frame independently, so with
+Whole-clip plans.  Only two operations of the model see the call grouping: the temporal differences (mirrored edges at
+the first / last frame of a call, model.py:194-198) and the context prior's repeat interleave (model.py:361).  Both kernels
+take the call size as a parameter, and the ConvTWA state simply runs on from one call's last frame to the next call's first,
+so with ``whole_clip=True`` (default) ALL kept frames of a clip go through ONE plan (n = 60 for a 64-frame clip, group = 20):
+every GEMM / depthwise launch works on three times the rows (better wave quantisation of the persistent kernels, a third of
+the launches) and the results are those of the three chained reference calls.
+
+Batching.  With ``whole_clip=False`` the reference's call loop is kept.  The SRF-Net (backbone + ASPP + 3x3 fuse, model.py:139-158) treats every frame independently, so with
 ``clip_backbone=True`` (default) it runs ONCE over all kept frames of a clip (stage "sfnet" plan) and the per-call plans
 (stage "head": ST blocks, prior fusion, ConvTWA, readout) read their 20-frame slices of its output.  The 12x20 / 23x40
 layers of MobileNetV2 are launch-latency-bound at 20 frames; at 60 they do three times the work in about the same time.
@@ -33,7 +40,7 @@ from .model import UAVSal
 class ClipRunner:
     def __init__(self, model: UAVSal, gauss: np.ndarray, ob: np.ndarray, batch_size: int = 4, out_hw: Optional[Tuple[int, int]] = None,
                  use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2, clip_backbone: bool = True,
-                 single_stream: bool = False):
+                 single_stream: bool = False, whole_clip: bool = True):
         """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw';
         depth = calls in flight (1 = strictly serial on the caller's stream order); clip_backbone: run the SRF-Net once per
         clip instead of once per call."""
@@ -55,16 +62,17 @@ class ClipRunner:
         self.back_stream = one or torch.cuda.Stream(self.dev)
         self._slot_free = [None] * self.depth          # event: the slot's previous call has left the back stream
         self._calls = 0
+        self.whole_clip = bool(whole_clip)
         self.clip_backbone = bool(clip_backbone)
         self.bb_stream = one or torch.cuda.Stream(self.dev)
         self._sf_free = [[], []]                       # events: the heads of the previous clip on this slot have read its SRF-Net output
         self._clips = 0
 
-    def _plan(self, n, H, W, slot, stage=None):
+    def _plan(self, n, H, W, slot, stage=None, group=0):
         post = self.out_hw or (H, W)
         stage = stage or ("head" if self.clip_backbone else "all")
         plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=None if stage == "sfnet" else post, cb_shared=True,
-                                   slot=slot, stage=stage)
+                                   slot=slot, stage=stage, group=group)
         if "ready" not in plan.named:
             torch.cuda.synchronize(self.dev)
             if stage != "sfnet":
@@ -82,6 +90,10 @@ class ClipRunner:
     def warm(self, n_frames: int, H: int, W: int):
         """Build (and capture) the plans a clip of n_frames will use on every slot, outside any timed region."""
         keep = (n_frames // self.T) * self.T
+        if self.whole_clip:
+            for slot in range(2):
+                self._plan(keep, H, W, slot, "all", self.per_call)
+            return
         sizes = {min(self.per_call, keep - i * self.per_call) for i in range(math.ceil(keep / self.per_call))}
         for slot in range(self.depth):
             for n in sizes:
@@ -106,6 +118,8 @@ class ClipRunner:
         F_ = frames.shape[0]
         H, W = (frames.shape[1], frames.shape[2]) if self.kind == 2 else (frames.shape[2], frames.shape[3])
         keep = (F_ // self.T) * self.T
+        if self.whole_clip:
+            return self._run_whole(frames, keep, H, W, want_maps, out, sync)
         ncalls = math.ceil(keep / self.per_call)
         plans = []
         for i in range(ncalls):                                     # build before queueing (capture synchronises)
@@ -182,6 +196,45 @@ class ClipRunner:
         with torch.cuda.stream(bs):
             m = torch.cat(maps, 0) if want_maps else None
             u8 = out[:done] if out is not None else torch.cat(u8s, 0)
+        if sync:
+            cur.wait_stream(bs)
+            for t in (m, u8):
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
+        return m, u8
+
+    def _run_whole(self, frames, keep, H, W, want_maps, out, sync):
+        """One plan for the whole clip (see the module docstring); front of clip k+1 overlaps the recurrent back of clip k."""
+        slot = self._clips % 2
+        self._clips += 1
+        plan = self._plan(keep, H, W, slot, "all", self.per_call)
+        nm = plan.named
+        cur = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        fs, bs = self.front_streams[slot % self.depth], self.back_stream
+        fs.wait_event(ready)
+        bs.wait_event(ready)
+        for ev in self._sf_free[slot]:
+            fs.wait_event(ev)
+        with torch.cuda.stream(fs):
+            nm["x_in"].copy_(frames[:keep], non_blocking=True)
+            plan.launch("front")
+            fdone = torch.cuda.Event()
+            fdone.record(fs)
+        bs.wait_event(fdone)
+        with torch.cuda.stream(bs):
+            nm["h_in"].zero_()                                      # a clip starts from the zero state (Demo_Test.py:75)
+            plan.launch("back")
+            m = nm["out"].clone() if want_maps else None
+            if out is not None:
+                out[:keep].copy_(nm["out_u8"], non_blocking=True)
+                u8 = out[:keep]
+            else:
+                u8 = nm["out_u8"].clone()
+            free = torch.cuda.Event()
+            free.record(bs)
+            self._sf_free[slot] = [free]
         if sync:
             cur.wait_stream(bs)
             for t in (m, u8):

@@ -121,13 +121,16 @@ int uavsal_conv3x3_simt(const uint16_t* in, int64_t in_plane, int in_ld, int n, 
 
 /* ---- K5: F.interpolate(bilinear, align_corners=True) written into a concat slot (model.py:152-153,360)
  *      with the context prior's repeat(T,1,1,1) folded in: output frame i reads source frame i % n_src
- *      (model.py:361, quirk Q3). */
+ *      (model.py:361, quirk Q3).  src_group / dst_group > 0 batch several reference calls in one launch: output frame
+ *      i = g*dst_group + j reads source frame g*src_group + j % src_group (0, 0 = one call). */
 int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_src, int hs, int ws, int c,
-                       uint16_t* out, int64_t out_plane, int out_ld, int n_dst, int hd, int wd, void* stream);
+                       uint16_t* out, int64_t out_plane, int out_ld, int n_dst, int hd, int wd,
+                       int src_group, int dst_group, void* stream);
 
-/* ---- K6: teConv_sub neighbour differences over the call batch (model.py:194-200): x1 (n,hw,c) -> (n,hw,2c) */
+/* ---- K6: teConv_sub neighbour differences over the call batch (model.py:194-200): x1 (n,hw,c) -> (n,hw,2c).
+ *      group > 0: the n frames are consecutive reference calls of `group` frames (mirrored edges at each call boundary). */
 int uavsal_tdiff_cat(const uint16_t* in, int64_t in_plane, int in_ld, int n, int hw, int c,
-                     uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+                     uint16_t* out, int64_t out_plane, int out_ld, int group, void* stream);
 
 /* ---- K7: context prior T-sum: x.view(B,T,C,H,W).sum(1) (model.py:357-358): (b*t,hw,c) -> (b,hw,c) */
 int uavsal_ctx_sum(const uint16_t* in, int64_t in_plane, int in_ld, int b, int t, int hw, int c,

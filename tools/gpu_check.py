@@ -414,7 +414,7 @@ def g_runner():
     m = UAVSal().eval()
     m.load_state_dict(synth.make_state_dict("lively", 0), strict=True)
     m = m.cuda()
-    r = ClipRunner(m, gauss, ob, batch_size=4)
+    r = ClipRunner(m, gauss, ob, batch_size=4, whole_clip=False)
     clip = torch.from_numpy(synth.make_clip(2, 64, 360, 640)).cuda()
     maps, u8 = r.run_clip(clip)
     torch.cuda.synchronize()
@@ -424,18 +424,22 @@ def g_runner():
     print("RUNNER config#2 max-abs %.3e (tol 2e-3) %s" % (d.max(), "ok" if d.max() < 2e-3 else "FAIL"), flush=True)
     du = np.abs(u8[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int))
     print("RUNNER uint8 maxdiff %d (tol 1), frac>0 %.3e %s" % (du.max(), (du > 0).mean(), "ok" if du.max() <= 1 else "FAIL"), flush=True)
-    # pipelining must not change a single bit: serial (depth 1) vs 3 calls in flight, clips queued back to back
+    # (a) stream pipelining must not change a single bit; (b) one plan per clip vs the reference's loop of 20-frame calls may
+    # differ in the last bit from call 2 on: the loop hands the ConvTWA state over as NCHW fp32 and re-splits it into bf16
+    # hi/lo planes (same value, different decomposition), the clip plan keeps the planes - both sit inside +-1 LSB.
     clips = [clip] + [torch.from_numpy(synth.make_clip(20 + i, 64, 360, 640)).cuda() for i in range(2)]
     outs = {}
-    for depth in (1, 3):
-        rr = ClipRunner(m, gauss, ob, batch_size=4, depth=depth, clip_backbone=(depth != 1))   # serial per-call reference vs batched + pipelined
+    for name, kw in (("per-call serial", dict(depth=1, whole_clip=False, clip_backbone=False)),
+                     ("per-call pipelined", dict(depth=3, whole_clip=False, clip_backbone=True)),
+                     ("clip-plan single-stream", dict(single_stream=True)), ("clip-plan pipelined", dict())):
+        rr = ClipRunner(m, gauss, ob, batch_size=4, **kw)
         rr.warm(64, 360, 640)
         bufs = [torch.empty(60, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
         for c, b in zip(clips, bufs):
             rr.run_clip(c, want_maps=False, out=b, sync=False)
         rr.finish()
         torch.cuda.synchronize()
-        outs[depth] = [b.cpu() for b in bufs]
+        outs[name] = [b.cpu() for b in bufs]
         for reps in (1, 2):
             t0 = time.time()
             for _ in range(4):
@@ -444,10 +448,17 @@ def g_runner():
             rr.finish()
             torch.cuda.synchronize()
             dt = (time.time() - t0) / 12
-        print("RUNNER depth=%d clip_backbone=%s: 64-frame clip %.2f ms -> %.1f frames/s (60 outputs)" % (depth, depth != 1, dt * 1e3, 60 / dt), flush=True)
-    same = all(torch.equal(a, b) for a, b in zip(outs[1], outs[3]))
-    same0 = torch.equal(outs[1][0], torch.from_numpy(u8))
-    print("RUNNER pipelined == serial: %s, == sync run: %s  %s" % (same, same0, "ok" if same and same0 else "FAIL"), flush=True)
+        print("RUNNER %-24s 64-frame clip %.2f ms -> %.1f frames/s (60 outputs)" % (name, dt * 1e3, 60 / dt), flush=True)
+        del rr
+        m._plan_cache().clear()
+        torch.cuda.empty_cache()
+    eq = lambda a, b: all(torch.equal(x, y) for x, y in zip(outs[a], outs[b]))
+    same_call = eq("per-call serial", "per-call pipelined") and torch.equal(outs["per-call serial"][0], torch.from_numpy(u8))
+    same_clip = eq("clip-plan single-stream", "clip-plan pipelined")
+    ndiff = max(int((a.int() - b.int()).abs().max()) for a, b in zip(outs["per-call serial"], outs["clip-plan pipelined"]))
+    gd = np.abs(outs["clip-plan pipelined"][0].numpy()[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int)).max()
+    print("RUNNER pipelined == serial: per-call %s, clip-plan %s; clip-plan vs per-call max uint8 diff %d; clip-plan vs reference golden %d  %s"
+          % (same_call, same_clip, ndiff, gd, "ok" if same_call and same_clip and ndiff <= 1 and gd <= 1 else "FAIL"), flush=True)
 
 
 def main():
