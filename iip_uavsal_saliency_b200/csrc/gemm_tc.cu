@@ -506,6 +506,11 @@ static inline bool act_ok16(const void* p, int64_t plane, int ld) {
 }
 
 extern int g_dw_fast;
+namespace uavsal {
+extern int g_twa_resident;
+int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int out_img, int H, int W, int c, const uint16_t* wgt, int wk_total,
+                      int wk_off, const float* gx, int terms, cudaStream_t s, int dbg);
+}
 
 extern "C" {
 
@@ -516,6 +521,7 @@ int uavsal_set_option(int key, int value) {
     if (key == 4 && (value == 1 || value == 2)) { g_tc_cluster = value; return 0; }
     if (key == 5 && value >= 1 && value <= 8) { g_tc_max_stages = value; return 0; }
     if (key == 6 && (value == 0 || value == 1)) { g_pdl = value; return 0; }
+    if (key == 7 && value >= 0 && value <= 2) { g_twa_resident = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }
@@ -588,6 +594,12 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
         if (rc) return rc;
         const int64_t fr = (int64_t)h * w * c;
         for (int t = 0; t < t_steps; ++t) {
+            if (g_twa_resident && c % 64 == 0 && c <= 512) {         // resident-A step kernel (twa_step.cu)
+                rc = t == 0 ? twa_step_resident(H0, 1, 0, X, S, 0, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug)
+                            : twa_step_resident(SA, t_steps, t - 1, X, S, t, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug);
+                if (rc) return rc;
+                continue;
+            }
             if (t == 0)
                 rc = conv_tc(H0, 1, 0, 0, c, H0, 1, 0, 0, 0, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S, t_steps, 0, 0,
                              s, "twa_sequence(h half)", 2 * c, c, gx_workspace, nullptr);

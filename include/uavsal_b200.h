@@ -51,7 +51,8 @@ int         uavsal_set_option(int key, int value);/* key 1: tcgen05 GEMM kernel 
                                                      key 3: timing-ablation bits (dev only; results invalid when non-zero);
                                                      key 4: CTAs per cluster of the persistent GEMM (2 = cta_group::2 pair mode, default; 1);
                                                      key 5: cap on the GEMM's shared-memory pipeline depth (dev);
-                                                     key 6: programmatic dependent launch of the product-path kernels (1 = on, default; 0) */
+                                                     key 6: programmatic dependent launch of the product-path kernels (1 = on, default; 0);
+                                                     key 7: ConvTWA step kernel (1 = resident-A shifted-view kernel, default; 0 = generic implicit GEMM) */
 
 /* ---- layout conversion at the module boundary (torch NCHW fp32 <-> arena) ---------------------- */
 /* NCHW fp32 -> act NHWC with channels zero-padded to cpad (cb priors, Demo_Test.py:16,22; states).  */

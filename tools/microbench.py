@@ -149,6 +149,20 @@ def main():
         dwproj(20, 45, 80, 1536, 256, terms=1); dw(2, 20, 45, 80, 1536, 1, True); gemm("tc", M, 1536, 256, res=True)
     if what == "dwproj1":
         dwproj(20, 45, 80, 1536, 256)
+    if what == "twa2":
+        lib = _ext.load()
+        for mode in (0, 1):
+            lib.uavsal_set_option(7, mode)
+            print("--- twa step kernel mode", mode)
+            twa("tc", 20, 45, 80, 256); twa("tc", 60, 45, 80, 256)
+        lib.uavsal_set_option(7, 1)
+    if what == "twa_ablate":
+        lib = _ext.load()
+        for mask, name in ((0, "full"), (1 << 16, "no-mma"), (1 << 17, "no-epilogue-io"), (1 << 18, "no-B"), (7 << 16, "none of them")):
+            lib.uavsal_set_option(3, mask)
+            print("---", name)
+            twa("tc", 60, 45, 80, 256)
+        lib.uavsal_set_option(3, 0)
     if what == "stages":
         lib = _ext.load()
         for st in (1, 2, 3, 6):
