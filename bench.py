@@ -157,6 +157,15 @@ def time_op_classes(plan, torch, detail=None):
             t_steps, hh, ww, c = a[6], a[7], a[8], a[9]
             fl = 2.0 * t_steps * hh * ww * 9 * 2 * c * c
             by = 4.0 * t_steps * hh * ww * 3 * c
+        elif op.name == "uavsal_dw_project":
+            nimg, hh, ww, hidden, cout = a[2], a[3], a[4], a[5], a[10]
+            fl = 2.0 * nimg * hh * ww * hidden * cout + 18.0 * nimg * hh * ww * hidden
+            by = 4.0 * nimg * hh * ww * (hidden + cout)
+        elif op.name == "uavsal_expand_dw3x3":
+            nimg, hh, ww, cin, hidden, stride = a[3], a[4], a[5], a[6], a[10], a[11]
+            ho, wo = (hh if stride == 1 else (hh - 1) // 2 + 1), (ww if stride == 1 else (ww - 1) // 2 + 1)
+            fl = 2.0 * nimg * hh * ww * cin * hidden + 18.0 * nimg * ho * wo * hidden
+            by = 4.0 * nimg * (hh * ww * cin + ho * wo * hidden)
         elif op.name == "uavsal_dw3x3":
             nimg, hh, ww, c, stride = a[3], a[4], a[5], a[6], a[7]
             ho, wo = (hh if stride == 1 else (hh - 1) // 2 + 1), (ww if stride == 1 else (ww - 1) // 2 + 1)
@@ -261,11 +270,17 @@ def run_product_arm(args):
     tens_peak = float(peaks.get("bf16_tflops_sustained", 1590.0 * 0.88))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
-    plan20 = model.get_plan(dev, 20, H, W, x_kind=2, post_hw=(H, W), cb_shared=True)
-    plan20.named["x_in"].copy_(dev_clips[0][:20])
-    cls = time_op_classes(plan20, torch)
+    # per-op CUDA-event timing of the plan the runner actually replays (whole clip: 60 frames = three 20-frame reference calls)
+    if args.per_call:
+        plan_m = model.get_plan(dev, 20, H, W, x_kind=2, post_hw=(H, W), cb_shared=True)
+        prof_frames, prof_json = 20, "r01_call20_summary.json"
+    else:
+        plan_m = runner._plan(OUT_PER_CLIP, H, W, 0, "all", BATCH * T)
+        prof_frames, prof_json = OUT_PER_CLIP, "r01_clip60_summary.json"
+    plan_m.named["x_in"].copy_(dev_clips[0][:prof_frames])
+    cls = time_op_classes(plan_m, torch)
     detail = []
-    cls = time_op_classes(plan20, torch, detail)
+    cls = time_op_classes(plan_m, torch, detail)
     if args.dump_ops:
         with open(args.dump_ops, "w") as fh:
             fh.write("\n".join(detail) + "\n")
@@ -276,7 +291,7 @@ def run_product_arm(args):
     # measured DRAM traffic per kernel family from the committed ncu capture of the same 20-frame call (tools/profile_call.py)
     traffic = {}
     try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r01_call20_summary.json")))
+        summ = json.load(open(os.path.join(ROOT, "profiles", prof_json)))
         for k in summ["kernels"]:
             fam = "uavsal_pw_gemm" if k["kernel"].startswith("gemm_tc2_kernel<0") else ("uavsal_dw3x3" if k["kernel"].startswith("dw3x3") else None)
             if fam:
@@ -293,16 +308,16 @@ def run_product_arm(args):
     terms = 3 if args.precision == "exact" else 1
     dom = "uavsal_pw_gemm"
     ach = cls[dom][1] / cls[dom][0] / 1e9
-    roofline = {"kernel": "gemm_tc2_kernel<MODE_PW,EPI_STD,TERMS=%d,CL=1|2> (tcgen05 pointwise-conv GEMM, %d launches per 20-frame call)" % (terms, cls[dom][3]),
+    roofline = {"kernel": "gemm_tc2_kernel<MODE_PW,EPI_STD,TERMS=%d,CL=1|2> (tcgen05 pointwise-conv GEMM, %d launches per %d-frame plan)" % (terms, cls[dom][3], prof_frames),
                 "bound": "tensor", "achieved": round(ach, 2), "peak": tens_peak, "unit": "TFLOP/s", "frac": round(ach / tens_peak, 4),
                 "traffic": per_launch_traffic(dom), "peak_source": peak_src,
                 "algorithmic_flops_per_launch": round(cls[dom][1] / cls[dom][3]), "avg_launch_us": round(1e3 * cls[dom][0] / cls[dom][3], 2),
                 "issued_frac": round(terms * ach / tens_peak, 4),
                 "note": "achieved = algorithmic 2*M*K*N flops (1x) summed over the class / summed CUDA-event time; the bf16x3 split issues "
-                        "3x that on the tensor pipe (issued_frac); traffic = ncu dram bytes per launch (profiles/r01_call20_summary.json)"}
+                        "3x that on the tensor pipe (issued_frac); traffic = ncu dram bytes per launch (profiles/%s)" % prof_json}
     hb = "uavsal_dw3x3"
     ach_h = cls[hb][2] / cls[hb][0] / 1e6
-    roofline_hbm = {"kernel": "dw3x3_tma_kernel / dw3x3_kernel (depthwise 3x3 + BN + ReLU6, %d launches per 20-frame call)" % cls[hb][3],
+    roofline_hbm = {"kernel": "dw3x3_tma_kernel / dw3x3_kernel (depthwise 3x3 + BN + ReLU6, %d launches per %d-frame plan)" % (cls[hb][3], prof_frames),
                     "bound": "hbm", "achieved": round(ach_h, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach_h / hbm_peak, 4),
                     "traffic": per_launch_traffic(hb), "algorithmic_bytes_per_launch": round(cls[hb][2] / cls[hb][3]),
                     "avg_launch_us": round(1e3 * cls[hb][0] / cls[hb][3], 2)}
@@ -326,7 +341,7 @@ def run_product_arm(args):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.clips * OUT_PER_CLIP * H * W * 3,
                     "d2h_bytes_per_step": args.clips * OUT_PER_CLIP * H * W},
             "gpu_launches": launches * args.clips * args.steps, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
-            "breakdown_20_frame_call": breakdown, "hbm_peak_gbs": hbm_peak}
+            "breakdown_per_plan": breakdown, "breakdown_frames": prof_frames, "hbm_peak_gbs": hbm_peak}
     print(json.dumps(line), flush=True)
     D.shutdown()
     return 0

@@ -23,12 +23,13 @@ struct TwaStepArgs {
     int tmem_cols;
     int base_off_mode;                // descriptor base-offset convention for row-shifted views (see umma_desc_shift)
     int dbg;                          // DBG_* timing-ablation bits
+    int bstages;                      // depth of the weight ring
 };
 
 constexpr int kTwTW = 8, kTwTH = 16, kTwIW = kTwTW + 2, kTwIH = kTwTH + 2;
 constexpr uint32_t kTwAPlaneBytes = kTwIW * kTwIH * 128;              // 23 040 bytes landed per plane
 constexpr uint32_t kTwAPlane = 23 * 1024;                             // plane pitch (1024-aligned for the 128-B swizzle)
-constexpr int kTwBStages = 7;
+constexpr int kTwBStagesMax = 7;
 
 // K-major SW128 descriptor with an arbitrary stride between 8-row groups and an optional base offset
 __device__ __forceinline__ uint64_t umma_desc_shift(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
@@ -46,12 +47,12 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
     const uint32_t b_plane = (uint32_t)g.bn * 128, b_stage = NPL * b_plane;
     uint8_t* abuf = smem;                                                     // [2][a_stage]
     uint8_t* bbuf = abuf + 2 * a_stage;                                       // [kTwBStages][b_stage]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + kTwBStages * b_stage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + g.bstages * b_stage);
     uint64_t* a_full = bars;                   // [2]
     uint64_t* a_empty = bars + 2;              // [2]
     uint64_t* b_full = bars + 4;               // [kTwBStages]
-    uint64_t* b_empty = b_full + kTwBStages;   // [kTwBStages]
-    uint64_t* acc_full = b_empty + kTwBStages;
+    uint64_t* b_empty = b_full + kTwBStagesMax;
+    uint64_t* acc_full = b_empty + kTwBStagesMax;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < kTwBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < g.bstages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
                 for (int p = 0; p < NPL; ++p)
                     tma_load_5d(&tmA, a_full + sa, abuf + sa * a_stage + p * kTwAPlane, cb * 64, x0 - 1, y0 - 1, g.a_img, p);
                 for (int tap = 0; tap < 9; ++tap, ++kbB) {
-                    const int s = kbB % kTwBStages;
-                    mbar_wait(b_empty + s, ((kbB / kTwBStages) & 1) ^ 1);
+                    const int s = kbB % g.bstages;
+                    mbar_wait(b_empty + s, ((kbB / g.bstages) & 1) ^ 1);
                     if (g.dbg & DBG_NO_B) { mbar_arrive(b_full + s); continue; }
                     mbar_expect_tx(b_full + s, b_stage);
 #pragma unroll
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
             const int sa = cb & 1;
             mbar_wait(a_full + sa, (cb >> 1) & 1);
             for (int tap = 0; tap < 9; ++tap, ++kbB) {
-                const int s = kbB % kTwBStages;
-                mbar_wait(b_full + s, (kbB / kTwBStages) & 1);
+                const int s = kbB % g.bstages;
+                mbar_wait(b_full + s, (kbB / g.bstages) & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     // rows of the tap's view: haloed pixel ((g + tap/3) * 10 + i + tap%3), g = 0..15 (stride 1280 B), i = 0..7
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
 }
 
+int g_twa_bn = 64;          // uavsal_set_option key 8 (dev): N tile of the resident-A step kernel (64 | 128)
 int g_twa_resident = 1;     // uavsal_set_option key 7: 0 = generic implicit GEMM per step, 1 = resident-A kernel (2 = with descriptor base
                             // offsets: WRONG results - kept as the record of the experiment that settled the swizzle convention)
 
@@ -219,12 +221,13 @@ int g_twa_resident = 1;     // uavsal_set_option key 7: 0 = generic implicit GEM
 int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int out_img, int H, int W, int c, const uint16_t* wgt, int wk_total,
                       int wk_off, const float* gx, int terms, cudaStream_t s, int dbg) {
     TwaStepArgs g{};
-    g.H = H; g.W = W; g.C = c; g.bn = 64;
+    const uint32_t npl = terms == 3 ? 2 : 1;
+    g.H = H; g.W = W; g.C = c; g.bn = (g_twa_bn == 128 && c % 128 == 0) ? 128 : 64;
     g.tiles_x = div_up(W, kTwTW); g.tiles_y = div_up(H, kTwTH); g.ncb = c / 64;
     g.a_img = a_img; g.out_img = out_img;
     g.bk_tap_stride = wk_total; g.bk_off = wk_off;
     g.gx = gx; g.x = x; g.hprev = hsrc; g.out = seq;
-    g.tmem_cols = 64;
+    g.tmem_cols = g.bn;
     g.base_off_mode = g_twa_resident == 2;
     g.dbg = dbg;
     CUtensorMap tA, tB;
@@ -244,8 +247,9 @@ int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int o
         int rc = tc_encode(&tB, wgt, 3, dims, str, box, "twa_step B (weights)", 1);
         if (rc) return rc;
     }
-    const uint32_t npl = terms == 3 ? 2 : 1;
-    const size_t smem = 2 * (size_t)npl * kTwAPlane + (size_t)kTwBStages * npl * g.bn * 128 + 256 + 1024;
+    g.bstages = (int)((220u * 1024u - 2u * npl * kTwAPlane) / (npl * (uint32_t)g.bn * 128u));
+    if (g.bstages > kTwBStagesMax) g.bstages = kTwBStagesMax;
+    const size_t smem = 2 * (size_t)npl * kTwAPlane + (size_t)g.bstages * npl * g.bn * 128 + 256 + 1024;
     cudaError_t e;
     if (terms == 3) {
         static bool attr = false;

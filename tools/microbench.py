@@ -87,8 +87,8 @@ def conv(engine, n, h, w, c, co, terms=3):
     print("conv3x3[%s,t%d] n=%d %dx%d c=%d co=%d: %.1f us  %.1f TF/s(alg)" % (engine, terms, n, h, w, c, co, ms * 1e3, fl / ms / 1e9), flush=True)
 
 
-def twa(engine, t, h, w, c):
-    p = Plan(dev, 3, engine)
+def twa(engine, t, h, w, c, terms=3):
+    p = Plan(dev, terms, engine)
     x = p.alloc(t * h * w, c); x.t.normal_()
     h0 = p.alloc(h * w, c)
     seq = p.alloc(t * h * w, c)
@@ -163,6 +163,20 @@ def main():
             print("---", name)
             twa("tc", 60, 45, 80, 256)
         lib.uavsal_set_option(3, 0)
+    if what == "twa_bn":
+        lib = _ext.load()
+        for bn in (64, 128):
+            lib.uavsal_set_option(8, bn)
+            print("--- twa step kernel bn", bn)
+            twa("tc", 60, 45, 80, 256)
+            lib.uavsal_set_option(3, 1 << 16); twa("tc", 60, 45, 80, 256); lib.uavsal_set_option(3, 0)
+        lib.uavsal_set_option(8, 64)
+    if what == "twa_t1":
+        lib = _ext.load()
+        for terms in (3, 1):
+            print("--- terms", terms)
+            twa("tc", 60, 45, 80, 256, terms)
+            lib.uavsal_set_option(3, 1 << 16); twa("tc", 60, 45, 80, 256, terms); lib.uavsal_set_option(3, 0)
     if what == "stages":
         lib = _ext.load()
         for st in (1, 2, 3, 6):
