@@ -199,7 +199,8 @@ def run_product_arm(args):
     model = model.to(dev).set_mode(precision=args.precision)
     gauss, ob = load_priors()
     runner = ClipRunner(model, gauss, ob, batch_size=BATCH, out_hw=(H, W), use_graph=not args.no_graph, depth=args.depth,
-                        clip_backbone=not args.per_call_backbone, single_stream=args.single_stream, whole_clip=not args.per_call)
+                        clip_backbone=not args.per_call_backbone, single_stream=args.single_stream, whole_clip=not args.per_call,
+                        clips_per_plan=args.clips_per_plan)
     runner.warm(FRAMES, H, W)
 
     # distinct clips rotated across steps so inputs (4 x 44 MB) exceed the 126 MB L2; the arena traffic of a step
@@ -250,8 +251,13 @@ def run_product_arm(args):
     value = frames_per_step * args.steps / t_res
     e2e = frames_per_step * args.steps / t_e2e
     calls = [20, 20, 20]
+    cpp = args.clips_per_plan if not args.per_call else 1
     if not args.per_call:
-        launches = runner._plan(OUT_PER_CLIP, H, W, 0, "all", BATCH * T).num_launches
+        # launches per step of `--clips` clips: full batches of cpp clips plus single-clip plans for the remainder
+        nfull, nrem = divmod(args.clips * args.steps, cpp)
+        l_full = runner._plan(OUT_PER_CLIP * cpp, H, W, 0, "all", BATCH * T, cpp).num_launches
+        l_one = runner._plan(OUT_PER_CLIP, H, W, 0, "all", BATCH * T).num_launches
+        launches = (nfull * l_full + nrem * l_one) / float(args.clips * args.steps)
     elif args.per_call_backbone:
         launches = sum(runner._plan(n, H, W, 0).num_launches for n in calls)
     else:           # one SRF-Net plan per clip + one head plan per call
@@ -275,9 +281,11 @@ def run_product_arm(args):
         plan_m = model.get_plan(dev, 20, H, W, x_kind=2, post_hw=(H, W), cb_shared=True)
         prof_frames, prof_json = 20, "r01_call20_summary.json"
     else:
-        plan_m = runner._plan(OUT_PER_CLIP, H, W, 0, "all", BATCH * T)
-        prof_frames, prof_json = OUT_PER_CLIP, "r01_clip60_summary.json"
-    plan_m.named["x_in"].copy_(dev_clips[0][:prof_frames])
+        plan_m = runner._plan(OUT_PER_CLIP * cpp, H, W, 0, "all", BATCH * T, cpp)
+        prof_frames, prof_json = OUT_PER_CLIP * cpp, ("r01_clip60_summary.json" if cpp == 1 else "r01_clip120_summary.json")
+    for ci in range(prof_frames // min(prof_frames, OUT_PER_CLIP)):
+        nfr = min(prof_frames, OUT_PER_CLIP)
+        plan_m.named["x_in"][ci * nfr:(ci + 1) * nfr].copy_(dev_clips[ci % n_rot][:nfr])
     cls = time_op_classes(plan_m, torch)
     detail = []
     cls = time_op_classes(plan_m, torch, detail)
@@ -336,11 +344,11 @@ def run_product_arm(args):
             "warmup": warm, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split (fp32 accumulate)" if args.precision == "exact" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_step_per_gpu": args.clips, "frames_in_per_clip": FRAMES, "maps_out_per_clip": OUT_PER_CLIP,
-                       "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth, "plan": "one per clip (60 frames, call size 20 passed to the call-granular kernels)" if not args.per_call else "one per 20-frame call",
+                       "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth, "clips_per_plan": args.clips_per_plan, "plan": "one per clip (60 frames, call size 20 passed to the call-granular kernels)" if not args.per_call else "one per 20-frame call",
                        "l2": "inputs larger than L2: %d distinct clips rotated (%.0f MB) and ~9.5 GB of arena traffic per call" % (n_rot, n_rot * 44.2)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": args.clips * OUT_PER_CLIP * H * W * 3,
                     "d2h_bytes_per_step": args.clips * OUT_PER_CLIP * H * W},
-            "gpu_launches": launches * args.clips * args.steps, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
+            "gpu_launches": int(round(launches * args.clips * args.steps)), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "breakdown_per_plan": breakdown, "breakdown_frames": prof_frames, "hbm_peak_gbs": hbm_peak}
     print(json.dumps(line), flush=True)
     D.shutdown()
@@ -356,6 +364,8 @@ def main():
     ap.add_argument("--clips", type=int, default=1, help="clips per step per GPU")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--clips-per-plan", type=int, default=2, help="clips the runner queues into one plan (ConvTWA advances them as a batch); "
+                    "1 = every clip on its own")
     ap.add_argument("--per-call", action="store_true", help="keep Demo_Test's loop of 20-frame calls instead of one plan per clip")
     ap.add_argument("--single-stream", action="store_true", help="queue all stages of all calls on one stream (no overlap)")
     ap.add_argument("--per-call-backbone", action="store_true", help="run the SRF-Net per 20-frame call (as Demo_Test does) instead of once per clip")

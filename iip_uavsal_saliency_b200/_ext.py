@@ -37,7 +37,7 @@ _SIGNATURES = {
     "uavsal_tdiff_cat": ACT + [I, I, I] + ACT + [I, P],
     "uavsal_ctx_sum": ACT + [I, I, I, I] + ACT + [P],
     "uavsal_add": ACT + ACT + [L, I] + ACT + [P],
-    "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [P],
+    "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [I, P],
     "uavsal_convlstm_sequence": ACT + ACT + [P, I, I, I, I, I, I, P, P, P, I] + ACT + [P],
     "uavsal_dot_sigmoid": ACT + [L, I, P, F, P, P],
     "uavsal_post_u8": [P, I, I, I, I, I, P, P, P],

@@ -508,8 +508,8 @@ static inline bool act_ok16(const void* p, int64_t plane, int ld) {
 extern int g_dw_fast;
 namespace uavsal {
 extern int g_twa_resident, g_twa_bn;
-int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int out_img, int H, int W, int c, const uint16_t* wgt, int wk_total,
-                      int wk_off, const float* gx, int terms, cudaStream_t s, int dbg);
+int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, int a_stride, Act x, ActW seq, int out_img, int out_stride, int batch, int H, int W, int c,
+                      const uint16_t* wgt, int wk_total, int wk_off, const float* gx, int terms, cudaStream_t s, int dbg);
 }
 
 extern "C" {
@@ -572,35 +572,18 @@ int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h
                    ActW{out, out_plane, out_ld}, n, 1, 0, (cudaStream_t)stream, "conv3x3");
 }
 
-int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
-                        int t_steps, int h, int w, int c, const uint16_t* wgt, const float* wgt_f32, int terms,
-                        float* gx_workspace, uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream) {
-    UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
-                       t_steps > 0 && c % 8 == 0 && x_ld >= c && h0_ld >= c && seq_ld >= c,
-                   UAVSAL_EINVAL, "twa_sequence: bad arguments");
-    UAVSAL_REQUIRE((wgt != nullptr) != (wgt_f32 != nullptr), UAVSAL_EINVAL,
-                   "twa_sequence: pass exactly one of wgt (tcgen05) / wgt_f32 (SIMT)");
-    Act X{x, x_plane, x_ld}, H0{h0, h0_plane, h0_ld};
-    ActW S{seq_out, seq_plane, seq_ld};
-    cudaStream_t s = (cudaStream_t)stream;
-    if (wgt_f32) return twa_sequence_simt(X, H0, t_steps, h, w, c, wgt_f32, S, s);
-    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
-                   "twa_sequence: terms=3 needs lo planes");
-    Act SA{seq_out, seq_plane, seq_ld};
+// one sequence (batch element): x (t_steps images), h0 (1 image), seq (t_steps images)
+static int twa_sequence_one(Act X, Act H0, ActW S, int t_steps, int h, int w, int c, const uint16_t* wgt, int terms, float* gx_workspace,
+                            cudaStream_t s) {
+    Act SA{S.p, S.plane, S.ld};
+    int rc;
     if (gx_workspace && g_tc_version == 2) {
         // hoisted: G_x = W_x * x_t for ALL steps in one batched implicit GEMM (fp32 pre-activations), then per step only the
         // recurrent half W_h * h_{t-1} (K = 9c instead of 18c) with G_x[t] added in the epilogue before the gate
-        int rc = conv_tc(X, t_steps, 1, 0, c, X, t_steps, 1, 0, 0, t_steps, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
-                         nullptr, ActW{}, t_steps, 1, 0, s, "twa_sequence(x half)", 2 * c, 0, nullptr, gx_workspace);
+        rc = conv_tc(X, t_steps, 1, 0, c, X, t_steps, 1, 0, 0, t_steps, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
+                     nullptr, ActW{}, t_steps, 1, 0, s, "twa_sequence(x half)", 2 * c, 0, nullptr, gx_workspace);
         if (rc) return rc;
-        const int64_t fr = (int64_t)h * w * c;
         for (int t = 0; t < t_steps; ++t) {
-            if (g_twa_resident && c % 64 == 0 && c <= 512) {         // resident-A step kernel (twa_step.cu)
-                rc = t == 0 ? twa_step_resident(H0, 1, 0, X, S, 0, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug)
-                            : twa_step_resident(SA, t_steps, t - 1, X, S, t, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug);
-                if (rc) return rc;
-                continue;
-            }
             if (t == 0)
                 rc = conv_tc(H0, 1, 0, 0, c, H0, 1, 0, 0, 0, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S, t_steps, 0, 0,
                              s, "twa_sequence(h half)", 2 * c, c, gx_workspace, nullptr);
@@ -609,18 +592,54 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
                              S, t_steps, 0, t, s, "twa_sequence(h half)", 2 * c, c, gx_workspace, nullptr);
             if (rc) return rc;
         }
-        (void)fr;
         return 0;
     }
     for (int t = 0; t < t_steps; ++t) {
         // step t: A = [x_t, h_{t-1}], out = seq[t]
-        int rc;
         if (t == 0)
             rc = conv_tc(X, t_steps, 0, 0, c, H0, 1, 0, 0, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, H0, nullptr, S,
                          t_steps, 0, 0, s, "twa_sequence");
         else
             rc = conv_tc(X, t_steps, 0, t, c, SA, t_steps, 0, t - 1, c, 1, h, w, wgt, c, nullptr, 0, terms, EPI_TWA, X, SA,
                          nullptr, S, t_steps, 0, t, s, "twa_sequence");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
+                        int t_steps, int h, int w, int c, const uint16_t* wgt, const float* wgt_f32, int terms,
+                        float* gx_workspace, uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* stream) {
+    UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
+                       t_steps > 0 && batch > 0 && c % 8 == 0 && x_ld >= c && h0_ld >= c && seq_ld >= c,
+                   UAVSAL_EINVAL, "twa_sequence: bad arguments");
+    UAVSAL_REQUIRE((wgt != nullptr) != (wgt_f32 != nullptr), UAVSAL_EINVAL,
+                   "twa_sequence: pass exactly one of wgt (tcgen05) / wgt_f32 (SIMT)");
+    UAVSAL_REQUIRE(wgt_f32 || terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
+                   "twa_sequence: terms=3 needs lo planes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t hw = (int64_t)h * w;
+    if (!wgt_f32 && gx_workspace && g_tc_version == 2 && g_twa_resident && c % 64 == 0 && c <= 512) {
+        // all sequences of the batch advance together: W_x * x hoisted over batch*t_steps frames, then per step one launch of the
+        // resident-A kernel (twa_step.cu) with the batch in blockIdx.z
+        Act X{x, x_plane, x_ld}, H0{h0, h0_plane, h0_ld}, SA{seq_out, seq_plane, seq_ld};
+        ActW S{seq_out, seq_plane, seq_ld};
+        const int nimg = batch * t_steps;
+        int rc = conv_tc(X, nimg, 1, 0, c, X, nimg, 1, 0, 0, nimg, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
+                         nullptr, ActW{}, nimg, 1, 0, s, "twa_sequence(x half)", 2 * c, 0, nullptr, gx_workspace);
+        if (rc) return rc;
+        for (int t = 0; t < t_steps; ++t) {
+            rc = t == 0 ? twa_step_resident(H0, batch, 0, 1, X, S, 0, t_steps, batch, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug)
+                        : twa_step_resident(SA, nimg, t - 1, t_steps, X, S, t, t_steps, batch, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    for (int b = 0; b < batch; ++b) {
+        Act X{x + b * t_steps * hw * x_ld, x_plane, x_ld}, H0{h0 + b * hw * h0_ld, h0_plane, h0_ld};
+        ActW S{seq_out + b * t_steps * hw * seq_ld, seq_plane, seq_ld};
+        int rc = wgt_f32 ? twa_sequence_simt(X, H0, t_steps, h, w, c, wgt_f32, S, s)
+                         : twa_sequence_one(X, H0, S, t_steps, h, w, c, wgt, terms, gx_workspace ? gx_workspace + b * t_steps * hw * c : nullptr, s);
         if (rc) return rc;
     }
     return 0;

@@ -15,7 +15,8 @@ namespace uavsal {
 struct TwaStepArgs {
     int H, W, C, bn;                  // map size, channels (input = hidden = output), N tile
     int tiles_x, tiles_y, ncb;        // ncb = C / 64
-    int a_img, out_img;               // image index of h_{t-1} in its tensor, of h_t / x_t in theirs
+    int a_img, out_img;               // image index of h_{t-1} in its tensor, of h_t / x_t in theirs (sequence 0)
+    int a_stride, out_stride;         // image-index stride between the sequences of a batch (blockIdx.z)
     int bk_tap_stride, bk_off;        // weight K coordinate of (tap, cb) = tap * bk_tap_stride + bk_off + cb * 64
     const float* gx;                  // hoisted W_x * x_t pre-activations [rows][C] (fp32)
     Act x, hprev;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, n0 = blockIdx.y * g.bn;
+    const int a_img = g.a_img + (int)blockIdx.z * g.a_stride, out_img = g.out_img + (int)blockIdx.z * g.out_stride;
     const int y0 = (tile / g.tiles_x) * kTwTH, x0 = (tile % g.tiles_x) * kTwTW;
 
     if (threadIdx.x == 0) {
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
                 mbar_expect_tx(a_full + sa, NPL * kTwAPlaneBytes);
 #pragma unroll
                 for (int p = 0; p < NPL; ++p)
-                    tma_load_5d(&tmA, a_full + sa, abuf + sa * a_stage + p * kTwAPlane, cb * 64, x0 - 1, y0 - 1, g.a_img, p);
+                    tma_load_5d(&tmA, a_full + sa, abuf + sa * a_stage + p * kTwAPlane, cb * 64, x0 - 1, y0 - 1, a_img, p);
                 for (int tap = 0; tap < 9; ++tap, ++kbB) {
                     const int s = kbB % g.bstages;
                     mbar_wait(b_empty + s, ((kbB / g.bstages) & 1) ^ 1);
@@ -145,13 +147,13 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
         const int r = q * 32 + lane;
         const int64_t pix = pix_of(r);
         const int64_t hw = (int64_t)g.H * g.W;
-        const int64_t orow = (int64_t)g.out_img * hw + pix, hrow = (int64_t)g.a_img * hw + pix;
-        // the blend operands and the hoisted W_x*x_t term do not depend on the accumulator: fetch them while the MMAs run
-        // (issued after the wait they cost 8 us of a 33 us step: three dependent global round trips per thread)
-        const int n = n0 + sub;
+        const int64_t orow = (int64_t)out_img * hw + pix, hrow = (int64_t)a_img * hw + pix;
+        // the blend operands and the hoisted W_x*x_t term do not depend on the accumulator: those of the first 64-column chunk
+        // are fetched while the MMAs run (issued after the wait they cost 8 us of a 33 us step: three dependent global round
+        // trips per thread); wider N tiles load the later chunks' operands in the loop
         float gxv[16], xv[16], hv[16];
-        const bool live = pix >= 0 && sub < g.bn && !(g.dbg & DBG_NO_STORE);
-        if (live) {
+        const bool rowlive = pix >= 0 && !(g.dbg & DBG_NO_STORE);
+        auto fetch = [&](int n) {
             const float4* gp = reinterpret_cast<const float4*>(g.gx + orow * g.C + n);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -163,17 +165,21 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
                 load8(g.x.p + orow * g.x.ld + n + half * 8, g.x.plane, xv + half * 8);
                 load8(g.hprev.p + hrow * g.hprev.ld + n + half * 8, g.hprev.plane, hv + half * 8);
             }
-        }
+        };
+        if (rowlive) fetch(n0 + sub);
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (sub < g.bn) {
+        for (int ch = 0; ch < (g.bn >> 6); ++ch) {
+            const int n = n0 + ch * 64 + sub;
+            if (ch > 0 && rowlive) fetch(n);
             uint32_t raw[16];
-            tmem_ld16(trow + sub, raw);
+            __syncwarp();
+            tmem_ld16(trow + ch * 64 + sub, raw);
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-            if (live) {
+            if (rowlive) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float gi = sigmoid_acc(v[j] + gxv[j]);
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(kThreads2, 1) twa_step_kernel(const __grid_con
                 const uint4 lv4 = lds128(wst + 1024 + off);
                 const int64_t px = pix_of(q * 32 + row);
                 if (px >= 0 && !(g.dbg & DBG_NO_STORE)) {
-                    uint16_t* dst = g.out.p + ((int64_t)g.out_img * hw + px) * g.out.ld + n + c * 8;
+                    uint16_t* dst = g.out.p + ((int64_t)out_img * hw + px) * g.out.ld + n + c * 8;
                     *reinterpret_cast<uint4*>(dst) = hv4;
                     if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = lv4;
                 }
@@ -218,13 +224,21 @@ int g_twa_resident = 1;     // uavsal_set_option key 7: 0 = generic implicit GEM
                             // offsets: WRONG results - kept as the record of the experiment that settled the swizzle convention)
 
 // one step: seq[out_img] = blend(sigmoid(gx[out_img] + conv3x3(hsrc[a_img]; W_h)), x[out_img], hsrc[a_img])
-int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int out_img, int H, int W, int c, const uint16_t* wgt, int wk_total,
-                      int wk_off, const float* gx, int terms, cudaStream_t s, int dbg) {
+// batch sequences per launch: sequence b reads image a_img + b*a_stride and writes image out_img + b*out_stride
+int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, int a_stride, Act x, ActW seq, int out_img, int out_stride, int batch, int H, int W, int c,
+                      const uint16_t* wgt, int wk_total, int wk_off, const float* gx, int terms, cudaStream_t s, int dbg) {
     TwaStepArgs g{};
     const uint32_t npl = terms == 3 ? 2 : 1;
-    g.H = H; g.W = W; g.C = c; g.bn = (g_twa_bn == 128 && c % 128 == 0) ? 128 : 64;
+    g.H = H; g.W = W; g.C = c;
+    // N tile: as narrow as keeps the whole step on one wave of SMs (the step is latency-bound; measured equal time at 64 / 128)
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int tiles = div_up(W, kTwTW) * div_up(H, kTwTH);
+    g.bn = 64;
+    while (g.bn < 256 && c % (2 * g.bn) == 0 && (int64_t)tiles * batch * (c / g.bn) > sms) g.bn *= 2;
+    if (g_twa_bn == 128 && c % 128 == 0 && g.bn < 128) g.bn = 128;
     g.tiles_x = div_up(W, kTwTW); g.tiles_y = div_up(H, kTwTH); g.ncb = c / 64;
-    g.a_img = a_img; g.out_img = out_img;
+    g.a_img = a_img; g.out_img = out_img; g.a_stride = a_stride; g.out_stride = out_stride;
     g.bk_tap_stride = wk_total; g.bk_off = wk_off;
     g.gx = gx; g.x = x; g.hprev = hsrc; g.out = seq;
     g.tmem_cols = g.bn;
@@ -258,7 +272,7 @@ int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int o
             if (e != cudaSuccess) { set_error("twa_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
             attr = true;
         }
-        e = launch_k(twa_step_kernel<3>, dim3(g.tiles_x * g.tiles_y, c / g.bn), dim3(kThreads2), smem, s, 1, tA, tB, g);
+        e = launch_k(twa_step_kernel<3>, dim3(g.tiles_x * g.tiles_y, c / g.bn, batch), dim3(kThreads2), smem, s, 1, tA, tB, g);
     } else {
         static bool attr = false;
         if (!attr) {
@@ -266,7 +280,7 @@ int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, Act x, ActW seq, int o
             if (e != cudaSuccess) { set_error("twa_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
             attr = true;
         }
-        e = launch_k(twa_step_kernel<1>, dim3(g.tiles_x * g.tiles_y, c / g.bn), dim3(kThreads2), smem, s, 1, tA, tB, g);
+        e = launch_k(twa_step_kernel<1>, dim3(g.tiles_x * g.tiles_y, c / g.bn, batch), dim3(kThreads2), smem, s, 1, tA, tB, g);
     }
     if (e != cudaSuccess) { set_error("twa_step: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("twa_step");

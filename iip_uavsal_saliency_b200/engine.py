@@ -251,16 +251,17 @@ class Plan:
     def ctx_sum(self, x: Buf, b, t, hw, c, out: Buf, tag=""):
         self._add("uavsal_ctx_sum", (*x.act(), b, t, hw, c, *out.act()), tag)
 
-    def twa(self, x: Buf, h0: Buf, t_steps, h, w, c, w4d: torch.Tensor, seq: Buf, tag=""):
+    def twa(self, x: Buf, h0: Buf, t_steps, h, w, c, w4d: torch.Tensor, seq: Buf, tag="", batch: int = 1):
+        """``batch`` independent sequences (x / seq: batch*t_steps frames, sequence-major; h0: batch frames) advance together."""
         w2d = conv3x3_as_2d(w4d.detach().float())
         if self.engine != "simt":
             wp = self.hold(split_bf16(w2d))
-            gx = self.tensor((t_steps * h * w, c)) if (self.engine == "tc" and c % 64 == 0) else None     # hoisted W_x*x_t workspace
+            gx = self.tensor((batch * t_steps * h * w, c)) if (self.engine == "tc" and c % 64 == 0) else None     # hoisted W_x*x_t workspace
             self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, wp.data_ptr(), 0, self.terms,
-                                              gx.data_ptr() if gx is not None else 0, *seq.act()), tag)
+                                              gx.data_ptr() if gx is not None else 0, *seq.act(), batch), tag)
         else:
             wp = self.hold(w2d.t().contiguous())
-            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, 0, wp.data_ptr(), self.terms, 0, *seq.act()), tag)
+            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, 0, wp.data_ptr(), self.terms, 0, *seq.act(), batch), tag)
 
     def lstm(self, x: Buf, h0: Buf, c_state: torch.Tensor, b, t_steps, h, w, cin, ch, w4d, bias, seq: Buf, tag=""):
         wi = interleave_gates(w4d.detach().float(), ch)
@@ -339,7 +340,7 @@ class Plan:
         n = 0
         for op in self.ops:
             if op.name == "uavsal_twa_sequence":
-                n += op.args[6] + (1 if op.args[13] else 0)
+                n += op.args[6] * (1 if op.args[13] else op.args[17]) + (1 if op.args[13] else 0)
             elif op.name == "uavsal_convlstm_sequence":
                 n += op.args[8] * (1 if self.engine != "simt" else op.args[7])
             elif op.name == "uavsal_post_u8":

@@ -201,7 +201,7 @@ class UAVSal(KernelModule):
 
     # -----------------------------------------------------------------------------------------------
     def build_plan(self, plan: Plan, n: int, h: int, w: int, x_kind: int = 0, post_hw=None, taps: bool = False,
-                   cb_shared: bool = False, stage: str = "all", group: int = 0):
+                   cb_shared: bool = False, stage: str = "all", group: int = 0, clips: int = 1):
         """Emit the whole forward for a call of n frames of (h, w) pixels.
         x_kind: 0 fp32 NCHW normalised, 1 uint8 NCHW raw, 2 uint8 NHWC raw.  post_hw=(H,W) adds the uint8 post-process.
         cb_shared: cb tensors hold ONE frame that is broadcast to all n (Demo_Test's np.repeat'ed priors).
@@ -209,9 +209,13 @@ class UAVSal(KernelModule):
         runner may batch a whole clip), "head" (everything after the SRF-Net, fed from the arena input ``sf_in``).
         group: > 0 = the n frames are CONSECUTIVE reference calls of `group` frames each (the last may be shorter) emitted as
         one plan: the only call-granular operations - the temporal differences' mirrored edges (model.py:194-198) and the
-        context prior's repeat interleave (model.py:361) - are told the call size; the ConvTWA state simply runs through."""
+        context prior's repeat interleave (model.py:361) - are told the call size; the ConvTWA state simply runs through.
+        clips: the n frames are `clips` independent clips of n/clips frames each (clip-major); everything up to the ConvTWA is
+        per frame / per call group anyway, the ConvTWA runs the clips as a batch of sequences (own state each)."""
         planes, T = self._planes, self.time_dims
         assert stage in ("all", "sfnet", "head")
+        if clips > 1 and (n % clips or not group or (n // clips) % group):
+            raise ValueError("batched clips need n divisible by clips and clips made of whole calls (n=%d clips=%d group=%d)" % (n, clips, group))
         if group:
             if group % T or (n % group) % T:
                 raise ValueError("call size %d / batch %d must be multiples of time_dims=%d" % (group, n, T))
@@ -294,14 +298,15 @@ class UAVSal(KernelModule):
         # temporal weighted average over the call's frames, batch 1 (model.py:367-370).  Everything from here on depends on
         # the previous call's hidden state: it is the plan's "back" part (runner.ClipRunner overlaps it with the next front)
         plan.mark_split()
-        h_in = plan.tensor((1, planes, mh, mw))
-        hb = plan.alloc(mh * mw, planes)
-        plan.pack_nchw(h_in, 1, planes, mh, mw, hb, tag="state.pack")
+        h_in = plan.tensor((clips, planes, mh, mw))
+        hb = plan.alloc(clips * mh * mw, planes)
+        plan.pack_nchw(h_in, clips, planes, mh, mw, hb, tag="state.pack")
         seq = plan.alloc(rows, planes)
-        emit_twa(plan, self.rnn.cell_list[0], x, hb, seq, 1, n, mh, mw)
-        h_out = plan.tensor((1, planes, mh, mw))
-        last = Buf(seq.t, seq.rows, planes, seq.ld, (n - 1) * mh * mw * seq.ld)
-        plan.unpack_nchw(last, 1, planes, mh, mw, h_out, tag="state.unpack")
+        emit_twa(plan, self.rnn.cell_list[0], x, hb, seq, clips, n // clips, mh, mw)
+        h_out = plan.tensor((clips, planes, mh, mw))
+        for ci in range(clips):
+            last = Buf(seq.t, seq.rows, planes, seq.ld, ((ci + 1) * (n // clips) - 1) * mh * mw * seq.ld)
+            plan.unpack_nchw(last, 1, planes, mh, mw, h_out[ci:ci + 1], tag="state.unpack")
         # readout: expand + dw (dwBlock 256->1), then the 1536->1 project + BN + sigmoid as a dot product (model.py:372-373)
         ro = self.conv_out_st
         e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", f32_out=plan.f32_hidden)
@@ -320,10 +325,10 @@ class UAVSal(KernelModule):
         plan.named.update(named)
         return plan
 
-    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0, stage="all", group=0) -> Plan:
+    def get_plan(self, dev, n, h, w, x_kind=0, post_hw=None, taps=False, cb_shared=False, slot=0, stage="all", group=0, clips=1) -> Plan:
         """``slot`` selects one of several independent plan instances (own arena) so that calls can be in flight together."""
-        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot, stage, group)
-        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared, stage, group))
+        key = (torch.device(dev), "uavsal", n, h, w, x_kind, post_hw, taps, cb_shared, slot, stage, group, clips)
+        return self._cached_plan(key, lambda plan: self.build_plan(plan, n, h, w, x_kind, post_hw, taps, cb_shared, stage, group, clips))
 
     def forward(self, x, cb, in_state):
         require_cuda(x, "UAVSal")

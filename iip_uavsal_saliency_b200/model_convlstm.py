@@ -113,13 +113,8 @@ def _run_twa(cell: ConvTWACell, x5: torch.Tensor, h0: torch.Tensor):
 
 
 def emit_twa(plan, cell, xb, hb, seq, b, t, h, w):
-    from .engine import Buf
-    c = cell.hidden_dim
-    hw = h * w
-    for bi in range(b):
-        def rows(buf, r0):
-            return Buf(buf.t, buf.rows, buf.c, buf.ld, buf.off + r0 * buf.ld)
-        plan.twa(rows(xb, bi * t * hw), rows(hb, bi * hw), t, h, w, c, cell.rnn_conv.weight, rows(seq, bi * t * hw), tag="rnn")
+    """b independent sequences of t frames (sequence-major rows) through one batched sequence op."""
+    plan.twa(xb, hb, t, h, w, cell.hidden_dim, cell.rnn_conv.weight, seq, tag="rnn", batch=b)
 
 
 def _run_lstm(cell: ConvLSTMCell, x5, h0, c0):

@@ -40,7 +40,7 @@ from .model import UAVSal
 class ClipRunner:
     def __init__(self, model: UAVSal, gauss: np.ndarray, ob: np.ndarray, batch_size: int = 4, out_hw: Optional[Tuple[int, int]] = None,
                  use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2, clip_backbone: bool = True,
-                 single_stream: bool = False, whole_clip: bool = True):
+                 single_stream: bool = False, whole_clip: bool = True, clips_per_plan: int = 1):
         """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw';
         depth = calls in flight (1 = strictly serial on the caller's stream order); clip_backbone: run the SRF-Net once per
         clip instead of once per call."""
@@ -63,16 +63,21 @@ class ClipRunner:
         self._slot_free = [None] * self.depth          # event: the slot's previous call has left the back stream
         self._calls = 0
         self.whole_clip = bool(whole_clip)
+        # throughput mode: queue `clips_per_plan` equally shaped clips into ONE plan (the ConvTWA then advances them as a batch
+        # of sequences - its per-step launches are latency-bound - and every other launch sees that many times the rows).
+        # Only run_clip(..., out=buffer, want_maps=False, sync=False) calls are combined; finish() flushes a partial batch.
+        self.clips_per_plan = max(1, int(clips_per_plan))
+        self._pending = []
         self.clip_backbone = bool(clip_backbone)
         self.bb_stream = one or torch.cuda.Stream(self.dev)
         self._sf_free = [[], []]                       # events: the heads of the previous clip on this slot have read its SRF-Net output
         self._clips = 0
 
-    def _plan(self, n, H, W, slot, stage=None, group=0):
+    def _plan(self, n, H, W, slot, stage=None, group=0, clips=1):
         post = self.out_hw or (H, W)
         stage = stage or ("head" if self.clip_backbone else "all")
         plan = self.model.get_plan(self.dev, n, H, W, x_kind=self.kind, post_hw=None if stage == "sfnet" else post, cb_shared=True,
-                                   slot=slot, stage=stage, group=group)
+                                   slot=slot, stage=stage, group=group, clips=clips)
         if "ready" not in plan.named:
             torch.cuda.synchronize(self.dev)
             if stage != "sfnet":
@@ -93,6 +98,8 @@ class ClipRunner:
         if self.whole_clip:
             for slot in range(2):
                 self._plan(keep, H, W, slot, "all", self.per_call)
+                if self.clips_per_plan > 1 and keep % self.per_call == 0:
+                    self._plan(keep * self.clips_per_plan, H, W, slot, "all", self.per_call, self.clips_per_plan)
             return
         sizes = {min(self.per_call, keep - i * self.per_call) for i in range(math.ceil(keep / self.per_call))}
         for slot in range(self.depth):
@@ -104,6 +111,7 @@ class ClipRunner:
 
     def finish(self):
         """Make the caller's stream wait for everything the runner has queued (needed after run_clip(sync=False))."""
+        self._flush()
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_stream(self.back_stream)
         cur.wait_stream(self.bb_stream)
@@ -203,11 +211,41 @@ class ClipRunner:
                     t.record_stream(cur)
         return m, u8
 
+    def _flush(self):
+        """Launch whatever run_clip has queued for batching (a partial batch runs clip by clip)."""
+        pend, self._pending = self._pending, []
+        if not pend:
+            return
+        if len(pend) == self.clips_per_plan:
+            self._launch_whole([p[0] for p in pend], pend[0][1], pend[0][2], pend[0][3], False, [p[4] for p in pend])
+        else:
+            for fr, keep, H, W, out in pend:
+                self._launch_whole([fr], keep, H, W, False, [out])
+
     def _run_whole(self, frames, keep, H, W, want_maps, out, sync):
         """One plan for the whole clip (see the module docstring); front of clip k+1 overlaps the recurrent back of clip k."""
+        if self.clips_per_plan > 1 and not sync and not want_maps and out is not None and keep % self.per_call == 0:
+            if self._pending and (self._pending[0][1], self._pending[0][2], self._pending[0][3]) != (keep, H, W):
+                self._flush()
+            self._pending.append((frames, keep, H, W, out))
+            if len(self._pending) == self.clips_per_plan:
+                self._flush()
+            return None, out[:keep]
+        self._flush()
+        m, u8 = self._launch_whole([frames], keep, H, W, want_maps, [out])
+        if sync:
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_stream(self.back_stream)
+            for t in (m, u8):
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
+        return m, u8
+
+    def _launch_whole(self, clips, keep, H, W, want_maps, outs):
+        nc = len(clips)
         slot = self._clips % 2
         self._clips += 1
-        plan = self._plan(keep, H, W, slot, "all", self.per_call)
+        plan = self._plan(keep * nc, H, W, slot, "all", self.per_call, nc)
         nm = plan.named
         cur = torch.cuda.current_stream(self.dev)
         ready = torch.cuda.Event()
@@ -218,26 +256,24 @@ class ClipRunner:
         for ev in self._sf_free[slot]:
             fs.wait_event(ev)
         with torch.cuda.stream(fs):
-            nm["x_in"].copy_(frames[:keep], non_blocking=True)
+            for ci, fr in enumerate(clips):
+                nm["x_in"][ci * keep:(ci + 1) * keep].copy_(fr[:keep], non_blocking=True)
             plan.launch("front")
             fdone = torch.cuda.Event()
             fdone.record(fs)
         bs.wait_event(fdone)
         with torch.cuda.stream(bs):
-            nm["h_in"].zero_()                                      # a clip starts from the zero state (Demo_Test.py:75)
+            nm["h_in"].zero_()                                      # every clip starts from the zero state (Demo_Test.py:75)
             plan.launch("back")
             m = nm["out"].clone() if want_maps else None
-            if out is not None:
-                out[:keep].copy_(nm["out_u8"], non_blocking=True)
-                u8 = out[:keep]
-            else:
-                u8 = nm["out_u8"].clone()
+            u8 = None
+            for ci, out in enumerate(outs):
+                if out is not None:
+                    out[:keep].copy_(nm["out_u8"][ci * keep:(ci + 1) * keep], non_blocking=True)
+                    u8 = out[:keep]
+                else:
+                    u8 = nm["out_u8"][ci * keep:(ci + 1) * keep].clone()
             free = torch.cuda.Event()
             free.record(bs)
             self._sf_free[slot] = [free]
-        if sync:
-            cur.wait_stream(bs)
-            for t in (m, u8):
-                if t is not None and t.is_cuda:
-                    t.record_stream(cur)
         return m, u8

@@ -149,8 +149,9 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
                         const uint16_t* h0, int64_t h0_plane, int h0_ld,
                         int t_steps, int h, int w, int c,
                         const uint16_t* wgt, const float* wgt_f32, int terms, float* gx_workspace,
-                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream);
-/*      gx_workspace (optional, t_steps*h*w*c floats): when given, the input half W_x*x_t of the gate conv is hoisted out
+                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* stream);
+/*      batch independent sequences advance together (x, seq: batch*t_steps images, sequence-major; h0: batch images).
+ *      gx_workspace (optional, batch*t_steps*h*w*c floats): when given, the input half W_x*x_t of the gate conv is hoisted out
  *      of the recurrence into one batched implicit GEMM and only W_h*h_{t-1} (K = 9c) runs per step. */
 
 /* ---- K9: ConvLSTM sequence, one layer, batch_first (model_convlstm.py:111-126 cell, 199-212 loop).

@@ -338,6 +338,62 @@ def test_clip_runner_config2_and_config1(cuda, gold_dir):
         assert np.abs(u8.cpu().numpy()[[0, 7, 14]].astype(int) - g1[kind + "_u8_frames"].astype(int)).max() <= 1
 
 
+def test_scheduling_variants_agree(cuda, gold_dir):
+    """ClipRunner's scheduling choices must not change results: stream pipelining and batching two clips into one plan are
+    bit-exact; one plan per clip vs Demo_Test's loop of 20-frame calls agrees to the last bit of the state re-split (<= 1 LSB)."""
+    from iip_uavsal_saliency_b200.model import UAVSal
+    from iip_uavsal_saliency_b200.runner import ClipRunner
+    pr = np.load(os.path.join(gold_dir, "priors.npz"))
+    gauss, ob = pr["gauss"], pr["uav2_u8"].astype(np.float32) / 255
+    m = UAVSal().eval()
+    m.load_state_dict(synth.make_state_dict("lively", 0), strict=True)
+    m = m.cuda()
+    clips = [torch.from_numpy(synth.make_clip(30 + i, 44, 360, 640)).cuda() for i in range(3)]      # 44 frames -> 40 kept = 2 calls
+    outs = {}
+    for name, kw in (("loop", dict(depth=1, whole_clip=False, clip_backbone=False)), ("clip", dict(single_stream=True)),
+                     ("clip+streams", dict()), ("two-clips", dict(clips_per_plan=2))):
+        r = ClipRunner(m, gauss, ob, batch_size=4, **kw)
+        bufs = [torch.empty(40, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
+        for c, b in zip(clips, bufs):
+            r.run_clip(c, want_maps=False, out=b, sync=False)
+        r.finish()
+        torch.cuda.synchronize()
+        outs[name] = [b.cpu() for b in bufs]
+        del r
+        m._plan_cache().clear()
+        torch.cuda.empty_cache()
+    for a, b in (("clip", "clip+streams"), ("clip", "two-clips")):
+        assert all(torch.equal(x, y) for x, y in zip(outs[a], outs[b])), (a, b)
+    assert max(int((x.int() - y.int()).abs().max()) for x, y in zip(outs["loop"], outs["clip"])) <= 1
+
+
+def test_batched_twa_sequences(cuda):
+    """ConvTWA over a batch of independent sequences (wide N tile of the resident-A step kernel) == one sequence at a time."""
+    from iip_uavsal_saliency_b200.engine import Buf
+    torch.manual_seed(13)
+    for (b, t, h, w, c) in [(2, 4, 45, 80, 256), (3, 3, 20, 24, 128)]:
+        wgt = torch.randn(c, 2 * c, 3, 3, device="cuda") * 0.02
+        x, h0 = torch.randn(b * t * h * w, c, device="cuda"), torch.randn(b * h * w, c, device="cuda") * 0.5
+        outs = []
+        for batched in (True, False):
+            p = _plan()
+            xb, hb, seq = p.alloc(b * t * h * w, c), p.alloc(b * h * w, c), p.alloc(b * t * h * w, c)
+            for buf, src in ((xb, x), (hb, h0)):
+                hi = src.to(torch.bfloat16)
+                buf.t[0].copy_(hi)
+                buf.t[1].copy_((src - hi.float()).to(torch.bfloat16))
+            if batched:
+                p.twa(xb, hb, t, h, w, c, wgt, seq, batch=b)
+            else:
+                for bi in range(b):
+                    rows = lambda buf, r0: Buf(buf.t, buf.rows, buf.c, buf.ld, buf.off + r0 * buf.ld)
+                    p.twa(rows(xb, bi * t * h * w), rows(hb, bi * h * w), t, h, w, c, wgt, rows(seq, bi * t * h * w))
+            p.run()
+            torch.cuda.synchronize()
+            outs.append(seq.to_float().clone())
+        assert torch.equal(outs[0], outs[1])
+
+
 def test_fast_mode_is_reported_not_claimed(cuda, gold_dir):
     """bf16x1 'fast' mode: runs, stays highly correlated, but is NOT held to the 2e-3 bar."""
     from iip_uavsal_saliency_b200.model import UAVSal

@@ -16,7 +16,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["simt_units", "f32_hidden", "expdw", "dwproj", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
+GROUPS = ["simt_units", "f32_hidden", "expdw", "dwproj", "twa_batch", "tc_pw", "tc_conv", "rnn_simt", "rnn_tc", "post_metrics", "e2e_simt", "e2e_tc1", "e2e_tc", "runner"]
 
 
 def rel(a, b):
@@ -310,6 +310,36 @@ def g_rnn_tc():
     rnn_cases("tc")
 
 
+def g_twa_batch():
+    """batched ConvTWA sequences (several clips advance together; wide N tile) == the sequences run one by one."""
+    import torch
+    from iip_uavsal_saliency_b200.engine import Plan
+    torch.manual_seed(13)
+    dev = torch.device("cuda")
+    for (b, t, h, w, c) in [(2, 6, 45, 80, 256), (3, 4, 20, 24, 128), (2, 3, 45, 80, 64)]:
+        wgt = torch.randn(c, 2 * c, 3, 3, device=dev) * 0.02
+        x = torch.randn(b * t * h * w, c, device=dev)
+        h0 = torch.randn(b * h * w, c, device=dev) * 0.5
+        outs = []
+        for mode in ("batched", "single"):
+            p = Plan(dev, 3, "tc")
+            xb, hb, seq = p.alloc(b * t * h * w, c), p.alloc(b * h * w, c), p.alloc(b * t * h * w, c)
+            for buf, src in ((xb, x), (hb, h0)):
+                hi = src.to(torch.bfloat16)
+                buf.t[0].copy_(hi); buf.t[1].copy_((src - hi.float()).to(torch.bfloat16))
+            if mode == "batched":
+                p.twa(xb, hb, t, h, w, c, wgt, seq, batch=b)
+            else:
+                from iip_uavsal_saliency_b200.engine import Buf
+                for bi in range(b):
+                    rows = lambda buf, r0: Buf(buf.t, buf.rows, buf.c, buf.ld, buf.off + r0 * buf.ld)
+                    p.twa(rows(xb, bi * t * h * w), rows(hb, bi * h * w), t, h, w, c, wgt, rows(seq, bi * t * h * w))
+            p.run(); torch.cuda.synchronize()
+            outs.append(seq.to_float().clone())
+        d = (outs[0] - outs[1]).abs().max().item()
+        print("ConvTWA batched b=%d t=%d %dx%d c=%d vs one-by-one: max diff %.3e  %s" % (b, t, h, w, c, d, "ok" if d == 0 else "FAIL"), flush=True)
+
+
 def g_post_metrics():
     import numpy as np
     import torch
@@ -431,7 +461,8 @@ def g_runner():
     outs = {}
     for name, kw in (("per-call serial", dict(depth=1, whole_clip=False, clip_backbone=False)),
                      ("per-call pipelined", dict(depth=3, whole_clip=False, clip_backbone=True)),
-                     ("clip-plan single-stream", dict(single_stream=True)), ("clip-plan pipelined", dict())):
+                     ("clip-plan single-stream", dict(single_stream=True)), ("clip-plan pipelined", dict()),
+                     ("two clips per plan", dict(clips_per_plan=2))):
         rr = ClipRunner(m, gauss, ob, batch_size=4, **kw)
         rr.warm(64, 360, 640)
         bufs = [torch.empty(60, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
@@ -454,7 +485,7 @@ def g_runner():
         torch.cuda.empty_cache()
     eq = lambda a, b: all(torch.equal(x, y) for x, y in zip(outs[a], outs[b]))
     same_call = eq("per-call serial", "per-call pipelined") and torch.equal(outs["per-call serial"][0], torch.from_numpy(u8))
-    same_clip = eq("clip-plan single-stream", "clip-plan pipelined")
+    same_clip = eq("clip-plan single-stream", "clip-plan pipelined") and eq("clip-plan pipelined", "two clips per plan")
     ndiff = max(int((a.int() - b.int()).abs().max()) for a, b in zip(outs["per-call serial"], outs["clip-plan pipelined"]))
     gd = np.abs(outs["clip-plan pipelined"][0].numpy()[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int)).max()
     print("RUNNER pipelined == serial: per-call %s, clip-plan %s; clip-plan vs per-call max uint8 diff %d; clip-plan vs reference golden %d  %s"
