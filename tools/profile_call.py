@@ -24,11 +24,14 @@ def main():
     m = UAVSal().eval()
     m.load_state_dict(synth.make_state_dict("lively", 0), strict=True)
     m = m.to(dev).set_mode(precision=precision)
-    plan = m.get_plan(dev, n, 360, 640, x_kind=2, post_hw=(360, 640), cb_shared=True, group=20 if n > 20 else 0)
+    clips = max(1, n // 60)                                       # 120 = two clips batched into one plan
+    plan = m.get_plan(dev, n, 360, 640, x_kind=2, post_hw=(360, 640), cb_shared=True, group=20 if n > 20 else 0, clips=clips)
     pr = np.load(os.path.join(ROOT, "tests", "golden", "priors.npz"))
     plan.named["cb_gauss_in"].copy_(torch.from_numpy(pr["gauss"].transpose(2, 0, 1)[None]))
     plan.named["cb_ob_in"].copy_(torch.from_numpy((pr["uav2_u8"].astype(np.float32) / 255).transpose(2, 0, 1)[None]))
-    plan.named["x_in"].copy_(torch.from_numpy(synth.make_clip(2, n, 360, 640)))
+    for ci in range(clips):
+        per = n // clips
+        plan.named["x_in"][ci * per:(ci + 1) * per].copy_(torch.from_numpy(synth.make_clip(2 + ci, per, 360, 640)))
     plan.run()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
