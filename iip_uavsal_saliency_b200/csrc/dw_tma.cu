@@ -20,6 +20,8 @@ struct DwArgs {
     const float* bias;     // [c]
     int relu6;
     ActW out;
+    const float* wproj;    // DOT mode: weights of a following 1-output pointwise conv [c]
+    float* partial;        // DOT mode: per-(pixel, 64-channel block) partial dot products [n*ho*wo][cblocks]
 };
 
 template <int STRIDE>
@@ -53,7 +55,10 @@ __device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pi
 
 // thread = (4-channel quad, output column[, row group]); it keeps its 36 folded weights in registers for the tile and
 // slides a 3x3x4 register window down RPT output rows.
-template <int STRIDE, bool F32IN>
+// DOT: instead of storing the depthwise output, every thread folds its 4 channels into the dot product with `wproj` (the
+// dwBlock's project conv when it has ONE output channel: the readout, model.py:372), the 16 threads sharing a pixel reduce by
+// shuffles and one partial per (pixel, channel block) is written; dot_finish_kernel adds the blocks in a fixed order.
+template <int STRIDE, bool F32IN, bool DOT>
 __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs g) {
     using G = DwGeom<STRIDE>;
     extern __shared__ uint8_t smem_raw[];
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
         decode(t, cblk, x0, y0, img);
         const int c0 = cblk * 64 + quad * 4;
         const bool cvalid = c0 < g.c;
-        float wr[9][4], br[4];
+        float wr[9][4], br[4], wp[4] = {0.f, 0.f, 0.f, 0.f};
         if (cvalid) {                                                          // overlaps the TMA flight time (L1/L2 hits)
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -111,11 +116,19 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
             }
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
             br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
+            if (DOT) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.wproj + c0));
+                wp[0] = p4.x; wp[1] = p4.y; wp[2] = p4.z; wp[3] = p4.w;
+            }
+        } else if (DOT) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { wr[k][0] = wr[k][1] = wr[k][2] = wr[k][3] = 0.f; }
+            br[0] = br[1] = br[2] = br[3] = 0.f;
         }
         mbar_wait(bar + b, (it >> 1) & 1);
 
         const int ox = x0 + col;
-        if (cvalid && ox < g.wo) {
+        if (DOT || (cvalid && ox < g.wo)) {                                    // DOT: all lanes stay for the shuffles
             const uint32_t tile = smem_u32(smem) + b * G::TILE_BYTES;
             float win[3][3][4];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
@@ -153,6 +166,14 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
                 }
+                if (DOT) {
+                    float d = acc[0] * wp[0] + acc[1] * wp[1] + acc[2] * wp[2] + acc[3] * wp[3];
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);      // the 16 quads of this pixel
+                    if (quad == 0 && ox < g.wo)
+                        g.partial[(((int64_t)img * g.ho + oy) * g.wo + ox) * g.cblocks + cblk] = d;
+                    continue;
+                }
                 store4(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
             }
         }
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     }
 }
 
-template <int STRIDE, bool F32IN>
+template <int STRIDE, bool F32IN, bool DOT = false>
 static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     using G = DwGeom<STRIDE>;
     g.tiles_x = div_up(g.wo, G::TW);
@@ -170,14 +191,14 @@ static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     const size_t smem = 2 * G::TILE_BYTES + 64 + 128;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE, F32IN, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("dw3x3(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = g.num_tiles < sms * 2 ? g.num_tiles : sms * 2;           // 2 resident CTAs per SM (registers, 2 x 92 KiB smem)
-    cudaError_t e = launch_k(dw3x3_tma_kernel<STRIDE, F32IN>, dim3(grid), dim3(256), smem, s, 1, tm, g);
+    cudaError_t e = launch_k(dw3x3_tma_kernel<STRIDE, F32IN, DOT>, dim3(grid), dim3(256), smem, s, 1, tm, g);
     if (e != cudaSuccess) { set_error("dw3x3(tma): launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("dw3x3(tma)");
 }
@@ -220,6 +241,38 @@ int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, 
     rc = tc_encode(&tm, in.p, 5, dims, str, box, "dw input", 0);
     if (rc) return rc;
     return launch_dw_tma<2, false>(tm, g, s);
+}
+
+// readout tail: sum the channel-block partials of a pixel in a fixed order, add the folded BN bias, sigmoid (model.py:373)
+__global__ void __launch_bounds__(256) dot_finish_kernel(const float* __restrict__ partial, int64_t rows, int cblocks, float bias,
+                                                         float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int k = 0; k < cblocks; ++k) s += partial[r * cblocks + k];
+    out[r] = 1.f / (1.f + expf(-(s + bias)));
+}
+
+int dw3x3_dot_tma(const float* in, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
+                  float bias_proj, float* partial, float* out, cudaStream_t s) {
+    DwArgs g{};
+    g.n = n; g.h = h; g.w = w; g.c = c; g.ho = h; g.wo = w;
+    g.wgt = wgt; g.bias = bias; g.relu6 = 1; g.wproj = wproj; g.partial = partial;
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t row = (uint64_t)in_ld * 4;
+    const uint64_t str[3] = {row, row * w, row * w * h};
+    const uint32_t box[4] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1};
+    CUtensorMap tm;
+    int rc = tc_encode(&tm, in, 4, dims, str, box, "dw_dot input (f32)", 2);
+    if (rc) return rc;
+    rc = launch_dw_tma<1, true, true>(tm, g, s);
+    if (rc) return rc;
+    const int64_t rows = (int64_t)n * h * w;
+    cudaError_t e = launch_k(dot_finish_kernel, dim3(div_up(rows, 256)), dim3(256), 0, s, 1, (const float*)partial, rows, g.cblocks, bias_proj, out);
+    if (e != cudaSuccess) { set_error("dw_dot: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return check_launch("dw_dot(finish)");
 }
 
 }  // namespace uavsal

@@ -543,6 +543,11 @@ static inline bool act_ok(const void* p, int64_t plane, int ld) {
     return p != nullptr && aligned16(p) && (ld % 8) == 0 && (plane % 8) == 0 && plane >= 0;
 }
 
+namespace uavsal {
+int dw3x3_dot_tma(const float* in, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
+                  float bias_proj, float* partial, float* out, cudaStream_t s);
+}
+
 extern "C" {
 
 int uavsal_version(void) { return 1; }
@@ -674,6 +679,15 @@ int uavsal_add(const uint16_t* a, int64_t a_plane, int a_ld, const uint16_t* b, 
     add_kernel<<<div_up(rows * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(Act{a, a_plane, a_ld}, Act{b, b_plane, b_ld},
                                                                              rows, c, ActW{out, out_plane, out_ld});
     return check_launch("add");
+}
+
+int uavsal_dw3x3_dot_sigmoid(const float* in, int in_ld, int n, int h, int w, int c, const float* wd, const float* bd,
+                             const float* wproj, float bias_proj, float* partial_ws, float* out_f32, void* stream) {
+    UAVSAL_REQUIRE(in && wd && bd && wproj && partial_ws && out_f32 && aligned16(in) && aligned16(wd) && aligned16(bd) && aligned16(wproj) &&
+                       n > 0 && h > 0 && w > 0 && c > 0 && in_ld % 4 == 0 && in_ld >= c,
+                   UAVSAL_EINVAL, "dw3x3_dot_sigmoid: bad arguments");
+    UAVSAL_REQUIRE(c % 4 == 0, UAVSAL_ENOTSUP, "dw3x3_dot_sigmoid: channels must be a multiple of 4");
+    return dw3x3_dot_tma(in, in_ld, n, h, w, c, wd, bd, wproj, bias_proj, partial_ws, out_f32, (cudaStream_t)stream);
 }
 
 int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t rows, int k, const float* wgt, float bias,

@@ -278,6 +278,13 @@ class Plan:
             args = (*x.act(), *h0.act(), c_state.data_ptr(), b, t_steps, h, w, cin, ch, 0, wp.data_ptr(), bp, self.terms, *seq.act())
         self._add("uavsal_convlstm_sequence", args, tag)
 
+    def dw_dot_sigmoid(self, hid: Buf, n, h, w, c, wd: torch.Tensor, bd: torch.Tensor, wproj: torch.Tensor, bias: float, out: torch.Tensor, tag=""):
+        """Readout tail fused: depthwise 3x3 + BN + ReLU6 on the fp32 hidden tensor -> 1-output project + BN + sigmoid."""
+        assert hid.f32 and hid.c == c
+        ws = self.tensor((n * h * w, (c + 63) // 64))
+        self._add("uavsal_dw3x3_dot_sigmoid", (hid.ptr, hid.ld, n, h, w, c, self.hold(wd).data_ptr(), self.hold(bd.float()).data_ptr(),
+                                               self.hold(wproj.float()).data_ptr(), float(bias), ws.data_ptr(), out.data_ptr()), tag)
+
     def dot_sigmoid(self, x: Buf, rows, k, wgt: torch.Tensor, bias: float, out: torch.Tensor, tag=""):
         wv = self.hold(wgt.float())
         self._add("uavsal_dot_sigmoid", (*x.act(), rows, k, wv.data_ptr(), float(bias), out.data_ptr()), tag)
@@ -343,7 +350,7 @@ class Plan:
                 n += op.args[6] * (1 if op.args[13] else op.args[17]) + (1 if op.args[13] else 0)
             elif op.name == "uavsal_convlstm_sequence":
                 n += op.args[8] * (1 if self.engine != "simt" else op.args[7])
-            elif op.name == "uavsal_post_u8":
+            elif op.name in ("uavsal_post_u8", "uavsal_dw3x3_dot_sigmoid"):
                 n += 2
             else:
                 n += 1

@@ -310,10 +310,15 @@ class UAVSal(KernelModule):
         # readout: expand + dw (dwBlock 256->1), then the 1536->1 project + BN + sigmoid as a dot product (model.py:372-373)
         ro = self.conv_out_st
         e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", f32_out=plan.f32_hidden)
-        d, _, _ = ro.conv[1]._emit(plan, e, n, mh, mw, tag="readout.dw")
         wf, bf = ro.project_folded()
         out = plan.tensor((n, 1, mh, mw))
-        plan.dot_sigmoid(d, rows, wf.shape[1], wf.reshape(-1), float(bf.reshape(-1)[0].item()), out, tag="readout.dot")
+        if e.f32 and getattr(plan, "fuse_readout", True):
+            from .engine import pack_dw
+            wdw, bdw = ro.conv[1].folded()
+            plan.dw_dot_sigmoid(e, n, mh, mw, e.c, pack_dw(wdw), bdw, wf.reshape(-1), float(bf.reshape(-1)[0].item()), out, tag="readout.dw+dot")
+        else:
+            d, _, _ = ro.conv[1]._emit(plan, e, n, mh, mw, tag="readout.dw")
+            plan.dot_sigmoid(d, rows, wf.shape[1], wf.reshape(-1), float(bf.reshape(-1)[0].item()), out, tag="readout.dot")
         named.update(h_in=h_in, h_out=h_out, out=out, map_hw=(mh, mw))
         if taps:
             tp["rnn"] = (seq, mh, mw)

@@ -165,6 +165,12 @@ int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
                              const uint16_t* wgt, const float* wgt_f32, const float* bias, int terms,
                              uint16_t* seq_out, int64_t seq_plane, int seq_ld, void* stream);
 
+/* ---- K10b: readout fused: depthwise 3x3 + BN + ReLU6 of the fp32 hidden tensor (conv_out_st.conv.1) folded straight into
+ *      the 1-output project conv + BN + sigmoid (conv_out_st.conv.2/.3, model.py:372-373): the 1536-channel depthwise
+ *      output is never written.  partial_ws: n*h*w*ceil(c/64) floats of workspace. */
+int uavsal_dw3x3_dot_sigmoid(const float* in, int in_ld, int n, int h, int w, int c, const float* wd, const float* bd,
+                             const float* wproj, float bias_proj, float* partial_ws, float* out_f32, void* stream);
+
 /* ---- K10a: readout project conv 1536->1 + BN + sigmoid (conv_out_st.conv.2/.3 + model.py:373):
  *      out_f32[row] = sigmoid( dot(A[row][:k], wgt[:k]) + bias ). */
 int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t rows, int k,
