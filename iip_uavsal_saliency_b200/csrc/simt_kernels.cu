@@ -80,8 +80,17 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
     pdl_wait();
     __shared__ float4 sw[27 * 8];
     __shared__ float sb[32];
+    __shared__ float lut[3][256];      // uint8 -> normalised fp32 with the reference's exact expression (utils_data.py:56-60)
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    if (KIND != 0) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int ch = i >> 8, u = i & 255;
+            const float mean = ch == 0 ? 0.485f : (ch == 1 ? 0.456f : 0.406f);
+            const float sd = ch == 0 ? 0.229f : (ch == 1 ? 0.224f : 0.225f);
+            lut[ch][u] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), mean), sd);
+        }
+    }
     __syncthreads();
     __shared__ float st[128 * 33];                                         // output tile, row pitch 33 floats (conflict-free)
     const int64_t total = (int64_t)n * ho * wo;
@@ -104,7 +113,10 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
                 if (xx < 0 || xx >= w) continue;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const float v = stem_fetch<KIND>(x, img, ch, y, xx, h, w);
+                    float v;
+                    if (KIND == 0) v = __ldg(reinterpret_cast<const float*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
+                    else if (KIND == 1) v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx)];
+                    else v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch)];
                     const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {

@@ -96,10 +96,12 @@ class ClipRunner:
         """Build (and capture) the plans a clip of n_frames will use on every slot, outside any timed region."""
         keep = (n_frames // self.T) * self.T
         if self.whole_clip:
+            batched = self.clips_per_plan > 1 and keep % self.per_call == 0
             for slot in range(2):
-                self._plan(keep, H, W, slot, "all", self.per_call)
-                if self.clips_per_plan > 1 and keep % self.per_call == 0:
+                if batched:
                     self._plan(keep * self.clips_per_plan, H, W, slot, "all", self.per_call, self.clips_per_plan)
+                if not batched or slot == 0:                        # a left-over single clip always runs on slot 0 (arena memory)
+                    self._plan(keep, H, W, slot, "all", self.per_call)
             return
         sizes = {min(self.per_call, keep - i * self.per_call) for i in range(math.ceil(keep / self.per_call))}
         for slot in range(self.depth):
@@ -243,7 +245,7 @@ class ClipRunner:
 
     def _launch_whole(self, clips, keep, H, W, want_maps, outs):
         nc = len(clips)
-        slot = self._clips % 2
+        slot = self._clips % 2 if (nc > 1 or self.clips_per_plan == 1) else 0
         self._clips += 1
         plan = self._plan(keep * nc, H, W, slot, "all", self.per_call, nc)
         nm = plan.named
