@@ -1,11 +1,13 @@
 // Persistent tcgen05 GEMM / implicit-GEMM 3x3 (version 2 of gemm_tc_kernel).
 //
-// One CTA per SM walks a static round-robin list of output tiles (n fastest, so CTAs running at the same time
-// share A tiles in L2).  Three asynchronous pipelines overlap across tiles:
-//   TMA producer  -> smem ring (full/empty mbarriers, runs ahead into the next tile's k-blocks)
+// One CTA per SM (or one CTA pair per TPC) walks a static round-robin list of output tiles (n fastest, so CTAs running at
+// the same time share A tiles in L2).  Three asynchronous pipelines overlap across tiles:
+//   TMA producer  -> smem ring (full/empty mbarriers, runs ahead into the next tile's k-blocks, L2 prefetch of A)
 //   MMA issuer    -> TWO TMEM accumulators (acc_full/acc_empty mbarriers): tile i+1 accumulates while
-//   epilogue      -> tile i is drained: tcgen05.ld -> bias/ReLU6/residual/sigmoid | TWA blend -> hi/lo split ->
-//                    128-byte-swizzled smem staging -> TMA tensor stores (coalesced, clipped at M/N/image edges).
+//   epilogue      -> tile i is drained: tcgen05.ld -> bias/ReLU6/residual/sigmoid | TWA blend | LSTM cell -> hi/lo split (or fp32)
+//                    -> per-warp transpose buffer -> coalesced global stores (clipped at M/N/image edges).
+// (The output tensor map parameter tmO is unused: TMA stores queued behind the producer's loads and were replaced by the
+//  LSU copy-out; the parameter is kept so the launch signature stays stable.)
 #pragma once
 #include "tc_common.cuh"
 

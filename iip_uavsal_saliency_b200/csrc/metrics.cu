@@ -236,6 +236,244 @@ metrics4_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw,
     cluster.sync();     // keep every CTA's shared memory alive until rank 0 has read it
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming variant (default when h*w is a multiple of 16): same arithmetic, but the maps flow through a 4-stage shared-memory
+// ring filled by cp.async.bulk (one producer warp, mbarrier full/empty), so the loads in flight are limited by shared memory
+// (36 KiB per CTA, several CTAs per SM) instead of registers.  The register-batched kernel above stalled on `long_sb` and on
+// the cluster barrier (39 % of HBM peak); this one keeps the HBM pipe full.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStChunkBytes = 4096;            // bytes per plane per stage (1024 fp32 or 4096 uint8 pixels)
+constexpr int kStStages = 3;
+constexpr int kStConsumers = 256;              // 8 consumer warps + 1 producer warp
+constexpr int kStThreads = kStConsumers + 32;
+
+__device__ __forceinline__ uint32_t m_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void m_bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void m_bar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void m_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(m_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void m_bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; !ok; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity) : "memory");
+        if (it > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void m_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(m_smem_u32(dst)), "l"(src), "r"(bytes), "r"(m_smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void lds4v(const T* p, float v[4]);
+template <>
+__device__ __forceinline__ void lds4v<float>(const float* p, float v[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void lds4v<uint8_t>(const uint8_t* p, float v[4]) {
+    const uint32_t q = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = (float)(q & 0xFF); v[1] = (float)((q >> 8) & 0xFF); v[2] = (float)((q >> 16) & 0xFF); v[3] = (float)(q >> 24);
+}
+
+template <typename T>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kStThreads)
+metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, float* __restrict__ out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int pair = blockIdx.y;
+    const T* P = pred + (int64_t)pair * hw;
+    const T* D = truth + (int64_t)pair * 2 * hw;
+    const T* Fx = D + hw;
+
+    constexpr int kStChunk = kStChunkBytes / (int)sizeof(T);                // pixels per chunk
+    __shared__ __align__(128) T ring[kStStages][3][kStChunk];
+    __shared__ uint64_t full[kStStages], empty[kStStages];
+    __shared__ double wpart[kStConsumers / 32][S_COUNT];
+    __shared__ double part1[S_COUNT];
+    __shared__ double part2[2];
+    __shared__ double tot[S_COUNT];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == kStConsumers / 32;
+    if (tid == 0) {
+        for (int s = 0; s < kStStages; ++s) { m_bar_init(full + s, 1); m_bar_init(empty + s, kStConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // this CTA's chunks: rank, rank + 8, ... ; the same list is walked twice (pass 1: P, D, F; pass 2: P, D)
+    const int nchunks = (hw + kStChunk - 1) / kStChunk;
+    const int mine = (nchunks - rank + kCluster - 1) / kCluster;
+    auto chunk_of = [&](int i) { return rank + i * kCluster; };
+    auto chunk_len = [&](int c) { return min(kStChunk, hw - c * kStChunk); };
+
+    // producer lane: chunk i of the doubled list (pass 1: P, D, F; pass 2: P, D).  It must join the block / cluster barriers
+    // between the passes, so before them it runs only kStStages chunks into pass 2 (their stages are freed by pass-1 consumers)
+    auto produce = [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            const int s = i % kStStages;
+            m_bar_wait(empty + s, ((i / kStStages) & 1) ^ 1);
+            const int pass2 = i >= mine;
+            const int c = chunk_of(pass2 ? i - mine : i);
+            const uint32_t bytes = (uint32_t)chunk_len(c) * sizeof(T);
+            m_bar_expect(full + s, bytes * (pass2 ? 2 : 3));
+            m_bulk_load(ring[s][0], P + (int64_t)c * kStChunk, bytes, full + s);
+            m_bulk_load(ring[s][1], D + (int64_t)c * kStChunk, bytes, full + s);
+            if (!pass2) m_bulk_load(ring[s][2], Fx + (int64_t)c * kStChunk, bytes, full + s);
+        }
+    };
+    const int ahead = min(2 * mine, mine + kStStages);
+    if (producer && lane == 0) produce(0, ahead);
+
+    // ------------------------------- pass 1 (consumers) -------------------------------
+    double s[S_COUNT];
+#pragma unroll
+    for (int i = 0; i < S_COUNT; ++i) s[i] = 0.0;
+    float mnP = 3.0e38f, mxP = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
+    if (!producer) {
+        float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < mine; ++i) {
+            const int st = i % kStStages;
+            m_bar_wait(full + st, (i / kStStages) & 1);
+            const int len = chunk_len(chunk_of(i));
+#pragma unroll
+            for (int e0 = 0; e0 < kStChunk; e0 += kStConsumers * 4) {
+                const int e = e0 + tid * 4;
+                if (e < len) {
+                    float p[4], t[4], f[4];
+                    lds4v<T>(&ring[st][0][e], p); lds4v<T>(&ring[st][1][e], t); lds4v<T>(&ring[st][2][e], f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[0] += p[j]; a[1] = fmaf(p[j], p[j], a[1]); a[2] += t[j]; a[3] = fmaf(t[j], t[j], a[3]);
+                        a[4] = fmaf(t[j], p[j], a[4]); a[5] += f[j]; a[6] = fmaf(f[j], p[j], a[6]);
+                        mnP = fminf(mnP, p[j]); mxP = fmaxf(mxP, p[j]); mnT = fminf(mnT, t[j]); mxT = fmaxf(mxT, t[j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) m_bar_arrive(empty + st);
+            if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) {       // fold the fp32 run (<= 32 pixels per thread: exact for uint8-valued maps) into fp64
+                s[S_P] += a[0]; s[S_P2] += a[1]; s[S_T] += a[2]; s[S_T2] += a[3]; s[S_TP] += a[4]; s[S_F] += a[5]; s[S_FP] += a[6];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) a[j] = 0.f;
+            }
+        }
+        s[S_MINP] = mnP; s[S_MAXP] = mxP; s[S_MINT] = mnT; s[S_MAXT] = mxT;
+#pragma unroll
+        for (int i = 0; i < S_COUNT; ++i) {
+            double v = s[i];
+            if (i == S_MINP || i == S_MINT) v = warp_min(v);
+            else if (i == S_MAXP || i == S_MAXT) v = warp_max(v);
+            else v = warp_sum(v);
+            if (lane == 0) wpart[warp][i] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < S_COUNT) {
+        const int i = tid;
+        double v = wpart[0][i];
+        for (int w = 1; w < kStConsumers / 32; ++w) {
+            if (i == S_MINP || i == S_MINT) v = fmin(v, wpart[w][i]);
+            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, wpart[w][i]);
+            else v += wpart[w][i];
+        }
+        part1[i] = v;
+    }
+    cluster.sync();
+    if (tid < S_COUNT) {
+        const int i = tid;
+        double v = 0.0;
+        for (int r = 0; r < kCluster; ++r) {
+            const double o = *cluster.map_shared_rank(&part1[i], r);
+            if (r == 0) v = o;
+            else if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+            else v += o;
+        }
+        tot[i] = v;
+    }
+    __syncthreads();
+
+    const double n = (double)hw;
+    const float sumP = (float)tot[S_P], sumT = (float)tot[S_T];
+    const float minP = (float)tot[S_MINP], minT = (float)tot[S_MINT];
+    const float rngP = ((float)tot[S_MAXP] - minP) + kEpsF, rngT = ((float)tot[S_MAXT] - minT) + kEpsF;
+    const float nsumP = (float)((tot[S_P] - n * tot[S_MINP]) / (double)rngP) + kEpsF;
+    const float nsumT = (float)((tot[S_T] - n * tot[S_MINT]) / (double)rngT) + kEpsF;
+    const float dP = sumP + kEpsF, dT = sumT + kEpsF;
+    const float rdT = 1.0f / dT, rdP = 1.0f / dP;
+    const float rnT = 1.0f / (rngT * nsumT), rnP = 1.0f / (rngP * nsumP);
+
+    // ------------------------------- pass 2 (consumers; the chunks come back from L2) -------------------------------
+    double kld = 0.0, sim = 0.0;
+    if (producer && lane == 0) produce(ahead, 2 * mine);
+    if (!producer) {
+        float k = 0.f, sm = 0.f;
+        for (int i = 0; i < mine; ++i) {
+            const int ii = mine + i;
+            const int st = ii % kStStages;
+            m_bar_wait(full + st, (ii / kStStages) & 1);
+            const int len = chunk_len(chunk_of(i));
+#pragma unroll
+            for (int e0 = 0; e0 < kStChunk; e0 += kStConsumers * 4) {
+                const int e = e0 + tid * 4;
+                if (e < len) {
+                    float p[4], t[4];
+                    lds4v<T>(&ring[st][0][e], p); lds4v<T>(&ring[st][1][e], t);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float th = t[j] * rdT, ph = p[j] * rdP;
+                        k = fmaf(th, __logf(__fdividef(th, ph + kEpsF) + kEpsF), k);
+                        sm += fminf((t[j] - minT) * rnT, (p[j] - minP) * rnP);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) m_bar_arrive(empty + st);
+            if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) { kld += k; sim += sm; k = 0.f; sm = 0.f; }
+        }
+        kld = warp_sum(kld);
+        sim = warp_sum(sim);
+        if (lane == 0) { wpart[warp][0] = kld; wpart[warp][1] = sim; }
+    }
+    __syncthreads();
+    if (tid < 2) {
+        double v = 0.0;
+        for (int w = 0; w < kStConsumers / 32; ++w) v += wpart[w][tid];
+        part2[tid] = v;
+    }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        double k = 0.0, smm = 0.0;
+        for (int r = 0; r < kCluster; ++r) {
+            k += *cluster.map_shared_rank(&part2[0], r);
+            smm += *cluster.map_shared_rank(&part2[1], r);
+        }
+        const double mP = tot[S_P] / n, mT = tot[S_T] / n;
+        const double ssP = fmax(tot[S_P2] - tot[S_P] * mP, 0.0), ssT = fmax(tot[S_T2] - tot[S_T] * mT, 0.0);
+        const double sdP = sqrt(ssP / (n - 1.0)), sdT = sqrt(ssT / (n - 1.0));
+        const double cov = tot[S_TP] - tot[S_T] * mP;
+        const double zz = (sdP + kEps) * (sdT + kEps);
+        const double r1 = cov / zz;
+        const double r2 = sqrt((ssP / ((sdP + kEps) * (sdP + kEps))) * (ssT / ((sdT + kEps) * (sdT + kEps))));
+        out[pair * 4 + 0] = (float)(r1 / (r2 + kEps));
+        out[pair * 4 + 1] = (float)(((tot[S_FP] - mP * tot[S_F]) / (sdP + kEps)) / (tot[S_F] + kEps));
+        out[pair * 4 + 2] = (float)k;
+        out[pair * 4 + 3] = (float)smm;
+    }
+    cluster.sync();
+}
+
+int g_metrics_stream = 1;      // uavsal_set_option key 9: 1 = streaming kernel (default), 0 = register-batched kernel
+
 }  // namespace uavsal
 
 using namespace uavsal;
@@ -252,6 +490,15 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
                                : ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 3) == 0 && hw % 4 == 0;
     UAVSAL_REQUIRE(al, UAVSAL_ENOTSUP, "metrics4: h*w must be a multiple of 4 and the tensors 16-byte aligned");
     dim3 grid(kCluster, n);
+    if (g_metrics_stream && hw % 16 == 0 && hw >= kCluster * kStChunkBytes) {
+        if (dtype == 0)
+            metrics4_stream_kernel<float><<<grid, kStThreads, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out);
+        else
+            metrics4_stream_kernel<uint8_t><<<grid, kStThreads, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const uint8_t*>(pred), reinterpret_cast<const uint8_t*>(truth), hw, out);
+        return check_launch("metrics4(stream)");
+    }
     if (dtype == 0)
         metrics4_kernel<float><<<grid, kMetThreads, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out);
