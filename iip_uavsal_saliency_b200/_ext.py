@@ -62,7 +62,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("UAVSAL_LIB") or _build.LIB              # UAVSAL_LIB: developer override (A/B of two builds)
     if not os.path.exists(path):
         path = _build.build()
     try:
@@ -77,6 +77,10 @@ def load():
         fn.argtypes = argtypes
         fn.restype = c_int
     _lib = lib
+    # developer knob: UAVSAL_OPTIONS="key=value,key=value" applies uavsal_set_option at load time (A/B runs of bench.py / tools)
+    for kv in filter(None, os.environ.get("UAVSAL_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        lib.uavsal_set_option(int(k), int(v, 0))
     return lib
 
 

@@ -8,9 +8,14 @@
 // stage of dw_tma.cu straight from that buffer.  HBM traffic per block drops from (1 + 6 + 6 + 6s) x to (1 + 6s) x
 // activations (s = 1 or 1/4 for stride 2); the halo recompute (1.4x of a K <= 64 GEMM) is free.
 //
-// The expand is a [<=304 pixels] x [64 channels] x [K = cin <= 32] product per tile: too small and too irregular (haloed
-// pixel rows, per-tile weight block) for a TMA/tcgen05 pipeline to pay off, and the kernel is HBM/latency-bound, so it
-// uses warp-level mma.sync (m16n8k16, bf16 hi/lo 3-term split, fp32 accumulate) with ldmatrix operands.
+// The expand is a [<=192 pixels] x [64 channels] x [K = cin <= 32] product per tile: too small and too irregular (haloed
+// pixel rows, per-tile weight block) for a TMA/tcgen05 pipeline to pay off, so it uses warp-level mma.sync (m16n8k16,
+// bf16 hi/lo 3-term split, fp32 accumulate, bias as the initial accumulator) with ldmatrix operands.  The kernel is
+// instruction/latency-bound (ncu: ~100 thread instructions per output value in the first version, FFMA 9 of them), so
+// the structure is about instruction count: weights resident in shared memory for the whole (persistent) CTA, the next
+// tile's input fetched by cp.async under the depthwise stage, ReLU6 + out-of-image mask as ONE mul.sat per hidden value
+// (the factor 6 moves into the depthwise taps), warp-uniform control flow (no WARPSYNC around ldmatrix/mma).
+// Measured (20 frames, 180x320, 16 -> 96, stride 2): 275 us -> 180 us.
 #include "tc_common.cuh"
 
 namespace uavsal {
@@ -35,7 +40,7 @@ struct EdGeom {
     static constexpr int IW = (TW - 1) * STRIDE + 3;      // haloed input box
     static constexpr int IH = (TH - 1) * STRIDE + 3;
     static constexpr int PIX = IW * IH;                   // 180 | 153
-    static constexpr int MT = (PIX + 15) / 16;            // m16 tiles: 12 | 10
+    static constexpr int MT = (PIX + 31) / 32 * 2;        // m16 tiles (an even number: two per round): 12 | 10
     static constexpr int ROWS = MT * 16;
     static constexpr int RGRPS = 256 / (16 * TW);
     static constexpr int RPT = TH / RGRPS;
@@ -54,146 +59,202 @@ __device__ __forceinline__ void mma_bf16(float c[4], const uint32_t a[4], uint32
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {      // src_bytes 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ed_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Persistent CTA, work item = (spatial tile, group of 64-channel blocks).  All weights of the block (expand hi/lo, both
+// bias vectors, depthwise taps) stay in shared memory for the whole kernel; the haloed input tile of the NEXT work item is
+// fetched with cp.async into the (single) x buffer while the depthwise stage of the last channel block runs - the buffer
+// is dead from the moment that block's expand stage has finished.  Two barriers per channel block.
 template <int STRIDE>
 __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
     using G = EdGeom<STRIDE>;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 127) & ~127u;
+    const uint32_t sraw = smem_u32(smem_raw);
+    const uint32_t sbase = (sraw + 127) & ~127u;
+    uint8_t* const sgen = smem_raw + (sbase - sraw);                          // generic-space view of sbase
     const int kpitch = (g.kp + 8) * 2;                                        // bytes per operand row (16 B pad: conflict-free ldmatrix)
+    const int cb64 = g.cblocks * 64;
     const uint32_t xs_hi = sbase;                                             // [ROWS][kp+8] bf16
     const uint32_t xs_lo = xs_hi + G::ROWS * kpitch;
-    const uint32_t ws_hi = xs_lo + G::ROWS * kpitch;                          // [64][kp+8] bf16
-    const uint32_t ws_lo = ws_hi + 64 * kpitch;
-    const uint32_t hid = (ws_lo + 64 * kpitch + 15) & ~15u;                   // [PIX][HPITCH] fp32
+    const uint32_t ws_hi = xs_lo + G::ROWS * kpitch;                          // [cb64][kp+8] bf16, every channel block
+    const uint32_t ws_lo = ws_hi + cb64 * kpitch;
+    const uint32_t b1s = ws_lo + cb64 * kpitch;                               // [cb64] expand bias
+    const uint32_t wds = b1s + cb64 * 4;                                      // [9][cb64] depthwise taps
+    const uint32_t bds = wds + 9 * cb64 * 4;                                  // [cb64] depthwise bias
+    const uint32_t hid = bds + cb64 * 4;                                      // [ROWS][HPITCH] fp32
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                   // tells the compiler the index is warp-uniform
     const int cpp = g.cin >> 3;                                               // 16-byte chunks per pixel per plane
     const int kchunks = g.kp >> 3;
-    // staging map: 16 consecutive threads serve one row (pixel / weight row): chunk lc of plane lp
-    const int lrow = tid >> 4, lp = tid & 1, lc = (tid & 15) >> 1;
     pdl_trigger();
-    // zero the K padding columns once (they are multiplied by zero weights, but must not hold NaN bit patterns)
-    if (lc >= cpp && lc < kchunks)
-        for (int r = lrow; r < G::ROWS; r += 16) sts128((lp ? xs_lo : xs_hi) + r * kpitch + lc * 16, 0, 0, 0, 0);
+    // ---- once: weights -> shared memory (constants: no need to wait for the producer kernel), K padding of the x tile = 0 ----
+    for (int i = tid; i < 2 * cb64 * kchunks; i += 256) {
+        const int c = i % kchunks, r = (i / kchunks) % cb64, pl = i / (kchunks * cb64);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.w1 + ((int64_t)pl * cb64 + r) * g.kp + c * 8));
+        *reinterpret_cast<uint4*>(sgen + ((pl ? ws_lo : ws_hi) - sbase) + r * kpitch + c * 16) = v;
+    }
+    for (int i = tid; i < cb64; i += 256) {
+        const bool v = i < g.hidden;
+        reinterpret_cast<float*>(sgen + (b1s - sbase))[i] = __ldg(g.b1 + i);
+        reinterpret_cast<float*>(sgen + (bds - sbase))[i] = v ? __ldg(g.bd + i) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) reinterpret_cast<float*>(sgen + (wds - sbase))[k * cb64 + i] = v ? 6.f * __ldg(g.wd + k * g.hidden + i) : 0.f;   // x6: see the expand stage
+    }
+    for (int i = tid; i < 2 * G::ROWS * (kchunks - cpp); i += 256) {
+        const int c = cpp + i % (kchunks - cpp), r = (i / (kchunks - cpp)) % G::ROWS, pl = i / ((kchunks - cpp) * G::ROWS);
+        *reinterpret_cast<uint4*>(sgen + ((pl ? xs_lo : xs_hi) - sbase) + r * kpitch + c * 16) = make_uint4(0, 0, 0, 0);
+    }
+
+    auto decode = [&](int t, int& img, int& y0, int& x0, int& cg) {
+        int r = t;
+        cg = r % g.cgroups; r /= g.cgroups;
+        x0 = (r % g.tiles_x) * G::TW; r /= g.tiles_x;
+        y0 = (r % g.tiles_y) * G::TH;
+        img = r / g.tiles_y;
+    };
+    // haloed input tile (both planes) -> shared memory: 8 consecutive threads serve one pixel (slot = plane x 16-byte chunk)
+    auto issue_x = [&](int img, int y0, int x0) {
+        const int slot = tid & 7;
+        const int pl = slot >= cpp ? 1 : 0, c = slot - (pl ? cpp : 0);
+        const int gx0 = x0 * STRIDE - 1, gy0 = y0 * STRIDE - 1;
+        const uint16_t* base = g.x.p + (pl ? g.x.plane : 0) + c * 8;
+        const uint32_t dst0 = (pl ? xs_lo : xs_hi) + c * 16;
+        if (slot < 2 * cpp) {
+#pragma unroll
+            for (int u = 0; u < (G::PIX + 31) / 32; ++u) {
+                const int p = u * 32 + (tid >> 3);
+                if (p < G::PIX) {
+                    const int iy = p / G::IW, ix = p - iy * G::IW;
+                    const int gy = gy0 + iy, gx = gx0 + ix;
+                    const bool inb = gy >= 0 && gy < g.h && gx >= 0 && gx < g.w;
+                    const uint16_t* src = inb ? base + (((int64_t)img * g.h + gy) * g.w + gx) * g.x.ld : g.x.p;
+                    cp_async16(dst0 + p * kpitch, src, inb ? 16u : 0u);
+                }
+            }
+        }
+        cp_async_commit();
+    };
 
     const int quad = tid & 15;
     const int col = (tid >> 4) % G::TW;
     const int rgrp = (tid >> 4) / G::TW;
+    int img, y0, x0, cg;
+    decode(blockIdx.x, img, y0, x0, cg);
     pdl_wait();
+    issue_x(img, y0, x0);
     for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-        int r = t;
-        const int cg = r % g.cgroups; r /= g.cgroups;
-        const int x0 = (r % g.tiles_x) * G::TW; r /= g.tiles_x;
-        const int y0 = (r % g.tiles_y) * G::TH;
-        const int img = r / g.tiles_y;
+        const int tn = t + gridDim.x;
+        int nimg = 0, ny0 = 0, nx0 = 0, ncg = 0;
+        if (tn < g.num_tiles) decode(tn, nimg, ny0, nx0, ncg);
         const int gx0 = x0 * STRIDE - 1, gy0 = y0 * STRIDE - 1;
+        const bool border = gx0 < 0 || gy0 < 0 || gx0 + G::IW > g.w || gy0 + G::IH > g.h;   // some haloed pixels lie outside the image
 
-        // ---- stage 1: haloed input tile (both planes) -> shared memory, once for all channel blocks of this work item ----
-        // chunk i -> (pixel, plane, 16-byte chunk); every thread issues all of its loads before the first (ordered, asm) store,
-        // so one L2 round trip covers the tile
-        {
-            const int cpp2 = 2 * cpp, total = G::PIX * cpp2;
-            const uint32_t inv = (1u << 20) / (uint32_t)cpp2 + 1;             // exact i / cpp2 for i < 8192
-            constexpr int kMaxU = (G::PIX * 8 + 255) / 256;                   // cin <= 32: at most 8 chunks per pixel
-            uint4 v[kMaxU];
-            uint32_t dst[kMaxU];
-#pragma unroll
-            for (int u = 0; u < kMaxU; ++u) {
-                const int i = tid + u * 256;
-                dst[u] = 0;
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (i < total) {
-                    const int p = (int)(((uint32_t)i * inv) >> 20), rem = i - p * cpp2;
-                    const int pl = rem & 1, c = rem >> 1;
-                    const int iy = p / G::IW, ix = p - iy * G::IW;
-                    const int gy = gy0 + iy, gx = gx0 + ix;
-                    if (gy >= 0 && gy < g.h && gx >= 0 && gx < g.w)
-                        v[u] = __ldg(reinterpret_cast<const uint4*>(g.x.p + (pl ? g.x.plane : 0) + c * 8 + (((int64_t)img * g.h + gy) * g.w + gx) * g.x.ld));
-                    dst[u] = (pl ? xs_lo : xs_hi) + p * kpitch + c * 16;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kMaxU; ++u)
-                if (dst[u]) sts128(dst[u], v[u].x, v[u].y, v[u].z, v[u].w);
-        }
+        const int cb_begin = cg * g.cpg, cb_end = min(g.cblocks, (cg + 1) * g.cpg);
+        for (int cblk = cb_begin; cblk < cb_end; ++cblk) {
+            if (cblk == cb_begin) cp_async_wait_all();
+            __syncthreads();                                                   // x tile staged; previous block's depthwise stage done
 
-        const int cb_end = min(g.cblocks, (cg + 1) * g.cpg);
-        for (int cblk = cg * g.cpg; cblk < cb_end; ++cblk) {
-            // expand weights of this channel block -> shared memory; this lane's 16 expand biases -> registers
-            if (lc < kchunks) {
-                uint4 v[4];
+            // ---- expand: hidden[pix][64] = ReLU6(x . W1^T + b1) / 6, zero outside the image (tensor cores, 3-term split) ----
+            // warp -> one 16-channel quarter of the block (B fragments and bias stay in registers) x every (8/nqd)-th pair of m16
+            // tiles; a partially filled last block spreads its valid quarters over all warps.  ReLU6(v)/6 = sat(v * 1/6) is ONE
+            // instruction (mul.sat) and the out-of-image mask rides on its multiplier; the depthwise taps carry the factor 6.
+            {
+                const int nq_valid = (min(64, g.hidden - cblk * 64) + 15) >> 4;
+                const int sh = nq_valid <= 1 ? 0 : nq_valid <= 2 ? 1 : 2;     // log2 of the quarters the warps are dealt over
+                const int nq = warp & ((1 << sh) - 1);
+                if (nq < nq_valid) {
+                    uint32_t bh[2][4], bl[2][4];
+                    const uint32_t b_off = (cblk * 64 + nq * 16 + (lane >> 4) * 8 + (lane & 7)) * kpitch + ((lane >> 3) & 1) * 16;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = __ldg(reinterpret_cast<const uint4*>(g.w1 + ((int64_t)lp * g.cblocks * 64 + cblk * 64 + u * 16 + lrow) * g.kp + lc * 8));
-#pragma unroll
-                for (int u = 0; u < 4; ++u) sts128((lp ? ws_lo : ws_hi) + (u * 16 + lrow) * kpitch + lc * 16, v[u].x, v[u].y, v[u].z, v[u].w);
-            }
-            float2 eb[8];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) eb[nt] = __ldg(reinterpret_cast<const float2*>(g.b1 + cblk * 64 + nt * 8 + 2 * (lane & 3)));
-            __syncthreads();                                                   // x tile + weights staged; previous block's depthwise stage done
-
-            // ---- stage 2: hidden[pix][64] = ReLU6(x . W1^T + b1), zero outside the image (tensor cores, 3-term split) ----
-            // task = (m16 tile, 32-channel half): 2*MT tasks round-robin over the 8 warps; the three split products of the
-            // four n8 tiles are issued term-major so that consecutive HMMAs never depend on each other
-            for (int task = warp; task < 2 * G::MT; task += 8) {
-                const int mt = task >> 1, nh = task & 1;
-                float acc[4][4];
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-                const uint32_t a_off = (mt * 16 + (lane & 15)) * kpitch + (lane >> 4) * 16;
-                const uint32_t b_off = (nh * 32 + (lane & 7)) * kpitch + ((lane >> 3) & 1) * 16;
-                for (int ks = 0; ks < (g.kp >> 4); ++ks) {
-                    uint32_t ah[4], al[4], bh[4][2], bl[4][2];
-                    ldsm_x4(xs_hi + a_off + ks * 32, ah[0], ah[1], ah[2], ah[3]);
-                    ldsm_x4(xs_lo + a_off + ks * 32, al[0], al[1], al[2], al[3]);
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        ldsm_x2(ws_hi + b_off + nt * 8 * kpitch + ks * 32, bh[nt][0], bh[nt][1]);
-                        ldsm_x2(ws_lo + b_off + nt * 8 * kpitch + ks * 32, bl[nt][0], bl[nt][1]);
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ah, bh[nt][0], bh[nt][1]);
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ah, bl[nt][0], bl[nt][1]);
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], al, bh[nt][0], bh[nt][1]);
-                }
-                // accumulator fragment: rows lane/4 and lane/4 + 8 of the m-tile, columns nh*32 + nt*8 + 2*(lane%4) + {0,1}
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int p = mt * 16 + (lane >> 2) + half * 8;
-                    if (p < G::PIX) {
-                        const int iy = p / G::IW, ix = p - iy * G::IW;
-                        const int gy = gy0 + iy, gx = gx0 + ix;
-                        const bool inb = gy >= 0 && gy < g.h && gx >= 0 && gx < g.w;
-                        const uint32_t dst = hid + p * G::HPITCH + nh * 128 + 8 * (lane & 3);
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            const float2 b2 = nh ? eb[4 + nt] : eb[nt];
-                            float v0 = relu6f(acc[nt][half * 2 + 0] + b2.x), v1 = relu6f(acc[nt][half * 2 + 1] + b2.y);
-                            if (!inb) { v0 = 0.f; v1 = 0.f; }
-                            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst + nt * 32), "f"(v0), "f"(v1) : "memory");
+                    for (int ks = 0; ks < 2; ++ks)
+                        if (ks < (g.kp >> 4)) {
+                            ldsm_x4(ws_hi + b_off + ks * 32, bh[ks][0], bh[ks][1], bh[ks][2], bh[ks][3]);
+                            ldsm_x4(ws_lo + b_off + ks * 32, bl[ks][0], bl[ks][1], bl[ks][2], bl[ks][3]);
                         }
+                    float2 eb[2];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(eb[nt].x), "=f"(eb[nt].y)
+                                     : "r"(b1s + (cblk * 64 + nq * 16 + nt * 8 + 2 * (lane & 3)) * 4));
+                    const uint32_t a_lane = (lane & 15) * kpitch + (lane >> 4) * 16;
+                    const uint32_t h_lane = hid + (lane >> 2) * G::HPITCH + nq * 64 + 8 * (lane & 3);
+                    for (int mb = warp >> sh; mb < G::MT / 2; mb += 8 >> sh) {
+                        // two adjacent m-tiles per round: four independent accumulator chains, bias as the initial accumulator
+                        float acc[2][2][4];
+#pragma unroll
+                        for (int m2 = 0; m2 < 2; ++m2)
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) { acc[m2][nt][0] = acc[m2][nt][2] = eb[nt].x; acc[m2][nt][1] = acc[m2][nt][3] = eb[nt].y; }
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            if (ks < (g.kp >> 4)) {
+                                uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                                for (int m2 = 0; m2 < 2; ++m2) {
+                                    const uint32_t a_off = (mb * 2 + m2) * 16 * kpitch + a_lane + ks * 32;
+                                    ldsm_x4(xs_hi + a_off, ah[m2][0], ah[m2][1], ah[m2][2], ah[m2][3]);
+                                    ldsm_x4(xs_lo + a_off, al[m2][0], al[m2][1], al[m2][2], al[m2][3]);
+                                }
+#pragma unroll
+                                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                                    for (int m2 = 0; m2 < 2; ++m2)
+#pragma unroll
+                                        for (int nt = 0; nt < 2; ++nt) {
+                                            const uint32_t* bb = term == 1 ? bl[ks] : bh[ks];
+                                            mma_bf16(acc[m2][nt], term == 2 ? al[m2] : ah[m2], bb[2 * nt], bb[2 * nt + 1]);
+                                        }
+                            }
+                        // accumulator fragment: rows lane/4 and lane/4 + 8 of the m-tile, columns nq*16 + nt*8 + 2*(lane%4) + {0,1};
+                        // rows >= PIX of the last tile land in the tile's padding rows
+#pragma unroll
+                        for (int m2 = 0; m2 < 2; ++m2)
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const int pr = (mb * 2 + m2) * 16 + half * 8;
+                                float mul = 1.f / 6.f;
+                                if (border) {
+                                    const int p = pr + (lane >> 2);
+                                    const int iy = p / G::IW, ix = p - iy * G::IW;
+                                    const int gy = gy0 + iy, gx = gx0 + ix;
+                                    if (!(gy >= 0 && gy < g.h && gx >= 0 && gx < g.w)) mul = 0.f;
+                                }
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) {
+                                    float v0, v1;
+                                    asm("mul.sat.f32 %0, %1, %2;" : "=f"(v0) : "f"(acc[m2][nt][half * 2 + 0]), "f"(mul));
+                                    asm("mul.sat.f32 %0, %1, %2;" : "=f"(v1) : "f"(acc[m2][nt][half * 2 + 1]), "f"(mul));
+                                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(h_lane + pr * G::HPITCH + nt * 32), "f"(v0), "f"(v1) : "memory");
+                                }
+                            }
                     }
                 }
             }
-            // depthwise weights of this thread's 4 channels (global/L1; loaded here to keep them out of the MMA stage's registers)
+            // depthwise taps / bias of this thread's 4 channels
             const int c0 = cblk * 64 + quad * 4;
             const bool cvalid = c0 < g.hidden;
             float wr[9][4], br[4];
-            if (cvalid) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wd + k * g.hidden + c0));
-                    wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
-                }
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bd + c0));
-                br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
-            }
-            __syncthreads();                                                   // hidden tile complete
+            for (int k = 0; k < 9; ++k)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wr[k][0]), "=f"(wr[k][1]), "=f"(wr[k][2]), "=f"(wr[k][3])
+                             : "r"(wds + (k * cb64 + c0) * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(br[0]), "=f"(br[1]), "=f"(br[2]), "=f"(br[3]) : "r"(bds + c0 * 4));
+            __syncthreads();                                                   // hidden tile complete; the x tile is dead
+            if (cblk == cb_end - 1 && tn < g.num_tiles) issue_x(nimg, ny0, nx0);
 
-            // ---- stage 3: depthwise 3x3 + bias + ReLU6 from the hidden tile (sliding 3x3x4 register window, as dw_tma.cu) ----
+            // ---- depthwise 3x3 + bias + ReLU6 from the hidden tile (sliding 3x3x4 register window, as dw_tma.cu) ----
             const int ox = x0 + col;
             if (cvalid && ox < g.wo) {
                 float win[3][3][4];
@@ -208,6 +269,7 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                 const int oyl0 = rgrp * G::RPT;
                 if (STRIDE == 1) { load_row(0, oyl0); load_row(1, oyl0 + 1); }
                 else             { load_row(0, oyl0 * 2); }
+                uint16_t* orow = g.out.p + (((int64_t)img * g.ho + y0 + oyl0) * g.wo + ox) * g.out.ld + c0;
 #pragma unroll
                 for (int i = 0; i < G::RPT; ++i) {
                     const int oyl = oyl0 + i;
@@ -220,8 +282,7 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                         load_row(s1, oyl * 2 + 1);
                         load_row(s2, oyl * 2 + 2);
                     }
-                    const int oy = y0 + oyl;
-                    if (oy >= g.ho) break;
+                    if (y0 + oyl >= g.ho) break;
                     float acc[4] = {br[0], br[1], br[2], br[3]};
                     const int slots[3] = {s0, s1, s2};
 #pragma unroll
@@ -232,15 +293,16 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
                         }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
-                    store4(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
+                    uint32_t h0, l0, h1, l1;
+                    ed_split2(relu6f(acc[0]), relu6f(acc[1]), h0, l0);
+                    ed_split2(relu6f(acc[2]), relu6f(acc[3]), h1, l1);
+                    uint16_t* dst = orow + (int64_t)i * g.wo * g.out.ld;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                    if (g.out.plane) *reinterpret_cast<uint2*>(dst + g.out.plane) = make_uint2(l0, l1);
                 }
             }
-            // no barrier here: the next block's weight stores touch only ws (idle since stage 2) and its first barrier orders
-            // this depthwise stage before the hidden tile is overwritten
         }
-        __syncthreads();                                                       // the x tile may be refilled
+        img = nimg; y0 = ny0; x0 = nx0; cg = ncg;
     }
 }
 
@@ -257,8 +319,9 @@ static int launch_expdw(ExpDwArgs& g, cudaStream_t s) {
     while (g.cpg > 1 && (int64_t)spatial * div_up(g.cblocks, g.cpg) < 8LL * sms) --g.cpg;
     g.cgroups = div_up(g.cblocks, g.cpg);
     g.num_tiles = spatial * g.cgroups;
-    const int kpitch = (g.kp + 8) * 2;
-    const size_t smem = 2 * (size_t)G::ROWS * kpitch + 2 * 64 * (size_t)kpitch + (size_t)G::PIX * G::HPITCH + 256;
+    const int kpitch = (g.kp + 8) * 2, cb64 = g.cblocks * 64;
+    const size_t smem = 2 * (size_t)G::ROWS * kpitch + 2 * (size_t)cb64 * kpitch + 11 * (size_t)cb64 * 4 + (size_t)G::ROWS * G::HPITCH + 256;
+    if (smem > 227 * 1024) { set_error("expand_dw3x3: hidden %d needs %zu bytes of shared memory", g.hidden, smem); return UAVSAL_ENOTSUP; }
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(expdw_kernel<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         const int sub = (ew >> 2) * 16;                                       // column offset inside a 64-column chunk
         const int r = q * 32 + lane;                                          // tile row = TMEM lane
         const uint32_t wst = smem_u32(ostage) + ew * 2048;                    // 32 rows x 16 columns: fp32, or hi | lo bf16
+        constexpr bool kStd = EPI == EPI_STD || EPI == EPI_RES;
+        constexpr bool kRes = EPI == EPI_RES;                                  // residual: bf16 hi/lo output, no sigmoid (host-checked)
         const bool f32out = EPI == EPI_STD && (g.flags & UAVSAL_F_OUT_F32);
         const bool do_store = !(g.flags & DBG_NO_STORE);
         int it = 0;
@@ -242,12 +244,38 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             int64_t hrow = 0;
             if (MODE == MODE_CONV && rvalid)
                 hrow = orow + (int64_t)((bidx * g.a1_mul + g.a1_off) - img_out) * g.H * g.W;
+            const int nchunks = (g.bn + 63) >> 6;
+            // EPI_RES: this lane's two (row, 8-column) cells of a piece; the residual loads of piece ch+1 are issued before piece
+            // ch is processed (those of piece 0 before the accumulator is waited for), so their latency is hidden
+            uint4 res_h[2], res_l[2], nres_h[2], nres_l[2];
+            int64_t gro[2] = {-1, -1};
+            auto issue_res = [&](int ch, uint4 (&h)[2], uint4 (&l)[2]) {
+                const int col = n0 + ch * 64 + sub + (lane & 1) * 8;
+                if (sub < min(64, g.bn - ch * 64) && col < g.N) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (gro[i] >= 0) {
+                            const uint16_t* a = g.res.p + gro[i] * g.res.ld + col;
+                            h[i] = __ldg(reinterpret_cast<const uint4*>(a));
+                            if (g.res.plane) l[i] = __ldg(reinterpret_cast<const uint4*>(a + g.res.plane));
+                        }
+                }
+            };
+            if (kRes) {
+                gro[0] = grow_of(q * 32 + (lane >> 1));
+                gro[1] = grow_of(q * 32 + 16 + (lane >> 1));
+                issue_res(0, nres_h, nres_l);
+            }
             mbar_wait(acc_full + buf, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * g.bn);
-            const int nchunks = (g.bn + 63) >> 6;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
+                if (kRes) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { res_h[i] = nres_h[i]; res_l[i] = nres_l[i]; }
+                    if (ch + 1 < nchunks) issue_res(ch + 1, nres_h, nres_l);
+                }
                 if (sub < ncols) {
                     uint32_t raw[16];
                     __syncwarp();
@@ -307,12 +335,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                                     v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
                                 }
                             }
-                            if (EPI == EPI_STD) {
+                            if (kStd) {
                                 if (g.flags & UAVSAL_F_RELU6) {
 #pragma unroll
                                     for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
                                 }
-                                if (g.flags & UAVSAL_F_RESIDUAL) {
+                                if (!kRes && (g.flags & UAVSAL_F_RESIDUAL)) {
                                     float rr[8];
                                     load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
 #pragma unroll
@@ -367,6 +395,44 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                                 const int64_t gr = grow_of(q * 32 + row);
                                 const int col = n + c * 4;
                                 if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<uint4*>(outf + gr * g.out.ld + col) = val;
+                            }
+                        } else if (kRes) {
+                            // stage fp32 (layout as above); each lane then owns 8 columns of two rows: residual hi/lo arrive as
+                            // 16 rows x 32 contiguous bytes per plane per instruction, like the stores
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                sts128(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int row = 16 * i + (lane >> 1), c = lane & 1;
+                                const int64_t gr = gro[i];
+                                const int col = n + c * 8;
+                                if (gr >= 0 && col < g.N) {
+                                    const uint4 a0 = lds128(wst + row * 64 + (((2 * c) ^ ((row >> 1) & 3)) << 4));
+                                    const uint4 a1 = lds128(wst + row * 64 + (((2 * c + 1) ^ ((row >> 1) & 3)) << 4));
+                                    float rr[8], rl[8];
+                                    unpack2(res_h[i].x, rr[0], rr[1]); unpack2(res_h[i].y, rr[2], rr[3]);
+                                    unpack2(res_h[i].z, rr[4], rr[5]); unpack2(res_h[i].w, rr[6], rr[7]);
+                                    if (g.res.plane) {
+                                        unpack2(res_l[i].x, rl[0], rl[1]); unpack2(res_l[i].y, rl[2], rl[3]);
+                                        unpack2(res_l[i].z, rl[4], rl[5]); unpack2(res_l[i].w, rl[6], rl[7]);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) rr[j] += rl[j];
+                                    }
+                                    const float o[8] = {__uint_as_float(a0.x) + rr[0], __uint_as_float(a0.y) + rr[1], __uint_as_float(a0.z) + rr[2],
+                                                        __uint_as_float(a0.w) + rr[3], __uint_as_float(a1.x) + rr[4], __uint_as_float(a1.y) + rr[5],
+                                                        __uint_as_float(a1.z) + rr[6], __uint_as_float(a1.w) + rr[7]};
+                                    uint32_t h[4], l[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) split2(o[2 * j], o[2 * j + 1], h[j], l[j]);
+                                    if (do_store) {
+                                        uint16_t* dst = g.out.p + gr * g.out.ld + col;
+                                        *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+                                        if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = make_uint4(l[0], l[1], l[2], l[3]);
+                                    }
+                                }
                             }
                         } else {
                             // hi plane rows of 32 bytes at wst, lo plane at wst + 1024; chunk j of row at j ^ ((lane >> 2) & 1)

@@ -7,9 +7,9 @@
 namespace uavsal {
 
 enum { MODE_PW = 0, MODE_CONV = 1 };
-enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3 };
+enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3, EPI_RES = 4 };   // EPI_RES: EPI_STD + residual added in the coalesced copy-out phase
 // timing-ablation switches (uavsal_set_option key 3; results are garbage, never set on the product path)
-enum { DBG_NO_MMA = 1 << 16, DBG_NO_STORE = 1 << 17, DBG_NO_B = 1 << 18, DBG_NO_A = 1 << 19 };
+enum { DBG_NO_MMA = 1 << 16, DBG_NO_STORE = 1 << 17, DBG_NO_B = 1 << 18, DBG_NO_A = 1 << 19, DBG_ROW_RES = 1 << 20 };
 
 constexpr int kBM = 128;          // rows per tile = TMEM lanes
 constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row

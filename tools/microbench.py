@@ -140,6 +140,16 @@ def main():
     if what == "expdw":
         expdw(20, 180, 320, 16, 96, 2); expdw(20, 90, 160, 24, 144, 1); expdw(20, 90, 160, 24, 144, 2); expdw(20, 45, 80, 32, 192, 1)
         expdw(20, 45, 80, 32, 192, 2)
+    if what == "res":
+      lib = _ext.load()
+      for mask in (0, 1 << 20):
+        lib.uavsal_set_option(3, mask)
+        print("--- residual loads:", "row-strided" if mask else "coalesced")
+        gemm("tc", 432000, 32, 256, res=True); gemm("tc", 432000, 256, 256, res=True); gemm("tc", 110400, 384, 64, res=True)
+        gemm("tc", 1728000, 144, 24, res=True); gemm("tc", M, 1536, 256, res=True)
+      lib.uavsal_set_option(3, 0)
+    if what == "expdw2":
+        expdw(20, 180, 320, 16, 96, 2)
     if what == "expdw1":
         expdw(20, 45, 80, 64, 384, 1)
     if what == "lstm":
