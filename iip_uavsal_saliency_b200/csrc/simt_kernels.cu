@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include "common.cuh"
 
 namespace uavsal {
@@ -93,69 +94,74 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
     }
     __syncthreads();
     __shared__ float st[128 * 33];                                         // output tile, row pitch 33 floats (conflict-free)
-    const int64_t total = (int64_t)n * ho * wo;
-    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
-    const int64_t i = i0 + threadIdx.x;
-    if (i < total) {
-        const int ox = (int)(i % wo);
-        const int oy = (int)((i / wo) % ho);
-        const int img = (int)(i / ((int64_t)wo * ho));
-        float acc[32];
+    // persistent blocks over tiles of 128 consecutive output pixels: the weight / LUT set-up above (two IEEE divisions per
+    // LUT entry) is paid once per block, not once per 128 pixels; 32-bit index arithmetic
+    const unsigned total = (unsigned)n * ho * wo;                          // host-checked < 2^31
+    for (unsigned i0 = blockIdx.x * 128u; i0 < total; i0 += gridDim.x * 128u) {
+        const unsigned i = i0 + threadIdx.x;
+        if (i < total) {
+            const unsigned row = i / (unsigned)wo;
+            const int ox = (int)(i - row * (unsigned)wo);
+            const int img = (int)(row / (unsigned)ho);
+            const int oy = (int)(row - (unsigned)img * (unsigned)ho);
+            float acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = sb[j];
+            for (int j = 0; j < 32; ++j) acc[j] = sb[j];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int y = oy * 2 - 1 + ky;
-            if (y < 0 || y >= h) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int y = oy * 2 - 1 + ky;
+                if (y < 0 || y >= h) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = ox * 2 - 1 + kx;
-                if (xx < 0 || xx >= w) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = ox * 2 - 1 + kx;
+                    if (xx < 0 || xx >= w) continue;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    float v;
-                    if (KIND == 0) v = __ldg(reinterpret_cast<const float*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
-                    else if (KIND == 1) v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx)];
-                    else v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch)];
-                    const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float v;
+                        if (KIND == 0) v = __ldg(reinterpret_cast<const float*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
+                        else if (KIND == 1) v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx)];
+                        else v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch)];
+                        const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 ww = wr[q];
-                        acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
-                        acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
-                        acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
-                        acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 ww = wr[q];
+                            acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+                            acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+                            acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+                            acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st[threadIdx.x * 33 + j] = relu6f(acc[j]);
         }
+        __syncthreads();
+        // cooperative copy-out: consecutive threads write consecutive 16-byte pieces of the tile's pixels (the per-thread
+        // version wrote one 128-byte row per lane, 32 lines per store instruction)
+        if (out.plane == UAVSAL_PLANE_F32) {                               // fp32 rows (input of features.1's depthwise conv)
+            float* of = reinterpret_cast<float*>(out.p);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[threadIdx.x * 33 + j] = relu6f(acc[j]);
-    }
-    __syncthreads();
-    // cooperative copy-out: consecutive threads write consecutive 16-byte pieces of the tile's pixels (the per-thread
-    // version wrote one 128-byte row per lane, 32 lines per store instruction)
-    if (out.plane == UAVSAL_PLANE_F32) {                                   // fp32 rows (input of features.1's depthwise conv)
-        float* of = reinterpret_cast<float*>(out.p);
+            for (int k = 0; k < 8; ++k) {
+                const int idx = k * 128 + threadIdx.x, px = idx >> 3, q = idx & 7;
+                if (i0 + px < total) {
+                    const float* sp = st + px * 33 + q * 4;
+                    *reinterpret_cast<float4*>(of + (int64_t)(i0 + px) * out.ld + q * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+            }
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int idx = k * 128 + threadIdx.x, px = idx >> 3, q = idx & 7;
-            if (i0 + px < total) {
-                const float* sp = st + px * 33 + q * 4;
-                *reinterpret_cast<float4*>(of + (i0 + px) * out.ld + q * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            for (int k = 0; k < 4; ++k) {
+                const int idx = k * 128 + threadIdx.x, px = idx >> 2, q = idx & 3;
+                if (i0 + px < total) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = st[px * 33 + q * 8 + j];
+                    store8(out.p + (int64_t)(i0 + px) * out.ld + q * 8, out.plane, v);
+                }
             }
         }
-        return;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = k * 128 + threadIdx.x, px = idx >> 2, q = idx & 3;
-        if (i0 + px < total) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = st[px * 33 + q * 8 + j];
-            store8(out.p + (i0 + px) * out.ld + q * 8, out.plane, v);
-        }
+        __syncthreads();                                                   // st is rewritten by the next tile
     }
 }
 
@@ -318,15 +324,15 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int
                                                           int n_dst, int hd, int wd, float ry, float rx, int src_group, int dst_group) {
     pdl_trigger();
     pdl_wait();
-    const int groups = c >> 3;
-    const int64_t total = (int64_t)n_dst * hd * wd * groups;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int g = (int)(i % groups);
-    const int64_t pix = i / groups;
-    const int ox = (int)(pix % wd);
-    const int oy = (int)((pix / wd) % hd);
-    const int img = (int)(pix / ((int64_t)wd * hd));
+    // grid: x covers (output column, 8-channel group) pairs of one output row, y = output row, z = output frame
+    // (no 64-bit index arithmetic: the first version spent most of its instructions on four int64 div/mod pairs)
+    const unsigned groups = (unsigned)c >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)wd * groups) return;
+    const int ox = (int)(idx / groups);
+    const int g = (int)(idx - (unsigned)ox * groups);
+    const int oy = blockIdx.y, img = blockIdx.z;
+    const int64_t pix = ((int64_t)img * hd + oy) * wd + ox;
     // output frame i = (call g, local j) reads source frame g*src_group + j % (sources of call g): with one group this is the
     // reference's repeat(T) interleave i % n_src (quirk Q3); several groups = several reference calls batched in one launch
     const int grp = img / dst_group, j = img - grp * dst_group;
@@ -477,8 +483,96 @@ __device__ __forceinline__ float post_value(const float* __restrict__ m, const P
     return __fadd_rn(__fmul_rn(r0, ay), __fmul_rn(r1, wy));
 }
 
+// The u8 path works on quads of 4 output pixels of one row: the row taps (fp64 coordinate arithmetic) are evaluated once
+// per quad and the column taps come from a per-block table in shared memory, with exactly the arithmetic of post_value()
+// (the first version recomputed both fp64 tap pairs for every pixel in both kernels).
+constexpr int kPostMaxW = 2048;
+
+__device__ __forceinline__ void post_xtaps(const PostGeom& g, uint2* xt) {
+    for (int x = threadIdx.x; x < g.wd; x += blockDim.x) {
+        int x0, x1;
+        float wx;
+        cv_tap(x + g.ox, g.sx, g.ws, x0, x1, wx);
+        xt[x] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), __float_as_uint(wx));
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void post_quad(const float* __restrict__ m, const PostGeom& g, const uint2* xt, int y, int x, float v[4]) {
+    int y0, y1;
+    float wy;
+    cv_tap(y + g.oy, g.sy, g.hs, y0, y1, wy);
+    const float ay = 1.f - wy;
+    const float* r0p = m + y0 * g.ws;
+    const float* r1p = m + y1 * g.ws;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint2 t = xt[x + j];
+        const int x0 = t.x & 0xFFFF, x1 = t.x >> 16;
+        const float wx = __uint_as_float(t.y), ax = 1.f - wx;
+        const float r0 = __fadd_rn(__fmul_rn(r0p[x0], ax), __fmul_rn(r0p[x1], wx));
+        const float r1 = __fadd_rn(__fmul_rn(r1p[x0], ax), __fmul_rn(r1p[x1], wx));
+        v[j] = __fadd_rn(__fmul_rn(r0, ay), __fmul_rn(r1, wy));
+    }
+}
+
 __global__ void __launch_bounds__(256) post_max_kernel(const float* __restrict__ maps, PostGeom g,
                                                        float* __restrict__ frame_max) {
+    __shared__ uint2 xt[kPostMaxW];
+    __shared__ float s[8];
+    pdl_trigger();
+    post_xtaps(g, xt);
+    pdl_wait();
+    const int img = blockIdx.y;
+    const float* m = maps + (int64_t)img * g.hs * g.ws;
+    const int qpr = g.wd >> 2, total4 = g.hd * qpr;     // wd % 4 == 0 is required by the host wrapper
+    float mx = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int y = i / qpr, x = (i - y * qpr) << 2;
+        float v[4];
+        post_quad(m, g, xt, y, x, v);
+        mx = fmaxf(fmaxf(mx, fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmaxf(mx, s[k]);
+        atomicMax(reinterpret_cast<int*>(frame_max) + img, __float_as_int(mx));   // maps are positive (sigmoid)
+    }
+}
+
+__global__ void __launch_bounds__(256) post_write_kernel(const float* __restrict__ maps, PostGeom g,
+                                                         const float* __restrict__ frame_max,
+                                                         uint8_t* __restrict__ out) {
+    __shared__ uint2 xt[kPostMaxW];
+    pdl_trigger();
+    post_xtaps(g, xt);
+    pdl_wait();
+    const int img = blockIdx.y;
+    const float* m = maps + (int64_t)img * g.hs * g.ws;
+    const float mx = frame_max[img];
+    const int qpr = g.wd >> 2, total4 = g.hd * qpr;
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (int64_t)img * g.hd * g.wd);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int y = i / qpr, x = (i - y * qpr) << 2;
+        float q[4];
+        post_quad(m, g, xt, y, x, q);
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = __fmul_rn(__fdiv_rn(q[j], mx), 255.f);
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            pk |= ((uint32_t)__float2int_rn(v) & 0xFFu) << (8 * j);   // rint = round half to even
+        }
+        o[i] = pk;
+    }
+}
+
+// fp32 output (tests / any width): one pixel per thread
+__global__ void __launch_bounds__(256) post_max_px_kernel(const float* __restrict__ maps, PostGeom g,
+                                                          float* __restrict__ frame_max) {
     pdl_trigger();
     pdl_wait();
     const int img = blockIdx.y;
@@ -494,31 +588,7 @@ __global__ void __launch_bounds__(256) post_max_kernel(const float* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmaxf(mx, s[k]);
-        atomicMax(reinterpret_cast<int*>(frame_max) + img, __float_as_int(mx));   // maps are positive (sigmoid)
-    }
-}
-
-__global__ void __launch_bounds__(256) post_write_kernel(const float* __restrict__ maps, PostGeom g,
-                                                         const float* __restrict__ frame_max,
-                                                         uint8_t* __restrict__ out) {
-    pdl_trigger();
-    pdl_wait();
-    const int img = blockIdx.y;
-    const float* m = maps + (int64_t)img * g.hs * g.ws;
-    const float mx = frame_max[img];
-    const int total4 = (g.hd * g.wd) >> 2;     // wd % 4 == 0 is required by the host wrapper
-    uint32_t* o = reinterpret_cast<uint32_t*>(out + (int64_t)img * g.hd * g.wd);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-        const int p = i << 2;
-        const int y = p / g.wd, x = p % g.wd;
-        uint32_t pk = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v = __fmul_rn(__fdiv_rn(post_value(m, g, y, x + j), mx), 255.f);
-            v = fminf(fmaxf(v, 0.f), 255.f);
-            pk |= ((uint32_t)__float2int_rn(v) & 0xFFu) << (8 * j);   // rint = round half to even
-        }
-        o[i] = pk;
+        atomicMax(reinterpret_cast<int*>(frame_max) + img, __float_as_int(mx));
     }
 }
 
@@ -599,7 +669,19 @@ int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const 
                    UAVSAL_EINVAL, "stem_conv3x3s2: bad arguments");
     const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
     const int64_t total = (int64_t)n * ho * wo;
-    const dim3 grid(div_up(total, 128));
+    UAVSAL_REQUIRE(total < (1LL << 31) - (1 << 20), UAVSAL_ENOTSUP, "stem_conv3x3s2: more than 2^31 output pixels");
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    static int bps[3] = {0, 0, 0};                                                        // resident blocks per SM (persistent grid)
+    if (!bps[x_kind]) {
+        int b = 0;
+        cudaError_t e = x_kind == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<0>, 128, 0)
+                      : x_kind == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<1>, 128, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<2>, 128, 0);
+        if (e != cudaSuccess || b <= 0) { b = 4; cudaGetLastError(); }
+        bps[x_kind] = b;
+    }
+    const dim3 grid((unsigned)std::min<int64_t>(div_up(total, 128), (int64_t)sms * bps[x_kind]));
     ActW o{out, out_plane, out_ld};
     cudaStream_t s = (cudaStream_t)stream;
     if (x_kind == 0) launch_k(stem_kernel<0>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
@@ -650,11 +732,11 @@ int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_sr
                    UAVSAL_EINVAL, "bilinear_ac: bad arguments");
     const float ry = hd > 1 ? (float)(hs - 1) / (float)(hd - 1) : 0.f;
     const float rx = wd > 1 ? (float)(ws - 1) / (float)(wd - 1) : 0.f;
-    const int64_t total = (int64_t)n_dst * hd * wd * (c / 8);
     if (src_group <= 0 || dst_group <= 0) { src_group = n_src; dst_group = n_dst; }
     UAVSAL_REQUIRE((int64_t)div_up(n_dst, dst_group) * src_group >= n_src && div_up(n_dst, dst_group) == div_up(n_src, src_group), UAVSAL_EINVAL,
                    "bilinear_ac: %d sources in groups of %d do not match %d outputs in groups of %d", n_src, src_group, n_dst, dst_group);
-    launch_k(bilinear_ac_kernel, dim3(div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n_src, hs, ws, c,
+    UAVSAL_REQUIRE(hd <= 65535 && n_dst <= 65535, UAVSAL_ENOTSUP, "bilinear_ac: more than 65535 output rows / frames");
+    launch_k(bilinear_ac_kernel, dim3(div_up((int64_t)wd * (c / 8), 256), hd, n_dst), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n_src, hs, ws, c,
                                                                             ActW{out, out_plane, out_ld}, n_dst, hd, wd,
                                                                             ry, rx, src_group, dst_group);
     return check_launch("bilinear_ac");
@@ -715,8 +797,8 @@ static int post_common(const float* maps, int n, int hs, int ws, int hd, int wd,
                        float* out_f32, void* stream) {
     UAVSAL_REQUIRE(maps && frame_max && (out_u8 || out_f32) && n > 0 && hs > 0 && ws > 0 && hd > 0 && wd > 0, UAVSAL_EINVAL,
                    "post: bad arguments");
-    UAVSAL_REQUIRE(out_f32 || (wd % 4 == 0 && (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0), UAVSAL_ENOTSUP,
-                   "post_u8: output width must be a multiple of 4");
+    UAVSAL_REQUIRE(out_f32 || (wd % 4 == 0 && wd <= kPostMaxW && ws < 65536 && (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0), UAVSAL_ENOTSUP,
+                   "post_u8: output width must be a multiple of 4 and <= 2048");
     PostGeom g;
     g.hs = hs; g.ws = ws; g.hd = hd; g.wd = wd;
     // utils_data.py:291-301: compare rates, resize keeping aspect, centre-crop
@@ -735,7 +817,9 @@ static int post_common(const float* maps, int n, int hs, int ws, int hd, int wd,
     cudaError_t e = cudaMemsetAsync(frame_max, 0, sizeof(float) * n, s);
     if (e != cudaSuccess) { set_error("post_u8 memset: %s", cudaGetErrorString(e)); return (int)e; }
     const int bpf = max(1, min(64, div_up((int64_t)hd * wd, 256 * 16)));
-    launch_k(post_max_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max);
+    const bool quads = wd % 4 == 0 && wd <= kPostMaxW && ws < 65536;
+    if (quads) launch_k(post_max_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max);
+    else       launch_k(post_max_px_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max);
     if (out_u8) launch_k(post_write_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max, out_u8);
     else        launch_k(post_write_f32_kernel, dim3(dim3(bpf, n)), dim3(256), 0, s, 1, maps, g, frame_max, out_f32);
     return check_launch("post");
