@@ -136,9 +136,10 @@ class dwBlock(KernelModule):
         fuse_dp = getattr(plan, "fuse_dw_project", "auto")
         if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
             fuse_dp = h * w >= 3600 and n * h * w >= 32768
-        if (fuse_dp and has_expand and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and hidden % 128 == 0 and
-                oup % 64 == 0 and oup <= 256):
-            wdw, bdw = self.conv[1].folded()
+        wide = has_expand and hidden % 128 == 0 and oup % 64 == 0 and oup <= 256          # tcgen05 pair kernel (dwproj.cu)
+        narrow = (hidden, oup) == (32, 16) and not self.use_res_connect                    # features.1: fp32 FFMA kernel (dwproj32.cu)
+        if fuse_dp and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and (wide or narrow):
+            wdw, bdw = self.conv[i].folded()
             wf, bf = self.project_folded()
             out = out if out is not None else plan.alloc(n * h * w, oup)
             plan.dwproj(cur, n, h, w, pack_dw(wdw), bdw, wf, bf, out, res=x if self.use_res_connect else None, tag=tag + ".dw+project")

@@ -349,6 +349,11 @@ static int launch_dwproj(const CUtensorMap& tH, const CUtensorMap& tB, DwProjArg
 
 using namespace uavsal;
 
+namespace uavsal {
+int dw_project32(const float* hid, int hid_ld, int n, int h, int w, const float* wd, const float* bd, const uint16_t* wgt, int kpad,
+                 const float* bias, ActW out, cudaStream_t s);
+}
+
 extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hidden, const float* wd, const float* bd,
                                  const uint16_t* wgt, int kpad, int cout, const float* bias, int flags, int terms,
                                  const uint16_t* res, int64_t res_plane, int res_ld, uint16_t* out, int64_t out_plane, int out_ld,
@@ -358,8 +363,12 @@ extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int
                        hid_ld % 4 == 0 && hid_ld >= hidden && out_ld % 8 == 0 && out_ld >= cout && out_plane > 0 && out_plane % 8 == 0 &&
                        kpad >= hidden && kpad % 8 == 0,
                    UAVSAL_EINVAL, "dw_project: bad arguments");
+    if (hidden == 32 && cout == 16) {                             // features.1: fp32 FFMA kernel (dwproj32.cu), exact in both precision modes
+        UAVSAL_REQUIRE(!flags, UAVSAL_ENOTSUP, "dw_project: the 32 -> 16 kernel has no residual input");
+        return dw_project32(hid, hid_ld, n, h, w, wd, bd, wgt, kpad, bias, ActW{out, out_plane, out_ld}, (cudaStream_t)stream);
+    }
     UAVSAL_REQUIRE(hidden % 128 == 0 && cout % 64 == 0 && cout <= 256 && (terms == 1 || terms == 3), UAVSAL_ENOTSUP,
-                   "dw_project: hidden %d must be a multiple of 128, cout %d a multiple of 64 up to 256", hidden, cout);
+                   "dw_project: hidden %d must be a multiple of 128 and cout %d a multiple of 64 up to 256 (or 32 -> 16)", hidden, cout);
     UAVSAL_REQUIRE(!(flags & UAVSAL_F_RESIDUAL) || (al16(res) && res_ld % 8 == 0 && res_plane % 8 == 0 && res_plane > 0), UAVSAL_EINVAL,
                    "dw_project: residual requested without a residual tensor");
     UAVSAL_REQUIRE(!(flags & ~UAVSAL_F_RESIDUAL), UAVSAL_ENOTSUP, "dw_project: only the residual flag is supported (the project conv is linear)");

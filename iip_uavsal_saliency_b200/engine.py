@@ -199,7 +199,8 @@ class Plan:
                res: Optional[Buf] = None, tag=""):
         """Fused depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (+ residual) from the fp32 hidden tensor (stride 1)."""
         cout, hidden = w2d.shape
-        assert hid.f32 and hid.c == hidden and hidden % 128 == 0 and cout % 64 == 0 and cout <= 256 and self.engine == "tc"
+        assert hid.f32 and hid.c == hidden and self.engine == "tc"
+        assert (hidden % 128 == 0 and cout % 64 == 0 and cout <= 256) or ((hidden, cout) == (32, 16) and res is None)
         wp = self.hold(pack_pw_tc(w2d, hidden))
         b = self.hold(bias.float())
         r = res.act() if res is not None else NULL_ACT

@@ -89,7 +89,8 @@ int uavsal_expand_dw3x3(const uint16_t* x, int64_t x_plane, int x_ld, int n, int
 
 /* dwBlock conv[1] + conv[2] + conv[3] fused (model.py:92-101): depthwise 3x3 (pad 1, stride 1) + BN + ReLU6 on the fp32 hidden
  * tensor `hid` (n, h, w, hidden) [rows of hid_ld floats], immediately consumed as the A operand of the 1x1 project conv + BN
- * (+ residual) on the tensor cores - the depthwise output never reaches HBM.  hidden % 128 == 0, cout % 64 == 0, cout <= 256.
+ * (+ residual) on the tensor cores - the depthwise output never reaches HBM.  hidden % 128 == 0, cout % 64 == 0, cout <= 256;
+ * also hidden == 32 with cout == 16 and no residual (torchvision features[1]): an fp32 FFMA kernel, `terms` ignored.
  * wd [9][hidden], bd [hidden] as uavsal_dw3x3; wgt/kpad/bias/res/out as uavsal_pw_gemm (flags: UAVSAL_F_RESIDUAL only). */
 int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hidden,
                       const float* wd, const float* bd,

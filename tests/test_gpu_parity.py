@@ -105,10 +105,12 @@ def test_fused_expand_depthwise(cuda, cin, ch, s, n, h, w):
 
 
 @pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
-                                              (128, 128, 1, 45, 80, False), (384, 256, 1, 9, 40, True)])
+                                              (128, 128, 1, 45, 80, False), (384, 256, 1, 9, 40, True),
+                                              (32, 16, 2, 45, 80, False), (32, 16, 1, 13, 21, False), (32, 16, 3, 8, 16, False)])
 def test_fused_depthwise_project(cuda, ch, co, n, h, w, res):
     """dwBlock conv[1..3] in one kernel (model.py:92-101): depthwise tiles feed the tcgen05 project GEMM from shared memory;
-    single-tile, odd-tile-count and ragged-edge cases exercise the CTA-pair bookkeeping."""
+    single-tile, odd-tile-count and ragged-edge cases exercise the CTA-pair bookkeeping.  32 -> 16 (torchvision features[1]) is
+    the fp32 FFMA kernel behind the same entry point."""
     from iip_uavsal_saliency_b200.engine import pack_dw
     torch.manual_seed(11)
     p = _plan()

@@ -230,7 +230,7 @@ def g_dwproj():
     from iip_uavsal_saliency_b200.engine import pack_dw
     torch.manual_seed(11)
     for (ch, co, n, h, w, res) in [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True), (128, 128, 1, 45, 80, False),
-                                   (384, 256, 1, 9, 40, True), (1152, 64, 1, 45, 80, False)]:
+                                   (384, 256, 1, 9, 40, True), (1152, 64, 1, 45, 80, False), (32, 16, 2, 45, 80, False), (32, 16, 1, 13, 21, False), (32, 16, 2, 180, 320, False)]:
         for terms in (3,):
             p = mk_plan("tc", terms)
             hid = torch.rand(n, ch, h, w) * 6

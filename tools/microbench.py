@@ -157,6 +157,10 @@ def main():
     if what == "dwproj":
         dwproj(20, 45, 80, 1536, 256); dwproj(20, 45, 80, 1536, 256, res=True); dwproj(20, 45, 80, 1920, 256); dwproj(20, 45, 80, 1152, 64)
         dwproj(20, 45, 80, 1536, 256, terms=1); dw(2, 20, 45, 80, 1536, 1, True); gemm("tc", M, 1536, 256, res=True)
+    if what == "dwproj32only":
+        dwproj(20, 180, 320, 32, 16)
+    if what == "dwproj32":
+        dwproj(20, 180, 320, 32, 16); dw(2, 20, 180, 320, 32, 1, True); gemm("tc", 20 * 180 * 320, 32, 16)
     if what == "dwproj1":
         dwproj(20, 45, 80, 1536, 256)
     if what == "twa2":
