@@ -101,24 +101,29 @@ __device__ __forceinline__ float load1(const uint16_t* hi, int64_t plane) {
     return v;
 }
 
+// split two fp32 into packed (hi, hi) / (lo, lo) bf16 pairs: one packed conversion per plane (F2FP) instead of two scalar F2F
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ void store8(uint16_t* hi, int64_t plane, const float v[8]) {
-    uint32_t h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split1(v[i], h[i], l[i]);
-    uint4 H = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-    *reinterpret_cast<uint4*>(hi) = H;
-    if (plane) {
-        uint4 L = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
-        *reinterpret_cast<uint4*>(hi + plane) = L;
-    }
+    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (plane) *reinterpret_cast<uint4*>(hi + plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __device__ __forceinline__ void store4(uint16_t* hi, int64_t plane, const float v[4]) {
-    uint32_t h[4], l[4];
+    uint32_t h[2], l[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split1(v[i], h[i], l[i]);
-    *reinterpret_cast<uint2*>(hi) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-    if (plane) *reinterpret_cast<uint2*>(hi + plane) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    for (int i = 0; i < 2; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint2*>(hi) = make_uint2(h[0], h[1]);
+    if (plane) *reinterpret_cast<uint2*>(hi + plane) = make_uint2(l[0], l[1]);
 }
 
 __device__ __forceinline__ void store1(uint16_t* hi, int64_t plane, float v) {

@@ -64,13 +64,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void ed_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 
 // Persistent CTA, work item = (spatial tile, group of 64-channel blocks).  All weights of the block (expand hi/lo, both
 // bias vectors, depthwise taps) stay in shared memory for the whole kernel; the haloed input tile of the NEXT work item is
@@ -294,8 +287,8 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                             for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
                         }
                     uint32_t h0, l0, h1, l1;
-                    ed_split2(relu6f(acc[0]), relu6f(acc[1]), h0, l0);
-                    ed_split2(relu6f(acc[2]), relu6f(acc[3]), h1, l1);
+                    split2(relu6f(acc[0]), relu6f(acc[1]), h0, l0);
+                    split2(relu6f(acc[2]), relu6f(acc[3]), h1, l1);
                     uint16_t* dst = orow + (int64_t)i * g.wo * g.out.ld;
                     *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
                     if (g.out.plane) *reinterpret_cast<uint2*>(dst + g.out.plane) = make_uint2(l0, l1);

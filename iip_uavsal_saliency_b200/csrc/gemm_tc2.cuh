@@ -20,15 +20,6 @@ constexpr int kPF = 6;                                     // L2 prefetch distan
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads2 = 64 + kEpiThreads;                // producer warp + MMA warp + epilogue warps
 
-// two fp32 -> packed (hi, lo) bf16x2 words; element 0 in the low half
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // CL = CTAs per cluster (1 | 2).  With CL = 2 the two CTAs of a cluster (the two SMs of a TPC) run cta_group::2 MMAs on
 // a 256-row tile: each CTA stages its own 128 rows of A and HALF of the B tile, keeps its 128 accumulator lanes in its own
 // TMEM and drains them with its own epilogue warps; the even CTA issues the MMAs and its commits arrive on both CTAs'

@@ -128,6 +128,8 @@ def main():
     if what in ("dw", "all"):
         for fast in (0, 2):
             dw(fast, 20, 45, 80, 1536, 1); dw(fast, 20, 180, 320, 96, 2); dw(fast, 20, 180, 320, 32, 1); dw(fast, 20, 90, 160, 144, 1); dw(fast, 20, 23, 40, 384, 1)
+    if what == "dwbigf32":
+        dw(2, 20, 45, 80, 1536, 1, True)
     if what == "dwbig":
         dw(int(sys.argv[2]) if len(sys.argv) > 2 else 2, 20, 45, 80, 1536, 1)
     if what == "r2":
