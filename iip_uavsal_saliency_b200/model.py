@@ -196,8 +196,13 @@ class UAVSal(KernelModule):
         self._planes, self._iosize, self._bias_type = planes, list(iosize), list(bias_type)
         if os.path.exists(pre_model_path):
             print("Load pre-trained weights")
-            obj = torch.load(pre_model_path, map_location=device, weights_only=False)
-            self.load_state_dict(obj.state_dict() if hasattr(obj, "state_dict") else obj, strict=False)
+            self.load_reference(pre_model_path, strict=False)                  # model.py:339
+
+    def load_reference(self, path, strict: bool = True):
+        """``self.load_state_dict(torch.load(path).state_dict())`` (Demo_Test.py:39) for the reference's whole-module pickles,
+        without its classes (or the torchvision version it was saved with) being importable: see checkpoint.py."""
+        from . import checkpoint
+        return checkpoint.load_into(self, path, strict=strict)
 
     # -----------------------------------------------------------------------------------------------
     def build_plan(self, plan: Plan, n: int, h: int, w: int, x_kind: int = 0, post_hw=None, taps: bool = False,
