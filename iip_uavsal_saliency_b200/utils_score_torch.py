@@ -4,8 +4,8 @@ metric_kl / metric_sim, :180-218, with the reduction helpers :20-50 and EPS :13)
 All four metrics of a batch come out of ONE fused sm_100a kernel launch (csrc/metrics.cu); the per-metric
 functions keep the reference signatures ``metric_x(y_pred (N,1,H,W), y_true (N,2,H,W)) -> (N,1)`` and share the
 launch through a one-entry memo, because the reference's evaluation loop calls them back to back on the same
-tensors (utils_score_torch.py:551-561).  AUC-Judd/Borji/shuffled and the file-walking evaluation loops are
-out of scope.
+tensors (utils_score_torch.py:551-561).  AUC-Judd / Borji / shuffled (csrc/auc.cu) follow below; the file-walking
+evaluation loop stays with the caller.
 """
 from __future__ import annotations
 
@@ -63,7 +63,79 @@ def metric_sim(y_pred, y_true):
     return metrics4(y_pred, y_true)[:, 3:4]
 
 
-metrics = {"NSS": metric_nss, "CC": metric_cc, "SIM": metric_sim, "KLD": metric_kl}
+# ---------------------------------------------------------------------------------------------------
+# AUC metrics (utils_score_torch.py:53-177).  The kernels (csrc/auc.cu) do the counting; the random draws stay on the host
+# and consume the SAME global generators in the SAME order as the reference (torch.rand for the jitter :82, np.random.randint
+# for the sampled pixels :103 / :143), so a seeded run reproduces the reference's scores.
+# ---------------------------------------------------------------------------------------------------
+def _auc_inputs(y_pred, y_true):
+    if y_pred.dim() != 4 or y_true.dim() != 4 or y_pred.shape[1] != 1 or y_true.shape[1] != 2 or \
+            y_pred.shape[0] != y_true.shape[0] or y_pred.shape[2:] != y_true.shape[2:]:
+        raise ValueError("expected y_pred (N,1,H,W) and y_true (N,2,H,W), got %s and %s" % (tuple(y_pred.shape), tuple(y_true.shape)))
+    dev = y_pred.device if y_pred.is_cuda else (y_true.device if y_true.is_cuda else torch.device("cuda"))
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("uavsal-b200 metrics run on CUDA (sm_100a) only; there is no CPU fallback")
+    return y_pred.to(dev, torch.float32).contiguous(), y_true.to(dev, torch.float32).contiguous(), dev
+
+
+def metric_auc_j(y_pred, y_true, jitter=1):
+    """utils_score_torch.py:77-88 -> (N,1); NaN for an empty map / fixation set (:54)."""
+    if jitter == True:  # noqa: E712  (the reference's comparison, :81)
+        y_pred = y_pred + (torch.rand(y_pred.shape) * 1e-7).to(y_pred.device)
+    p, t, dev = _auc_inputs(y_pred, y_true)
+    n, _, h, w = p.shape
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    _ext.call("uavsal_auc_judd", p.data_ptr(), t.data_ptr(), n, h, w, out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    return out.unsqueeze(1)
+
+
+def _auc_sampled(p, t, dev, draw, n_rep=100, step=0.1):
+    """draw(i, n_fix) -> int array (k, n_rep) of flat pixel indices for pair i (or None: the reference returns NaN before drawing)."""
+    import numpy as np
+    n, _, h, w = p.shape
+    flat = p.flatten(1)
+    valid = ((flat.amax(1) > flat.amin(1)) & torch.isfinite(flat.amax(1))).cpu().numpy()       # any(S > 0), :92
+    n_fix = (t[:, 1].flatten(1) > 0.5).sum(1).cpu().numpy()
+    draws = [draw(i, int(n_fix[i])) if (valid[i] and n_fix[i] > 0) else None for i in range(n)]
+    max_k = max([d.shape[0] for d in draws if d is not None] + [1])
+    idx = np.zeros((n, max_k, n_rep), np.int32)
+    n_k = np.zeros((n,), np.int32)
+    for i, d in enumerate(draws):
+        if d is not None:
+            idx[i, :d.shape[0]] = d
+            n_k[i] = d.shape[0]
+    idx_d, nk_d = torch.from_numpy(idx).to(dev), torch.from_numpy(n_k).to(dev)
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    _ext.call("uavsal_auc_sampled", p.data_ptr(), t.data_ptr(), n, h, w, idx_d.data_ptr(), nk_d.data_ptr(), max_k, n_rep, float(step),
+              out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    return out.unsqueeze(1)
+
+
+def metric_auc_b(y_pred, y_true):
+    """utils_score_torch.py:123-132 (auc_b :91-120) -> (N,1)."""
+    import numpy as np
+    p, t, dev = _auc_inputs(y_pred, y_true)
+    n_pixels = p.shape[2] * p.shape[3]
+    return _auc_sampled(p, t, dev, lambda i, n_fix: np.random.randint(0, n_pixels, [n_fix, 100]))
+
+
+def metric_auc_s(y_pred, y_true, shuff_map):
+    """utils_score_torch.py:162-172 (auc_s :135-159) -> (N,1).  shuff_map (N,1,H,W): other frames' fixation counts."""
+    import numpy as np
+    p, t, dev = _auc_inputs(y_pred, y_true)
+    oth = torch.flatten(shuff_map, 1, -1).cpu().numpy()
+
+    def draw(i, n_fix):
+        ind = np.nonzero(oth[i])[0]
+        n_ind = len(ind)
+        r = np.random.randint(0, n_ind, [n_ind, 100])[:min(n_fix, n_ind), :]       # the reference draws n_ind rows and keeps n_fix_oth (:143)
+        return ind[r]
+
+    return _auc_sampled(p, t, dev, draw)
+
+
+metrics = {"AUC_shuffled": metric_auc_s, "AUC_Judd": metric_auc_j, "AUC_Borji": metric_auc_b,
+           "NSS": metric_nss, "CC": metric_cc, "SIM": metric_sim, "KLD": metric_kl}
 
 
 # reduction helpers of the reference (utils_score_torch.py:20-50): per-(n,c) scalars broadcast back to (H,W).

@@ -193,6 +193,20 @@ int uavsal_post_f32(const float* maps, int n, int hs, int ws, int hd, int wd, fl
 int uavsal_metrics4(const void* pred, const void* truth, int dtype, int n, int h, int w,
                     double* scratch, float* out, void* stream);
 
+/* ---- utils_score_torch.metric_auc_j (53-88), deterministic part: S = min-max normalised pred (fp32, as :83), fixations =
+ *      truth channel 1 > 0.5; out[n] = AUC-Judd (NaN when the map has no positive value or the frame no fixation, :54).
+ *      The reference's optional jitter (:82, global torch generator) is added to `pred` by the caller.  pred (n,1,h,w),
+ *      truth (n,2,h,w) fp32.  At most 4096 fixations per frame (more: NaN). */
+int uavsal_auc_judd(const float* pred, const float* truth, int n, int h, int w, float* out, void* stream);
+
+/* ---- auc_b (91-120) / auc_s (135-159): sampled AUC with thresholds k*step below the largest sample.  The random pixel
+ *      indices are the CALLER's draw (the reference uses the global numpy generator, :103 / :143-144):
+ *      rand_idx int32 (n, max_k, n_rep) = flat pixel index of sample k of repetition rep; n_k[n] = samples per repetition
+ *      (Borji: n_fix; shuffled: min(n_fix, n_ind)) and the false-positive denominator.  n_rep <= 128, step >= 1/62.
+ *      out[n] fp32 (NaN as above, or when n_k is 0). */
+int uavsal_auc_sampled(const float* pred, const float* truth, int n, int h, int w, const int32_t* rand_idx,
+                       const int32_t* n_k, int max_k, int n_rep, double step, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

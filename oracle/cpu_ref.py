@@ -359,3 +359,98 @@ def metrics4(y_pred, y_true):
     """(N,4) columns CC, NSS, KLD, SIM."""
     return torch.cat([metric_cc(y_pred, y_true), metric_nss(y_pred, y_true), metric_kl(y_pred, y_true),
                       metric_sim(y_pred, y_true)], 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# AUC metrics (utils_score_torch.py:53-177).  The reference draws from the GLOBAL torch / numpy generators (jitter :82,
+# random pixels :103 / :143): seed them before calling for reproducible values; the draws below happen in the same order.
+# ---------------------------------------------------------------------------------------------------
+def _minmax_norm(y_pred):
+    return (y_pred - _amin(y_pred)) / (_amax(y_pred) - _amin(y_pred) + EPS)
+
+
+def auc_j(S, F):
+    """utils_score_torch.py:53-74.  S (P,) fp32 in [0,1], F (P,) bool."""
+    if not torch.any(S > 0) or not torch.any(F > 0):
+        return torch.tensor(float("nan"))
+    S_fix = S[F]
+    n_fix, n_pixels = S_fix.shape[0], S.shape[0]
+    thresholds, _ = torch.sort(S_fix, descending=True)
+    tp, fp = torch.zeros(n_fix + 2), torch.zeros(n_fix + 2)
+    tp[-1] = 1
+    fp[-1] = 1
+    tp[1:-1] = (torch.arange(0, n_fix) + 1) / float(n_fix)
+    # above_th[i] = #{S >= thresholds[i]}: the reference loops over the thresholds; one sort + searchsorted gives the same counts
+    s_sorted, _ = torch.sort(S)
+    above_th = n_pixels - torch.searchsorted(s_sorted, thresholds.contiguous(), right=False)
+    fp[1:-1] = (above_th - torch.arange(0, n_fix) - 1) / float(n_pixels - n_fix)
+    return torch.trapz(tp, fp)
+
+
+def metric_auc_j(y_pred, y_true, jitter=1):
+    """utils_score_torch.py:77-88."""
+    f = y_true[:, 1:2] > 0.5
+    if jitter == True:  # noqa: E712  (the reference's comparison)
+        y_pred = y_pred + (torch.rand(y_pred.shape) * 1e-7).to(y_pred.device)
+    y_pred = _minmax_norm(y_pred)
+    S, F = torch.flatten(y_pred, 1, -1), torch.flatten(f, 1, -1)
+    return torch.Tensor([auc_j(S[i], F[i]) for i in range(S.shape[0])]).unsqueeze(1)
+
+
+_trapz = getattr(np, "trapezoid", None) or np.trapz          # np.trapz (the reference's call) was renamed in numpy 2
+
+
+def _auc_sampled(S_fix, S_rand, n_den, step_size=0.1):
+    """Shared tail of auc_b / auc_s (utils_score_torch.py:106-119, 146-158): S_rand (k, n_rep)."""
+    n_fix, n_rep = len(S_fix), S_rand.shape[1]
+    auc = np.zeros(n_rep) * np.nan
+    for rep in range(n_rep):
+        thresholds = np.r_[0:np.max(np.r_[S_fix, S_rand[:, rep]]):step_size][::-1]
+        tp, fp = np.zeros(len(thresholds) + 2), np.zeros(len(thresholds) + 2)
+        tp[-1] = 1
+        fp[-1] = 1
+        for k, thresh in enumerate(thresholds):
+            tp[k + 1] = np.sum(S_fix >= thresh) / float(n_fix)
+            fp[k + 1] = np.sum(S_rand[:, rep] >= thresh) / float(n_den)
+        auc[rep] = _trapz(tp, fp)
+    return np.mean(auc)
+
+
+def auc_b(S, F, n_rep=100):
+    """utils_score_torch.py:91-120 (numpy; S float32 (P,), F bool (P,))."""
+    if not np.any(S > 0) or not np.any(F > 0):
+        return torch.tensor(float("nan"))
+    S_fix = S[F]
+    n_fix, n_pixels = len(S_fix), len(S)
+    r = np.random.randint(0, n_pixels, [n_fix, n_rep])
+    return _auc_sampled(S_fix, S[r], n_fix)
+
+
+def auc_s(S, F, Oth, n_rep=100):
+    """utils_score_torch.py:135-159."""
+    if not np.any(S > 0) or not np.any(F > 0):
+        return torch.tensor(float("nan"))
+    S_fix = S[F]
+    n_fix = len(S_fix)
+    ind = np.nonzero(Oth)[0]
+    n_ind = len(ind)
+    n_fix_oth = min(n_fix, n_ind)
+    r = np.random.randint(0, n_ind, [n_ind, n_rep])[:n_fix_oth, :]
+    return _auc_sampled(S_fix, S[ind[r]], n_fix_oth)
+
+
+def metric_auc_b(y_pred, y_true):
+    """utils_score_torch.py:123-132."""
+    f = y_true[:, 1:2] > 0.5
+    y_pred = _minmax_norm(y_pred)
+    S, F = torch.flatten(y_pred, 1, -1).numpy(), torch.flatten(f, 1, -1).numpy()
+    return torch.Tensor([auc_b(S[i], F[i]) for i in range(S.shape[0])]).unsqueeze(1)
+
+
+def metric_auc_s(y_pred, y_true, shuff_map):
+    """utils_score_torch.py:162-172."""
+    f = y_true[:, 1:2] > 0.5
+    y_pred = _minmax_norm(y_pred)
+    S, F = torch.flatten(y_pred, 1, -1).numpy(), torch.flatten(f, 1, -1).numpy()
+    O = torch.flatten(shuff_map, 1, -1).numpy()
+    return torch.Tensor([auc_s(S[i], F[i], O[i]) for i in range(S.shape[0])]).unsqueeze(1)

@@ -174,6 +174,24 @@ def gen_metrics(ref):
                         ka_zero=ka_zero)
 
 
+def gen_auc(ref):
+    """AUC-Judd / Borji / shuffled of the UNMODIFIED reference on seeded inputs (global torch / numpy generators seeded
+    right before each call, which is what makes the reference's Monte-Carlo draws reproducible)."""
+    us = ref.utils_score_torch
+    pred, true, shuf = synth.make_auc_case(0)
+    p, t, o = torch.from_numpy(pred), torch.from_numpy(true), torch.from_numpy(shuf)
+    res = {}
+    res["judd_nojitter"] = us.metric_auc_j(p, t, jitter=0).numpy()
+    torch.manual_seed(1234)
+    res["judd_jitter"] = us.metric_auc_j(p, t).numpy()
+    np.random.seed(4321)
+    res["borji"] = us.metric_auc_b(p, t).numpy()
+    np.random.seed(987)
+    res["shuffled"] = us.metric_auc_s(p, t, o).numpy()
+    np.savez_compressed(os.path.join(GOLD, "auc_metrics.npz"), **res)
+    print({k: v.ravel().round(5).tolist() for k, v in res.items()})
+
+
 def gen_rnn_small(ref):
     mc = ref.model_convlstm
     res = {}
@@ -222,7 +240,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "rnn": gen_rnn_small, "post": gen_post}
 
 
 def main():

@@ -164,3 +164,15 @@ def make_metric_pairs(n: int, H: int = 360, W: int = 640, seed: int = 0):
         true[i, 0] = dens_u8
         true[i, 1] = fix.reshape(H, W)
     return pred, true
+
+
+def make_auc_case(seed: int = 0, n: int = 6, H: int = 360, W: int = 640):
+    """Inputs of the AUC metrics: `n` correlated pairs (make_metric_pairs) followed by two degenerate ones (an all-zero
+    prediction; a pair without fixations - both score NaN, utils_score_torch.py:54,92,136), and a shuffle map per pair
+    (fixations of the OTHER pairs, as getshufmap builds it)."""
+    pred, true = make_metric_pairs(n + 2, H, W, seed=seed)
+    pred[n] = 0.0
+    true[n + 1, 1] = 0.0
+    fix = true[:, 1]
+    shuf = np.stack([np.clip(fix.sum(0) - fix[i], 0, None) for i in range(n + 2)], 0)[:, None].astype(np.float32)
+    return pred, true, shuf

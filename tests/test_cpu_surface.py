@@ -66,7 +66,11 @@ def test_constructor_signatures_and_defaults():
     assert list(inspect.signature(MC.ConvLSTMCell.forward).parameters) == ["self", "input_tensor", "cur_state"]
     for name in ("metric_cc", "metric_nss", "metric_kl", "metric_sim"):
         assert list(inspect.signature(getattr(US, name)).parameters) == ["y_pred", "y_true"]
-    assert US.EPS == 2.2204e-16 and set(US.metrics) == {"NSS", "CC", "SIM", "KLD"}
+    # the reference's `metrics` dict (utils_score_torch.py:221-229), AUC metrics included
+    assert US.EPS == 2.2204e-16 and set(US.metrics) == {"AUC_shuffled", "AUC_Judd", "AUC_Borji", "NSS", "CC", "SIM", "KLD"}
+    assert list(inspect.signature(US.metric_auc_j).parameters) == ["y_pred", "y_true", "jitter"]
+    assert list(inspect.signature(US.metric_auc_b).parameters) == ["y_pred", "y_true"]
+    assert list(inspect.signature(US.metric_auc_s).parameters) == ["y_pred", "y_true", "shuff_map"]
 
 
 def test_error_behaviour_follows_reference():

@@ -413,3 +413,33 @@ def test_fast_mode_is_reported_not_claimed(cuda, gold_dir):
     o = out.cpu().numpy()
     cc = cpu_ref.metric_cc(torch.from_numpy(o), torch.cat([torch.from_numpy(g["out"])] * 2, 1))
     assert cc.min().item() > 0.95 and np.abs(o - g["out"]).max() < 0.2     # measured: CC 0.989 - below the 0.999 bar, hence the x3 split
+
+
+def test_auc_metrics_match_reference_and_oracle(cuda, gold_dir):
+    """AUC-Judd / Borji / shuffled (utils_score_torch.py:53-177) through the C ABI against the reference's own values
+    (tests/golden/auc_metrics.npz: the unmodified reference under the same generator seeds) and the oracle; the degenerate
+    pairs give NaN exactly where the reference does.  Tolerance 1e-5 absolute on scores in [0, 1] (fp32 trapezoid order)."""
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    g = np.load(os.path.join(gold_dir, "auc_metrics.npz"))
+    pred, true, shuf = synth.make_auc_case(0)
+    p, t, o = torch.from_numpy(pred).cuda(), torch.from_numpy(true).cuda(), torch.from_numpy(shuf)
+    np.testing.assert_allclose(us.metric_auc_j(p, t, jitter=0).cpu().numpy(), g["judd_nojitter"], atol=1e-5, rtol=0, equal_nan=True)
+    torch.manual_seed(1234)
+    np.testing.assert_allclose(us.metric_auc_j(p, t).cpu().numpy(), g["judd_jitter"], atol=1e-5, rtol=0, equal_nan=True)
+    np.random.seed(4321)
+    np.testing.assert_allclose(us.metric_auc_b(p, t).cpu().numpy(), g["borji"], atol=1e-6, rtol=0, equal_nan=True)
+    np.random.seed(987)
+    np.testing.assert_allclose(us.metric_auc_s(p, t, o).cpu().numpy(), g["shuffled"], atol=1e-6, rtol=0, equal_nan=True)
+    # a different size and seed, against the oracle run on the same draws
+    pred, true, shuf = synth.make_auc_case(3, n=3, H=90, W=160)
+    pc, tc, oc = torch.from_numpy(pred), torch.from_numpy(true), torch.from_numpy(shuf)
+    np.testing.assert_allclose(us.metric_auc_j(pc.cuda(), tc.cuda(), jitter=0).cpu().numpy(), cpu_ref.metric_auc_j(pc, tc, jitter=0).numpy(),
+                               atol=1e-5, rtol=0, equal_nan=True)
+    np.random.seed(5)
+    mine = us.metric_auc_b(pc.cuda(), tc.cuda()).cpu().numpy()
+    np.random.seed(5)
+    np.testing.assert_allclose(mine, cpu_ref.metric_auc_b(pc, tc).numpy(), atol=1e-6, rtol=0, equal_nan=True)
+    np.random.seed(6)
+    mine = us.metric_auc_s(pc.cuda(), tc.cuda(), oc).cpu().numpy()
+    np.random.seed(6)
+    np.testing.assert_allclose(mine, cpu_ref.metric_auc_s(pc, tc, oc).numpy(), atol=1e-6, rtol=0, equal_nan=True)
