@@ -44,6 +44,7 @@ _SIGNATURES = {
     "uavsal_post_u8": [P, I, I, I, I, I, P, P, P],
     "uavsal_post_f32": [P, I, I, I, I, I, P, P, P],
     "uavsal_metrics4": [P, P, I, I, I, I, P, P, P],
+    "uavsal_letterbox_u8": [P, I, I, I, P, I, I, I, P],
     "uavsal_auc_judd": [P, P, I, I, I, P, P],
     "uavsal_auc_sampled": [P, P, I, I, I, P, P, I, I, c_double, P, P],
 }

@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libuavsal_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["simt_kernels.cu", "gemm_simt.cu", "gemm_tc.cu", "dw_tma.cu", "expdw.cu", "dwproj.cu", "dwproj32.cu", "twa_step.cu", "metrics.cu", "auc.cu"]
+SOURCES = ["simt_kernels.cu", "gemm_simt.cu", "gemm_tc.cu", "dw_tma.cu", "expdw.cu", "dwproj.cu", "dwproj32.cu", "twa_step.cu", "metrics.cu", "auc.cu", "frontend.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

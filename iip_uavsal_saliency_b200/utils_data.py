@@ -1,7 +1,7 @@
 """Drop-in for the hot-path helpers of the reference's utils_data.py: normalize_data (:43-65), im2uint8 /
 np2mat (:68-82), postprocess_predictions (:289-303), st_get_gaussmaps (:391-412), get_guasspriors (:449-469),
-read_ob_priors / get_ob_priors (:552-604).  Video decoding and dataset plumbing are out of scope (SURVEY §2.1
-row 5b).  The device pipeline (runner.py) fuses normalisation into the stem kernel and the whole post-process
+read_ob_priors / get_ob_priors (:552-604), padding / preprocess_videos (:255-287, :321-343; decode on the host with cv2 as
+the reference does, letterbox resize + BGR->RGB on the device).  Dataset plumbing is out of scope.  The device pipeline (runner.py) fuses normalisation into the stem kernel and the whole post-process
 into uavsal_post_u8; the functions here keep the reference's host-facing signatures.
 """
 from __future__ import annotations
@@ -118,3 +118,62 @@ def get_ob_priors(datapath, DataSet="", phase_gen="train", b_s=2, shape_r=45, sh
     if ims.shape[0] != shape_r or ims.shape[1] != shape_c:
         ims = _quirk_q4_resize(ims, shape_r, shape_c)
     return np.repeat(np.expand_dims(ims, axis=0), b_s, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# video front-end (utils_data.py:255-287, 321-343)
+# ---------------------------------------------------------------------------------------------------
+def letterbox_frames(frames_bgr, shape_r: int, shape_c: int, mode: str = "RGB") -> torch.Tensor:
+    """(n,h,w,3) uint8 frames in cv2's BGR order (numpy, CPU or CUDA tensor) -> (n,shape_r,shape_c,3) uint8 CUDA tensor:
+    ``padding(frame, shape_r, shape_c, 3)`` for every frame (+ the RGB reorder), bit-exact with the reference's cv2 path.
+    This is the tensor ``ClipRunner.run_clip`` / the stem kernel take directly (normalisation is fused there)."""
+    if mode not in ("RGB", "BGR"):
+        raise ValueError
+    if not torch.cuda.is_available():
+        raise RuntimeError("the video front-end runs on CUDA (sm_100a) only; there is no CPU fallback")
+    t = torch.from_numpy(np.ascontiguousarray(frames_bgr)) if isinstance(frames_bgr, np.ndarray) else frames_bgr
+    if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
+        raise ValueError("expected (n,h,w,3) uint8 frames, got %s %s" % (tuple(t.shape), t.dtype))
+    t = t.cuda(non_blocking=True).contiguous()
+    n, h, w, _ = t.shape
+    out = torch.empty((n, shape_r, shape_c, 3), dtype=torch.uint8, device=t.device)
+    _ext.call("uavsal_letterbox_u8", t.data_ptr(), n, h, w, out.data_ptr(), shape_r, shape_c, 1 if mode == "RGB" else 0,
+              ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream))
+    return out
+
+
+def padding(img, shape_r=480, shape_c=640, channels=3):
+    """utils_data.py:321-343 for 3-channel uint8 images (numpy in, numpy out)."""
+    if channels != 3 or img.ndim != 3:
+        raise NotImplementedError("only the 3-channel frame path of preprocess_videos is on the device")
+    return letterbox_frames(img[None], shape_r, shape_c, mode="BGR")[0].cpu().numpy()
+
+
+def preprocess_videos(path, shape_r, shape_c, frames=float("inf"), mode="RGB", normalize=True, device=None):
+    """utils_data.py:255-287: decode with cv2.VideoCapture (host, as the reference), letterbox + channel order on the device.
+    Returns (ims, nframes, height, width) with ims a numpy array like the reference's - or, with ``device='cuda'``, the uint8
+    (n,shape_r,shape_c,3) CUDA tensor to hand to the runner (``normalize`` must then be False: the stem kernel normalises)."""
+    import cv2
+    if mode not in ("RGB", "BGR"):
+        raise ValueError
+    cap = cv2.VideoCapture(path)
+    nframes = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    width, height = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    nframes = int(min(nframes, frames))
+    raw = np.zeros((nframes, height, width, 3), np.uint8)
+    for i in range(nframes):
+        ret, frame = cap.read()
+        raw[i] = frame
+    cap.release()
+    ims = letterbox_frames(raw, shape_r, shape_c, mode)
+    if device is not None:
+        if normalize:
+            raise ValueError("device output is uint8; the normalisation is fused into the stem kernel")
+        return ims.to(device), nframes, height, width
+    ims = ims.cpu().numpy()
+    if normalize:
+        mean, std = (_MEAN, _STD) if mode == "RGB" else (_MEAN[::-1], _STD[::-1])
+        ims = ims.astype(np.float32) / 255.0
+        for c in range(3):
+            ims[:, :, :, c] = (ims[:, :, :, c] - mean[c]) / std[c]
+    return ims, nframes, height, width

@@ -193,6 +193,12 @@ int uavsal_post_f32(const float* maps, int n, int hs, int ws, int hd, int wd, fl
 int uavsal_metrics4(const void* pred, const void* truth, int dtype, int n, int h, int w,
                     double* scratch, float* out, void* stream);
 
+/* ---- video front-end after decode: utils_data.padding (321-343) as called by preprocess_videos (255-287).
+ *      src (n, sh, sw, 3) uint8 frames as cv2.VideoCapture delivers them (BGR); dst (n, dh, dw, 3) uint8: the frame resized
+ *      with cv2.resize's 8-bit INTER_LINEAR arithmetic (bit-exact, incl. its exact-2x INTER_AREA shortcut) keeping the aspect
+ *      ratio, centred on a zero canvas; swap_rb = 1 also applies the BGR -> RGB reorder of :270.  dw <= 4096. */
+int uavsal_letterbox_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, void* stream);
+
 /* ---- utils_score_torch.metric_auc_j (53-88), deterministic part: S = min-max normalised pred (fp32, as :83), fixations =
  *      truth channel 1 > 0.5; out[n] = AUC-Judd (NaN when the map has no positive value or the frame no fixation, :54).
  *      The reference's optional jitter (:82, global torch generator) is added to `pred` by the caller.  pred (n,1,h,w),

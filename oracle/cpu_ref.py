@@ -454,3 +454,75 @@ def metric_auc_s(y_pred, y_true, shuff_map):
     S, F = torch.flatten(y_pred, 1, -1).numpy(), torch.flatten(f, 1, -1).numpy()
     O = torch.flatten(shuff_map, 1, -1).numpy()
     return torch.Tensor([auc_s(S[i], F[i], O[i]) for i in range(S.shape[0])]).unsqueeze(1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# video front-end after decode: utils_data.padding (:321-343) inside preprocess_videos (:255-287).
+# cv2.resize(uint8, INTER_LINEAR) is third-party code (opencv-python, unpinned by the reference; 4.13 in this image): its
+# published algorithm is restated here and checked against cv2 itself in tests/test_oracle_golden.py.
+# ---------------------------------------------------------------------------------------------------
+def _cv_taps(dst, src, zero_at_border):
+    """OpenCV resize.cpp: f = (float)((d + 0.5) * scale - 0.5), s = floor(f), 11-bit fixed-point weights rounded half to even
+    (saturate_cast<short>); the x taps are clamped with a zeroed fraction at the image border, the y taps clamp their rows."""
+    scale = src / dst
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s0 = np.floor(f).astype(np.int64)
+    f = (f - s0.astype(np.float32)).astype(np.float32)
+    if zero_at_border:
+        lo = s0 < 0
+        f[lo] = 0
+        s0[lo] = 0
+        hi = s0 >= src - 1
+        f[hi] = 0
+        s0[hi] = src - 1
+    a0 = np.rint((np.float32(1.0) - f) * np.float32(2048.0)).astype(np.int64)
+    a1 = np.rint(f * np.float32(2048.0)).astype(np.int64)
+    return s0, a0, a1
+
+
+def cv_resize_linear_u8(img, dw, dh):
+    """cv2.resize(img, (dw, dh)) for uint8 (H,W[,C]) images, default INTER_LINEAR: identity copy, the exact-2x case that
+    OpenCV routes to its INTER_AREA 2x2 average, else horizontal pass in 11-bit fixed point and the vertical pass
+    ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2 (VResizeLinear<uchar>)."""
+    sh, sw = img.shape[:2]
+    a = img.astype(np.int64).reshape(sh, sw, -1)
+    if (dw, dh) == (sw, sh):
+        return img.copy()
+    if sw == 2 * dw and sh == 2 * dh:
+        out = (a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8).reshape((dh, dw) + img.shape[2:])
+    sx, ax0, ax1 = _cv_taps(dw, sw, True)
+    sy, ay0, ay1 = _cv_taps(dh, sh, False)
+    hp = a[:, sx] * ax0[None, :, None] + a[:, np.minimum(sx + 1, sw - 1)] * ax1[None, :, None]
+    s0, s1 = hp[np.clip(sy, 0, sh - 1)], hp[np.clip(sy + 1, 0, sh - 1)]
+    out = (((ay0[:, None, None] * (s0 >> 4)) >> 16) + ((ay1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((dh, dw) + img.shape[2:])
+
+
+def letterbox_geometry(sh, sw, shape_r, shape_c):
+    """utils_data.padding (:321-343): (resized width, resized height, x offset, y offset) of the aspect-preserving resize."""
+    if sh / shape_r > sw / shape_c:
+        new_cols = (sw * shape_r) // sh
+        return new_cols, shape_r, (shape_c - min(new_cols, shape_c)) // 2, 0
+    new_rows = (sh * shape_c) // sw
+    return shape_c, new_rows, 0, (shape_r - min(new_rows, shape_r)) // 2
+
+
+def padding(img, shape_r=480, shape_c=640, channels=3):
+    """utils_data.py:321-343 with the resize restated."""
+    out = np.zeros((shape_r, shape_c, channels) if channels != 1 else (shape_r, shape_c), np.uint8)
+    nw, nh, ox, oy = letterbox_geometry(img.shape[0], img.shape[1], shape_r, shape_c)
+    out[oy:oy + nh, ox:ox + nw] = cv_resize_linear_u8(img, nw, nh)
+    return out
+
+
+def preprocess_frames(frames_bgr, shape_r, shape_c, mode="RGB"):
+    """preprocess_videos (:255-287) after the decode, normalize=False: (n,h,w,3) uint8 BGR frames (cv2.VideoCapture order) ->
+    (n,shape_r,shape_c,3) uint8, channels swapped to RGB for mode 'RGB' (:270)."""
+    ims = np.stack([padding(f, shape_r, shape_c, 3) for f in frames_bgr], 0)
+    if mode == "RGB":
+        ims = ims[:, :, :, [2, 1, 0]]
+    elif mode != "BGR":
+        raise ValueError
+    return ims

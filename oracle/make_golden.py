@@ -192,6 +192,33 @@ def gen_auc(ref):
     print({k: v.ravel().round(5).tolist() for k, v in res.items()})
 
 
+def gen_frontend(ref):
+    """utils_data.padding (:321-343) and preprocess_videos (:255-287) of the UNMODIFIED reference: seeded frames through
+    padding() for the wide / tall / exact-2x / identity geometries, and a tiny MJPG clip (committed next to the values)
+    through the whole preprocess_videos (decode + letterbox + BGR->RGB, normalize=False and True)."""
+    import cv2
+    ud = ref.utils_data
+    rs = np.random.RandomState(21)
+    res = {}
+    for name, (sh, sw, r, c) in {"wide": (54, 160, 72, 128), "tall": (150, 100, 72, 128), "x2": (144, 256, 72, 128),
+                                 "same": (72, 128, 72, 128), "up": (30, 40, 72, 128)}.items():
+        img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+        res["pad_in_" + name] = img
+        res["pad_out_" + name] = ud.padding(img, r, c, 3)
+    path = os.path.join(GOLD, "clip_tiny.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (200, 120))
+    clip = synth.make_clip(9, 6, 120, 200)                      # (6,120,200,3) uint8
+    for f in clip:
+        wr.write(np.ascontiguousarray(f[:, :, ::-1]))
+    wr.release()
+    ims, nframes, height, width = ud.preprocess_videos(path, 72, 128, normalize=False)
+    res["vid_u8"], res["vid_meta"] = ims, np.array([nframes, height, width])
+    imsn, _, _, _ = ud.preprocess_videos(path, 72, 128, frames=4, normalize=True)
+    res["vid_norm4"] = imsn
+    np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **res)
+    print("frontend:", ims.shape, ims.dtype, imsn.shape, imsn.dtype, os.path.getsize(path), "B avi")
+
+
 def gen_rnn_small(ref):
     mc = ref.model_convlstm
     res = {}
@@ -240,7 +267,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "rnn": gen_rnn_small, "post": gen_post}
 
 
 def main():

@@ -443,3 +443,25 @@ def test_auc_metrics_match_reference_and_oracle(cuda, gold_dir):
     mine = us.metric_auc_s(pc.cuda(), tc.cuda(), oc).cpu().numpy()
     np.random.seed(6)
     np.testing.assert_allclose(mine, cpu_ref.metric_auc_s(pc, tc, oc).numpy(), atol=1e-6, rtol=0, equal_nan=True)
+
+
+def test_video_frontend_is_bit_exact(cuda, gold_dir):
+    """utils_data.padding / preprocess_videos (:255-287, :321-343) on the device: bit-exact against the reference's own outputs
+    (tests/golden/frontend.npz) and against the oracle at the real frame sizes - 720p (OpenCV's exact-2x area path), 1080p
+    (general 8-bit bilinear), 4:3 and portrait sources (letterbox on either axis), identity."""
+    from iip_uavsal_saliency_b200 import utils_data as ud
+    g = np.load(os.path.join(gold_dir, "frontend.npz"))
+    for name in ("wide", "tall", "x2", "same", "up"):
+        assert np.array_equal(ud.padding(g["pad_in_" + name], 72, 128, 3), g["pad_out_" + name]), name
+    ims, nframes, height, width = ud.preprocess_videos(os.path.join(gold_dir, "clip_tiny.avi"), 72, 128, normalize=False)
+    assert [nframes, height, width] == g["vid_meta"].tolist() and np.array_equal(ims, g["vid_u8"])
+    imsn, n4, _, _ = ud.preprocess_videos(os.path.join(gold_dir, "clip_tiny.avi"), 72, 128, frames=4, normalize=True)
+    assert n4 == 4 and imsn.dtype == np.float32
+    np.testing.assert_allclose(imsn, g["vid_norm4"], rtol=0, atol=1e-6)
+    dev, _, _, _ = ud.preprocess_videos(os.path.join(gold_dir, "clip_tiny.avi"), 72, 128, normalize=False, device="cuda")
+    assert dev.is_cuda and dev.dtype == torch.uint8 and np.array_equal(dev.cpu().numpy(), g["vid_u8"])
+    rs = np.random.RandomState(3)
+    for sh, sw in [(720, 1280), (1080, 1920), (480, 640), (640, 360), (360, 640), (719, 1279)]:
+        fr = rs.randint(0, 256, (2, sh, sw, 3)).astype(np.uint8)
+        out = ud.letterbox_frames(fr, 360, 640).cpu().numpy()
+        assert np.array_equal(out, cpu_ref.preprocess_frames(fr, 360, 640)), (sh, sw)
