@@ -18,7 +18,7 @@ from ._kernel_module import KernelModule, require_cuda
 from .blocks import BasicConv2d, dwBlock, init_func, init_weights
 from .engine import F_RELU6, Buf, Plan, out_size
 from .model_convlstm import *            # noqa: F401,F403  (the reference re-exports these, model.py:11)
-from .model_convlstm import ConvTWA, emit_twa
+from .model_convlstm import ConvLSTM, ConvTWA, emit_twa
 from .model_feature import ReMobileNetV2
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")     # model.py:8
@@ -161,6 +161,7 @@ class STBlock(KernelModule):
 class UAVSal(KernelModule):
     """model.py:254-375.  forward(x (N,3,H,W) normalised fp32 | raw uint8, cb=[gauss (N,8,h,w), ob (N,20,h,w)],
     in_state=[h (1,planes,h,w)] | None) -> (out (N,1,h,w) in (0,1), [h_last])."""
+    _RNN = "twa"
 
     def __init__(self, cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1],
                  iosize=[360, 640, 45, 80], planes=256, pre_model_path=""):
@@ -188,7 +189,8 @@ class UAVSal(KernelModule):
             self.fucb_layer = nn.Sequential(dwBlock(nb, planes // 4, kernel_size=3))
             self.fucbst_layer = nn.Sequential(dwBlock(planes + planes // 4, planes, kernel_size=3))
         _, _, r_out, c_out = iosize
-        self.rnn = ConvTWA((r_out, c_out), planes, planes, kernel_size=(3, 3), num_layers=1, batch_first=True, bias=False,
+        rnn_cls = ConvTWA if self._RNN == "twa" else ConvLSTM                # UAVSAL_LSTM (model.py:1033) swaps the recurrence
+        self.rnn = rnn_cls((r_out, c_out), planes, planes, kernel_size=(3, 3), num_layers=1, batch_first=True, bias=False,
                            return_all_layers=False)
         self.conv_out_st = dwBlock(planes, 1, kernel_size=3)
         for part in (self.st_layer, self.fust_layer, self.conv_out_st):
@@ -307,7 +309,14 @@ class UAVSal(KernelModule):
         hb = plan.alloc(clips * mh * mw, planes)
         plan.pack_nchw(h_in, clips, planes, mh, mw, hb, tag="state.pack")
         seq = plan.alloc(rows, planes)
-        emit_twa(plan, self.rnn.cell_list[0], x, hb, seq, clips, n // clips, mh, mw)
+        cell = self.rnn.cell_list[0]
+        if isinstance(self.rnn, ConvLSTM):
+            # UAVSAL_LSTM (model.py:1065-1068): 4-gate ConvLSTM over the call's frames; the cell state lives in the plan as NHWC fp32
+            c_state = plan.tensor((clips, mh * mw, planes))
+            plan.lstm(x, hb, c_state, clips, n // clips, mh, mw, planes, planes, cell.rnn_conv.weight, cell.rnn_conv.bias, seq, tag="rnn")
+            named.update(c_state=c_state)
+        else:
+            emit_twa(plan, cell, x, hb, seq, clips, n // clips, mh, mw)
         h_out = plan.tensor((clips, planes, mh, mw))
         for ci in range(clips):
             last = Buf(seq.t, seq.rows, planes, seq.ld, ((ci + 1) * (n // clips) - 1) * mh * mw * seq.ld)
@@ -358,3 +367,37 @@ class UAVSal(KernelModule):
             nm["h_in"].copy_(in_state[0])
         plan.launch()
         return nm["out"].clone(), [nm["h_out"].clone()]
+
+
+class UAVSAL_LSTM(UAVSal):
+    """model.py:960-1076 (the Table-V ablation): UAVSal with the 4-gate ``ConvLSTM`` as the recurrence.
+    forward(x, cb, in_state=[[h, c]] | None) -> (out (N,1,h,w), [h_last, c_last]) as ``ConvLSTM.forward`` returns them
+    (model_convlstm.py:196-218: one [h, c] pair per layer in, the last layer's pair out)."""
+    _RNN = "lstm"
+
+    def __init__(self, cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1],
+                 iosize=[360, 640, 45, 80], planes=256, pre_model_path=""):
+        super().__init__(cnn_type, time_dims, num_stblock, bias_type, iosize, planes, pre_model_path)
+
+    def forward(self, x, cb, in_state):
+        require_cuda(x, "UAVSAL_LSTM")
+        n, _, h, w = x.shape
+        plan = self.get_plan(x.device, n, h, w, 1 if x.dtype == torch.uint8 else 0)
+        nm = plan.named
+        nm["x_in"].copy_(x)
+        mh, mw = nm["map_hw"]
+        if self.use_gauss_prior:
+            nm["cb_gauss_in"].copy_(cb[0])
+        if self.use_ob_prior:
+            nm["cb_ob_in"].copy_(cb[1])
+        if in_state is None:
+            nm["h_in"].zero_()
+            nm["c_state"].zero_()
+        else:
+            h0, c0 = in_state[0]
+            nm["h_in"].copy_(h0)
+            nm["c_state"].copy_(c0.permute(0, 2, 3, 1).reshape(nm["c_state"].shape))      # boundary layout change (NCHW -> NHWC)
+        plan.launch()
+        c_last = nm["c_state"].view(1, mh, mw, self._planes).permute(0, 3, 1, 2).contiguous()
+        return nm["out"].clone(), [nm["h_out"].clone(), c_last]
+

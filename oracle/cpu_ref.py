@@ -143,7 +143,8 @@ def lstm_sequence(w, b, x, h, c):
 def uavsal_forward(sd: Dict[str, torch.Tensor], x, cb, h0, time_dims=5, num_stblock=2,
                    bias_type=(1, 1, 1), trace: Optional[dict] = None):
     """UAVSal.forward (model.py:341-375).  x (N,3,H,W) normalised fp32, cb=[gauss (N,8,h,w), ob (N,20,h,w)],
-    h0 (1,256,h,w).  Returns out (N,1,h,w), h_last (1,256,h,w).  ``trace`` collects named intermediates."""
+    h0 (1,256,h,w).  Returns out (N,1,h,w), h_last (1,256,h,w).  ``trace`` collects named intermediates.
+    With h0 = (h, c) the recurrence is the ConvLSTM of the UAVSAL_LSTM ablation (model.py:960-1076) and (h, c) is returned."""
     tr = trace if trace is not None else {}
     with torch.no_grad():
         x = srfnet(sd, "sfnet", x, tr)
@@ -176,7 +177,12 @@ def uavsal_forward(sd: Dict[str, torch.Tensor], x, cb, h0, time_dims=5, num_stbl
             tr["fucb"] = xcb
             x = dw_block(sd, "fucbst_layer.0", torch.cat([x, xcb], 1))
             tr["fucbst"] = x
-        seq, h = twa_sequence(sd["rnn.cell_list.0.rnn_conv.weight"], x, h0)
+        if isinstance(h0, (list, tuple)):
+            # UAVSAL_LSTM.forward (model.py:1065-1068): 4-gate ConvLSTM over the call's frames, batch 1; h0 = (h, c)
+            seq5, (h, c) = lstm_sequence(sd["rnn.cell_list.0.rnn_conv.weight"], None, x[None], h0[0], h0[1])
+            seq, h = seq5[0], (h, c)
+        else:
+            seq, h = twa_sequence(sd["rnn.cell_list.0.rnn_conv.weight"], x, h0)
         tr["rnn"] = seq
         out = torch.sigmoid(dw_block(sd, "conv_out_st", seq))
         tr["out"] = out

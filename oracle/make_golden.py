@@ -219,6 +219,29 @@ def gen_frontend(ref):
     print("frontend:", ims.shape, ims.dtype, imsn.shape, imsn.dtype, os.path.getsize(path), "B avi")
 
 
+def gen_lstm_model(ref):
+    """UAVSAL_LSTM (model.py:960-1076, the Table-V ablation) of the unmodified reference: two chained calls of 10 frames at
+    288x512 (state [h, c] handed over as ConvLSTM.forward expects it: one pair per layer)."""
+    clip = synth.make_clip(4, 20, 288, 512)
+    g, o = synth.make_priors(1, 36, 64, seed=0)
+    m = ref.model.UAVSAL_LSTM(cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1], iosize=[288, 512, 36, 64],
+                              planes=256, pre_model_path="").eval()
+    m.load_state_dict(synth.make_state_dict_lstm(0), strict=True)
+    x = torch.tensor(ref.utils_data.normalize_data(clip.transpose((0, 3, 1, 2)))).float()
+    cb = [torch.tensor(np.repeat(g, 10, 0)).float(), torch.tensor(np.repeat(o, 10, 0)).float()]
+    state = [[torch.zeros(1, 256, 36, 64), torch.zeros(1, 256, 36, 64)]]
+    res = {}
+    with torch.no_grad():
+        for call in range(2):
+            out, st = m(x[call * 10:(call + 1) * 10], cb, state)
+            res["out%d" % call] = out.numpy()
+            res["h%d" % call] = st[0].numpy().ravel()[sample_idx(st[0].numel(), "lstm_h")]
+            res["c%d" % call] = st[1].numpy().ravel()[sample_idx(st[1].numel(), "lstm_c")]
+            state = [st]
+    np.savez_compressed(os.path.join(GOLD, "uavsal_lstm_288.npz"), **res)
+    print("uavsal_lstm:", res["out1"].shape, float(res["out1"].min()), float(res["out1"].max()), float(np.abs(res["c1"]).max()))
+
+
 def gen_rnn_small(ref):
     mc = ref.model_convlstm
     res = {}
@@ -267,7 +290,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "rnn": gen_rnn_small, "post": gen_post}
 
 
 def main():

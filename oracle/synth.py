@@ -176,3 +176,13 @@ def make_auc_case(seed: int = 0, n: int = 6, H: int = 360, W: int = 640):
     fix = true[:, 1]
     shuf = np.stack([np.clip(fix.sum(0) - fix[i], 0, None) for i in range(n + 2)], 0)[:, None].astype(np.float32)
     return pred, true, shuf
+
+
+def make_state_dict_lstm(seed: int = 0):
+    """State dict of the UAVSAL_LSTM ablation (model.py:960-1076): the UAVSal set with the recurrent conv replaced by a
+    4-gate ConvLSTM kernel (4*256, 512, 3, 3), fan-in scaled so that the gates are neither saturated nor idle."""
+    import torch
+    sd = make_state_dict("lively", seed)
+    rs = np.random.RandomState(6000 + seed)
+    sd["rnn.cell_list.0.rnn_conv.weight"] = torch.from_numpy((rs.randn(1024, 512, 3, 3) * (1.5 / np.sqrt(512 * 9))).astype(np.float32))
+    return sd

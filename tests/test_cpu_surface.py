@@ -54,6 +54,10 @@ def test_constructor_signatures_and_defaults():
         return {k: v.default for k, v in inspect.signature(fn).parameters.items() if v.default is not inspect._empty}
     assert defaults(M.UAVSal.__init__) == dict(cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1],
                                                iosize=[360, 640, 45, 80], planes=256, pre_model_path="")
+    assert defaults(M.UAVSAL_LSTM.__init__) == dict(cnn_type="mobilenet_v2", time_dims=5, num_stblock=2, bias_type=[1, 1, 1],
+                                                    iosize=[360, 640, 45, 80], planes=256, pre_model_path="")
+    lstm = M.UAVSAL_LSTM()
+    assert tuple(lstm.state_dict()["rnn.cell_list.0.rnn_conv.weight"].shape) == (1024, 512, 3, 3) and len(lstm.state_dict()) == 685
     assert defaults(M.dwBlock.__init__) == dict(kernel_size=3, stride=1, expand_ratio=6, dilation=1, res_connect=None)
     assert defaults(M.BasicConv2d.__init__) == dict(kernel_size=3, stride=1, dilation=1, groups=1)
     assert defaults(M.teConv_sub.__init__) == dict(planes=256, time_dims=8, reduction=8, res_connect=False)

@@ -465,3 +465,27 @@ def test_video_frontend_is_bit_exact(cuda, gold_dir):
         fr = rs.randint(0, 256, (2, sh, sw, 3)).astype(np.uint8)
         out = ud.letterbox_frames(fr, 360, 640).cpu().numpy()
         assert np.array_equal(out, cpu_ref.preprocess_frames(fr, 360, 640)), (sh, sw)
+
+
+def test_uavsal_lstm_ablation_model(cuda, gold_dir):
+    """UAVSAL_LSTM (model.py:960-1076): UAVSal with the 4-gate ConvLSTM recurrence, two chained 10-frame calls at 288x512
+    against the unmodified reference's outputs; state handed over as [[h, c]] in, [h, c] out (model_convlstm.py:196-218)."""
+    from iip_uavsal_saliency_b200.model import UAVSAL_LSTM
+    g = np.load(os.path.join(gold_dir, "uavsal_lstm_288.npz"))
+    m = UAVSAL_LSTM(iosize=[288, 512, 36, 64]).eval()
+    r = m.load_state_dict(synth.make_state_dict_lstm(0), strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    m = m.cuda()
+    clip = synth.make_clip(4, 20, 288, 512)
+    ga, ob = synth.make_priors(1, 36, 64, seed=0)
+    x = torch.from_numpy(cpu_ref.normalize_data(clip.transpose(0, 3, 1, 2))).cuda()
+    cb = [torch.from_numpy(np.repeat(ga, 10, 0)).float().cuda(), torch.from_numpy(np.repeat(ob, 10, 0)).float().cuda()]
+    state = None
+    for call in range(2):
+        out, st = m(x[call * 10:(call + 1) * 10], cb, state)
+        assert out.shape == (10, 1, 36, 64) and len(st) == 2 and st[0].shape == st[1].shape == (1, 256, 36, 64)
+        assert np.abs(out.cpu().numpy() - g["out%d" % call]).max() <= 2e-3
+        h, c = st[0].cpu().numpy().ravel(), st[1].cpu().numpy().ravel()
+        assert np.abs(h[sample_idx(h.size, "lstm_h")] - g["h%d" % call]).max() <= 5e-3
+        assert np.abs(c[sample_idx(c.size, "lstm_c")] - g["c%d" % call]).max() <= 2e-2      # |c| reaches 18
+        state = [st]
