@@ -162,3 +162,130 @@ def get_mean(input):
 
 def get_std(input):
     return _bcast(torch.std(input, (2, 3), keepdim=True), input)
+
+
+# ---------------------------------------------------------------------------------------------------
+# evaluation driver (utils_score_torch.py:231-582): directory walking and .mat I/O on the host (mat73 instead of hdf5storage),
+# all seven metrics on the device.  Random draws (shuffle maps :334, sampled AUCs) consume the global numpy generator in the
+# reference's order, so a seeded run reproduces the reference's score files.
+# ---------------------------------------------------------------------------------------------------
+shuff_size = {"SALICON": (480, 640), "DIEM": (480, 640), "DIEM20": (480, 640), "CITIUS": (240, 320), "SFU": (288, 352),
+              "LEDOV": (1080, 1920), "LEDOV41": (1080, 1920), "UAV2-TE": (720, 1280), "UAV2": (720, 1280), "default": (480, 640),
+              "AVS1K-TE": (720, 1280), "AVS1K": (720, 1280)}
+
+
+def resize_fixation(img, rows=480, cols=640):
+    """utils_score_torch.py:248-263."""
+    import numpy as np
+    out = np.zeros((rows, cols), np.uint8)
+    fr, fc = rows / img.shape[0], cols / img.shape[1]
+    for coord in np.argwhere(img):
+        r, c = int(np.round(coord[0] * fr)), int(np.round(coord[1] * fc))
+        out[r - 1 if r == rows else r, c - 1 if c == cols else c] = 1
+    return out
+
+
+def getALLFix_vid(fixsDir, DataSet="DIEM20", maxframes=float("inf")):
+    """utils_score_torch.py:300-330: normalised fixation coordinates of every frame of every video."""
+    import os
+    import numpy as np
+    from . import mat73
+    names = sorted(f for f in os.listdir(fixsDir) if f.endswith(".mat"))
+    num = 45 if DataSet.upper() == "CITIUS" else len(names)
+    if DataSet.upper() == "DIEM20":
+        maxframes = 300
+    pts = []
+    for name in names[:num]:
+        fix = mat73.loadmat(fixsDir + name)["fixLoc"]
+        for f in range(int(min(maxframes, fix.shape[3]))):
+            fx, fy = np.where(fix[:, :, 0, f])
+            pts.append(np.concatenate((np.expand_dims(fx / fix.shape[0], 1), np.expand_dims(fy / fix.shape[1], 1)), 1))
+    return pts
+
+
+def getshufmap(ALLFixPts, size=(480, 640), nframes=10):
+    """utils_score_torch.py:333-357 (np.random.randint on the global generator, :335)."""
+    import numpy as np
+    nframes = min(nframes, len(ALLFixPts))
+    idx = np.random.randint(0, len(ALLFixPts), int(nframes))
+    fix = np.concatenate([ALLFixPts[i] for i in idx], 0).astype(np.float64)      # a copy: the reference scales its list entry in place
+    fix[:, 0] *= size[0]
+    fix[:, 1] *= size[1]
+    fix = np.round(fix).astype(np.int64)
+    fix = fix[(fix[:, 0] < size[0]) * (fix[:, 1] < size[1])]
+    out = np.zeros(size, dtype=np.uint8)
+    out[fix[:, 0], fix[:, 1]] = 1
+    return out
+
+
+def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_order, batch_size=64):
+    """utils_score_torch.py:473-582: per-video score files ``Scores/<method>/Score_<video>.mat`` ({'iscore': (frames, metrics)})
+    from ``Saliency/<method>/<video>.mat`` (salmap), ``maps/<video>_fixMaps.mat`` and ``fixations/maps/<video>_fixPts.mat``.
+    Returns {method: {video: iscores}} (the reference keeps this dict local)."""
+    import math
+    import os
+    import numpy as np
+    from . import mat73
+    mapsDir, fixsDir = RootDir + "maps/", RootDir + "fixations/maps/"
+    salsDir, scoreDir = SalDir + "Saliency/", SalDir + "Scores/"
+    os.makedirs(scoreDir, exist_ok=True)
+    all_pts = []
+    if "AUC_shuffled" in keys_order:
+        pts_path = RootDir + "ALLFixPts_" + DataSet.upper() + ".npy"
+        if not os.path.exists(pts_path):
+            all_pts = getALLFix_vid(fixsDir, DataSet)
+            arr = np.empty(len(all_pts), dtype=object)                 # ragged list: an object array, as old numpy made implicitly
+            for i, a in enumerate(all_pts):
+                arr[i] = a
+            np.save(pts_path, arr)
+        else:
+            all_pts = list(np.load(pts_path, allow_pickle=True))
+    result = {}
+    for method in MethodNames:
+        if os.path.exists(scoreDir + "Score_" + method + ".mat"):
+            continue
+        iscoreDir = scoreDir + method + "/"
+        os.makedirs(iscoreDir, exist_ok=True)
+        salmap_dir = salsDir + method + "/"
+        scores = {}
+        for sal_name in sorted(f for f in os.listdir(salmap_dir) if f.endswith(".mat")):
+            file_name = sal_name[:-4]
+            iscore_path = iscoreDir + "Score_" + file_name + ".mat"
+            if os.path.exists(iscore_path):
+                scores[file_name] = mat73.loadmat(iscore_path)["iscore"]
+                continue
+            salmap = mat73.loadmat(salmap_dir + file_name + ".mat")["salmap"]
+            fixmap = mat73.loadmat(mapsDir + file_name + "_fixMaps.mat")["fixMap"]
+            fixpts = mat73.loadmat(fixsDir + file_name + "_fixPts.mat")["fixLoc"]
+            nframes = min(salmap.shape[3], min(fixpts.shape[3], fixmap.shape[3]))
+            iscores = np.zeros((nframes, len(keys_order)))
+            if salmap.shape[:2] != fixmap.shape[:2]:
+                import cv2
+                rs = np.zeros((nframes, 1, fixmap.shape[0], fixmap.shape[1]))
+                for i in range(nframes):
+                    rs[i, 0] = cv2.resize(salmap[:, :, 0, i], (fixmap.shape[1], fixmap.shape[0]))
+                salmap = rs
+            else:
+                salmap = salmap[:, :, :, :nframes].transpose((3, 2, 0, 1))
+            fixmap = np.concatenate((fixmap[:, :, :, :nframes], fixpts[:, :, :, :nframes]), axis=2).transpose((3, 2, 0, 1))
+            for k, metric in enumerate(keys_order):
+                func = metrics[metric]
+                for b in range(math.ceil(nframes / batch_size)):
+                    ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
+                    itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
+                    if metric == "AUC_shuffled":
+                        shuf = np.array([getshufmap(all_pts, size=fixmap.shape[2:]) for _ in range(itrue.shape[0])])
+                        m = func(ipred, itrue, torch.tensor(shuf).float().unsqueeze(1))
+                    elif metric == "AUC_Borji":
+                        m = func(ipred, itrue)
+                    else:
+                        m = func(ipred.to(device), itrue.to(device))
+                    iscores[b * batch_size:(b + 1) * batch_size, k] = m.data.cpu()[:, 0]
+            for f in range(nframes):
+                if not np.any(salmap[f, 0]) or not np.any(fixmap[f], axis=(1, 2)).all():
+                    iscores[f] = np.nan
+            scores[file_name] = iscores
+            mat73.savemat(iscore_path, {"iscore": iscores})
+        result[method] = scores
+    return result
+

@@ -242,6 +242,28 @@ def gen_lstm_model(ref):
     print("uavsal_lstm:", res["out1"].shape, float(res["out1"].min()), float(res["out1"].max()), float(np.abs(res["c1"]).max()))
 
 
+def gen_eval_driver(ref):
+    """evalscores_vid_torch (utils_score_torch.py:473-582) of the unmodified reference on synth.make_eval_dataset, all seven
+    metrics, generators seeded.  The reference spells np.int / np.NaN (:347, :570), which numpy 2 dropped: the two names are
+    aliased for the run (no source change)."""
+    import tempfile
+    us = ref.utils_score_torch
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "NaN"):
+        np.NaN = np.nan
+    with tempfile.TemporaryDirectory() as td:
+        root, sal = td + "/data/", td + "/res/"
+        synth.make_eval_dataset(root, sal, 0)
+        np.random.seed(11)
+        torch.manual_seed(11)
+        us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], batch_size=3)
+        from iip_uavsal_saliency_b200 import mat73
+        res = {n: mat73.loadmat(sal + "Scores/UAVSal/Score_%s.mat" % n)["iscore"] for n in ("vidA", "vidB")}
+    np.savez_compressed(os.path.join(GOLD, "eval_driver.npz"), keys=np.array(list(us.keys_order)), **res)
+    print(list(us.keys_order)); print(res["vidA"].round(4)); print(res["vidB"].round(4))
+
+
 def gen_rnn_small(ref):
     mc = ref.model_convlstm
     res = {}
@@ -290,7 +312,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "rnn": gen_rnn_small, "post": gen_post}
 
 
 def main():

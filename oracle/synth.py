@@ -186,3 +186,33 @@ def make_state_dict_lstm(seed: int = 0):
     rs = np.random.RandomState(6000 + seed)
     sd["rnn.cell_list.0.rnn_conv.weight"] = torch.from_numpy((rs.randn(1024, 512, 3, 3) * (1.5 / np.sqrt(512 * 9))).astype(np.float32))
     return sd
+
+
+def make_eval_dataset(root: str, sal: str, seed: int = 0, method: str = "UAVSal"):
+    """A tiny evaluation tree in the layout evalscores_vid_torch walks (utils_score_torch.py:473-490): two 5-frame videos at
+    36x64 (12 fixations per frame), the second one's saliency maps at half size (the driver's cv2.resize path).  Written with
+    the package's MAT v7.3 writer.  Returns the arrays for reference."""
+    import os
+    from iip_uavsal_saliency_b200 import mat73
+    H, W, F = 36, 64, 5
+    for d in (root + "maps/", root + "fixations/maps/", sal + "Saliency/" + method + "/"):
+        os.makedirs(d, exist_ok=True)
+    out = {}
+    for v, name in enumerate(("vidA", "vidB")):
+        pred, true = make_metric_pairs(F, H, W, seed=50 + seed + v)
+        fixmap = np.rint(true[:, 0]).astype(np.uint8).transpose(1, 2, 0)[:, :, None, :]           # (H,W,1,F)
+        fixpts = np.zeros((H, W, 1, F), np.uint8)
+        rs = np.random.RandomState(70 + seed + v)
+        for f in range(F):
+            p = true[f, 0].ravel().astype(np.float64) + 1e-3
+            idx = rs.choice(H * W, size=12, replace=False, p=p / p.sum())
+            fixpts[:, :, 0, f].flat[idx] = 1
+        sal_u8 = np.rint(pred[:, 0]).astype(np.uint8)
+        if v == 1:
+            sal_u8 = sal_u8[:, ::2, ::2]
+        salmap = np.ascontiguousarray(sal_u8.transpose(1, 2, 0)[:, :, None, :])
+        mat73.savemat(sal + "Saliency/" + method + "/" + name + ".mat", {"salmap": salmap})
+        mat73.savemat(root + "maps/" + name + "_fixMaps.mat", {"fixMap": fixmap})
+        mat73.savemat(root + "fixations/maps/" + name + "_fixPts.mat", {"fixLoc": fixpts})
+        out[name] = (salmap, fixmap, fixpts)
+    return out

@@ -489,3 +489,27 @@ def test_uavsal_lstm_ablation_model(cuda, gold_dir):
         assert np.abs(h[sample_idx(h.size, "lstm_h")] - g["h%d" % call]).max() <= 5e-3
         assert np.abs(c[sample_idx(c.size, "lstm_c")] - g["c%d" % call]).max() <= 2e-2      # |c| reaches 18
         state = [st]
+
+
+def test_eval_driver_reproduces_reference_score_files(cuda, gold_dir, tmp_path):
+    """evalscores_vid_torch (utils_score_torch.py:473-582): the seven-metric score files of the unmodified reference
+    (tests/golden/eval_driver.npz, generators seeded with 11) from the same synthetic evaluation tree; covers the .mat I/O,
+    the driver's cv2.resize of half-size saliency maps, shuffle-map sampling and the RNG order of the sampled AUCs."""
+    from iip_uavsal_saliency_b200 import mat73
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    g = np.load(os.path.join(gold_dir, "eval_driver.npz"))
+    assert list(g["keys"]) == us.keys_order
+    root, sal = str(tmp_path) + "/data/", str(tmp_path) + "/res/"
+    synth.make_eval_dataset(root, sal, 0)
+    np.random.seed(11)
+    torch.manual_seed(11)
+    res = us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], batch_size=3)
+    for name in ("vidA", "vidB"):
+        mine = mat73.loadmat(sal + "Scores/UAVSal/Score_%s.mat" % name)["iscore"]
+        assert mine.shape == g[name].shape == (5, 7) and np.array_equal(mine, res["UAVSal"][name])
+        for k, key in enumerate(us.keys_order):
+            tol = dict(atol=2e-5, rtol=0) if key.startswith("AUC") else dict(atol=1e-6, rtol=1e-4)
+            np.testing.assert_allclose(mine[:, k], g[name][:, k], err_msg="%s %s" % (name, key), **tol)
+    # second run: the per-video score files are picked up instead of recomputed (utils_score_torch.py:513-516)
+    again = us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], batch_size=3)
+    assert np.array_equal(again["UAVSal"]["vidB"], res["UAVSal"]["vidB"])
