@@ -513,3 +513,34 @@ def test_eval_driver_reproduces_reference_score_files(cuda, gold_dir, tmp_path):
     # second run: the per-video score files are picked up instead of recomputed (utils_score_torch.py:513-516)
     again = us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], batch_size=3)
     assert np.array_equal(again["UAVSal"]["vidB"], res["UAVSal"]["vidB"])
+
+
+def test_frontend_and_auc_edge_cases(cuda):
+    """Limits and degenerate inputs of the widened-path kernels: tiny sources, extreme aspect ratios, unsupported widths
+    (error, not a wrong answer), fixation sets beyond the AUC kernel's shared-memory capacity (NaN, documented in the header)."""
+    from iip_uavsal_saliency_b200 import utils_data as ud
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    rs = np.random.RandomState(9)
+    for sh, sw, r, c in [(2, 2, 72, 128), (3, 200, 72, 128), (200, 3, 72, 128), (72, 128, 36, 64), (1, 1, 8, 8), (37, 53, 360, 640)]:
+        fr = rs.randint(0, 256, (1, sh, sw, 3)).astype(np.uint8)
+        assert np.array_equal(ud.letterbox_frames(fr, r, c).cpu().numpy(), cpu_ref.preprocess_frames(fr, r, c)), (sh, sw, r, c)
+        assert np.array_equal(ud.letterbox_frames(fr, r, c, mode="BGR").cpu().numpy(), cpu_ref.preprocess_frames(fr, r, c, mode="BGR"))
+    with pytest.raises(ValueError):
+        ud.letterbox_frames(rs.randint(0, 256, (1, 8, 8, 3)).astype(np.uint8), 16, 5000)
+    with pytest.raises(ValueError):
+        ud.letterbox_frames(np.zeros((1, 8, 8, 4), np.uint8), 16, 16)
+    # AUC: dense fixation plane (> 4096 fixations) -> NaN; constant map -> NaN; a single fixation works
+    p = torch.rand(3, 1, 90, 160).cuda()
+    t = torch.zeros(3, 2, 90, 160)
+    t[0, 1] = 1.0                                   # 14400 fixations
+    t[1, 1, 10, 20] = 1.0                           # one fixation
+    t[2, 1, 5, 5] = 1.0
+    p[2] = 0.25                                     # constant prediction: min-max normalisation gives all zeros
+    out = us.metric_auc_j(p, t.cuda(), jitter=0).cpu().numpy().ravel()
+    ref = cpu_ref.metric_auc_j(p.cpu(), t, jitter=0).numpy().ravel()
+    assert np.isnan(out[0]) and np.isnan(out[2]) and np.isnan(ref[2]) and abs(out[1] - ref[1]) < 1e-5
+    np.random.seed(3)
+    b = us.metric_auc_b(p, t.cuda()).cpu().numpy().ravel()
+    np.random.seed(3)
+    rb = cpu_ref.metric_auc_b(p.cpu(), t).numpy().ravel()
+    assert np.isnan(b[2]) and np.isnan(rb[2]) and abs(b[1] - rb[1]) < 1e-6 and abs(b[0] - rb[0]) < 1e-6
