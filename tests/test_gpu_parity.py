@@ -544,3 +544,40 @@ def test_frontend_and_auc_edge_cases(cuda):
     np.random.seed(3)
     rb = cpu_ref.metric_auc_b(p.cpu(), t).numpy().ravel()
     assert np.isnan(b[2]) and np.isnan(rb[2]) and abs(b[1] - rb[1]) < 1e-6 and abs(b[0] - rb[0]) < 1e-6
+
+
+@pytest.mark.parametrize("bias_type,time_dims,n", [([0, 0, 0], 5, 5), ([1, 0, 1], 5, 10), ([0, 1, 0], 4, 8), ([0, 0, 1], 8, 8), ([1, 1, 0], 5, 5)])
+def test_uavsal_constructor_variants(cuda, bias_type, time_dims, n):
+    """The prior branches are constructor options of the reference (model.py:262-325: bias_type, time_dims); every combination
+    builds a different fusion head (fucb input width, no fucb/fucbst at all for [0,0,0]).  Checked against the oracle's
+    functional forward on the variant's own (randomised) state dict at 288x512."""
+    from iip_uavsal_saliency_b200.model import UAVSal
+    torch.manual_seed(100 + sum(bias_type) + time_dims)
+    m = UAVSal(time_dims=time_dims, bias_type=bias_type, iosize=[288, 512, 36, 64]).eval()
+    with torch.no_grad():                                         # lively BN statistics, larger weights than the stock init
+        for name, b in m.named_buffers():
+            if name.endswith("running_mean"):
+                b.normal_(0, 0.1)
+            elif name.endswith("running_var"):
+                b.uniform_(0.8, 1.2)
+        for name, p in m.named_parameters():
+            if p.ndim == 4:
+                fan_in = p.shape[1] * p.shape[2] * p.shape[3]
+                p.normal_(0, (1.0 if name.endswith("conv.2.weight") or "rnn_conv" in name else 2.0 ** 0.5) / fan_in ** 0.5)
+            elif name.endswith("weight"):
+                p.uniform_(0.8, 1.2)
+            else:
+                p.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    clip = synth.make_clip(6, n, 288, 512)
+    ga, ob = synth.make_priors(1, 36, 64, seed=1)
+    x = torch.from_numpy(cpu_ref.normalize_data(clip.transpose(0, 3, 1, 2)))
+    cb_cpu = [torch.from_numpy(np.repeat(ga, n, 0)).float() if bias_type[0] else torch.empty(0),
+              torch.from_numpy(np.repeat(ob, n, 0)).float() if bias_type[1] else torch.empty(0)]
+    h0 = torch.randn(1, 256, 36, 64) * 0.3
+    ref_out, ref_h = cpu_ref.uavsal_forward(sd, x, cb_cpu, h0, time_dims=time_dims, bias_type=tuple(bias_type))
+    m = m.cuda()
+    out, st = m(x.cuda(), [c.cuda() for c in cb_cpu], [h0.cuda()])
+    assert out.shape == (n, 1, 36, 64)
+    assert (out.cpu() - ref_out).abs().max().item() <= 2e-3
+    assert (st[0].cpu() - ref_h).abs().max().item() <= 5e-3
