@@ -264,6 +264,41 @@ def gen_eval_driver(ref):
     print(list(us.keys_order)); print(res["vidA"].round(4)); print(res["vidB"].round(4))
 
 
+def gen_demo_test(ref):
+    """Demo_Test.test (Demo_Test.py:30-95) of the unmodified reference, end to end on the committed MJPG clip: decode, letterbox
+    to 360x640, one 5-frame call with the real UAV2 priors, post-process to the video's size, salmap .mat.  The model file is
+    the reference's own pickle of a UAVSal holding the 'lively' weights."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, shim.REFERENCE_ROOT)
+    try:
+        import Demo_Test as dt
+    finally:
+        sys.path.remove(shim.REFERENCE_ROOT)
+    dt.DataSet_Train = "UAV2"                                      # a module global set under __main__ (Demo_Test.py:121)
+    # the reference's torch.load(model_path) (Demo_Test.py:39) predates torch 2.6's weights_only=True default: restore the old
+    # default through torch's own environment switch (no source change)
+    os.environ["TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD"] = "1"
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(td + "/videos")
+        shutil.copy(os.path.join(GOLD, "clip_tiny.avi"), td + "/videos/clip_tiny.avi")
+        m = ref_model(ref, [360, 640, 45, 80], synth.make_state_dict("lively", 0))
+        torch.save(m, td + "/model.pth")
+        # ConvTWACell.init_hidden ends in .cuda() (model_convlstm.py:295, quirk Q5) and test() starts from x_state = None: on this
+        # GPU-less container Tensor.cuda is made a no-op for the duration of the run
+        real_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            with shim.reference_cwd():
+                dt.test(td + "/videos/", td + "/out/", td + "/model.pth", iosize=[360, 640, 45, 80], batch_size=4, time_dims=5)
+        finally:
+            torch.Tensor.cuda = real_cuda
+        from iip_uavsal_saliency_b200 import mat73
+        sal = mat73.loadmat(td + "/out/UAVSal/clip_tiny.mat")["salmap"]
+    np.savez_compressed(os.path.join(GOLD, "demo_test.npz"), salmap=sal)
+    print("demo_test:", sal.shape, sal.dtype, int(sal.max()), float(sal.mean()))
+
+
 def gen_rnn_small(ref):
     mc = ref.model_convlstm
     res = {}
@@ -312,7 +347,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "demo": gen_demo_test, "rnn": gen_rnn_small, "post": gen_post}
 
 
 def main():

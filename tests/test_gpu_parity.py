@@ -581,3 +581,29 @@ def test_uavsal_constructor_variants(cuda, bias_type, time_dims, n):
     assert out.shape == (n, 1, 36, 64)
     assert (out.cpu() - ref_out).abs().max().item() <= 2e-3
     assert (st[0].cpu() - ref_h).abs().max().item() <= 5e-3
+
+
+def test_demo_test_entry_point_end_to_end(cuda, gold_dir, tmp_path):
+    """Demo_Test.test (Demo_Test.py:30-95) as a user runs it: a directory of videos, a model file and prior .mat files in; one
+    salmap .mat per video out.  Against the unmodified reference's own output on the committed clip (tests/golden/demo_test.npz:
+    decode + letterbox to 360x640 + one 5-frame call with the UAV2 priors + post-process to 120x200), within 1 LSB."""
+    import shutil
+    from iip_uavsal_saliency_b200 import demo_test, mat73
+    g = np.load(os.path.join(gold_dir, "demo_test.npz"))
+    pr = np.load(os.path.join(gold_dir, "priors.npz"))
+    vids, out, pri = str(tmp_path) + "/videos/", str(tmp_path) + "/out/", str(tmp_path) + "/priors/"
+    os.makedirs(vids)
+    os.makedirs(pri)
+    shutil.copy(os.path.join(gold_dir, "clip_tiny.avi"), vids + "clip_tiny.avi")
+    mat73.savemat(pri + "gauss_priors.mat", {"PriorMaps": pr["gauss"].astype(np.float32)})
+    mat73.savemat(pri + "UAV2_ob_priors_train.mat", {"PriorMaps": (pr["uav2_u8"].astype(np.float32) / 255).astype(np.float32)})
+    torch.save(synth.make_state_dict("lively", 0), str(tmp_path) + "/model.pth")
+    files = demo_test.test(vids, out, str(tmp_path) + "/model.pth", iosize=[360, 640, 45, 80], batch_size=4, time_dims=5,
+                           DataSet_Train="UAV2", priors_path=pri)
+    assert files == [out + "UAVSal/clip_tiny.mat"]
+    sal = mat73.loadmat(files[0])["salmap"]
+    assert sal.shape == g["salmap"].shape == (120, 200, 1, 5) and sal.dtype == np.uint8
+    assert np.abs(sal.astype(np.int32) - g["salmap"].astype(np.int32)).max() <= 1
+    assert demo_test.test(vids, out, str(tmp_path) + "/model.pth", iosize=[360, 640, 45, 80], DataSet_Train="UAV2", priors_path=pri) == []   # :62-63
+    cb = demo_test.get_bias([1, 1, 1], 3, 45, 80, "UAV2", pri)
+    assert cb[0].shape == (3, 8, 45, 80) and cb[1].shape == (3, 20, 45, 80) and cb[0].is_cuda
