@@ -289,3 +289,24 @@ def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_
         result[method] = scores
     return result
 
+
+def getSumFix_vid(fixsDir, DataSet="DIEM20", size=None, maxframes=float("inf")):
+    """utils_score_torch.py:266-297: the dataset's summed fixation map (the fixed shuffle map of the `_sum` protocol)."""
+    import os
+    import numpy as np
+    from . import mat73
+    DataSet = DataSet.upper()
+    if size is None:
+        size = shuff_size[DataSet] if DataSet in shuff_size else shuff_size["default"]
+    if DataSet == "DIEM20":
+        maxframes = 300
+    shuf = np.zeros(size)
+    for name in sorted(f for f in os.listdir(fixsDir) if f.endswith(".mat")):
+        fix = mat73.loadmat(fixsDir + name)["fixLoc"]
+        use = int(min(maxframes, fix.shape[3]))
+        fix = fix[:, :, :, :use]
+        if fix.shape[:2] != tuple(size):
+            fix = np.expand_dims(np.array([resize_fixation(fix[:, :, 0, i], size[0], size[1]) for i in range(use)]).transpose((1, 2, 0)), axis=2)
+        shuf += np.sum(fix[:, :, 0, :], axis=2)
+        shuf = np.round(shuf)
+    return shuf

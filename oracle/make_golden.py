@@ -260,6 +260,8 @@ def gen_eval_driver(ref):
         us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], batch_size=3)
         from iip_uavsal_saliency_b200 import mat73
         res = {n: mat73.loadmat(sal + "Scores/UAVSal/Score_%s.mat" % n)["iscore"] for n in ("vidA", "vidB")}
+        res["sumfix_native"] = us.getSumFix_vid(root + "fixations/maps/", "UAV2", size=(36, 64))
+        res["sumfix_resized"] = us.getSumFix_vid(root + "fixations/maps/", "UAV2", size=(45, 80))      # resize_fixation path (:248-263)
     np.savez_compressed(os.path.join(GOLD, "eval_driver.npz"), keys=np.array(list(us.keys_order)), **res)
     print(list(us.keys_order)); print(res["vidA"].round(4)); print(res["vidB"].round(4))
 

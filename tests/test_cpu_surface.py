@@ -194,3 +194,23 @@ def test_prior_loaders_and_host_helpers(tmp_path, gold_dir, monkeypatch):
     with pytest.raises(ValueError):
         UD.normalize_data(np.zeros((4, 4), np.uint8))
     assert np.array_equal(UD.np2mat(np.array([0.5, 1.5, 2.5, 300., -3.])), np.array([0, 2, 2, 255, 0], np.uint8))   # rint = half-to-even
+
+
+def test_eval_host_helpers_match_reference(tmp_path):
+    """Host-side helpers of the evaluation driver (utils_score_torch.py:248-357): the dataset's summed fixation map at the
+    native size and through resize_fixation, against the unmodified reference on the same synthetic tree
+    (tests/golden/eval_driver.npz); getALLFix_vid / getshufmap shapes and value ranges (their effect on the scores is pinned
+    by the AUC_shuffled column of the driver test)."""
+    import numpy as np
+    from oracle import synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_driver.npz"))
+    root, sal = str(tmp_path) + "/data/", str(tmp_path) + "/res/"
+    synth.make_eval_dataset(root, sal, 0)
+    assert np.array_equal(US.getSumFix_vid(root + "fixations/maps/", "UAV2", size=(36, 64)), g["sumfix_native"])
+    assert np.array_equal(US.getSumFix_vid(root + "fixations/maps/", "UAV2", size=(45, 80)), g["sumfix_resized"])
+    pts = US.getALLFix_vid(root + "fixations/maps/", "UAV2")
+    assert len(pts) == 10 and all(p.shape == (12, 2) and p.min() >= 0 and p.max() < 1 for p in pts)
+    np.random.seed(0)
+    sm = US.getshufmap(pts, size=(36, 64))
+    assert sm.shape == (36, 64) and sm.dtype == np.uint8 and 12 <= sm.sum() <= 120
+    assert pts[0].max() < 1                                          # the list entries are not scaled in place
