@@ -202,9 +202,13 @@ def run_product_arm(args):
     from iip_uavsal_saliency_b200.runner import ClipRunner
     from oracle import synth   # synthetic inputs / weights only (seeded generators), not the checker
 
-    rank, world, local = D.init_process_group()
+    for attempt in range(4):                 # a freshly provisioned box occasionally fails its first driver initialisation
+        if torch.cuda.is_available():
+            break
+        time.sleep(5.0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py product arm needs a B200; the sm_100a library has no CPU fallback")
+    rank, world, local = D.init_process_group()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _ext.check(_ext.load().uavsal_device_ok(local), "device_ok")
