@@ -202,8 +202,11 @@ def run_product_arm(args):
     from iip_uavsal_saliency_b200.runner import ClipRunner
     from oracle import synth   # synthetic inputs / weights only (seeded generators), not the checker
 
-    for attempt in range(4):                 # a freshly provisioned box occasionally fails its first driver initialisation
-        if torch.cuda.is_available():
+    # a freshly provisioned box was seen to fail one CUDA driver initialisation (a failed cuInit can stick to the process): probe
+    # in a child process first, retrying, and touch CUDA here only once the probe has succeeded
+    probe = "import sys, torch; sys.exit(0 if torch.cuda.is_available() else 1)"
+    for attempt in range(4):
+        if subprocess.run([sys.executable, "-c", probe], capture_output=True).returncode == 0:
             break
         time.sleep(5.0)
     if not torch.cuda.is_available():
