@@ -26,6 +26,7 @@ _SIGNATURES = {
     "uavsal_pack_nchw_f32": [P, I, I, I, I] + ACT + [I, P],
     "uavsal_unpack_nchw_f32": ACT + [I, I, I, I, P, P],
     "uavsal_stem_conv3x3s2": [P, I, I, I, I, P, P] + ACT + [P],
+    "uavsal_stem_conv3x3s2_hw": [P, I, I, I, I, P, P] + ACT + [P],
     "uavsal_dw3x3": ACT + [I, I, I, I, I, I, P, P, I] + ACT + [P],
     "uavsal_expand_dw3x3": ACT + [I, I, I, I, P, I, P, I, I, P, P] + ACT + [P],
     "uavsal_dw_project": [P, I, I, I, I, I, P, P, P, I, I, P, I, I] + ACT + ACT + [P],

@@ -79,7 +79,7 @@ def emit_stem(plan: Plan, stem: BasicConv2d, x_src: torch.Tensor, kind: int, n, 
     wf, bf = stem.folded()
     ho, wo = out_size(h, 2), out_size(w, 2)
     out = plan.alloc_f32(n * ho * wo, 32) if plan.f32_hidden else plan.alloc(n * ho * wo, 32)   # features.1 starts with its depthwise conv
-    plan.stem(x_src, kind, n, h, w, plan.hold(wf.permute(2, 3, 1, 0).contiguous()), plan.hold(bf), out, tag="features.0")
+    plan.stem(x_src, kind, n, h, w, wf.permute(2, 3, 1, 0).contiguous(), bf, out, tag="features.0")
     return out, ho, wo
 
 

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 
 namespace uavsal {
@@ -73,17 +74,25 @@ __device__ __forceinline__ float stem_fetch(const void* x, int img, int ch, int 
     }
 }
 
-template <int KIND>
+// PW = true: weights [27][32] + bias [32] travel in the kernel parameters (constant bank): every FFMA takes its weight as a
+// warp-uniform constant operand instead of 216 shared-memory loads per pixel (uavsal_stem_conv3x3s2_hw: host weight pointers)
+struct StemW {
+    float w[27 * 32 + 32];
+};
+
+template <int KIND, bool PW>
 __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, int n, int h, int w, int ho, int wo,
                                                    const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                   ActW out) {
+                                                   ActW out, const __grid_constant__ StemW cw) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float4 sw[27 * 8];
+    __shared__ float4 sw[PW ? 1 : 27 * 8];
     __shared__ float sb[32];
     __shared__ float lut[3][256];      // uint8 -> normalised fp32 with the reference's exact expression (utils_data.py:56-60)
-    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
-    if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    if (!PW) {
+        for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(wgt)[i];
+        if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    }
     if (KIND != 0) {
         for (int i = threadIdx.x; i < 768; i += blockDim.x) {
             const int ch = i >> 8, u = i & 255;
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
             const int oy = (int)(row - (unsigned)img * (unsigned)ho);
             float acc[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = sb[j];
+            for (int j = 0; j < 32; ++j) acc[j] = PW ? cw.w[27 * 32 + j] : sb[j];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int y = oy * 2 - 1 + ky;
@@ -121,6 +130,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
                         if (KIND == 0) v = __ldg(reinterpret_cast<const float*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx);
                         else if (KIND == 1) v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx)];
                         else v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch)];
+                        if (PW) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = fmaf(v, cw.w[((ky * 3 + kx) * 3 + ch) * 32 + j], acc[j]);
+                            continue;
+                        }
                         const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -630,6 +644,38 @@ int dw3x3_dot_tma(const float* in, int in_ld, int n, int h, int w, int c, const 
                   float bias_proj, float* partial, float* out, cudaStream_t s);
 }
 
+template <bool PW>
+static int stem_launch(const void* x, int x_kind, int n, int h, int w, const float* wgt, const float* bias, const StemW* hw,
+                       uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(x && (PW ? hw != nullptr : (wgt && bias && aligned16(wgt))) &&
+                       (out_plane == UAVSAL_PLANE_F32 ? (out && aligned16(out) && out_ld % 4 == 0) : act_ok(out, out_plane, out_ld)) && out_ld >= 32 && n > 0 &&
+                       h >= 2 && w >= 2 && x_kind >= 0 && x_kind <= 2,
+                   UAVSAL_EINVAL, "stem_conv3x3s2: bad arguments");
+    const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+    const int64_t total = (int64_t)n * ho * wo;
+    UAVSAL_REQUIRE(total < (1LL << 31) - (1 << 20), UAVSAL_ENOTSUP, "stem_conv3x3s2: more than 2^31 output pixels");
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    static int bps[3] = {0, 0, 0};                                                        // resident blocks per SM (persistent grid)
+    if (!bps[x_kind]) {
+        int b = 0;
+        cudaError_t e = x_kind == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<0, PW>, 128, 0)
+                      : x_kind == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<1, PW>, 128, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<2, PW>, 128, 0);
+        if (e != cudaSuccess || b <= 0) { b = 4; cudaGetLastError(); }
+        bps[x_kind] = b;
+    }
+    const dim3 grid((unsigned)std::min<int64_t>(div_up(total, 128), (int64_t)sms * bps[x_kind]));
+    ActW o{out, out_plane, out_ld};
+    cudaStream_t s = (cudaStream_t)stream;
+    static const StemW none{};
+    const StemW& cw = PW ? *hw : none;
+    if (x_kind == 0) launch_k(stem_kernel<0, PW>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o, cw);
+    else if (x_kind == 1) launch_k(stem_kernel<1, PW>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o, cw);
+    else launch_k(stem_kernel<2, PW>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o, cw);
+    return check_launch("stem_conv3x3s2");
+}
+
 extern "C" {
 
 int uavsal_version(void) { return 1; }
@@ -663,31 +709,16 @@ int uavsal_unpack_nchw_f32(const uint16_t* src, int64_t plane, int ld, int n, in
 
 int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w, const float* wgt, const float* bias,
                           uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
-    UAVSAL_REQUIRE(x && wgt && bias && aligned16(wgt) &&
-                       (out_plane == UAVSAL_PLANE_F32 ? (out && aligned16(out) && out_ld % 4 == 0) : act_ok(out, out_plane, out_ld)) && out_ld >= 32 && n > 0 &&
-                       h >= 2 && w >= 2 && x_kind >= 0 && x_kind <= 2,
-                   UAVSAL_EINVAL, "stem_conv3x3s2: bad arguments");
-    const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-    const int64_t total = (int64_t)n * ho * wo;
-    UAVSAL_REQUIRE(total < (1LL << 31) - (1 << 20), UAVSAL_ENOTSUP, "stem_conv3x3s2: more than 2^31 output pixels");
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    static int bps[3] = {0, 0, 0};                                                        // resident blocks per SM (persistent grid)
-    if (!bps[x_kind]) {
-        int b = 0;
-        cudaError_t e = x_kind == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<0>, 128, 0)
-                      : x_kind == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<1>, 128, 0)
-                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stem_kernel<2>, 128, 0);
-        if (e != cudaSuccess || b <= 0) { b = 4; cudaGetLastError(); }
-        bps[x_kind] = b;
-    }
-    const dim3 grid((unsigned)std::min<int64_t>(div_up(total, 128), (int64_t)sms * bps[x_kind]));
-    ActW o{out, out_plane, out_ld};
-    cudaStream_t s = (cudaStream_t)stream;
-    if (x_kind == 0) launch_k(stem_kernel<0>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
-    else if (x_kind == 1) launch_k(stem_kernel<1>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
-    else launch_k(stem_kernel<2>, dim3(grid), dim3(128), 0, s, 1, x, n, h, w, ho, wo, wgt, bias, o);
-    return check_launch("stem_conv3x3s2");
+    return stem_launch<false>(x, x_kind, n, h, w, wgt, bias, nullptr, out, out_plane, out_ld, stream);
+}
+
+int uavsal_stem_conv3x3s2_hw(const void* x, int x_kind, int n, int h, int w, const float* wgt_host, const float* bias_host,
+                             uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
+    UAVSAL_REQUIRE(wgt_host && bias_host, UAVSAL_EINVAL, "stem_conv3x3s2_hw: host weight pointers required");
+    StemW hw;
+    memcpy(hw.w, wgt_host, 27 * 32 * sizeof(float));
+    memcpy(hw.w + 27 * 32, bias_host, 32 * sizeof(float));
+    return stem_launch<true>(x, x_kind, n, h, w, nullptr, nullptr, &hw, out, out_plane, out_ld, stream);
 }
 
 int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, int stride, int dilation,

@@ -175,7 +175,16 @@ class Plan:
         self._add("uavsal_unpack_nchw_f32", (*src.act(), n, c, h, w, dst.data_ptr()), tag)
 
     def stem(self, x: torch.Tensor, kind: int, n, h, w, wgt, bias, out: Buf, tag=""):
-        self._add("uavsal_stem_conv3x3s2", (x.data_ptr(), kind, n, h, w, wgt.data_ptr(), bias.data_ptr(), *out.act()), tag)
+        """wgt: folded fp32 [3][3][3][32] (ky, kx, cin, cout), bias [32].  The tcgen05 engines hand the 3.5 KB of weights over as
+        HOST arrays: they travel in the kernel parameters and every FFMA reads its weight from the constant bank."""
+        if self.engine != "simt" and tuple(wgt.shape) == (3, 3, 3, 32):
+            wh = wgt.detach().float().cpu().contiguous()
+            bh = bias.detach().float().cpu().contiguous()
+            self.keep += [wh, bh]
+            self._add("uavsal_stem_conv3x3s2_hw", (x.data_ptr(), kind, n, h, w, wh.data_ptr(), bh.data_ptr(), *out.act()), tag)
+            return
+        wd, bd = self.hold(wgt), self.hold(bias)
+        self._add("uavsal_stem_conv3x3s2", (x.data_ptr(), kind, n, h, w, wd.data_ptr(), bd.data_ptr(), *out.act()), tag)
 
     def dw(self, x: Buf, n, h, w, c, stride, dil, wgt, bias, relu6, out: Buf, tag=""):
         self._add("uavsal_dw3x3", (*x.act(), n, h, w, c, stride, dil, wgt.data_ptr(), bias.data_ptr(), int(relu6), *out.act()), tag)

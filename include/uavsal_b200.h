@@ -72,6 +72,11 @@ int uavsal_stem_conv3x3s2(const void* x, int x_kind, int n, int h, int w,
                           const float* wgt, const float* bias,
                           uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
+/* Same operation with the folded weights [27][32] and bias [32] given as HOST pointers: they are copied into the kernel's
+ * parameter block at launch (3.5 KB, read through the constant bank), so nothing has to stay alive after the call returns. */
+int uavsal_stem_conv3x3s2_hw(const void* x, int x_kind, int n, int h, int w, const float* wgt_host, const float* bias_host,
+                             uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
 /* ---- K2: depthwise 3x3 + BN + ReLU6 (model.py:92 BasicConv2d(groups=hidden); torchvision InvertedResidual dw)
  *      stride 1|2, dilation >= 1, padding = dilation.  wgt: [9][c] fp32 BN-folded, bias[c]. */
 int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c,
