@@ -210,6 +210,12 @@ class Plan:
         cout, hidden = w2d.shape
         assert hid.f32 and hid.c == hidden and self.engine == "tc"
         assert (hidden % 128 == 0 and cout % 64 == 0 and cout <= 256) or ((hidden, cout) == (32, 16) and res is None)
+        if (hidden, cout) == (32, 16) and getattr(self, "dwproj32_params", True):
+            # features.1: all 848 weights go into the kernel's parameter block as HOST arrays (constant-bank FFMA operands)
+            host = [t.detach().float().cpu().contiguous() for t in (wd, bd, w2d, bias)]
+            self.keep += host
+            self._add("uavsal_dw_project32_hw", (hid.ptr, hid.ld, n, h, w, *[t.data_ptr() for t in host], *out.act()), tag)
+            return
         wp = self.hold(pack_pw_tc(w2d, hidden))
         b = self.hold(bias.float())
         r = res.act() if res is not None else NULL_ACT

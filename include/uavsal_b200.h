@@ -103,6 +103,11 @@ int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hid
                       const uint16_t* res, int64_t res_plane, int res_ld,
                       uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
+/* The 32 -> 16 block (torchvision features[1]) with its weights as HOST arrays: wd [9][32], bd [32], wp [16][32] (cout, hidden)
+ * fp32 and bias [16] are copied into the kernel's parameter block at launch and read as constant-bank operands. */
+int uavsal_dw_project32_hw(const float* hid, int hid_ld, int n, int h, int w, const float* wd_host, const float* bd_host,
+                           const float* wp_host, const float* bias_host, uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
 /* ---- K3: pointwise 1x1 conv + BN (+ReLU6)(+residual)(+sigmoid) (model.py:89,94,120-128,181,184,230).
  *      out[m][n0..] = act( sum_k A[m][k] * W[n][k] + bias[n] ) (+ res[m][n])
  *      tcgen05 version: wgt = bf16 planes [2][n][kpad] (hi, lo), kpad % 8 == 0; terms = 1 (bf16x1) or 3.

@@ -105,7 +105,7 @@ def test_plan_structure_of_one_call():
     # ... and the seven large stride-1 blocks whose project conv has 64..256 outputs (st0/st1.sp, fust, gauss1, ob1, fucb, fucbst)
     # run depthwise + project fused
     # ... plus features.1 (32 -> 16, no expand conv), whose depthwise + project run as one fp32 FFMA kernel behind the same entry
-    assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7 + 1
+    assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7 and names.count("uavsal_dw_project32_hw") == 1
     # ... and the readout's depthwise conv is folded into its 1-output project (dw3x3_dot_sigmoid)
     assert names.count("uavsal_pw_gemm") == 76 - 2 - 8 and names.count("uavsal_dw3x3") == 34 - 2 - 8 - 1
     assert names.count("uavsal_dw3x3_dot_sigmoid") == 1 and names.count("uavsal_dot_sigmoid") == 0

@@ -114,6 +114,7 @@ def test_fused_depthwise_project(cuda, ch, co, n, h, w, res):
     from iip_uavsal_saliency_b200.engine import pack_dw
     torch.manual_seed(11)
     p = _plan()
+    p.dwproj32_params = (n != 3)          # the 32 -> 16 kernel: weights in the parameter block (default) / device-pointer variant
     hid = torch.rand(n, ch, h, w) * 6
     wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
     w2, b2 = torch.randn(co, ch) / ch ** 0.5, torch.randn(co) * 0.1
