@@ -150,6 +150,8 @@ def main():
         gemm("tc", 432000, 32, 256, res=True); gemm("tc", 432000, 256, 256, res=True); gemm("tc", 110400, 384, 64, res=True)
         gemm("tc", 1728000, 144, 24, res=True); gemm("tc", M, 1536, 256, res=True)
       lib.uavsal_set_option(3, 0)
+    if what == "pairbig":
+        gemm("tc", 432000, 256, 1536, f32=True)
     if what == "wr":
         gemm("tc", 432000, 32, 256, res=True); gemm("tc", 432000, 32, 192, f32=True); gemm("tc", 432000, 64, 384, f32=True)
     if what == "expdw2":
