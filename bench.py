@@ -49,6 +49,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -60,13 +67,18 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+        # the sampler is started before the warm-up (nvidia-smi needs ~0.2 s to deliver its first row); only rows that arrived
+        # inside the timed region count - for a region shorter than the sampling period, the rows closest to its end
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        if not rows and self.rows:
+            rows = [r for _, r in self.rows[-2:]]
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -223,6 +235,8 @@ def run_product_arm(args):
     runner = ClipRunner(model, gauss, ob, batch_size=BATCH, out_hw=(H, W), use_graph=not args.no_graph, depth=args.depth,
                         clip_backbone=not args.per_call_backbone, single_stream=args.single_stream, whole_clip=not args.per_call,
                         clips_per_plan=args.clips_per_plan)
+    sampler = ClockSampler(local)           # started ahead of the plan build: nvidia-smi is streaming by the time the timed region begins
+    sampler.start()
     runner.warm(FRAMES, H, W)
 
     # distinct clips rotated across steps so inputs (4 x 44 MB) exceed the 126 MB L2; the arena traffic of a step
@@ -243,7 +257,7 @@ def run_product_arm(args):
             # H2D of the uint8 frames and D2H of the uint8 maps are queued by run_clip on its streams
             runner.run_clip(host_clips[(i * args.clips + c) % n_rot], want_maps=False, out=host_out, sync=False)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for i in range(warmup):
             fn(i)
         runner.finish()
@@ -252,20 +266,22 @@ def run_product_arm(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark_begin()
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         runner.finish()
         e1.record()
         torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.mark_end()
         if world > 1:
             torch.distributed.barrier()
         return D.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
 
     warm = max(3, args.warmup)
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_res = timed(step_resident, args.steps, warm)
+    t_res = timed(step_resident, args.steps, warm, sampler)
     clocks = sampler.stop()
     t_e2e = timed(step_e2e, args.steps, warm)
 
