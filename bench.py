@@ -37,7 +37,7 @@ def load_priors():
     if os.path.exists(p):
         z = np.load(p)
         return z["gauss"], z["uav2_u8"].astype(np.float32) / 255
-    from oracle import synth
+    from iip_uavsal_saliency_b200 import synth
     g, o = synth.make_priors(1, MH, MW)
     return g[0].transpose(1, 2, 0), o[0].transpose(1, 2, 0)
 
@@ -114,7 +114,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import torch
-    from oracle import synth
+    from iip_uavsal_saliency_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.make_state_dict("lively", 0)
@@ -212,7 +212,7 @@ def run_product_arm(args):
     from iip_uavsal_saliency_b200 import _ext, dist as D
     from iip_uavsal_saliency_b200.model import UAVSal
     from iip_uavsal_saliency_b200.runner import ClipRunner
-    from oracle import synth   # synthetic inputs / weights only (seeded generators), not the checker
+    from iip_uavsal_saliency_b200 import synth   # seeded synthetic inputs / weights
 
     # a freshly provisioned box was seen to fail one CUDA driver initialisation (a failed cuInit can stick to the process): probe
     # in a child process first, retrying, and touch CUDA here only once the probe has succeeded
