@@ -7,8 +7,9 @@ and there only as the checker or the reported CPU baseline — never as the prod
 Contents
   shim.py        import the unmodified reference from /root/reference (authoring container only)
   cpu_ref.py     functional CPU restatement of the reference hot path (torch CPU fp32 primitives)
-  synth.py       seeded synthetic clips, priors, weights ("stock" and "lively") and metric pairs
+  synth.py       re-export of the seeded synthetic-input generators (iip_uavsal_saliency_b200/synth.py)
   make_golden.py regenerates tests/golden/*.npz by running the real reference through shim.py
+  make_ckpt_fixture.py  checkpoint-loader fixtures (reference modules pickled in the authoring container)
 
 Parity pin: the reference ships no tests or golden vectors, so cpu_ref.py is pinned
 against outputs of the reference itself executed in the authoring container (make_golden.py →
