@@ -270,6 +270,13 @@ __device__ __forceinline__ void m_bulk_load(void* dst, const void* src, uint32_t
                  ::"r"(m_smem_u32(dst)), "l"(src), "r"(bytes), "r"(m_smem_u32(bar)) : "memory");
 }
 
+// bulk load with an L2 eviction-priority hint: pass 1 keeps pred / density (re-read by pass 2) and lets the fixation plane and
+// everything pass 2 touches go first
+__device__ __forceinline__ void m_bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(m_smem_u32(dst)), "l"(src), "r"(bytes), "r"(m_smem_u32(bar)), "l"(policy) : "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ void lds4v(const T* p, float v[4]);
 template <>
@@ -317,6 +324,9 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
 
     // producer lane: chunk i of the doubled list (pass 1: P, D, F; pass 2: P, D).  It must join the block / cluster barriers
     // between the passes, so before them it runs only kStStages chunks into pass 2 (their stages are freed by pass-1 consumers)
+    uint64_t pol_keep, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     auto produce = [&](int i0, int i1) {
         for (int i = i0; i < i1; ++i) {
             const int s = i % kStStages;
@@ -325,9 +335,10 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
             const int c = chunk_of(pass2 ? i - mine : i);
             const uint32_t bytes = (uint32_t)chunk_len(c) * sizeof(T);
             m_bar_expect(full + s, bytes * (pass2 ? 2 : 3));
-            m_bulk_load(ring[s][0], P + (int64_t)c * kStChunk, bytes, full + s);
-            m_bulk_load(ring[s][1], D + (int64_t)c * kStChunk, bytes, full + s);
-            if (!pass2) m_bulk_load(ring[s][2], Fx + (int64_t)c * kStChunk, bytes, full + s);
+            const uint64_t pol = pass2 ? pol_first : pol_keep;
+            m_bulk_load_hint(ring[s][0], P + (int64_t)c * kStChunk, bytes, full + s, pol);
+            m_bulk_load_hint(ring[s][1], D + (int64_t)c * kStChunk, bytes, full + s, pol);
+            if (!pass2) m_bulk_load_hint(ring[s][2], Fx + (int64_t)c * kStChunk, bytes, full + s, pol_first);
         }
     };
     const int ahead = min(2 * mine, mine + kStStages);
