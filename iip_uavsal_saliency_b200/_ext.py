@@ -47,11 +47,11 @@ _SIGNATURES = {
     "uavsal_post_f32": [P, I, I, I, I, I, P, P, P],
     "uavsal_metrics4": [P, P, I, I, I, I, P, P, P],
     "uavsal_letterbox_u8": [P, I, I, I, P, I, I, I, P],
-    "uavsal_auc_judd": [P, P, I, I, I, P, P],
+    "uavsal_auc_judd": [P, P, I, I, I, P, P, L, P],
     "uavsal_auc_sampled": [P, P, I, I, I, P, P, I, I, c_double, P, P],
 }
 
-EXPORTS = ["uavsal_version", "uavsal_arch", "uavsal_last_error"] + list(_SIGNATURES)
+EXPORTS = ["uavsal_version", "uavsal_arch", "uavsal_last_error", "uavsal_auc_judd_workspace"] + list(_SIGNATURES)
 
 
 class UavsalError(RuntimeError):
@@ -77,6 +77,8 @@ def load():
     lib.uavsal_version.restype = c_int
     lib.uavsal_arch.restype = c_char_p
     lib.uavsal_last_error.restype = c_char_p
+    lib.uavsal_auc_judd_workspace.argtypes = [I, I, I]
+    lib.uavsal_auc_judd_workspace.restype = c_int64
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

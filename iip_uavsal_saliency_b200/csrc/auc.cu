@@ -7,7 +7,7 @@
 // for each (n_fix passes over 230 400 pixels).  Here the thresholds are sorted once in shared memory (bitonic), every pixel
 // finds by binary search the first threshold it reaches and bumps one histogram bin, and a prefix sum turns the bins into
 // all the counts: one pass over the map.  tp / fp are built with the reference's fp32 expressions, the trapezoid sum runs in
-// fp64.
+// fp64.  Frames with more than kAucMaxFix fixations run the same steps over the caller's global-memory workspace.
 //
 // Sampled AUCs (auc_b :91-120, auc_s :135-159): the random pixel indices are drawn by the CALLER exactly as the reference
 // draws them (np.random.randint under the caller's seed) and passed in; thread `rep` walks its column of samples, bins them
@@ -50,31 +50,51 @@ __device__ __forceinline__ MinMax block_minmax(const float* __restrict__ p, int 
     return MinMax{mn, mx};
 }
 
+// Storage of the thresholds / histogram bins: shared memory up to kAucMaxFix fixations per frame, the caller's global workspace
+// above that (dense fixation maps, mouse-click datasets): same algorithm, the bitonic passes then run over global memory (one CTA,
+// __syncthreads between passes), which costs milliseconds per such frame instead of microseconds - the reference (:53-74) has no
+// cap, so neither has this kernel.  ws layout per pair: float thr[np2(hw)] | unsigned hist[hw + 1].
 __global__ void __launch_bounds__(1024) auc_judd_kernel(const float* __restrict__ pred, const float* __restrict__ truth, int hw,
+                                                        float* __restrict__ ws, int64_t ws_pair_elems, int np2_hw,
                                                         float* __restrict__ out) {
-    __shared__ float thr[kAucMaxFix];
-    __shared__ unsigned hist[kAucMaxFix + 1];
+    __shared__ float thr_s[kAucMaxFix];
+    __shared__ unsigned hist_s[kAucMaxFix + 1];
     __shared__ float red[64];
     __shared__ double dred[32];
     __shared__ unsigned scan_base[32];
+    __shared__ unsigned carry_s;
     __shared__ int nfix_s;
     const int pair = blockIdx.x, tid = threadIdx.x;
     const float* P = pred + (int64_t)pair * hw;
     const float* F = truth + ((int64_t)pair * 2 + 1) * hw;
+    float* thr_g = ws ? ws + (int64_t)pair * ws_pair_elems : nullptr;
+    unsigned* hist_g = ws ? reinterpret_cast<unsigned*>(thr_g + np2_hw) : nullptr;
     if (tid == 0) nfix_s = 0;
     const MinMax mm = block_minmax(P, hw, red);                 // (also orders the nfix_s store)
     const float d = __fadd_rn(__fsub_rn(mm.mx, mm.mn), kEpsF);
     for (int i = tid; i < hw; i += blockDim.x)
         if (__ldg(F + i) > 0.5f) {
             const int k = atomicAdd(&nfix_s, 1);
-            if (k < kAucMaxFix) thr[k] = __fdiv_rn(__fsub_rn(__ldg(P + i), mm.mn), d);
+            const float s = __fdiv_rn(__fsub_rn(__ldg(P + i), mm.mn), d);
+            if (k < kAucMaxFix) thr_s[k] = s;
+            else if (thr_g) thr_g[k] = s;
         }
     __syncthreads();
     const int n_fix = nfix_s;
     const bool any_s = __fdiv_rn(__fsub_rn(mm.mx, mm.mn), d) > 0.f;
-    if (!any_s || n_fix == 0 || n_fix > kAucMaxFix || n_fix >= hw) {          // :54 (and the capacity of this kernel)
+    // :54 NaN cases; n_fix == hw divides by n_pixels - n_fix = 0 in the reference (NaN / inf there as well).  The launcher
+    // refuses maps above kAucMaxFix pixels without a workspace, so `big && !thr_g` cannot happen.
+    const bool big = n_fix > kAucMaxFix;
+    if (!any_s || n_fix == 0 || n_fix >= hw || (big && !thr_g)) {
         if (tid == 0) out[pair] = NAN;
         return;
+    }
+    float* thr = thr_s;
+    unsigned* hist = hist_s;
+    if (big) {
+        thr = thr_g;
+        hist = hist_g;
+        for (int i = tid; i < kAucMaxFix; i += blockDim.x) thr_g[i] = thr_s[i];
     }
     // ---- sort the thresholds, descending (bitonic; padding = -inf sinks to the end) ----
     int np2 = 1;
@@ -106,32 +126,36 @@ __global__ void __launch_bounds__(1024) auc_judd_kernel(const float* __restrict_
         }
         atomicAdd(&hist[lo], 1u);
     }
+    if (tid == 0) carry_s = 0;
     __syncthreads();
-    // ---- inclusive prefix sum: above[i] = #{S >= thr[i]} (4 consecutive bins per thread) ----
-    unsigned loc[4], run = 0;
+    // ---- inclusive prefix sum: above[i] = #{S >= thr[i]}; chunks of 4096 bins (4 consecutive bins per thread) with a carry ----
+    for (int c0 = 0; c0 < n_fix; c0 += kAucMaxFix) {
+        unsigned loc[4], run = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int i = tid * 4 + u;
-        run += i < n_fix ? hist[i] : 0u;
-        loc[u] = run;
-    }
-    unsigned inc = run;
+        for (int u = 0; u < 4; ++u) {
+            const int i = c0 + tid * 4 + u;
+            run += i < n_fix ? hist[i] : 0u;
+            loc[u] = run;
+        }
+        unsigned inc = run;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((tid & 31) >= o) inc += v;
-    }
-    if ((tid & 31) == 31) scan_base[tid >> 5] = inc;
-    __syncthreads();
-    unsigned base = inc - run;
-    for (int w = 0; w < (tid >> 5); ++w) base += scan_base[w];
-    __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((tid & 31) >= o) inc += v;
+        }
+        if ((tid & 31) == 31) scan_base[tid >> 5] = inc;
+        __syncthreads();
+        unsigned base = carry_s + inc - run;
+        for (int w = 0; w < (tid >> 5); ++w) base += scan_base[w];
+        __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int i = tid * 4 + u;
-        if (i < n_fix) hist[i] = base + loc[u];
+        for (int u = 0; u < 4; ++u) {
+            const int i = c0 + tid * 4 + u;
+            if (i < n_fix) hist[i] = base + loc[u];
+        }
+        if (tid == 1023) carry_s = base + run;
+        __syncthreads();
     }
-    __syncthreads();
     // ---- ROC points with the reference's fp32 expressions (:66-72), trapezoid in fp64 ----
     const float fn = (float)n_fix, fneg = (float)(hw - n_fix);
     auto tp_at = [&](int i) -> float { return i == 0 ? 0.f : (i == n_fix + 1 ? 1.f : __fdiv_rn((float)i, fn)); };
@@ -233,9 +257,28 @@ __global__ void __launch_bounds__(kAucMaxRep) auc_sampled_kernel(const float* __
 
 using namespace uavsal;
 
-extern "C" int uavsal_auc_judd(const float* pred, const float* truth, int n, int h, int w, float* out, void* stream) {
+static int64_t auc_np2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+extern "C" int64_t uavsal_auc_judd_workspace(int n, int h, int w) {
+    const int64_t hw = (int64_t)h * w;
+    if (n <= 0 || hw <= kAucMaxFix) return 0;                      // every frame fits the shared-memory path
+    return (int64_t)n * (auc_np2(hw) + ((hw + 1 + 3) & ~(int64_t)3)) * 4;
+}
+
+extern "C" int uavsal_auc_judd(const float* pred, const float* truth, int n, int h, int w, float* out, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
     UAVSAL_REQUIRE(pred && truth && out && n > 0 && h > 0 && w > 0 && (int64_t)h * w < (1 << 24), UAVSAL_EINVAL, "auc_judd: bad arguments");
-    auc_judd_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(pred, truth, h * w, out);
+    const int64_t need = uavsal_auc_judd_workspace(n, h, w);
+    UAVSAL_REQUIRE(need == 0 || (workspace && workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0), UAVSAL_EINVAL,
+                   "auc_judd: maps of more than %d pixels need uavsal_auc_judd_workspace(n,h,w) = %lld bytes of 16-byte-aligned workspace "
+                   "(a frame may hold that many fixations)", kAucMaxFix, (long long)need);
+    const int hw = h * w;
+    auc_judd_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(pred, truth, hw, need ? (float*)workspace : nullptr, need ? need / 4 / n : 0,
+                                                           (int)auc_np2(hw), out);
     return check_launch("auc_judd");
 }
 

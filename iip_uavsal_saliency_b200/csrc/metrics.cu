@@ -237,7 +237,7 @@ metrics4_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Streaming variant (default when h*w is a multiple of 16): same arithmetic, but the maps flow through a 4-stage shared-memory
+// Streaming variant (maps above 256 Ki pixels; h*w a multiple of 16): same arithmetic, but the maps flow through a 3-stage shared-memory
 // ring filled by cp.async.bulk (one producer warp, mbarrier full/empty), so the loads in flight are limited by shared memory
 // (36 KiB per CTA, several CTAs per SM) instead of registers.  The register-batched kernel above stalled on `long_sb` and on
 // the cluster barrier (39 % of HBM peak); this one keeps the HBM pipe full.
@@ -483,7 +483,273 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
     cluster.sync();
 }
 
-int g_metrics_stream = 1;      // uavsal_set_option key 9: 1 = streaming kernel (default), 0 = register-batched kernel
+// ---------------------------------------------------------------------------------------------------------------------
+// Resident variant (default for maps of 32 Ki .. 256 Ki pixels, i.e. the 360x640 evaluation maps): every input byte crosses
+// HBM exactly ONCE.  The streaming kernel above re-reads pred + density from L2 in pass 2; with tens of pairs in flight the
+// re-read misses L2 (ncu, round 1: 1.63x the algorithmic DRAM bytes).  Here a cluster of 8 persistent CTAs (one per SM) owns a
+// pair; a producer warp streams 2048-pixel chunks of the three planes through a 192 KiB shared-memory ring with
+// cp.async.bulk (evict-first: nothing is read twice), 16 consumer warps reduce the pass-1 moments from the ring AND stash
+// every (pred, density) value they touched in TENSOR MEMORY (tcgen05.st: 28 800 pixels x 2 planes x 4 B = 225 KiB of the
+// SM's 256 KiB; a warp only ever re-reads the cells it wrote, so the lane-quarter rule of tcgen05.ld/st costs nothing).
+// Pass 2 (KLD / SIM terms, which need the pass-1 statistics element-wise) runs out of tensor memory while the producer
+// is already filling the ring with the next pair - shared memory holds no resident data, so the HBM stream never stops for
+// the statistics exchange.  The cluster exchanges its 11 pass-1 partials by DSMEM pushes + remote mbarrier arrives (no
+// barrier.cluster in the loop: the producer warp never has to join it).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTmWarps = 16;                       // consumer warps
+constexpr int kTmConsumers = kTmWarps * 32;
+constexpr int kTmThreads = kTmConsumers + 32;      // + producer warp (also owns the TMEM allocation)
+constexpr int kTmChunkPx = kTmConsumers * 4;       // 2048 pixels per plane per stage: one float4 / uchar4 per consumer thread
+constexpr int kTmStages = 8;
+constexpr int kTmMaxChunks = 16;                   // 128 TMEM columns per warp / 8 columns per chunk
+
+template <typename T>
+struct TmSmem {
+    alignas(128) T ring[kTmStages][3][kTmChunkPx];
+    double stats[2][kCluster][S_COUNT];            // [pair parity][source rank][item], pushed by every CTA of the cluster
+    double part2[2][kCluster][2];                  // pass-2 partials, pushed to rank 0
+    double wpart1[kTmWarps][S_COUNT];
+    double wpart2[kTmWarps][2];
+    double tot[S_COUNT];
+    uint64_t full[kTmStages], empty[kTmStages], statbar[2], p2bar[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t m_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t m_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void m_st_remote_f64(uint32_t addr_cluster, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr_cluster), "d"(v) : "memory");
+}
+// the remote stores above are ordered before this arrive (release at cluster scope); the waiter acquires at cluster scope
+__device__ __forceinline__ void m_bar_arrive_remote(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void m_bar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; !ok; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity) : "memory");
+        if (it > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void m_tmem_st8(uint32_t taddr, const float v[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void m_tmem_ld8(uint32_t taddr, float v[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
+}
+
+template <typename T>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kTmThreads, 1)
+metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, int n_pairs, float* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t m_smem_raw[];
+    TmSmem<T>& sm = *reinterpret_cast<TmSmem<T>*>(m_smem_raw);
+    const int rank = (int)m_cluster_rank();
+    const int cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == kTmWarps;
+
+    if (tid == 0) {
+        for (int s = 0; s < kTmStages; ++s) { m_bar_init(sm.full + s, 1); m_bar_init(sm.empty + s, kTmWarps); }
+        for (int s = 0; s < 2; ++s) { m_bar_init(sm.statbar + s, kCluster * S_COUNT); m_bar_init(sm.p2bar + s, kCluster * 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (producer) {        // all 512 columns: the (pred, density) values of this CTA's slice live there between the passes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // every CTA's barriers exist before the first remote arrive
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // warp w may touch TMEM lanes 32*(w%4) .. +31; the four warps of a lane quarter take 128 columns each
+    const uint32_t tcol = sm.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+
+    // this CTA's chunks of a pair: rank, rank + 8, ...
+    const int nchunks = (hw + kTmChunkPx - 1) / kTmChunkPx;
+    const int mine = (nchunks - rank + kCluster - 1) / kCluster;          // <= kTmMaxChunks (launcher)
+    auto chunk_of = [&](int i) { return rank + i * kCluster; };
+    auto chunk_len = [&](int c) { return min(kTmChunkPx, hw - c * kTmChunkPx); };
+
+    if (producer) {
+        if (lane == 0) {
+            uint64_t pol_first;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            uint32_t it = 0;
+            for (int pair = cid; pair < n_pairs; pair += ncl) {
+                const T* P = pred + (int64_t)pair * hw;
+                const T* D = truth + (int64_t)pair * 2 * hw;
+                const T* Fx = D + hw;
+                for (int i = 0; i < mine; ++i, ++it) {
+                    const int s = it % kTmStages;
+                    m_bar_wait(sm.empty + s, ((it / kTmStages) & 1) ^ 1);
+                    const int c = chunk_of(i);
+                    const uint32_t bytes = (uint32_t)chunk_len(c) * sizeof(T);
+                    m_bar_expect(sm.full + s, bytes * 3);
+                    m_bulk_load_hint(sm.ring[s][0], P + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
+                    m_bulk_load_hint(sm.ring[s][1], D + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
+                    m_bulk_load_hint(sm.ring[s][2], Fx + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = tid * 4;                                            // this thread's 4 pixels of every chunk
+        uint32_t it = 0;
+        int k = 0;
+        for (int pair = cid; pair < n_pairs; pair += ncl, ++k) {
+            const int par = k & 1;
+            const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+            // ------------------------------- pass 1: ring -> moments + TMEM stash -------------------------------
+            double s[S_COUNT];
+#pragma unroll
+            for (int i = 0; i < S_COUNT; ++i) s[i] = 0.0;
+            float mnP = 3.0e38f, mxP = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
+            float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < mine; ++i, ++it) {
+                const int st = it % kTmStages;
+                m_bar_wait(sm.full + st, (it / kTmStages) & 1);
+                const int len = chunk_len(chunk_of(i));
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (e < len) {
+                    float f[4];
+                    lds4v<T>(&sm.ring[st][0][e], v); lds4v<T>(&sm.ring[st][1][e], v + 4); lds4v<T>(&sm.ring[st][2][e], f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float p = v[j], t = v[4 + j];
+                        a[0] += p; a[1] = fmaf(p, p, a[1]); a[2] += t; a[3] = fmaf(t, t, a[3]);
+                        a[4] = fmaf(t, p, a[4]); a[5] += f[j]; a[6] = fmaf(f[j], p, a[6]);
+                        mnP = fminf(mnP, p); mxP = fmaxf(mxP, p); mnT = fminf(mnT, t); mxT = fmaxf(mxT, t);
+                    }
+                }
+                m_tmem_st8(tcol + (uint32_t)(i * 8), v);                  // warp-collective: executed by every lane, also past the tail
+                __syncwarp();
+                if (lane == 0) m_bar_arrive(sm.empty + st);
+                if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) {    // fold the fp32 run (<= 32 pixels per thread: exact for uint8-valued maps) into fp64
+                    s[S_P] += a[0]; s[S_P2] += a[1]; s[S_T] += a[2]; s[S_T2] += a[3]; s[S_TP] += a[4]; s[S_F] += a[5]; s[S_FP] += a[6];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) a[j] = 0.f;
+                }
+            }
+            s[S_MINP] = mnP; s[S_MAXP] = mxP; s[S_MINT] = mnT; s[S_MAXT] = mxT;
+#pragma unroll
+            for (int i = 0; i < S_COUNT; ++i) {
+                double v = s[i];
+                if (i == S_MINP || i == S_MINT) v = warp_min(v);
+                else if (i == S_MAXP || i == S_MAXT) v = warp_max(v);
+                else v = warp_sum(v);
+                if (lane == 0) sm.wpart1[warp][i] = v;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+            if (tid < kCluster * S_COUNT) {                               // thread (dest, item): this CTA's partial -> CTA `dest`
+                const int item = tid % S_COUNT, dest = tid / S_COUNT;
+                double v = sm.wpart1[0][item];
+                for (int w = 1; w < kTmWarps; ++w) {
+                    if (item == S_MINP || item == S_MINT) v = fmin(v, sm.wpart1[w][item]);
+                    else if (item == S_MAXP || item == S_MAXT) v = fmax(v, sm.wpart1[w][item]);
+                    else v += sm.wpart1[w][item];
+                }
+                m_st_remote_f64(m_mapa(m_smem_u32(&sm.stats[par][rank][item]), (uint32_t)dest), v);
+                m_bar_arrive_remote(m_mapa(m_smem_u32(&sm.statbar[par]), (uint32_t)dest));
+            }
+            m_bar_wait_cluster(sm.statbar + par, ph);
+            if (tid < S_COUNT) {
+                const int i = tid;
+                double v = sm.stats[par][0][i];
+                for (int r = 1; r < kCluster; ++r) {
+                    const double o = sm.stats[par][r][i];
+                    if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+                    else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+                    else v += o;
+                }
+                sm.tot[i] = v;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+
+            const double n = (double)hw;
+            const double* tot = sm.tot;
+            const float sumP = (float)tot[S_P], sumT = (float)tot[S_T];
+            const float minP = (float)tot[S_MINP], minT = (float)tot[S_MINT];
+            const float rngP = ((float)tot[S_MAXP] - minP) + kEpsF, rngT = ((float)tot[S_MAXT] - minT) + kEpsF;
+            const float nsumP = (float)((tot[S_P] - n * tot[S_MINP]) / (double)rngP) + kEpsF;
+            const float nsumT = (float)((tot[S_T] - n * tot[S_MINT]) / (double)rngT) + kEpsF;
+            const float dP = sumP + kEpsF, dT = sumT + kEpsF;
+            const float rdT = 1.0f / dT, rdP = 1.0f / dP;
+            const float rnT = 1.0f / (rngT * nsumT), rnP = 1.0f / (rngP * nsumP);
+
+            // ------------------------------- pass 2: out of tensor memory -------------------------------
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            double kld = 0.0, sim = 0.0;
+            float kf = 0.f, sf = 0.f;
+            for (int i = 0; i < mine; i += 2) {
+                float v[2][8];
+                m_tmem_ld8(tcol + (uint32_t)(i * 8), v[0]);
+                if (i + 1 < mine) m_tmem_ld8(tcol + (uint32_t)((i + 1) * 8), v[1]);      // (mine is CTA-uniform: still warp-collective)
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (i + u < mine && e < chunk_len(chunk_of(i + u))) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float p = v[u][j], t = v[u][4 + j];
+                            const float th = t * rdT, phh = p * rdP;
+                            kf = fmaf(th, __logf(__fdividef(th, phh + kEpsF) + kEpsF), kf);
+                            sf += fminf((t - minT) * rnT, (p - minP) * rnP);
+                        }
+                    }
+                    if (sizeof(T) == 1 || ((i + u) & 7) == 7) { kld += kf; sim += sf; kf = 0.f; sf = 0.f; }
+                }
+            }
+            kld += kf; sim += sf;
+            kld = warp_sum(kld);
+            sim = warp_sum(sim);
+            if (lane == 0) { sm.wpart2[warp][0] = kld; sm.wpart2[warp][1] = sim; }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+            if (tid < 2) {
+                double v = 0.0;
+                for (int w = 0; w < kTmWarps; ++w) v += sm.wpart2[w][tid];
+                m_st_remote_f64(m_mapa(m_smem_u32(&sm.part2[par][rank][tid]), 0u), v);
+                m_bar_arrive_remote(m_mapa(m_smem_u32(&sm.p2bar[par]), 0u));
+            }
+            if (rank == 0 && tid == 0) {
+                m_bar_wait_cluster(sm.p2bar + par, ph);
+                double kk = 0.0, smm = 0.0;
+                for (int r = 0; r < kCluster; ++r) { kk += sm.part2[par][r][0]; smm += sm.part2[par][r][1]; }
+                // CC (:188-197) and NSS (:200-204) from the raw moments; std is unbiased (torch.std, :49)
+                const double mP = tot[S_P] / n, mT = tot[S_T] / n;
+                const double ssP = fmax(tot[S_P2] - tot[S_P] * mP, 0.0), ssT = fmax(tot[S_T2] - tot[S_T] * mT, 0.0);
+                const double sdP = sqrt(ssP / (n - 1.0)), sdT = sqrt(ssT / (n - 1.0));
+                const double cov = tot[S_TP] - tot[S_T] * mP;
+                const double zz = (sdP + kEps) * (sdT + kEps);
+                const double r1 = cov / zz;
+                const double r2 = sqrt((ssP / ((sdP + kEps) * (sdP + kEps))) * (ssT / ((sdT + kEps) * (sdT + kEps))));
+                out[(int64_t)pair * 4 + 0] = (float)(r1 / (r2 + kEps));
+                out[(int64_t)pair * 4 + 1] = (float)(((tot[S_FP] - mP * tot[S_F]) / (sdP + kEps)) / (tot[S_F] + kEps));
+                out[(int64_t)pair * 4 + 2] = (float)kk;
+                out[(int64_t)pair * 4 + 3] = (float)smm;
+            }
+        }
+    }
+    // no CTA leaves (its shared memory, barriers and TMEM go with it) while a peer may still push into it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (producer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(512u) : "memory");
+}
+
+int g_metrics_stream = 2;      // uavsal_set_option key 9: 2 = TMEM-resident persistent kernel where it applies (default), 1 = streaming
+                               // kernel (pass 2 from L2), 0 = register-batched kernel
 
 }  // namespace uavsal
 
@@ -494,14 +760,48 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
     (void)scratch;
     UAVSAL_REQUIRE(pred && truth && out && n > 0 && h > 0 && w > 0 && (dtype == 0 || dtype == 1), UAVSAL_EINVAL,
                    "metrics4: bad arguments");
-    UAVSAL_REQUIRE(n <= 65535, UAVSAL_ENOTSUP, "metrics4: at most 65535 pairs per call");
     const int hw = h * w;
     UAVSAL_REQUIRE(hw >= 2, UAVSAL_EINVAL, "metrics4: map must have at least 2 pixels (unbiased std)");
     const bool al = dtype == 0 ? ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0 && hw % 4 == 0
                                : ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 3) == 0 && hw % 4 == 0;
     UAVSAL_REQUIRE(al, UAVSAL_ENOTSUP, "metrics4: h*w must be a multiple of 4 and the tensors 16-byte aligned");
+    const int esz = dtype == 0 ? 4 : 1;
+    // cp.async.bulk needs 16-byte aligned global addresses and sizes: pred / truth bases, the fixation plane (truth + hw) and every
+    // pair / chunk offset.  Anything else takes the register-batched kernel (plain vector loads).
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0 && ((int64_t)hw * esz) % 16 == 0 &&
+                         hw % 16 == 0;
+    if (g_metrics_stream >= 2 && bulk_ok && hw >= kCluster * kStChunkBytes && hw <= kCluster * kTmMaxChunks * kTmChunkPx) {
+        static int max_clusters[2] = {0, 0};       // co-resident clusters of 8 (one CTA per SM; GPC-limited), per element type
+        const size_t smem = dtype == 0 ? sizeof(TmSmem<float>) : sizeof(TmSmem<uint8_t>);
+        const void* fn = dtype == 0 ? (const void*)metrics4_tmem_kernel<float> : (const void*)metrics4_tmem_kernel<uint8_t>;
+        if (!max_clusters[dtype]) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(kCluster * 64); cfg.blockDim = dim3(kTmThreads); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nc, fn, &cfg);
+            if (e != cudaSuccess || nc < 1) {
+                set_error("metrics4(resident): occupancy query failed: %s", cudaGetErrorString(e));
+                return e != cudaSuccess ? (int)e : UAVSAL_ENOTSUP;
+            }
+            max_clusters[dtype] = nc;
+        }
+        const int ncl = n < max_clusters[dtype] ? n : max_clusters[dtype];
+        if (dtype == 0)
+            metrics4_tmem_kernel<float><<<kCluster * ncl, kTmThreads, smem, (cudaStream_t)stream>>>(
+                reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, n, out);
+        else
+            metrics4_tmem_kernel<uint8_t><<<kCluster * ncl, kTmThreads, smem, (cudaStream_t)stream>>>(
+                reinterpret_cast<const uint8_t*>(pred), reinterpret_cast<const uint8_t*>(truth), hw, n, out);
+        return check_launch("metrics4(resident)");
+    }
+    UAVSAL_REQUIRE(n <= 65535, UAVSAL_ENOTSUP, "metrics4: at most 65535 pairs per call for this map size");
     dim3 grid(kCluster, n);
-    if (g_metrics_stream && hw % 16 == 0 && hw >= kCluster * kStChunkBytes) {
+    if (g_metrics_stream && bulk_ok && hw >= kCluster * kStChunkBytes) {
         if (dtype == 0)
             metrics4_stream_kernel<float><<<grid, kStThreads, 0, (cudaStream_t)stream>>>(
                 reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out);

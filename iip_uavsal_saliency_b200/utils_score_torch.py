@@ -1,11 +1,11 @@
 """Drop-in for the four saliency metrics of the reference's utils_score_torch.py (metric_cc / metric_nss /
 metric_kl / metric_sim, :180-218, with the reduction helpers :20-50 and EPS :13).
 
-All four metrics of a batch come out of ONE fused sm_100a kernel launch (csrc/metrics.cu); the per-metric
-functions keep the reference signatures ``metric_x(y_pred (N,1,H,W), y_true (N,2,H,W)) -> (N,1)`` and share the
-launch through a one-entry memo, because the reference's evaluation loop calls them back to back on the same
-tensors (utils_score_torch.py:551-561).  AUC-Judd / Borji / shuffled (csrc/auc.cu) follow below; the file-walking
-evaluation loop stays with the caller.
+All four metrics of a batch come out of ONE fused sm_100a kernel launch (csrc/metrics.cu): ``metrics4`` returns the (N,4)
+table.  The per-metric functions keep the reference signatures ``metric_x(y_pred (N,1,H,W), y_true (N,2,H,W)) -> (N,1)``;
+each is its own launch of the fused kernel (no result is cached between calls: tensors of successive batches reuse
+addresses, so nothing cheap identifies "the same inputs").  Callers that want all four - the evaluation driver below -
+call ``metrics4`` once per batch.  AUC-Judd / Borji / shuffled (csrc/auc.cu) follow below.
 """
 from __future__ import annotations
 
@@ -19,8 +19,6 @@ EPS = 2.2204e-16
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 keys_order = ["AUC_shuffled", "NSS", "AUC_Judd", "AUC_Borji", "KLD", "SIM", "CC"]
 
-_memo = {"key": None, "val": None}
-
 
 def metrics4(y_pred: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
     """(N,4) fp32 columns CC, NSS, KLD, SIM.  Inputs: fp32 or uint8 CUDA tensors, (N,1,H,W) and (N,2,H,W)."""
@@ -32,9 +30,9 @@ def metrics4(y_pred: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
     if y_pred.dtype != y_true.dtype or y_pred.dtype not in (torch.float32, torch.uint8):
         y_pred, y_true = y_pred.float(), y_true.float()
     y_pred, y_true = y_pred.contiguous(), y_true.contiguous()
-    key = (y_pred.data_ptr(), y_pred._version, y_true.data_ptr(), y_true._version, tuple(y_pred.shape), y_pred.dtype)
-    if _memo["key"] == key:
-        return _memo["val"]
+    if y_pred.dtype == torch.float32:                 # float4 loads: a view into the middle of a buffer is re-based
+        y_pred = y_pred.clone() if y_pred.data_ptr() % 16 else y_pred
+        y_true = y_true.clone() if y_true.data_ptr() % 16 else y_true
     n, _, h, w = y_pred.shape
     out = torch.empty((n, 4), dtype=torch.float32, device=y_pred.device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(y_pred.device).cuda_stream)
@@ -43,7 +41,6 @@ def metrics4(y_pred: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
         m = min(step, n - i)
         _ext.call("uavsal_metrics4", y_pred[i:i + m].data_ptr(), y_true[i:i + m].data_ptr(),
                   0 if y_pred.dtype == torch.float32 else 1, m, h, w, None, out[i:i + m].data_ptr(), stream)
-    _memo["key"], _memo["val"] = key, out
     return out
 
 
@@ -85,7 +82,12 @@ def metric_auc_j(y_pred, y_true, jitter=1):
     p, t, dev = _auc_inputs(y_pred, y_true)
     n, _, h, w = p.shape
     out = torch.empty((n,), dtype=torch.float32, device=dev)
-    _ext.call("uavsal_auc_judd", p.data_ptr(), t.data_ptr(), n, h, w, out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    # frames with more than 4096 fixations are sorted in this workspace instead of shared memory (the reference has no cap, :53-74)
+    ws_bytes = int(_ext.load().uavsal_auc_judd_workspace(n, h, w))
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    _ext.call("uavsal_auc_judd", p.data_ptr(), t.data_ptr(), n, h, w, out.data_ptr(), ws.data_ptr(), ws_bytes,
+              ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    ws.record_stream(torch.cuda.current_stream(dev))
     return out.unsqueeze(1)
 
 
@@ -268,7 +270,20 @@ def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_
             else:
                 salmap = salmap[:, :, :, :nframes].transpose((3, 2, 0, 1))
             fixmap = np.concatenate((fixmap[:, :, :, :nframes], fixpts[:, :, :, :nframes]), axis=2).transpose((3, 2, 0, 1))
+            # CC / NSS / KLD / SIM come out of one fused launch per batch; they draw no random numbers, so computing them ahead of
+            # the reference's metric-major loop (:541-561) leaves the generator order of the sampled AUCs untouched
+            fused = [m for m in ("CC", "NSS", "KLD", "SIM") if m in keys_order]
+            if fused:
+                col = {"CC": 0, "NSS": 1, "KLD": 2, "SIM": 3}
+                for b in range(math.ceil(nframes / batch_size)):
+                    ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
+                    itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
+                    m4 = metrics4(ipred.to(device), itrue.to(device)).cpu()
+                    for m in fused:
+                        iscores[b * batch_size:(b + 1) * batch_size, keys_order.index(m)] = m4[:, col[m]]
             for k, metric in enumerate(keys_order):
+                if metric in fused:
+                    continue
                 func = metrics[metric]
                 for b in range(math.ceil(nframes / batch_size)):
                     ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()

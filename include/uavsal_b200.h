@@ -212,8 +212,13 @@ int uavsal_letterbox_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst,
 /* ---- utils_score_torch.metric_auc_j (53-88), deterministic part: S = min-max normalised pred (fp32, as :83), fixations =
  *      truth channel 1 > 0.5; out[n] = AUC-Judd (NaN when the map has no positive value or the frame no fixation, :54).
  *      The reference's optional jitter (:82, global torch generator) is added to `pred` by the caller.  pred (n,1,h,w),
- *      truth (n,2,h,w) fp32.  At most 4096 fixations per frame (more: NaN). */
-int uavsal_auc_judd(const float* pred, const float* truth, int n, int h, int w, float* out, void* stream);
+ *      truth (n,2,h,w) fp32.  Frames with up to 4096 fixations are sorted in shared memory; the reference has no cap
+ *      (:53-74), so maps of more than 4096 pixels must come with `workspace` (16-byte aligned device memory of at least
+ *      uavsal_auc_judd_workspace(n,h,w) bytes, contents irrelevant) in which denser frames are sorted instead; without it
+ *      the call is refused (UAVSAL_EINVAL) rather than answering NaN for such a frame. */
+int64_t uavsal_auc_judd_workspace(int n, int h, int w);
+int uavsal_auc_judd(const float* pred, const float* truth, int n, int h, int w, float* out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 
 /* ---- auc_b (91-120) / auc_s (135-159): sampled AUC with thresholds k*step below the largest sample.  The random pixel
  *      indices are the CALLER's draw (the reference uses the global numpy generator, :103 / :143-144):

@@ -249,6 +249,74 @@ def test_post_u8_and_metrics(cuda, gold_dir):
     assert ((mine - ref).abs() / ref.abs()).max() < 1e-4
 
 
+def test_convlstm_config3_shape_pair_mode(cuda):
+    """BASELINE config #3's shape - hidden 256 ch at 45x80, batch 8 (model_convlstm.py:111-126, 168-218) - is the one that
+    runs the cta_group::2 pair-mode instantiation of the implicit-GEMM kernel with the fused LSTM cell epilogue (tiles_m x
+    tiles_n >= 148); the smaller recurrence tests all take the single-CTA path.  Two steps from a non-zero state against the
+    oracle: every h of the output sequence and the final (h, c), relative L2 <= 2e-4 and max-abs <= 1e-3."""
+    from iip_uavsal_saliency_b200.model_convlstm import ConvLSTM
+    torch.manual_seed(33)
+    net = ConvLSTM((45, 80), 256, 256, (3, 3), 1, batch_first=True, bias=False).cuda().set_mode(engine="tc")
+    x = torch.randn(8, 2, 256, 45, 80)
+    h0, c0 = torch.randn(8, 256, 45, 80) * 0.5, torch.randn(8, 256, 45, 80) * 0.5
+    y, (hh, cc) = net(x.cuda(), [[h0.cuda(), c0.cuda()]])
+    w = net.cell_list[0].rnn_conv.weight.detach().cpu()
+    ry, (rh, rc) = cpu_ref.lstm_sequence(w, None, x, h0, c0)
+    assert y.shape == (8, 2, 256, 45, 80) and torch.equal(hh, y[:, -1])
+    for mine, ref, what in ((y, ry, "h sequence"), (hh, rh, "h last"), (cc, rc, "c last")):
+        assert _rel(mine, ref) < KERNEL_TOL, (what, _rel(mine, ref))
+        assert (mine.cpu() - ref).abs().max().item() < 1e-3, what
+    # a second call continues from the returned state (ConvLSTM.forward's [h, c] contract)
+    y2, (h2, c2) = net(x[:, :1].cuda(), [[hh, cc]])
+    r2, (rh2, rc2) = cpu_ref.lstm_sequence(w, None, x[:, :1], rh, rc)
+    assert _rel(y2, r2) < 2 * KERNEL_TOL and _rel(c2, rc2) < 2 * KERNEL_TOL
+
+
+def test_metrics_kernel_variants(cuda):
+    """Every kernel behind uavsal_metrics4 against the oracle (1e-4 relative, the north-star band): the TMEM-resident persistent
+    kernel with more pairs than co-resident clusters (each cluster loops over several pairs: ring / barrier phase reuse), real-valued
+    (not uint8-valued) maps, uint8 storage, a 720x1280 map (streaming kernel), misaligned views (register kernel: cp.async.bulk
+    needs 16-byte aligned planes), and every option value on the same input."""
+    from iip_uavsal_saliency_b200 import _ext, utils_score_torch as us
+
+    def check(pred, true, what):
+        ref = cpu_ref.metrics4(pred.float(), true.float())
+        mine = us.metrics4(pred.cuda(), true.cuda()).cpu()
+        rel = ((mine - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+        assert rel < 1e-4, (what, rel)
+        return mine
+
+    pred, true = synth.make_metric_pairs(45, 360, 640, seed=9)
+    pred, true = torch.from_numpy(pred), torch.from_numpy(true)
+    base = check(pred, true, "resident fp32, 45 pairs")
+    check(pred.to(torch.uint8), true.to(torch.uint8), "resident uint8")
+    rs = torch.Generator().manual_seed(4)
+    noisy_p = pred[:5] / 255.0 + 0.01 * torch.rand(5, 1, 360, 640, generator=rs)
+    noisy_t = true[:5].clone()
+    noisy_t[:, 0] = noisy_t[:, 0] / 255.0 * 0.7 + 0.003 * torch.rand(5, 360, 640, generator=rs)
+    check(noisy_p, noisy_t, "resident fp32, real-valued maps")
+    lib = _ext.load()
+    try:
+        for opt in (1, 0):                                           # streaming / register-batched kernels on the same pairs
+            lib.uavsal_set_option(9, opt)
+            other = us.metrics4(pred[:9].cuda(), true[:9].cuda()).cpu()
+            assert ((other - base[:9]).abs() / base[:9].abs().clamp_min(1e-6)).max().item() < 2e-5, opt
+    finally:
+        lib.uavsal_set_option(9, 2)
+    big_p, big_t = synth.make_metric_pairs(2, 720, 1280, seed=10)
+    check(torch.from_numpy(big_p), torch.from_numpy(big_t), "720x1280 (streaming kernel)")
+    # misaligned storage: a view that starts 4 bytes (uint8) / 4 bytes (fp32: one element) into its buffer
+    pu, tu = pred[:3].to(torch.uint8).cuda(), true[:3].to(torch.uint8).cuda()
+    bufp = torch.empty(pu.numel() + 16, dtype=torch.uint8, device="cuda")
+    buft = torch.empty(tu.numel() + 16, dtype=torch.uint8, device="cuda")
+    vp, vt = bufp[4:4 + pu.numel()].view_as(pu), buft[4:4 + tu.numel()].view_as(tu)
+    vp.copy_(pu); vt.copy_(tu)
+    assert vp.data_ptr() % 16 == 4
+    mis = us.metrics4(vp, vt).cpu()
+    assert ((mis - base[:3]).abs() / base[:3].abs().clamp_min(1e-6)).max().item() < 2e-5
+    torch.cuda.synchronize()
+
+
 def test_block_modules_against_oracle(cuda):
     from iip_uavsal_saliency_b200 import model as M
     torch.manual_seed(6)
@@ -516,9 +584,66 @@ def test_eval_driver_reproduces_reference_score_files(cuda, gold_dir, tmp_path):
     assert np.array_equal(again["UAVSal"]["vidB"], res["UAVSal"]["vidB"])
 
 
+def test_auc_judd_dense_fixations_have_no_cap(cuda):
+    """utils_score_torch.py:53-74 sorts however many fixations a frame has.  Frames above the 4096 thresholds the kernel sorts in
+    shared memory (dense fixation / mouse-click ground truth) take the global-memory workspace path: 6000 of 14400 pixels at
+    90x160, 14400 of 230400 at 360x640 (with ties: uint8-valued saliency), next to a sparse frame in the same batch."""
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    rs = np.random.RandomState(21)
+    for (h, w, nfix, quant) in [(90, 160, 6000, False), (360, 640, 14400, True), (90, 160, 4097, True)]:
+        p = torch.from_numpy(rs.rand(2, 1, h, w).astype(np.float32))
+        if quant:
+            p = torch.round(p * 255)
+        t = torch.zeros(2, 2, h, w)
+        t[0, 1].view(-1)[torch.from_numpy(rs.choice(h * w, nfix, replace=False))] = 1.0
+        t[1, 1].view(-1)[torch.from_numpy(rs.choice(h * w, 40, replace=False))] = 1.0
+        out = us.metric_auc_j(p.cuda(), t.cuda(), jitter=0).cpu().numpy().ravel()
+        ref = cpu_ref.metric_auc_j(p, t, jitter=0).numpy().ravel()
+        assert np.isfinite(ref).all()
+        np.testing.assert_allclose(out, ref, atol=1e-5, rtol=0, err_msg=str((h, w, nfix)))
+
+
+def test_metrics_on_successive_equal_shaped_batches(cuda, gold_dir, tmp_path):
+    """The reference's evaluation loop (utils_score_torch.py:541-561) is metric-major, batch-minor and builds fresh device tensors
+    for every batch: equal-shaped batches land on the SAME addresses (caching allocator).  Each batch must get its own scores
+    (a result cache keyed on pointers / versions returns batch 0's scores for batch 1).  Direct calls first, then the driver
+    with nframes > 2 * batch_size against the reference-generated score files."""
+    from iip_uavsal_saliency_b200 import mat73
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    pa, ta = synth.make_metric_pairs(4, 72, 128, seed=31)
+    pb, tb = synth.make_metric_pairs(4, 72, 128, seed=32)
+    for fn, rf in ((us.metric_cc, cpu_ref.metric_cc), (us.metric_nss, cpu_ref.metric_nss), (us.metric_kl, cpu_ref.metric_kl),
+                   (us.metric_sim, cpu_ref.metric_sim)):
+        got = []
+        for pr, tr in ((pa, ta), (pb, tb), (pa, ta)):
+            got.append(fn(torch.from_numpy(pr).cuda(), torch.from_numpy(tr).cuda()).cpu().numpy())      # fresh temporaries, as :549-551
+        for g_, (pr, tr) in zip(got, ((pa, ta), (pb, tb), (pa, ta))):
+            np.testing.assert_allclose(g_, rf(torch.from_numpy(pr), torch.from_numpy(tr)).numpy(), rtol=1e-4, atol=1e-6)
+        assert not np.allclose(got[0], got[1])
+    # in-place edit through a raw pointer / copy_ of the same tensor object: the scores follow the content
+    x = torch.from_numpy(pa).cuda()
+    y = torch.from_numpy(ta).cuda()
+    first = us.metric_cc(x, y).cpu().numpy()
+    x.copy_(torch.from_numpy(pb))
+    y.copy_(torch.from_numpy(tb))
+    np.testing.assert_allclose(us.metric_cc(x, y).cpu().numpy(), cpu_ref.metric_cc(torch.from_numpy(pb), torch.from_numpy(tb)).numpy(), rtol=1e-4, atol=1e-6)
+    assert not np.allclose(first, us.metric_cc(x, y).cpu().numpy())
+    # the driver: 5 frames in batches of 2, 2, 1 (two equal-shaped batches of different frames)
+    g = np.load(os.path.join(gold_dir, "eval_driver.npz"))
+    root, sal = str(tmp_path) + "/data/", str(tmp_path) + "/res/"
+    synth.make_eval_dataset(root, sal, 0)
+    keys = ["NSS", "KLD", "SIM", "CC"]
+    res = us.evalscores_vid_torch(root, sal, "UAV2", ["UAVSal"], keys_order=keys, batch_size=2)
+    for name in ("vidA", "vidB"):
+        mine = mat73.loadmat(sal + "Scores/UAVSal/Score_%s.mat" % name)["iscore"]
+        assert mine.shape == (5, 4) and np.array_equal(mine, res["UAVSal"][name])
+        for k, key in enumerate(keys):
+            np.testing.assert_allclose(mine[:, k], g[name][:, list(g["keys"]).index(key)], atol=1e-6, rtol=1e-4, err_msg="%s %s" % (name, key))
+
+
 def test_frontend_and_auc_edge_cases(cuda):
     """Limits and degenerate inputs of the widened-path kernels: tiny sources, extreme aspect ratios, unsupported widths
-    (error, not a wrong answer), fixation sets beyond the AUC kernel's shared-memory capacity (NaN, documented in the header)."""
+    (error, not a wrong answer), degenerate AUC inputs."""
     from iip_uavsal_saliency_b200 import utils_data as ud
     from iip_uavsal_saliency_b200 import utils_score_torch as us
     rs = np.random.RandomState(9)
@@ -530,10 +655,11 @@ def test_frontend_and_auc_edge_cases(cuda):
         ud.letterbox_frames(rs.randint(0, 256, (1, 8, 8, 3)).astype(np.uint8), 16, 5000)
     with pytest.raises(ValueError):
         ud.letterbox_frames(np.zeros((1, 8, 8, 4), np.uint8), 16, 16)
-    # AUC: dense fixation plane (> 4096 fixations) -> NaN; constant map -> NaN; a single fixation works
+    # AUC: every pixel a fixation -> NaN (the reference divides by n_pixels - n_fix = 0, :72); constant map -> NaN; a single
+    # fixation works
     p = torch.rand(3, 1, 90, 160).cuda()
     t = torch.zeros(3, 2, 90, 160)
-    t[0, 1] = 1.0                                   # 14400 fixations
+    t[0, 1] = 1.0                                   # 14400 fixations = every pixel
     t[1, 1, 10, 20] = 1.0                           # one fixation
     t[2, 1, 5, 5] = 1.0
     p[2] = 0.25                                     # constant prediction: min-max normalisation gives all zeros
