@@ -23,6 +23,7 @@ ACT = [P, L, I]          # (pointer, plane, ld)
 _SIGNATURES = {
     "uavsal_device_ok": [I],
     "uavsal_set_option": [I, I],
+    "uavsal_pack_weights": [P, I, I, I, P, P, P, P, F, P, I, I, I, I, P, P, P],
     "uavsal_pack_nchw_f32": [P, I, I, I, I] + ACT + [I, P],
     "uavsal_unpack_nchw_f32": ACT + [I, I, I, I, P, P],
     "uavsal_stem_conv3x3s2": [P, I, I, I, I, P, P] + ACT + [P],

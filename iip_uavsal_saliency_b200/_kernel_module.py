@@ -37,12 +37,21 @@ class KernelModule(nn.Module):
         return c
 
     def _weights_signature(self) -> Tuple:
-        v = 0
-        ptr = 0
-        for t in list(self.parameters()) + list(self.buffers()):
-            v += t._version
-            ptr ^= t.data_ptr()
-        return (v, ptr)
+        """One (data_ptr, _version) pair per parameter / buffer: any re-allocation (``.to()``, ``.cuda()``) or tracked in-place
+        update (``load_state_dict``, ``copy_``) of any tensor gives a new signature, hence new plans and re-packed weights.
+        Edits the version counter does not see (``p.data.copy_``, raw-pointer writes) need ``invalidate()``."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate(self):
+        """Forget every cached plan and packed weight of this module (and its sub-modules)."""
+        from .engine import invalidate_packed
+        invalidate_packed(self)
+        for m in self.modules():
+            m.__dict__.pop("_plans", None)
+            h = m.__dict__.get("_holder")
+            if h is not None:
+                h.__dict__.pop("_plans", None)
+        return self
 
     def _mode(self) -> Tuple[int, str]:
         return (self.__dict__.get("_terms") or default_terms(), self.__dict__.get("_engine") or default_engine())
@@ -63,12 +72,16 @@ class KernelModule(nn.Module):
         cache = self._plan_cache()
         plan = cache.get(full)
         if plan is None:
-            if len(cache) > 32:
-                cache.clear()
-            dev = key[0]
-            plan = Plan(dev, terms=terms, engine=engine)
-            builder(plan)
-            cache[full] = plan
+            # evict by bytes, least recently used first (every distinct call shape / slot owns an arena)
+            budget = int(os.environ.get("UAVSAL_PLAN_CACHE_GB", "48")) << 30
+            while cache and (len(cache) > 64 or sum(p.arena_bytes for p in cache.values()) > budget):
+                cache.pop(next(iter(cache)))
+            plan = Plan.build(key[0], terms, engine, builder)
+            if plan.device.type == "cuda":
+                torch.cuda.current_stream(plan.device).synchronize()       # weight packing is done before any stream replays the plan
+        else:
+            cache.pop(full)                                                # re-insert: dict order = recency
+        cache[full] = plan
         return plan
 
     # generic single-input, single-output NCHW forward

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from ._kernel_module import KernelModule
-from .engine import F_RELU6, Buf, Plan, fold_bn, out_size, pack_dw
+from .engine import F_RELU6, Buf, Plan, W, fold_bn, out_size, pack_dw
 
 __all__ = ["BasicConv2d", "dwBlock", "init_weights", "emit_stem"]
 
@@ -48,25 +48,30 @@ class BasicConv2d(nn.Sequential):
 
     # ---- plan emission ----
     def folded(self):
+        """(w', b') with the BatchNorm folded in, as torch tensors (reference form; the plans use ``wspec``)."""
         return fold_bn(self[0].weight, self[1])
+
+    def wspec(self) -> W:
+        """This layer's parameters for ``Plan.packed`` (BN fold + layout + hi/lo split happen in uavsal_pack_weights)."""
+        return W(self[0].weight, bn=self[1], owner=self[0])
 
     def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag="", f32_out: bool = False):
         cin, cout, k, stride, dil, groups = self.spec
-        wf, bf = self.folded()
+        ws = self.wspec()
         if k == 1:
             assert stride == 1 and groups == 1
             if out is None:
                 out = plan.alloc_f32(n * h * w, cout) if f32_out else plan.alloc(n * h * w, cout)
-            plan.pw(x, n * h * w, wf.reshape(cout, cin), bf, F_RELU6, out, res=res, tag=tag)
+            plan.pw(x, n * h * w, ws, None, F_RELU6, out, res=res, tag=tag)
             return out, h, w
         if groups == cin and groups == cout:
             ho, wo = out_size(h, stride), out_size(w, stride)
             out = out if out is not None else plan.alloc(n * ho * wo, cout)
-            plan.dw(x, n, h, w, cout, stride, dil, plan.hold(pack_dw(wf)), plan.hold(bf), True, out, tag=tag)
+            plan.dw(x, n, h, w, cout, stride, dil, ws, None, True, out, tag=tag)
             return out, ho, wo
         if groups == 1 and stride == 1 and dil == 1 and k == 3:
             out = out if out is not None else plan.alloc(n * h * w, cout)
-            plan.conv3x3(x, n, h, w, cin, wf, bf, F_RELU6, out, tag=tag)
+            plan.conv3x3(x, n, h, w, cin, ws, None, F_RELU6, out, tag=tag)
             return out, h, w
         raise NotImplementedError("BasicConv2d%r has no sm_100a kernel on the UAVSal path" % (self.spec,))
 
@@ -76,10 +81,9 @@ class BasicConv2d(nn.Sequential):
 
 def emit_stem(plan: Plan, stem: BasicConv2d, x_src: torch.Tensor, kind: int, n, h, w):
     """features[0]: (normalise +) conv3x3 s2 (3->32) + BN + ReLU6 straight from the NCHW/NHWC input tensor."""
-    wf, bf = stem.folded()
     ho, wo = out_size(h, 2), out_size(w, 2)
     out = plan.alloc_f32(n * ho * wo, 32) if plan.f32_hidden else plan.alloc(n * ho * wo, 32)   # features.1 starts with its depthwise conv
-    plan.stem(x_src, kind, n, h, w, wf.permute(2, 3, 1, 0).contiguous(), bf, out, tag="features.0")
+    plan.stem(x_src, kind, n, h, w, stem.wspec(), None, out, tag="features.0")
     return out, ho, wo
 
 
@@ -108,6 +112,9 @@ class dwBlock(KernelModule):
         wf, bf = fold_bn(conv.weight, bn)
         return wf.reshape(wf.shape[0], wf.shape[1]), bf
 
+    def project_wspec(self) -> W:
+        return W(self.conv[-2].weight, bn=self.conv[-1], owner=self.conv[-2])
+
     def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, extra_res: Buf = None, tag=""):
         """``out`` lets the caller place the result in a concat slot.  Returns (Buf, h', w')."""
         inp, oup, hidden, stride, dil, has_expand = self.geom
@@ -118,16 +125,13 @@ class dwBlock(KernelModule):
             fuse = stride == 2 and h * w >= 10000       # per-frame size: the choice must not depend on how many frames are batched
         if has_expand and plan.engine == "tc" and dil == 1 and x.c <= 32 and not x.f32 and fuse:
             # few input channels: expand + depthwise in one kernel, the 6x hidden tensor never reaches HBM
-            w1, b1 = self.conv[0].folded()
-            wdw, bdw = self.conv[1].folded()
             ho, wo = out_size(h, stride), out_size(w, stride)
             cur = plan.alloc(n * ho * wo, hidden)
-            plan.expdw(x, n, h, w, w1.reshape(hidden, inp), b1, stride, pack_dw(wdw), bdw, cur, tag=tag + ".expand+dw")
-            wf, bf = self.project_folded()
+            plan.expdw(x, n, h, w, self.conv[0].wspec(), None, stride, self.conv[1].wspec(), None, cur, tag=tag + ".expand+dw")
             if oup % 8:
                 raise NotImplementedError("project conv with %d outputs is emitted by the readout path" % oup)
             out = out if out is not None else plan.alloc(n * ho * wo, oup)
-            plan.pw(cur, n * ho * wo, wf, bf, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
+            plan.pw(cur, n * ho * wo, self.project_wspec(), None, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
             return out, ho, wo
         if has_expand:
             # the 6x hidden tensor stays fp32 between the expand GEMM and the TMA depthwise kernel (dilation 1 only)
@@ -139,17 +143,15 @@ class dwBlock(KernelModule):
         wide = has_expand and hidden % 128 == 0 and oup % 64 == 0 and oup <= 256          # tcgen05 pair kernel (dwproj.cu)
         narrow = (hidden, oup) == (32, 16) and not self.use_res_connect                    # features.1: fp32 FFMA kernel (dwproj32.cu)
         if fuse_dp and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and (wide or narrow):
-            wdw, bdw = self.conv[i].folded()
-            wf, bf = self.project_folded()
             out = out if out is not None else plan.alloc(n * h * w, oup)
-            plan.dwproj(cur, n, h, w, pack_dw(wdw), bdw, wf, bf, out, res=x if self.use_res_connect else None, tag=tag + ".dw+project")
+            plan.dwproj(cur, n, h, w, self.conv[i].wspec(), None, self.project_wspec(), None, out, res=x if self.use_res_connect else None,
+                        tag=tag + ".dw+project")
             return out, h, w
         cur, ho, wo = self.conv[i]._emit(plan, cur, n, h, w, tag=tag + ".dw")
-        wf, bf = self.project_folded()
         if oup % 8:
             raise NotImplementedError("project conv with %d outputs is emitted by the readout path" % oup)
         out = out if out is not None else plan.alloc(n * ho * wo, oup)
-        plan.pw(cur, n * ho * wo, wf, bf, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
+        plan.pw(cur, n * ho * wo, self.project_wspec(), None, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
         return out, ho, wo
 
     def forward(self, x):

@@ -447,6 +447,8 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
             int batch, int H, int W, const uint16_t* wgt, int cout, const float* bias, int flags, int terms, int epi,
             Act x, Act hprev, float* c_state, ActW out, int out_nimg, int out_mul, int out_off, cudaStream_t s, const char* what,
             int wk_total = 0, int wk_off = 0, const float* gx = nullptr, float* raw_out = nullptr) {
+    const bool v2 = !(terms & UAVSAL_TERMS_GEN1) && g_tc_version == 2;      // per-call kernel generation (cross-check engine "tc1")
+    terms &= 0xFF;
     UAVSAL_REQUIRE(c0 % kBK == 0 && c1 % kBK == 0 && c0 > 0, UAVSAL_ENOTSUP, "%s: channels must be multiples of 64", what);
     UAVSAL_REQUIRE(cout % 8 == 0 && (terms == 1 || terms == 3), UAVSAL_EINVAL, "%s: bad cout/terms", what);
     TcArgs g{};
@@ -458,7 +460,6 @@ int conv_tc(Act a0, int n0img, int a0_mul, int a0_off, int c0, Act a1, int n1img
     g.a0_mul = a0_mul; g.a0_off = a0_off; g.a1_mul = a1_mul; g.a1_off = a1_off; g.out_mul = out_mul; g.out_off = out_off;
     g.M = batch * H * W; g.N = cout; g.bn = pick_bn(cout);
     const int tiles_m_ = batch * g.tiles_x * g.tiles_y;
-    const bool v2 = g_tc_version == 2;
     UAVSAL_REQUIRE(v2 || epi != EPI_RAW, UAVSAL_ENOTSUP, "%s: raw output needs the persistent kernel", what);
     if (v2) {   // small problems (one image per step in the recurrence): narrower N tiles so that more SMs get a tile
         while (g.bn > 64 && g.bn % 128 == 0 && tiles_m_ * div_up(cout, g.bn) < 100) g.bn /= 2;
@@ -532,7 +533,9 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
                    const float* bias, int flags, int terms, const uint16_t* res, int64_t res_plane, int res_ld,
                    uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
     const bool f32out = flags & UAVSAL_F_OUT_F32;
-    UAVSAL_REQUIRE(!f32out || (g_tc_version == 2 && !(flags & UAVSAL_F_SIGMOID)), UAVSAL_ENOTSUP, "pw_gemm: fp32 output needs the persistent kernel");
+    const bool v2 = !(terms & UAVSAL_TERMS_GEN1) && g_tc_version == 2;
+    terms &= 0xFF;
+    UAVSAL_REQUIRE(!f32out || (v2 && !(flags & UAVSAL_F_SIGMOID)), UAVSAL_ENOTSUP, "pw_gemm: fp32 output needs the persistent kernel");
     UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && (f32out ? (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_ld % 4 == 0) : act_ok16(out, out_plane, out_ld)) && wgt &&
                        (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 && m > 0 && k > 0 && n > 0 && k % 8 == 0 &&
                        kpad % 8 == 0 && kpad >= k && n % 8 == 0 && a_ld >= k && out_ld >= n,
@@ -549,10 +552,10 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
     CUtensorMap tA, tB;
     int rc = map_pw(&tA, Act{a, a_plane, a_ld}, m, k);
     if (rc) return rc;
-    const bool cl = g_tc_version == 2 && want_cluster(g, div_up(m, kBM));
+    const bool cl = v2 && want_cluster(g, div_up(m, kBM));
     rc = map_w(&tB, wgt, n, kpad, cl ? g.bn / 2 : g.bn);
     if (rc) return rc;
-    if (g_tc_version == 2) {
+    if (v2) {
         CUtensorMap tO = tA;                                   // (the copy-out uses the LSU path; the map is kept for TMA-store experiments)
         if (!f32out) rc = map_out_pw(&tO, g.out, m, n);
         if (rc) return rc;
@@ -571,7 +574,7 @@ int uavsal_conv3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h
     UAVSAL_REQUIRE(act_ok16(in, in_plane, in_ld) && act_ok16(out, out_plane, out_ld) && wgt && n > 0 && h > 0 && w > 0 &&
                        in_ld >= c && out_ld >= cout,
                    UAVSAL_EINVAL, "conv3x3: bad arguments");
-    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && in_plane != 0), UAVSAL_EINVAL, "conv3x3: terms must be 1, or 3 with a lo plane");
+    UAVSAL_REQUIRE((terms & 0xFF) == 1 || ((terms & 0xFF) == 3 && in_plane != 0), UAVSAL_EINVAL, "conv3x3: terms must be 1, or 3 with a lo plane");
     Act a{in, in_plane, in_ld};
     return conv_tc(a, n, 1, 0, c, a, n, 1, 0, 0, n, h, w, wgt, cout, bias, flags, terms, EPI_STD, Act{}, Act{}, nullptr,
                    ActW{out, out_plane, out_ld}, n, 1, 0, (cudaStream_t)stream, "conv3x3");
@@ -582,7 +585,7 @@ static int twa_sequence_one(Act X, Act H0, ActW S, int t_steps, int h, int w, in
                             cudaStream_t s) {
     Act SA{S.p, S.plane, S.ld};
     int rc;
-    if (gx_workspace && g_tc_version == 2) {
+    if (gx_workspace && !(terms & UAVSAL_TERMS_GEN1) && g_tc_version == 2) {
         // hoisted: G_x = W_x * x_t for ALL steps in one batched implicit GEMM (fp32 pre-activations), then per step only the
         // recurrent half W_h * h_{t-1} (K = 9c instead of 18c) with G_x[t] added in the epilogue before the gate
         rc = conv_tc(X, t_steps, 1, 0, c, X, t_steps, 1, 0, 0, t_steps, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
@@ -620,11 +623,11 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
                    UAVSAL_EINVAL, "twa_sequence: bad arguments");
     UAVSAL_REQUIRE((wgt != nullptr) != (wgt_f32 != nullptr), UAVSAL_EINVAL,
                    "twa_sequence: pass exactly one of wgt (tcgen05) / wgt_f32 (SIMT)");
-    UAVSAL_REQUIRE(wgt_f32 || terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
+    UAVSAL_REQUIRE(wgt_f32 || (terms & 0xFF) == 1 || ((terms & 0xFF) == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
                    "twa_sequence: terms=3 needs lo planes");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t hw = (int64_t)h * w;
-    if (!wgt_f32 && gx_workspace && g_tc_version == 2 && g_twa_resident && c % 64 == 0 && c <= 512) {
+    if (!wgt_f32 && gx_workspace && !(terms & UAVSAL_TERMS_GEN1) && g_tc_version == 2 && g_twa_resident && c % 64 == 0 && c <= 512) {
         // all sequences of the batch advance together: W_x * x hoisted over batch*t_steps frames, then per step one launch of the
         // resident-A kernel (twa_step.cu) with the batch in blockIdx.z
         Act X{x, x_plane, x_ld}, H0{h0, h0_plane, h0_ld}, SA{seq_out, seq_plane, seq_ld};
@@ -664,7 +667,7 @@ int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const
     ActW S{seq_out, seq_plane, seq_ld};
     cudaStream_t s = (cudaStream_t)stream;
     if (wgt_f32) return lstm_sequence_simt(X, H0, c_state, b, t_steps, h, w, cin, ch, wgt_f32, bias, S, s);
-    UAVSAL_REQUIRE(terms == 1 || (terms == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
+    UAVSAL_REQUIRE((terms & 0xFF) == 1 || ((terms & 0xFF) == 3 && x_plane && h0_plane && seq_plane), UAVSAL_EINVAL,
                    "convlstm_sequence: terms=3 needs lo planes");
     Act SA{seq_out, seq_plane, seq_ld};
     for (int t = 0; t < t_steps; ++t) {

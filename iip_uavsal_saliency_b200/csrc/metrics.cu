@@ -6,6 +6,7 @@
 // two quantities that need the pass-1 statistics element-wise (KLD terms, SIM min-sum).  Element-wise
 // arithmetic follows the reference's fp32 expressions; accumulation is fp64.
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -485,29 +486,38 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Resident variant (default for maps of 32 Ki .. 256 Ki pixels, i.e. the 360x640 evaluation maps): every input byte crosses
-// HBM exactly ONCE.  The streaming kernel above re-reads pred + density from L2 in pass 2; with tens of pairs in flight the
-// re-read misses L2 (ncu, round 1: 1.63x the algorithmic DRAM bytes).  Here a cluster of 8 persistent CTAs (one per SM) owns a
-// pair; a producer warp streams 2048-pixel chunks of the three planes through a 192 KiB shared-memory ring with
-// cp.async.bulk (evict-first: nothing is read twice), 16 consumer warps reduce the pass-1 moments from the ring AND stash
-// every (pred, density) value they touched in TENSOR MEMORY (tcgen05.st: 28 800 pixels x 2 planes x 4 B = 225 KiB of the
-// SM's 256 KiB; a warp only ever re-reads the cells it wrote, so the lane-quarter rule of tcgen05.ld/st costs nothing).
-// Pass 2 (KLD / SIM terms, which need the pass-1 statistics element-wise) runs out of tensor memory while the producer
-// is already filling the ring with the next pair - shared memory holds no resident data, so the HBM stream never stops for
-// the statistics exchange.  The cluster exchanges its 11 pass-1 partials by DSMEM pushes + remote mbarrier arrives (no
-// barrier.cluster in the loop: the producer warp never has to join it).
+// HBM ONCE.  The streaming kernel above re-reads pred + density in pass 2; with 74 pairs in flight the re-read misses L2
+// (ncu, round 1: 1.63x the algorithmic DRAM bytes).  Here:
+//   * persistent clusters of 8 CTAs, one CTA per SM; every CTA runs TWO independent groups (8 consumer warps + a producer warp
+//     each, own ring / barriers / TMEM half), group g of a cluster's CTAs owning pair 2c + g: while one group waits for its
+//     statistics exchange the other streams (a cluster's pair is one latency chain: load -> moments -> exchange -> pass 2).
+//     The producer warp of a group streams 2048-pixel chunks of the three planes through a 4-stage shared-memory ring with
+//     cp.async.bulk, the consumer warps reduce the pass-1 moments from the ring;
+//   * the prediction values a thread touched are stashed in TENSOR MEMORY (tcgen05.st; 28 800 px x 4 B = 112.5 KiB of the group's
+//     256 columns = 128 KiB; a warp only re-reads cells it wrote itself, so the lane-quarter rule of tcgen05.ld/st costs
+//     nothing) and never read from memory again;
+//   * the density plane is loaded `evict_last` in pass 1 and comes back through the same ring in pass 2: with ~30 clusters in
+//     flight the hot set is ~28 MB (three chunks per ring stage in pass 2), far inside the 126 MB L2 (the streaming kernel's was 136 MB);
+//   * the cluster exchanges its 11 pass-1 partials with st.async (remote store + complete_tx on the receiver's mbarrier): no
+//     barrier.cluster, no cluster-scope fence, and the producer warp never has to join anything;
+//   * arithmetic is packed (FFMA2 / FADD2 on pixel pairs, 3-input min / max), the KLD term is th * (lg2(th) - lg2(ph + EPS))
+//     (the reference's second +EPS, inside the log, only matters where th / ph < 1e-9, i.e. for < 4e-8 of the sum).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTmWarps = 16;                       // consumer warps
+constexpr int kTmWarps = 8;                        // consumer warps per group
 constexpr int kTmConsumers = kTmWarps * 32;
-constexpr int kTmThreads = kTmConsumers + 32;      // + producer warp (also owns the TMEM allocation)
-constexpr int kTmChunkPx = kTmConsumers * 4;       // 2048 pixels per plane per stage: one float4 / uchar4 per consumer thread
-constexpr int kTmStages = 8;
+constexpr int kTmGroupThreads = kTmConsumers + 32; // + the group's producer warp
+constexpr int kTmGroups = 2;                       // two independent groups per CTA, each working on its own pair
+constexpr int kTmThreads = kTmGroups * kTmGroupThreads;
+constexpr int kTmChunkPx = kTmConsumers * 8;       // 2048 pixels per plane per stage: two float4 / uchar4 per consumer thread
+constexpr int kTmStages = 4;
 constexpr int kTmMaxChunks = 16;                   // 128 TMEM columns per warp / 8 columns per chunk
+constexpr int kTmCols = 256;                      // TMEM columns per group (the CTA allocates all 512)
 
 template <typename T>
 struct TmSmem {
     alignas(128) T ring[kTmStages][3][kTmChunkPx];
-    double stats[2][kCluster][S_COUNT];            // [pair parity][source rank][item], pushed by every CTA of the cluster
-    double part2[2][kCluster][2];                  // pass-2 partials, pushed to rank 0
+    double stats[2][kCluster][S_COUNT];            // [pair parity][source rank][item], st.async'ed by every CTA of the cluster
+    double part2[2][kCluster][2];                  // pass-2 partials, st.async'ed to rank 0
     double wpart1[kTmWarps][S_COUNT];
     double wpart2[kTmWarps][2];
     double tot[S_COUNT];
@@ -525,20 +535,20 @@ __device__ __forceinline__ uint32_t m_mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void m_st_remote_f64(uint32_t addr_cluster, double v) {
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr_cluster), "d"(v) : "memory");
-}
-// the remote stores above are ordered before this arrive (release at cluster scope); the waiter acquires at cluster scope
-__device__ __forceinline__ void m_bar_arrive_remote(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void m_bar_wait_cluster(uint64_t* bar, uint32_t parity) {
+// wait with a suspend-time hint: the warp sleeps in hardware (up to ~10 us per try) instead of spinning through issue slots that the
+// CTA's other group needs
+__device__ __forceinline__ void m_bar_wait_sleep(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     for (uint32_t it = 0; !ok; ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity) : "memory");
-        if (it > (1u << 26)) __trap();
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity), "r"(10000u) : "memory");
+        if (it > (1u << 21)) __trap();
     }
+}
+// remote 8-byte store whose completion is counted (complete_tx, 8 bytes) on an mbarrier of the destination CTA
+__device__ __forceinline__ void m_st_async_f64(uint32_t addr_cluster, double v, uint32_t bar_cluster) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(addr_cluster), "l"(__double_as_longlong(v)), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void m_tmem_st8(uint32_t taddr, const float v[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -548,110 +558,171 @@ __device__ __forceinline__ void m_tmem_ld8(uint32_t taddr, float v[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ float m_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 8 pixels of one plane of a ring stage: elements [4*tid, 4*tid+4) and [kTmChunkPx/2 + 4*tid, ...)
+template <typename T>
+__device__ __forceinline__ void m_lds8(const T* plane, int tid, float v[8]) {
+    lds4v<T>(plane + 4 * tid, v);
+    lds4v<T>(plane + kTmChunkPx / 2 + 4 * tid, v + 4);
+}
 
 template <typename T>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kTmThreads, 1)
 metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, int n_pairs, float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t m_smem_raw[];
-    TmSmem<T>& sm = *reinterpret_cast<TmSmem<T>*>(m_smem_raw);
+    const int grp = threadIdx.x / kTmGroupThreads;                       // group: own pairs, ring, barriers, TMEM half
+    TmSmem<T>& sm = reinterpret_cast<TmSmem<T>*>(m_smem_raw)[grp];
+    TmSmem<T>& sm0 = reinterpret_cast<TmSmem<T>*>(m_smem_raw)[0];
     const int rank = (int)m_cluster_rank();
-    const int cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // "virtual clusters": group g of the CTAs of cluster c works on pairs 2c + g, 2c + g + 2 * clusters, ...
+    const int cid = kTmGroups * (blockIdx.x / kCluster) + grp, ncl = kTmGroups * (gridDim.x / kCluster);
+    const int tid = threadIdx.x % kTmGroupThreads, lane = tid & 31, warp = tid >> 5;      // within the group
+    const int warp_abs = threadIdx.x >> 5;
     const bool producer = warp == kTmWarps;
+    const int bar_id = 1 + grp;                                          // named barrier of the group's consumers
 
     if (tid == 0) {
         for (int s = 0; s < kTmStages; ++s) { m_bar_init(sm.full + s, 1); m_bar_init(sm.empty + s, kTmWarps); }
-        for (int s = 0; s < 2; ++s) { m_bar_init(sm.statbar + s, kCluster * S_COUNT); m_bar_init(sm.p2bar + s, kCluster * 2); }
+        for (int s = 0; s < 2; ++s) { m_bar_init(sm.statbar + s, 1); m_bar_init(sm.p2bar + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (producer) {        // all 512 columns: the (pred, density) values of this CTA's slice live there between the passes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    if (warp_abs == kTmWarps) {   // the SM's whole tensor memory: the prediction values of both groups' slices live there between the passes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m_smem_u32(&sm0.tmem_base)), "r"((uint32_t)(kTmGroups * kTmCols)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // every CTA's barriers exist before the first remote arrive
+    // every CTA's barriers exist before the first remote complete_tx
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    // warp w may touch TMEM lanes 32*(w%4) .. +31; the four warps of a lane quarter take 128 columns each
-    const uint32_t tcol = sm.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    // a warp may touch TMEM lanes 32 * (warp index in the CTA % 4) .. +31.  A group's 8 consumer warps are consecutive, so
+    // each lane quarter occurs twice among them: the first four warps take the lower 128 columns of the group's 256, the others
+    // the upper 128
+    const uint32_t tcol = sm0.tmem_base + ((uint32_t)((warp_abs & 3) * 32) << 16) + (uint32_t)(grp * kTmCols + (warp >> 2) * 128);
 
     // this CTA's chunks of a pair: rank, rank + 8, ...
     const int nchunks = (hw + kTmChunkPx - 1) / kTmChunkPx;
     const int mine = (nchunks - rank + kCluster - 1) / kCluster;          // <= kTmMaxChunks (launcher)
     auto chunk_of = [&](int i) { return rank + i * kCluster; };
     auto chunk_len = [&](int c) { return min(kTmChunkPx, hw - c * kTmChunkPx); };
+    // bytes of a (possibly partial) chunk land in two halves: elements [0, min(len, half)) and [half, len)
+    constexpr int kHalf = kTmChunkPx / 2;
 
     if (producer) {
         if (lane == 0) {
-            uint64_t pol_first;
+            uint64_t pol_first, pol_keep;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
             uint32_t it = 0;
             for (int pair = cid; pair < n_pairs; pair += ncl) {
                 const T* P = pred + (int64_t)pair * hw;
                 const T* D = truth + (int64_t)pair * 2 * hw;
                 const T* Fx = D + hw;
-                for (int i = 0; i < mine; ++i, ++it) {
+                for (int i = 0; i < mine; ++i, ++it) {                   // pass 1: P, D, F
                     const int s = it % kTmStages;
-                    m_bar_wait(sm.empty + s, ((it / kTmStages) & 1) ^ 1);
+                    m_bar_wait_sleep(sm.empty + s, ((it / kTmStages) & 1) ^ 1);
                     const int c = chunk_of(i);
                     const uint32_t bytes = (uint32_t)chunk_len(c) * sizeof(T);
+                    const int64_t off = (int64_t)c * kTmChunkPx;
                     m_bar_expect(sm.full + s, bytes * 3);
-                    m_bulk_load_hint(sm.ring[s][0], P + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
-                    m_bulk_load_hint(sm.ring[s][1], D + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
-                    m_bulk_load_hint(sm.ring[s][2], Fx + (int64_t)c * kTmChunkPx, bytes, sm.full + s, pol_first);
+                    m_bulk_load_hint(sm.ring[s][0], P + off, bytes, sm.full + s, pol_first);
+                    m_bulk_load_hint(sm.ring[s][1], D + off, bytes, sm.full + s, pol_keep);
+                    m_bulk_load_hint(sm.ring[s][2], Fx + off, bytes, sm.full + s, pol_first);
+                }
+                for (int i = 0; i < mine; i += 3, ++it) {                // pass 2: D again (L2), three chunks per stage
+                    const int s = it % kTmStages;
+                    m_bar_wait_sleep(sm.empty + s, ((it / kTmStages) & 1) ^ 1);
+                    uint32_t total = 0;
+                    for (int u = 0; u < 3 && i + u < mine; ++u) total += (uint32_t)chunk_len(chunk_of(i + u)) * sizeof(T);
+                    m_bar_expect(sm.full + s, total);
+                    for (int u = 0; u < 3 && i + u < mine; ++u) {
+                        const int c = chunk_of(i + u);
+                        m_bulk_load_hint(sm.ring[s][u], D + (int64_t)c * kTmChunkPx, (uint32_t)chunk_len(c) * sizeof(T), sm.full + s, pol_first);
+                    }
                 }
             }
         }
         __syncwarp();
     } else {
-        const int e = tid * 4;                                            // this thread's 4 pixels of every chunk
         uint32_t it = 0;
         int k = 0;
         for (int pair = cid; pair < n_pairs; pair += ncl, ++k) {
             const int par = k & 1;
             const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-            // ------------------------------- pass 1: ring -> moments + TMEM stash -------------------------------
+            if (tid == 0) m_bar_expect(sm.statbar + par, kCluster * S_COUNT * 8);          // this pair's 88 remote stores
+            if (tid == 0 && rank == 0) m_bar_expect(sm.p2bar + par, kCluster * 2 * 8);
+            // ------------------------------- pass 1: ring -> moments, pred -> TMEM -------------------------------
             double s[S_COUNT];
 #pragma unroll
             for (int i = 0; i < S_COUNT; ++i) s[i] = 0.0;
             float mnP = 3.0e38f, mxP = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
-            float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int i = 0; i < mine; ++i, ++it) {
-                const int st = it % kTmStages;
-                m_bar_wait(sm.full + st, (it / kTmStages) & 1);
-                const int len = chunk_len(chunk_of(i));
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (e < len) {
-                    float f[4];
-                    lds4v<T>(&sm.ring[st][0][e], v); lds4v<T>(&sm.ring[st][1][e], v + 4); lds4v<T>(&sm.ring[st][2][e], f);
+            float2 a[7];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float p = v[j], t = v[4 + j];
-                        a[0] += p; a[1] = fmaf(p, p, a[1]); a[2] += t; a[3] = fmaf(t, t, a[3]);
-                        a[4] = fmaf(t, p, a[4]); a[5] += f[j]; a[6] = fmaf(f[j], p, a[6]);
-                        mnP = fminf(mnP, p); mxP = fmaxf(mxP, p); mnT = fminf(mnT, t); mxT = fmaxf(mxT, t);
+            for (int j = 0; j < 7; ++j) a[j] = make_float2(0.f, 0.f);
+            // one chunk: 8 pixels per thread; FULL = every thread's 8 pixels exist (all chunks but a pair's last)
+            auto chunk1 = [&](auto full, int st, int i, int len) {
+                constexpr bool FULL = decltype(full)::value;
+                float p[8], t[8], f[8];
+                m_lds8<T>(sm.ring[st][0], tid, p); m_lds8<T>(sm.ring[st][1], tid, t); m_lds8<T>(sm.ring[st][2], tid, f);
+                const bool v0 = FULL || 4 * tid < len, v1 = FULL || kHalf + 4 * tid < len;           // (len is a multiple of 16)
+                if (!FULL) {
+                    if (!v0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { p[j] = 0.f; t[j] = 0.f; f[j] = 0.f; }
+                    }
+                    if (!v1) {
+#pragma unroll
+                        for (int j = 4; j < 8; ++j) { p[j] = 0.f; t[j] = 0.f; f[j] = 0.f; }
                     }
                 }
-                m_tmem_st8(tcol + (uint32_t)(i * 8), v);                  // warp-collective: executed by every lane, also past the tail
-                __syncwarp();
-                if (lane == 0) m_bar_arrive(sm.empty + st);
-                if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) {    // fold the fp32 run (<= 32 pixels per thread: exact for uint8-valued maps) into fp64
-                    s[S_P] += a[0]; s[S_P2] += a[1]; s[S_T] += a[2]; s[S_T2] += a[3]; s[S_TP] += a[4]; s[S_F] += a[5]; s[S_FP] += a[6];
+                m_tmem_st8(tcol + (uint32_t)(i * 8), p);                             // warp-collective: every lane, also past the tail
 #pragma unroll
-                    for (int j = 0; j < 7; ++j) a[j] = 0.f;
+                for (int j = 0; j < 8; j += 2) {
+                    const float2 pp = make_float2(p[j], p[j + 1]), tt = make_float2(t[j], t[j + 1]), ff = make_float2(f[j], f[j + 1]);
+                    a[0] = __fadd2_rn(a[0], pp); a[1] = __ffma2_rn(pp, pp, a[1]); a[2] = __fadd2_rn(a[2], tt); a[3] = __ffma2_rn(tt, tt, a[3]);
+                    a[4] = __ffma2_rn(tt, pp, a[4]); a[5] = __fadd2_rn(a[5], ff); a[6] = __ffma2_rn(ff, pp, a[6]);
                 }
+                if (v1) {                                                           // all 8 pixels count for the extrema
+                    mnP = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), fminf(fminf(fminf(p[4], p[5]), fminf(p[6], p[7])), mnP));
+                    mxP = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])), mxP));
+                    mnT = fminf(fminf(fminf(t[0], t[1]), fminf(t[2], t[3])), fminf(fminf(fminf(t[4], t[5]), fminf(t[6], t[7])), mnT));
+                    mxT = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])), mxT));
+                } else if (v0) {
+                    mnP = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), mnP); mxP = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), mxP);
+                    mnT = fminf(fminf(fminf(t[0], t[1]), fminf(t[2], t[3])), mnT); mxT = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), mxT);
+                }
+            };
+            for (int i = 0; i < mine; ++i, ++it) {
+                const int st = it % kTmStages;
+                m_bar_wait_sleep(sm.full + st, (it / kTmStages) & 1);
+                const int len = chunk_len(chunk_of(i));
+                if (len == kTmChunkPx) chunk1(std::true_type{}, st, i, len);
+                else chunk1(std::false_type{}, st, i, len);
+                __syncwarp();
+                if (lane == 0) m_bar_arrive(sm.empty + st);                          // every lane's values have been consumed: the stage may be refilled
             }
-            s[S_MINP] = mnP; s[S_MAXP] = mxP; s[S_MINT] = mnT; s[S_MAXT] = mxT;
+            // the fp32 runs end here: <= 4 * kTmMaxChunks = 64 pixels per accumulator lane, so every partial sum of uint8-valued maps
+            // (the reference's own case, utils_score_torch.py:549) is an integer below 2^24, i.e. exact; fp64 from here on
+            s[S_P] = (double)a[0].x + (double)a[0].y; s[S_P2] = (double)a[1].x + (double)a[1].y; s[S_T] = (double)a[2].x + (double)a[2].y;
+            s[S_T2] = (double)a[3].x + (double)a[3].y; s[S_TP] = (double)a[4].x + (double)a[4].y; s[S_F] = (double)a[5].x + (double)a[5].y;
+            s[S_FP] = (double)a[6].x + (double)a[6].y;
+            // warp reduction: extrema in fp32 (exact), sums in fp64
 #pragma unroll
-            for (int i = 0; i < S_COUNT; ++i) {
-                double v = s[i];
-                if (i == S_MINP || i == S_MINT) v = warp_min(v);
-                else if (i == S_MAXP || i == S_MAXT) v = warp_max(v);
-                else v = warp_sum(v);
+            for (int o = 16; o > 0; o >>= 1) {
+                mnP = fminf(mnP, __shfl_xor_sync(0xffffffffu, mnP, o)); mxP = fmaxf(mxP, __shfl_xor_sync(0xffffffffu, mxP, o));
+                mnT = fminf(mnT, __shfl_xor_sync(0xffffffffu, mnT, o)); mxT = fmaxf(mxT, __shfl_xor_sync(0xffffffffu, mxT, o));
+            }
+#pragma unroll
+            for (int i = 0; i < S_MINP; ++i) {
+                const double v = warp_sum(s[i]);
                 if (lane == 0) sm.wpart1[warp][i] = v;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+            if (lane == 0) { sm.wpart1[warp][S_MINP] = mnP; sm.wpart1[warp][S_MAXP] = mxP; sm.wpart1[warp][S_MINT] = mnT; sm.wpart1[warp][S_MAXT] = mxT; }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTmConsumers) : "memory");
             if (tid < kCluster * S_COUNT) {                               // thread (dest, item): this CTA's partial -> CTA `dest`
                 const int item = tid % S_COUNT, dest = tid / S_COUNT;
                 double v = sm.wpart1[0][item];
@@ -660,22 +731,23 @@ metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, in
                     else if (item == S_MAXP || item == S_MAXT) v = fmax(v, sm.wpart1[w][item]);
                     else v += sm.wpart1[w][item];
                 }
-                m_st_remote_f64(m_mapa(m_smem_u32(&sm.stats[par][rank][item]), (uint32_t)dest), v);
-                m_bar_arrive_remote(m_mapa(m_smem_u32(&sm.statbar[par]), (uint32_t)dest));
+                m_st_async_f64(m_mapa(m_smem_u32(&sm.stats[par][rank][item]), (uint32_t)dest), v, m_mapa(m_smem_u32(&sm.statbar[par]), (uint32_t)dest));
             }
-            m_bar_wait_cluster(sm.statbar + par, ph);
-            if (tid < S_COUNT) {
-                const int i = tid;
-                double v = sm.stats[par][0][i];
-                for (int r = 1; r < kCluster; ++r) {
-                    const double o = sm.stats[par][r][i];
-                    if (i == S_MINP || i == S_MINT) v = fmin(v, o);
-                    else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
-                    else v += o;
+            if (warp == 0) {                                                  // the group's other warps sleep in the named barrier below
+                m_bar_wait_sleep(sm.statbar + par, ph);
+                if (tid < S_COUNT) {
+                    const int i = tid;
+                    double v = sm.stats[par][0][i];
+                    for (int r = 1; r < kCluster; ++r) {
+                        const double o = sm.stats[par][r][i];
+                        if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+                        else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+                        else v += o;
+                    }
+                    sm.tot[i] = v;
                 }
-                sm.tot[i] = v;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTmConsumers) : "memory");
 
             const double n = (double)hw;
             const double* tot = sm.tot;
@@ -687,43 +759,63 @@ metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, in
             const float dP = sumP + kEpsF, dT = sumT + kEpsF;
             const float rdT = 1.0f / dT, rdP = 1.0f / dP;
             const float rnT = 1.0f / (rngT * nsumT), rnP = 1.0f / (rngP * nsumP);
+            const float2 rdT2 = make_float2(rdT, rdT), rdP2 = make_float2(rdP, rdP), eps2 = make_float2(kEpsF, kEpsF);
+            const float2 rnT2 = make_float2(rnT, rnT), rnP2 = make_float2(rnP, rnP);
+            const float2 cT2 = make_float2(-minT * rnT, -minT * rnT), cP2 = make_float2(-minP * rnP, -minP * rnP);
 
-            // ------------------------------- pass 2: out of tensor memory -------------------------------
+            // ------------------------------- pass 2: pred out of tensor memory, density back through the ring -------------------------------
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             double kld = 0.0, sim = 0.0;
-            float kf = 0.f, sf = 0.f;
-            for (int i = 0; i < mine; i += 2) {
-                float v[2][8];
-                m_tmem_ld8(tcol + (uint32_t)(i * 8), v[0]);
-                if (i + 1 < mine) m_tmem_ld8(tcol + (uint32_t)((i + 1) * 8), v[1]);      // (mine is CTA-uniform: still warp-collective)
+            float2 kf = make_float2(0.f, 0.f), sf = make_float2(0.f, 0.f);
+            for (int i0 = 0; i0 < mine; i0 += 3, ++it) {
+                const int st = it % kTmStages;
+                float p[3][8];
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (i0 + u < mine) m_tmem_ld8(tcol + (uint32_t)((i0 + u) * 8), p[u]);      // (mine is CTA-uniform: still warp-collective)
+                m_bar_wait_sleep(sm.full + st, (it / kTmStages) & 1);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (i + u < mine && e < chunk_len(chunk_of(i + u))) {
+                for (int u = 0; u < 3; ++u) {
+                    const int i = i0 + u;
+                    if (i < mine) {
+                        const int len = chunk_len(chunk_of(i));
+                        float t[8];
+                        m_lds8<T>(sm.ring[st][u], tid, t);
+                        const bool v0 = 4 * tid < len, v1 = kHalf + 4 * tid < len;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float p = v[u][j], t = v[u][4 + j];
-                            const float th = t * rdT, phh = p * rdP;
-                            kf = fmaf(th, __logf(__fdividef(th, phh + kEpsF) + kEpsF), kf);
-                            sf += fminf((t - minT) * rnT, (p - minP) * rnP);
+                        for (int j = 0; j < 8; j += 2) {
+                            if (j < 4 ? v0 : v1) {
+                                const float2 pp = make_float2(p[u][j], p[u][j + 1]), tt = make_float2(t[j], t[j + 1]);
+                                const float2 th = __fmul2_rn(tt, rdT2), phe = __ffma2_rn(pp, rdP2, eps2);
+                                // th * log(th / (ph + EPS) + EPS) in log2 units; th = 0 contributes 0 (the clamp keeps lg2 finite)
+                                const float2 d = make_float2(m_lg2(fmaxf(th.x, 1.2e-38f)) - m_lg2(phe.x), m_lg2(fmaxf(th.y, 1.2e-38f)) - m_lg2(phe.y));
+                                kf = __ffma2_rn(th, d, kf);
+                                const float2 uu = __ffma2_rn(tt, rnT2, cT2), vv = __ffma2_rn(pp, rnP2, cP2);
+                                sf = __fadd2_rn(sf, make_float2(fminf(uu.x, vv.x), fminf(uu.y, vv.y)));
+                            }
+                        }
+                        if ((i & 3) == 3) {                             // (general floats: keep the fp32 runs of the non-linear terms short)
+                            kld += (double)kf.x + (double)kf.y; sim += (double)sf.x + (double)sf.y;
+                            kf = make_float2(0.f, 0.f); sf = make_float2(0.f, 0.f);
                         }
                     }
-                    if (sizeof(T) == 1 || ((i + u) & 7) == 7) { kld += kf; sim += sf; kf = 0.f; sf = 0.f; }
                 }
+                __syncwarp();
+                if (lane == 0) m_bar_arrive(sm.empty + st);
             }
-            kld += kf; sim += sf;
+            kld += (double)kf.x + (double)kf.y; sim += (double)sf.x + (double)sf.y;
             kld = warp_sum(kld);
             sim = warp_sum(sim);
-            if (lane == 0) { sm.wpart2[warp][0] = kld; sm.wpart2[warp][1] = sim; }
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+            if (lane == 0) { sm.wpart2[warp][0] = kld * 0.6931471805599453; sm.wpart2[warp][1] = sim; }     // log2 -> natural log
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTmConsumers) : "memory");
             if (tid < 2) {
                 double v = 0.0;
                 for (int w = 0; w < kTmWarps; ++w) v += sm.wpart2[w][tid];
-                m_st_remote_f64(m_mapa(m_smem_u32(&sm.part2[par][rank][tid]), 0u), v);
-                m_bar_arrive_remote(m_mapa(m_smem_u32(&sm.p2bar[par]), 0u));
+                m_st_async_f64(m_mapa(m_smem_u32(&sm.part2[par][rank][tid]), 0u), v, m_mapa(m_smem_u32(&sm.p2bar[par]), 0u));
             }
             if (rank == 0 && tid == 0) {
-                m_bar_wait_cluster(sm.p2bar + par, ph);
+                m_bar_wait(sm.p2bar + par, ph);
                 double kk = 0.0, smm = 0.0;
                 for (int r = 0; r < kCluster; ++r) { kk += sm.part2[par][r][0]; smm += sm.part2[par][r][1]; }
                 // CC (:188-197) and NSS (:200-204) from the raw moments; std is unbiased (torch.std, :49)
@@ -741,11 +833,11 @@ metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, in
             }
         }
     }
-    // no CTA leaves (its shared memory, barriers and TMEM go with it) while a peer may still push into it
+    // no CTA leaves (its shared memory, barriers and TMEM go with it) while a peer may still store into it
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (producer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(512u) : "memory");
+    if (warp_abs == kTmWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm0.tmem_base), "r"((uint32_t)(kTmGroups * kTmCols)) : "memory");
 }
 
 int g_metrics_stream = 2;      // uavsal_set_option key 9: 2 = TMEM-resident persistent kernel where it applies (default), 1 = streaming
@@ -772,7 +864,7 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
                          hw % 16 == 0;
     if (g_metrics_stream >= 2 && bulk_ok && hw >= kCluster * kStChunkBytes && hw <= kCluster * kTmMaxChunks * kTmChunkPx) {
         static int max_clusters[2] = {0, 0};       // co-resident clusters of 8 (one CTA per SM; GPC-limited), per element type
-        const size_t smem = dtype == 0 ? sizeof(TmSmem<float>) : sizeof(TmSmem<uint8_t>);
+        const size_t smem = kTmGroups * (dtype == 0 ? sizeof(TmSmem<float>) : sizeof(TmSmem<uint8_t>));
         const void* fn = dtype == 0 ? (const void*)metrics4_tmem_kernel<float> : (const void*)metrics4_tmem_kernel<uint8_t>;
         if (!max_clusters[dtype]) {
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -790,7 +882,8 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
             }
             max_clusters[dtype] = nc;
         }
-        const int ncl = n < max_clusters[dtype] ? n : max_clusters[dtype];
+        const int want = (n + kTmGroups - 1) / kTmGroups;             // every cluster works on kTmGroups pairs at a time
+        const int ncl = want < max_clusters[dtype] ? want : max_clusters[dtype];
         if (dtype == 0)
             metrics4_tmem_kernel<float><<<kCluster * ncl, kTmThreads, smem, (cudaStream_t)stream>>>(
                 reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, n, out);

@@ -313,26 +313,23 @@ class UAVSal(KernelModule):
         if isinstance(self.rnn, ConvLSTM):
             # UAVSAL_LSTM (model.py:1065-1068): 4-gate ConvLSTM over the call's frames; the cell state lives in the plan as NHWC fp32
             c_state = plan.tensor((clips, mh * mw, planes))
-            plan.lstm(x, hb, c_state, clips, n // clips, mh, mw, planes, planes, cell.rnn_conv.weight, cell.rnn_conv.bias, seq, tag="rnn")
+            plan.lstm(x, hb, c_state, clips, n // clips, mh, mw, planes, planes, cell.wspec(), None, seq, tag="rnn")
             named.update(c_state=c_state)
         else:
             emit_twa(plan, cell, x, hb, seq, clips, n // clips, mh, mw)
         h_out = plan.tensor((clips, planes, mh, mw))
         for ci in range(clips):
-            last = Buf(seq.t, seq.rows, planes, seq.ld, ((ci + 1) * (n // clips) - 1) * mh * mw * seq.ld)
+            last = seq.at_row(((ci + 1) * (n // clips) - 1) * mh * mw)
             plan.unpack_nchw(last, 1, planes, mh, mw, h_out[ci:ci + 1], tag="state.unpack")
         # readout: expand + dw (dwBlock 256->1), then the 1536->1 project + BN + sigmoid as a dot product (model.py:372-373)
         ro = self.conv_out_st
         e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", f32_out=plan.f32_hidden)
-        wf, bf = ro.project_folded()
         out = plan.tensor((n, 1, mh, mw))
         if e.f32 and getattr(plan, "fuse_readout", True):
-            from .engine import pack_dw
-            wdw, bdw = ro.conv[1].folded()
-            plan.dw_dot_sigmoid(e, n, mh, mw, e.c, pack_dw(wdw), bdw, wf.reshape(-1), float(bf.reshape(-1)[0].item()), out, tag="readout.dw+dot")
+            plan.dw_dot_sigmoid(e, n, mh, mw, e.c, ro.conv[1].wspec(), None, ro.project_wspec(), None, out, tag="readout.dw+dot")
         else:
             d, _, _ = ro.conv[1]._emit(plan, e, n, mh, mw, tag="readout.dw")
-            plan.dot_sigmoid(d, rows, wf.shape[1], wf.reshape(-1), float(bf.reshape(-1)[0].item()), out, tag="readout.dot")
+            plan.dot_sigmoid(d, rows, e.c, ro.project_wspec(), None, out, tag="readout.dot")
         named.update(h_in=h_in, h_out=h_out, out=out, map_hw=(mh, mw))
         if taps:
             tp["rnn"] = (seq, mh, mw)

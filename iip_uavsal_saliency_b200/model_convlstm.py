@@ -42,6 +42,10 @@ class _CellBase(KernelModule):
         if self.input_dim % 8 or self.hidden_dim % 8:
             raise NotImplementedError("channel counts must be multiples of 8")
 
+    def wspec(self):
+        from .engine import W
+        return W(self.rnn_conv.weight, bias=self.rnn_conv.bias, owner=self.rnn_conv)
+
     def _zeros(self, batch, device):
         return torch.zeros(batch, self.hidden_dim, self.height, self.width, device=device)
 
@@ -114,7 +118,7 @@ def _run_twa(cell: ConvTWACell, x5: torch.Tensor, h0: torch.Tensor):
 
 def emit_twa(plan, cell, xb, hb, seq, b, t, h, w):
     """b independent sequences of t frames (sequence-major rows) through one batched sequence op."""
-    plan.twa(xb, hb, t, h, w, cell.hidden_dim, cell.rnn_conv.weight, seq, tag="rnn", batch=b)
+    plan.twa(xb, hb, t, h, w, cell.hidden_dim, cell.wspec(), seq, tag="rnn", batch=b)
 
 
 def _run_lstm(cell: ConvLSTMCell, x5, h0, c0):
@@ -133,7 +137,7 @@ def _run_lstm(cell: ConvLSTMCell, x5, h0, c0):
         seq = plan.alloc(b * t * h * w, ch)
         plan.pack_nchw(xin, b * t, cin, h, w, xb)
         plan.pack_nchw(hin, b, ch, h, w, hb)
-        plan.lstm(xb, hb, cst, b, t, h, w, cin, ch, cell.rnn_conv.weight, cell.rnn_conv.bias, seq, tag="lstm")
+        plan.lstm(xb, hb, cst, b, t, h, w, cin, ch, cell.wspec(), None, seq, tag="lstm")
         yout = plan.tensor((b * t, ch, h, w))
         plan.unpack_nchw(seq, b * t, ch, h, w, yout)
         plan.named.update(x_in=xin, h_in=hin, c_in=cin_t, c_state=cst, y_out=yout)

@@ -40,7 +40,7 @@ from .model import UAVSal
 class ClipRunner:
     def __init__(self, model: UAVSal, gauss: np.ndarray, ob: np.ndarray, batch_size: int = 4, out_hw: Optional[Tuple[int, int]] = None,
                  use_graph: bool = True, frame_layout: str = "nhwc", depth: int = 2, clip_backbone: bool = True,
-                 single_stream: bool = False, whole_clip: bool = True, clips_per_plan: int = 1):
+                 single_stream: bool = False, whole_clip: bool = True, clips_per_plan: int = 1, max_plan_frames: int = 240):
         """gauss (h,w,8) / ob (h,w,20) float32 prior maps; frame_layout 'nhwc' (decoder layout) or 'nchw';
         depth = calls in flight (1 = strictly serial on the caller's stream order); clip_backbone: run the SRF-Net once per
         clip instead of once per call."""
@@ -63,6 +63,10 @@ class ClipRunner:
         self._slot_free = [None] * self.depth          # event: the slot's previous call has left the back stream
         self._calls = 0
         self.whole_clip = bool(whole_clip)
+        # a whole-clip plan's arena grows with the clip (about 36 MB per frame at 360x640): longer clips run as consecutive
+        # plans of at most this many frames (a multiple of the call size, so the call grouping is unchanged), the ConvTWA state
+        # handed from one to the next exactly as Demo_Test hands it from call to call (Demo_Test.py:85-86)
+        self.max_plan_frames = max(self.per_call, (int(max_plan_frames) // self.per_call) * self.per_call)
         # throughput mode: queue `clips_per_plan` equally shaped clips into ONE plan (the ConvTWA then advances them as a batch
         # of sequences - its per-step launches are latency-bound - and every other launch sees that many times the rows).
         # Only run_clip(..., out=buffer, want_maps=False, sync=False) calls are combined; finish() flushes a partial batch.
@@ -230,6 +234,8 @@ class ClipRunner:
 
     def _run_whole(self, frames, keep, H, W, want_maps, out, sync):
         """One plan for the whole clip (see the module docstring); front of clip k+1 overlaps the recurrent back of clip k."""
+        if keep > self.max_plan_frames:
+            return self._run_long(frames, keep, H, W, want_maps, out, sync)
         if self.clips_per_plan > 1 and not sync and not want_maps and out is not None and keep % self.per_call == 0:
             if self._pending and (self._pending[0][1], self._pending[0][2], self._pending[0][3]) != (keep, H, W):
                 self._flush()
@@ -248,7 +254,35 @@ class ClipRunner:
                     t.record_stream(cur)
         return m, u8
 
-    def _launch_whole(self, clips, keep, H, W, want_maps, outs):
+    def _run_long(self, frames, keep, H, W, want_maps, out, sync):
+        """A clip longer than ``max_plan_frames``: consecutive whole-clip plans chained through the ConvTWA state."""
+        self._flush()
+        maps, u8s, state, done = [], [], None, 0
+        while done < keep:
+            seg = min(self.max_plan_frames, keep - done)
+            m, u8 = self._launch_whole([frames[done:done + seg]], seg, H, W, want_maps, [out[done:done + seg] if out is not None else None],
+                                       state=state, keep_state=True)
+            state = self._last_state
+            maps.append(m)
+            u8s.append(u8)
+            done += seg
+        with torch.cuda.stream(self.back_stream):
+            m = torch.cat(maps, 0) if want_maps else None
+        if out is not None:
+            u8 = out[:keep]
+        else:
+            with torch.cuda.stream(self.back_stream):
+                u8 = torch.cat(u8s, 0)
+        if sync:
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_stream(self.back_stream)
+            cur.wait_stream(self.out_stream)
+            for t in (m, u8):
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
+        return m, u8
+
+    def _launch_whole(self, clips, keep, H, W, want_maps, outs, state=None, keep_state=False):
         nc = len(clips)
         slot = self._clips % 2 if (nc > 1 or self.clips_per_plan == 1) else 0
         self._clips += 1
@@ -270,8 +304,13 @@ class ClipRunner:
             fdone.record(fs)
         bs.wait_event(fdone)
         with torch.cuda.stream(bs):
-            nm["h_in"].zero_()                                      # every clip starts from the zero state (Demo_Test.py:75)
+            if state is None:
+                nm["h_in"].zero_()                                  # every clip starts from the zero state (Demo_Test.py:75)
+            else:
+                nm["h_in"].copy_(state, non_blocking=True)          # continuation of a long clip: the previous plan's last h
             plan.launch("back")
+            if keep_state:
+                self._last_state = nm["h_out"]                      # read by the next segment on this same (back) stream
             m = nm["out"].clone() if want_maps else None
             u8 = None
             for ci, out in enumerate(outs):

@@ -39,6 +39,10 @@ extern "C" {
 #define UAVSAL_F_SIGMOID  4    /* out = sigmoid(out)        (model.py:373) */
 #define UAVSAL_F_OUT_F32  8    /* uavsal_pw_gemm only: `out` is a float* to fp32 rows [m][out_ld] (out_plane ignored); used for the
                                   hidden tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92) */
+/* `terms` arguments of the tcgen05 entry points: 1 (bf16 x 1, "fast") or 3 (hi*hi + hi*lo + lo*hi, "exact"), optionally ORed with
+   UAVSAL_TERMS_GEN1 to run the first-generation one-tile-per-CTA tcgen05 kernel instead of the persistent one (an independent
+   cross-check engine for the tests; per call, so two callers on concurrent streams cannot disturb each other) */
+#define UAVSAL_TERMS_GEN1 0x100
 /* plane value marking an activation argument as plain fp32 rows (uavsal_dw3x3 input) instead of split-bf16 planes */
 #define UAVSAL_PLANE_F32  (-1)
 
@@ -46,13 +50,32 @@ int         uavsal_version(void);                 /* ABI version, currently 1 */
 const char* uavsal_arch(void);                    /* "sm_100a" */
 const char* uavsal_last_error(void);
 int         uavsal_device_ok(int device);         /* 0 if `device` is compute capability 10.x */
-int         uavsal_set_option(int key, int value);/* key 1: tcgen05 GEMM kernel version (2 = persistent, default; 1 = one tile per CTA);
+int         uavsal_set_option(int key, int value);/* (process-global developer knobs for A/B timing; the product path never calls this)
+                                                     key 1: tcgen05 GEMM kernel version (2 = persistent, default; 1 = one tile per CTA; per call: UAVSAL_TERMS_GEN1);
                                                      key 2: depthwise path (2 = TMA-staged, default; 1 = sliding rows; 0 = generic);
                                                      key 3: timing-ablation bits (dev only; results invalid when non-zero);
                                                      key 4: CTAs per cluster of the persistent GEMM (2 = cta_group::2 pair mode, default; 1);
                                                      key 5: cap on the GEMM's shared-memory pipeline depth (dev);
                                                      key 6: programmatic dependent launch of the product-path kernels (1 = on, default; 0);
                                                      key 7: ConvTWA step kernel (1 = resident-A shifted-view kernel, default; 0 = generic implicit GEMM) */
+
+/* ---- weight preparation (BasicConv2d / dwBlock / rnn_conv parameters -> what the kernels below read) --------------------
+ * conv weight w (cout, cin, taps) fp32 [taps = kh*kw: 1 or 9; cin = input channels per group], optional BatchNorm2d (eval:
+ * model.py:69-70, 94-95, eps 1e-5) folded in fp32: w' = w * gamma / sqrt(var + eps), b' = beta + (conv_bias - mean) * gamma /
+ * sqrt(var + eps); without BatchNorm b' = conv_bias (or 0).  Destination element (row r, k = tap * cin + ci); rows >= cout and
+ * k >= taps * cin are zero padding.  gates > 1: rows g * (cout/gates) + c are emitted at c * gates + g (ConvLSTM gate conv,
+ * model_convlstm.py:111-117).  Layouts:
+ *   UAVSAL_W_ROWS_SPLIT  uint16 [2][n_pad][k_pad]: bf16 hi / lo planes, K-major rows (tcgen05 B operand: uavsal_pw_gemm,
+ *                        uavsal_conv3x3, uavsal_twa_sequence, uavsal_convlstm_sequence, uavsal_dw_project, uavsal_expand_dw3x3)
+ *   UAVSAL_W_ROWS_F32    float [n_pad][k_pad]
+ *   UAVSAL_W_COLS_F32    float [k_pad][n_pad] (depthwise [9][C], stem [27][32], the SIMT cross-check engine)
+ * out_bias: float [n_pad] or NULL. */
+#define UAVSAL_W_ROWS_SPLIT 0
+#define UAVSAL_W_ROWS_F32   1
+#define UAVSAL_W_COLS_F32   2
+int uavsal_pack_weights(const float* w, int cout, int cin, int taps, const float* bn_weight, const float* bn_bias,
+                        const float* bn_mean, const float* bn_var, float bn_eps, const float* conv_bias, int gates,
+                        int layout, int n_pad, int k_pad, void* out_w, float* out_bias, void* stream);
 
 /* ---- layout conversion at the module boundary (torch NCHW fp32 <-> arena) ---------------------- */
 /* NCHW fp32 -> act NHWC with channels zero-padded to cpad (cb priors, Demo_Test.py:16,22; states).  */

@@ -214,3 +214,79 @@ def test_eval_host_helpers_match_reference(tmp_path):
     sm = US.getshufmap(pts, size=(36, 64))
     assert sm.shape == (36, 64) and sm.dtype == np.uint8 and 12 <= sm.sum() <= 120
     assert pts[0].max() < 1                                          # the list entries are not scaled in place
+
+
+def test_two_pass_arena_plan_shares_memory_only_between_disjoint_lifetimes():
+    """Plan.build's measure pass + layout solver (engine.py), run here on the CPU: every allocation gets an offset in one arena;
+    two buffers overlap in memory only if one's last op precedes the other's first; module-boundary tensors and everything
+    reachable from ``named`` (debug taps) are persistent; the second pass reproduces the op list of a direct plan."""
+    from iip_uavsal_saliency_b200 import engine
+    from iip_uavsal_saliency_b200.model import UAVSal
+    torch.manual_seed(0)
+    m = UAVSal(iosize=[288, 512, 36, 64]).eval()
+    build = lambda plan: m.build_plan(plan, 10, 288, 512, x_kind=1, post_hw=(288, 512), taps=True)
+    probe = engine.Plan("cpu", 3, "tc", mode="measure")
+    build(probe)
+    offs, total = probe.solve_layout()
+    allocs = probe._allocs
+    trans = [a for a in allocs if not a.pinned]
+    assert trans and all(a.first is not None and a.last >= a.first for a in trans)
+    for i, a in enumerate(allocs):
+        for b in allocs[i + 1:]:
+            mem_overlap = not (a.off + a.nbytes <= b.off or b.off + b.nbytes <= a.off)
+            if a.pinned or b.pinned:
+                assert not mem_overlap
+            elif not (a.last < b.first or b.last < a.first):
+                assert not mem_overlap, (a.idx, b.idx)
+    taps = probe.named["taps"]
+    assert all(buf.root.pinned for buf, _, _ in taps.values())          # debug taps must survive the run
+    plan = engine.Plan("cpu", 3, "tc", mode="arena", layout=(offs, total))
+    build(plan)
+    direct = engine.Plan("cpu", 3, "tc")
+    build(direct)
+    assert [o.name for o in plan.ops] == [o.name for o in direct.ops] == [o.name for o in probe.ops]
+    assert len(plan._allocs) == len(allocs) and plan.arena_bytes == total < direct.arena_bytes / 3
+    lo, hi = plan._arena.data_ptr(), plan._arena.data_ptr() + total
+    for name in ("x_in", "out", "out_u8", "h_in", "h_out"):
+        t = plan.named[name]
+        assert lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= hi and t.shape == direct.named[name].shape
+    sf, _, _ = plan.named["taps"]["sfnet"]
+    assert sf.t.shape == (2, 10 * 36 * 64, 256) and sf.to_float().shape == (10 * 36 * 64, 256)
+    # packed weights are cached on the owning conv and follow the parameters' versions
+    conv = m.fust_layer[0].conv[0][0]
+    cache = conv.__dict__["_uavsal_packed"]
+    (key, (sig, wt, b)), = [(k, v) for k, v in cache.items() if k[0] == engine.W_ROWS_SPLIT]
+    assert wt.shape == (2, 1536, 256) and b.shape == (1536,)
+    again = engine.Plan("cpu", 3, "tc")
+    wt2, _ = again.packed(m.fust_layer[0].conv[0].wspec(), engine.W_ROWS_SPLIT, 1536, 256)
+    assert wt2 is wt
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+    wt3, _ = again.packed(m.fust_layer[0].conv[0].wspec(), engine.W_ROWS_SPLIT, 1536, 256)
+    assert wt3 is not wt and torch.equal(wt3[0].float(), (wt[0].float() * 2))
+    m.invalidate()
+    assert "_uavsal_packed" not in conv.__dict__
+
+
+def test_pack_reference_matches_the_module_level_folding():
+    """W.pack_reference (the torch restatement uavsal_pack_weights is checked against on the GPU) equals the explicit
+    fold_bn / conv3x3_as_2d / interleave_gates / split_bf16 pipeline it replaced."""
+    from iip_uavsal_saliency_b200 import engine
+    from iip_uavsal_saliency_b200.blocks import BasicConv2d
+    torch.manual_seed(1)
+    c = BasicConv2d(24, 40, 3)
+    c[1].running_mean.normal_(); c[1].running_var.uniform_(0.5, 2.0); c[1].weight.data.uniform_(0.5, 1.5); c[1].bias.data.normal_()
+    wf, bf = c.folded()
+    wp, b = c.wspec().pack_reference(engine.W_ROWS_SPLIT, 48, 9 * 24 + 8)
+    ref = torch.zeros(48, 9 * 24 + 8)
+    ref[:40, :216] = engine.conv3x3_as_2d(wf)
+    assert torch.equal(wp, engine.split_bf16(ref)) and torch.equal(b[:40], bf) and not b[40:].any()
+    wc, _ = c.wspec().pack_reference(engine.W_COLS_F32, 40, 216)
+    assert torch.equal(wc, engine.conv3x3_as_2d(wf).t())
+    w4 = torch.randn(32, 12, 3, 3)
+    bias = torch.randn(32)
+    wl, bl = engine.W(w4, bias=bias).pack_reference(engine.W_ROWS_F32, 32, 108, gates=4)
+    assert torch.equal(wl, engine.conv3x3_as_2d(engine.interleave_gates(w4, 8))) and torch.equal(bl, engine.interleave_gates(bias, 8))
+    dw = BasicConv2d(16, 16, 3, groups=16)
+    wd, bd = dw.wspec().pack_reference(engine.W_COLS_F32, 16, 9)
+    assert torch.equal(wd, engine.pack_dw(dw.folded()[0])) and torch.equal(bd, dw.folded()[1])

@@ -249,6 +249,36 @@ def test_post_u8_and_metrics(cuda, gold_dir):
     assert ((mine - ref).abs() / ref.abs()).max() < 1e-4
 
 
+def test_pack_weights_kernel_is_bit_exact(cuda):
+    """uavsal_pack_weights (BN fold + layout + bf16 hi/lo split on the device) against its torch restatement, bit for bit:
+    pointwise / dense 3x3 / depthwise / stem layouts, zero padding of rows and K, gate interleave with a conv bias."""
+    import copy
+    from iip_uavsal_saliency_b200 import engine
+    from iip_uavsal_saliency_b200.blocks import BasicConv2d
+    torch.manual_seed(2)
+
+    def lively(c):
+        c[1].running_mean.normal_(); c[1].running_var.uniform_(0.3, 3.0); c[1].weight.data.uniform_(0.5, 1.5); c[1].bias.data.normal_()
+        return c
+
+    p = engine.Plan("cuda")
+    cases = []
+    for conv, layouts in ((lively(BasicConv2d(20, 120, 1)), [(engine.W_ROWS_SPLIT, 120, 24), (engine.W_COLS_F32, 120, 24), (engine.W_ROWS_F32, 128, 32)]),
+                          (lively(BasicConv2d(448, 256, 3)), [(engine.W_ROWS_SPLIT, 256, 9 * 448), (engine.W_COLS_F32, 256, 9 * 448)]),
+                          (lively(BasicConv2d(1536, 1536, 3, groups=1536)), [(engine.W_COLS_F32, 1536, 9)]),
+                          (lively(BasicConv2d(3, 32, 3, stride=2)), [(engine.W_COLS_F32, 32, 27)]),
+                          (lively(BasicConv2d(16, 96, 1)), [(engine.W_ROWS_SPLIT, 128, 16)])):
+        for lay in layouts:
+            cases.append((copy.deepcopy(conv).wspec(), conv.cuda().wspec(), lay, 1))
+    w4, bias = torch.randn(4 * 64, 128, 3, 3) * 0.05, torch.randn(4 * 64)
+    cases.append((engine.W(w4, bias=bias), engine.W(w4.cuda(), bias=bias.cuda()), (engine.W_ROWS_SPLIT, 256, 9 * 128), 4))
+    cases.append((engine.W(w4), engine.W(w4.cuda()), (engine.W_COLS_F32, 256, 9 * 128), 1))
+    for ws_cpu, ws_gpu, (layout, n_pad, k_pad), gates in cases:
+        wt, b = p.packed(ws_gpu, layout, n_pad, k_pad, gates)
+        rw, rb = ws_cpu.pack_reference(layout, n_pad, k_pad, gates)
+        assert torch.equal(wt.cpu(), rw) and torch.equal(b.cpu(), rb), (layout, n_pad, k_pad, gates)
+
+
 def test_convlstm_config3_shape_pair_mode(cuda):
     """BASELINE config #3's shape - hidden 256 ch at 45x80, batch 8 (model_convlstm.py:111-126, 168-218) - is the one that
     runs the cta_group::2 pair-mode instantiation of the implicit-GEMM kernel with the fused LSTM cell epilogue (tiles_m x
@@ -411,7 +441,8 @@ def test_clip_runner_config2_and_config1(cuda, gold_dir):
 
 def test_scheduling_variants_agree(cuda, gold_dir):
     """ClipRunner's scheduling choices must not change results: stream pipelining and batching two clips into one plan are
-    bit-exact; one plan per clip vs Demo_Test's loop of 20-frame calls agrees to the last bit of the state re-split (<= 1 LSB)."""
+    bit-exact; one plan per clip vs Demo_Test's loop of 20-frame calls (or vs a long clip's chained plans) agrees to the last bit
+    of the state re-split (<= 1 LSB)."""
     from iip_uavsal_saliency_b200.model import UAVSal
     from iip_uavsal_saliency_b200.runner import ClipRunner
     pr = np.load(os.path.join(gold_dir, "priors.npz"))
@@ -422,7 +453,7 @@ def test_scheduling_variants_agree(cuda, gold_dir):
     clips = [torch.from_numpy(synth.make_clip(30 + i, 44, 360, 640)).cuda() for i in range(3)]      # 44 frames -> 40 kept = 2 calls
     outs = {}
     for name, kw in (("loop", dict(depth=1, whole_clip=False, clip_backbone=False)), ("clip", dict(single_stream=True)),
-                     ("clip+streams", dict()), ("two-clips", dict(clips_per_plan=2))):
+                     ("clip+streams", dict()), ("two-clips", dict(clips_per_plan=2)), ("chained", dict(max_plan_frames=20))):
         r = ClipRunner(m, gauss, ob, batch_size=4, **kw)
         bufs = [torch.empty(40, 360, 640, dtype=torch.uint8, device="cuda") for _ in clips]
         for c, b in zip(clips, bufs):
@@ -436,6 +467,8 @@ def test_scheduling_variants_agree(cuda, gold_dir):
     for a, b in (("clip", "clip+streams"), ("clip", "two-clips")):
         assert all(torch.equal(x, y) for x, y in zip(outs[a], outs[b])), (a, b)
     assert max(int((x.int() - y.int()).abs().max()) for x, y in zip(outs["loop"], outs["clip"])) <= 1
+    # a clip longer than max_plan_frames runs as chained plans (state handed over like Demo_Test's calls): same <= 1 LSB band
+    assert max(int((x.int() - y.int()).abs().max()) for x, y in zip(outs["chained"], outs["clip"])) <= 1
 
 
 def test_batched_twa_sequences(cuda):
@@ -457,7 +490,7 @@ def test_batched_twa_sequences(cuda):
                 p.twa(xb, hb, t, h, w, c, wgt, seq, batch=b)
             else:
                 for bi in range(b):
-                    rows = lambda buf, r0: Buf(buf.t, buf.rows, buf.c, buf.ld, buf.off + r0 * buf.ld)
+                    rows = lambda buf, r0: buf.at_row(r0)
                     p.twa(rows(xb, bi * t * h * w), rows(hb, bi * h * w), t, h, w, c, wgt, rows(seq, bi * t * h * w))
             p.run()
             torch.cuda.synchronize()

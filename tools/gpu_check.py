@@ -332,7 +332,7 @@ def g_twa_batch():
             else:
                 from iip_uavsal_saliency_b200.engine import Buf
                 for bi in range(b):
-                    rows = lambda buf, r0: Buf(buf.t, buf.rows, buf.c, buf.ld, buf.off + r0 * buf.ld)
+                    rows = lambda buf, r0: buf.at_row(r0)
                     p.twa(rows(xb, bi * t * h * w), rows(hb, bi * h * w), t, h, w, c, wgt, rows(seq, bi * t * h * w))
             p.run(); torch.cuda.synchronize()
             outs.append(seq.to_float().clone())
