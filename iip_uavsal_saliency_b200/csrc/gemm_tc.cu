@@ -524,7 +524,7 @@ int uavsal_set_option(int key, int value) {
     if (key == 6 && (value == 0 || value == 1)) { g_pdl = value; return 0; }
     if (key == 7 && value >= 0 && value <= 2) { g_twa_resident = value; return 0; }
     if (key == 8 && (value == 64 || value == 128)) { g_twa_bn = value; return 0; }
-    if (key == 9 && value >= 0 && value <= 2) { g_metrics_stream = value; return 0; }
+    if (key == 9 && value >= 0 && value <= 3) { g_metrics_stream = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }

@@ -840,8 +840,279 @@ metrics4_tmem_kernel(const T* __restrict__ pred, const T* __restrict__ truth, in
     if (warp_abs == kTmWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm0.tmem_base), "r"((uint32_t)(kTmGroups * kTmCols)) : "memory");
 }
 
-int g_metrics_stream = 2;      // uavsal_set_option key 9: 2 = TMEM-resident persistent kernel where it applies (default), 1 = streaming
-                               // kernel (pass 2 from L2), 0 = register-batched kernel
+// ---------------------------------------------------------------------------------------------------------------------
+// Resident variant, one pair per CLUSTER OF 16 (non-portable cluster size), several CTAs per SM.  Same data path as the
+// persistent kernel above (pred stashed in TMEM, density back from L2, st.async exchange), but a CTA is small - 8 consumer warps +
+// a producer warp, a 3-stage ring, 128 TMEM columns (14 400 px x 4 B = 56 KiB) - and lives for ONE pair, so three CTAs of
+// different pairs share an SM: 27 warps per SM instead of 18, every SM of every GPC usable (a cluster of 8 with one CTA per SM
+// strands 28 of the 148 SMs), and the hardware scheduler overlaps one pair's exchange latency with the others' streaming.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kC16 = 16;
+constexpr int kT16Stages = 3;
+constexpr int kT16Cols = 128;
+constexpr int kT16MaxChunks = 8;                   // 64 TMEM columns per warp / 8 columns per chunk
+constexpr int kT16Threads = kTmConsumers + 32;
+
+template <typename T>
+struct T16Smem {
+    alignas(128) T ring[kT16Stages][3][kTmChunkPx];
+    double stats[kC16][S_COUNT];                   // [source rank][item], st.async'ed by every CTA of the cluster
+    double part2[kC16][2];                         // pass-2 partials, st.async'ed to rank 0
+    double wpart1[kTmWarps][S_COUNT];
+    double wpart2[kTmWarps][2];
+    double tot[S_COUNT];
+    uint64_t full[kT16Stages], empty[kT16Stages], statbar, p2bar;
+    uint32_t tmem_base;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kT16Threads, 3)
+metrics4_tmem16_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, float* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t m_smem_raw[];
+    T16Smem<T>& sm = *reinterpret_cast<T16Smem<T>*>(m_smem_raw);
+    const int rank = (int)m_cluster_rank();
+    const int pair = blockIdx.x / kC16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == kTmWarps;
+
+    if (tid == 0) {
+        for (int s = 0; s < kT16Stages; ++s) { m_bar_init(sm.full + s, 1); m_bar_init(sm.empty + s, kTmWarps); }
+        m_bar_init(&sm.statbar, 1); m_bar_init(&sm.p2bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        m_bar_expect(&sm.statbar, kC16 * S_COUNT * 8);                     // the 176 remote stores of this pair's statistics
+        if (rank == 0) m_bar_expect(&sm.p2bar, kC16 * 2 * 8);
+    }
+    if (producer) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m_smem_u32(&sm.tmem_base)), "r"((uint32_t)kT16Cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // every CTA's barriers exist before the first remote complete_tx
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t tcol = sm.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+
+    const int nchunks = (hw + kTmChunkPx - 1) / kTmChunkPx;
+    const int mine = (nchunks - rank + kC16 - 1) / kC16;                  // <= kT16MaxChunks (launcher)
+    auto chunk_of = [&](int i) { return rank + i * kC16; };
+    auto chunk_len = [&](int c) { return min(kTmChunkPx, hw - c * kTmChunkPx); };
+    constexpr int kHalf = kTmChunkPx / 2;
+    const T* P = pred + (int64_t)pair * hw;
+    const T* D = truth + (int64_t)pair * 2 * hw;
+    const T* Fx = D + hw;
+
+    if (producer) {
+        if (lane == 0) {
+            uint64_t pol_first, pol_keep;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            uint32_t it = 0;
+            for (int i = 0; i < mine; ++i, ++it) {                       // pass 1: P, D, F
+                const int s = it % kT16Stages;
+                m_bar_wait_sleep(sm.empty + s, ((it / kT16Stages) & 1) ^ 1);
+                const int c = chunk_of(i);
+                const uint32_t bytes = (uint32_t)chunk_len(c) * sizeof(T);
+                const int64_t off = (int64_t)c * kTmChunkPx;
+                m_bar_expect(sm.full + s, bytes * 3);
+                m_bulk_load_hint(sm.ring[s][0], P + off, bytes, sm.full + s, pol_first);
+                m_bulk_load_hint(sm.ring[s][1], D + off, bytes, sm.full + s, pol_keep);
+                m_bulk_load_hint(sm.ring[s][2], Fx + off, bytes, sm.full + s, pol_first);
+            }
+            for (int i = 0; i < mine; i += 3, ++it) {                    // pass 2: D again (L2), three chunks per stage
+                const int s = it % kT16Stages;
+                m_bar_wait_sleep(sm.empty + s, ((it / kT16Stages) & 1) ^ 1);
+                uint32_t total = 0;
+                for (int u = 0; u < 3 && i + u < mine; ++u) total += (uint32_t)chunk_len(chunk_of(i + u)) * sizeof(T);
+                m_bar_expect(sm.full + s, total);
+                for (int u = 0; u < 3 && i + u < mine; ++u) {
+                    const int c = chunk_of(i + u);
+                    m_bulk_load_hint(sm.ring[s][u], D + (int64_t)c * kTmChunkPx, (uint32_t)chunk_len(c) * sizeof(T), sm.full + s, pol_first);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        uint32_t it = 0;
+        // ------------------------------- pass 1: ring -> moments, pred -> TMEM -------------------------------
+        float mnP = 3.0e38f, mxP = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
+        float2 a[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) a[j] = make_float2(0.f, 0.f);
+        auto chunk1 = [&](auto full, int st, int i, int len) {
+            constexpr bool FULL = decltype(full)::value;
+            float p[8], t[8], f[8];
+            m_lds8<T>(sm.ring[st][0], tid, p); m_lds8<T>(sm.ring[st][1], tid, t); m_lds8<T>(sm.ring[st][2], tid, f);
+            const bool v0 = FULL || 4 * tid < len, v1 = FULL || kHalf + 4 * tid < len;           // (len is a multiple of 16)
+            if (!FULL) {
+                if (!v0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { p[j] = 0.f; t[j] = 0.f; f[j] = 0.f; }
+                }
+                if (!v1) {
+#pragma unroll
+                    for (int j = 4; j < 8; ++j) { p[j] = 0.f; t[j] = 0.f; f[j] = 0.f; }
+                }
+            }
+            m_tmem_st8(tcol + (uint32_t)(i * 8), p);                             // warp-collective: every lane, also past the tail
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const float2 pp = make_float2(p[j], p[j + 1]), tt = make_float2(t[j], t[j + 1]), ff = make_float2(f[j], f[j + 1]);
+                a[0] = __fadd2_rn(a[0], pp); a[1] = __ffma2_rn(pp, pp, a[1]); a[2] = __fadd2_rn(a[2], tt); a[3] = __ffma2_rn(tt, tt, a[3]);
+                a[4] = __ffma2_rn(tt, pp, a[4]); a[5] = __fadd2_rn(a[5], ff); a[6] = __ffma2_rn(ff, pp, a[6]);
+            }
+            if (v1) {
+                mnP = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), fminf(fminf(fminf(p[4], p[5]), fminf(p[6], p[7])), mnP));
+                mxP = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])), mxP));
+                mnT = fminf(fminf(fminf(t[0], t[1]), fminf(t[2], t[3])), fminf(fminf(fminf(t[4], t[5]), fminf(t[6], t[7])), mnT));
+                mxT = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])), mxT));
+            } else if (v0) {
+                mnP = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), mnP); mxP = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), mxP);
+                mnT = fminf(fminf(fminf(t[0], t[1]), fminf(t[2], t[3])), mnT); mxT = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), mxT);
+            }
+        };
+        for (int i = 0; i < mine; ++i, ++it) {
+            const int st = it % kT16Stages;
+            m_bar_wait_sleep(sm.full + st, (it / kT16Stages) & 1);
+            const int len = chunk_len(chunk_of(i));
+            if (len == kTmChunkPx) chunk1(std::true_type{}, st, i, len);
+            else chunk1(std::false_type{}, st, i, len);
+            __syncwarp();
+            if (lane == 0) m_bar_arrive(sm.empty + st);
+        }
+        // <= 32 pixels per fp32 accumulator lane: exact for uint8-valued maps; fp64 from here on
+        double s[S_MINP];
+        s[S_P] = (double)a[0].x + (double)a[0].y; s[S_P2] = (double)a[1].x + (double)a[1].y; s[S_T] = (double)a[2].x + (double)a[2].y;
+        s[S_T2] = (double)a[3].x + (double)a[3].y; s[S_TP] = (double)a[4].x + (double)a[4].y; s[S_F] = (double)a[5].x + (double)a[5].y;
+        s[S_FP] = (double)a[6].x + (double)a[6].y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnP = fminf(mnP, __shfl_xor_sync(0xffffffffu, mnP, o)); mxP = fmaxf(mxP, __shfl_xor_sync(0xffffffffu, mxP, o));
+            mnT = fminf(mnT, __shfl_xor_sync(0xffffffffu, mnT, o)); mxT = fmaxf(mxT, __shfl_xor_sync(0xffffffffu, mxT, o));
+        }
+#pragma unroll
+        for (int i = 0; i < S_MINP; ++i) {
+            const double v = warp_sum(s[i]);
+            if (lane == 0) sm.wpart1[warp][i] = v;
+        }
+        if (lane == 0) { sm.wpart1[warp][S_MINP] = mnP; sm.wpart1[warp][S_MAXP] = mxP; sm.wpart1[warp][S_MINT] = mnT; sm.wpart1[warp][S_MAXT] = mxT; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+        if (tid < kC16 * S_COUNT) {                                       // thread (dest, item): this CTA's partial -> CTA `dest`
+            const int item = tid % S_COUNT, dest = tid / S_COUNT;
+            double v = sm.wpart1[0][item];
+            for (int w = 1; w < kTmWarps; ++w) {
+                if (item == S_MINP || item == S_MINT) v = fmin(v, sm.wpart1[w][item]);
+                else if (item == S_MAXP || item == S_MAXT) v = fmax(v, sm.wpart1[w][item]);
+                else v += sm.wpart1[w][item];
+            }
+            m_st_async_f64(m_mapa(m_smem_u32(&sm.stats[rank][item]), (uint32_t)dest), v, m_mapa(m_smem_u32(&sm.statbar), (uint32_t)dest));
+        }
+        if (warp == 0) {                                                  // the other warps sleep in the named barrier below
+            m_bar_wait_sleep(&sm.statbar, 0);
+            if (tid < S_COUNT) {
+                const int i = tid;
+                double v = sm.stats[0][i];
+                for (int r = 1; r < kC16; ++r) {
+                    const double o = sm.stats[r][i];
+                    if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+                    else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+                    else v += o;
+                }
+                sm.tot[i] = v;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+
+        const double n = (double)hw;
+        const double* tot = sm.tot;
+        const float sumP = (float)tot[S_P], sumT = (float)tot[S_T];
+        const float minP = (float)tot[S_MINP], minT = (float)tot[S_MINT];
+        const float rngP = ((float)tot[S_MAXP] - minP) + kEpsF, rngT = ((float)tot[S_MAXT] - minT) + kEpsF;
+        const float nsumP = (float)((tot[S_P] - n * tot[S_MINP]) / (double)rngP) + kEpsF;
+        const float nsumT = (float)((tot[S_T] - n * tot[S_MINT]) / (double)rngT) + kEpsF;
+        const float dP = sumP + kEpsF, dT = sumT + kEpsF;
+        const float rdT = 1.0f / dT, rdP = 1.0f / dP;
+        const float rnT = 1.0f / (rngT * nsumT), rnP = 1.0f / (rngP * nsumP);
+        const float2 rdT2 = make_float2(rdT, rdT), rdP2 = make_float2(rdP, rdP), eps2 = make_float2(kEpsF, kEpsF);
+        const float2 rnT2 = make_float2(rnT, rnT), rnP2 = make_float2(rnP, rnP);
+        const float2 cT2 = make_float2(-minT * rnT, -minT * rnT), cP2 = make_float2(-minP * rnP, -minP * rnP);
+
+        // ------------------------------- pass 2: pred out of tensor memory, density back through the ring -------------------------------
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        double kld = 0.0, sim = 0.0;
+        float2 kf = make_float2(0.f, 0.f), sf = make_float2(0.f, 0.f);
+        for (int i0 = 0; i0 < mine; i0 += 3, ++it) {
+            const int st = it % kT16Stages;
+            float p[3][8];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (i0 + u < mine) m_tmem_ld8(tcol + (uint32_t)((i0 + u) * 8), p[u]);      // (mine is CTA-uniform: still warp-collective)
+            m_bar_wait_sleep(sm.full + st, (it / kT16Stages) & 1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = i0 + u;
+                if (i < mine) {
+                    const int len = chunk_len(chunk_of(i));
+                    float t[8];
+                    m_lds8<T>(sm.ring[st][u], tid, t);
+                    const bool v0 = 4 * tid < len, v1 = kHalf + 4 * tid < len;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        if (j < 4 ? v0 : v1) {
+                            const float2 pp = make_float2(p[u][j], p[u][j + 1]), tt = make_float2(t[j], t[j + 1]);
+                            const float2 th = __fmul2_rn(tt, rdT2), phe = __ffma2_rn(pp, rdP2, eps2);
+                            const float2 d = make_float2(m_lg2(fmaxf(th.x, 1.2e-38f)) - m_lg2(phe.x), m_lg2(fmaxf(th.y, 1.2e-38f)) - m_lg2(phe.y));
+                            kf = __ffma2_rn(th, d, kf);
+                            const float2 uu = __ffma2_rn(tt, rnT2, cT2), vv = __ffma2_rn(pp, rnP2, cP2);
+                            sf = __fadd2_rn(sf, make_float2(fminf(uu.x, vv.x), fminf(uu.y, vv.y)));
+                        }
+                    }
+                    if ((i & 3) == 3) {
+                        kld += (double)kf.x + (double)kf.y; sim += (double)sf.x + (double)sf.y;
+                        kf = make_float2(0.f, 0.f); sf = make_float2(0.f, 0.f);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) m_bar_arrive(sm.empty + st);
+        }
+        kld += (double)kf.x + (double)kf.y; sim += (double)sf.x + (double)sf.y;
+        kld = warp_sum(kld);
+        sim = warp_sum(sim);
+        if (lane == 0) { sm.wpart2[warp][0] = kld * 0.6931471805599453; sm.wpart2[warp][1] = sim; }     // log2 -> natural log
+        asm volatile("bar.sync 1, %0;" ::"n"(kTmConsumers) : "memory");
+        if (tid < 2) {
+            double v = 0.0;
+            for (int w = 0; w < kTmWarps; ++w) v += sm.wpart2[w][tid];
+            m_st_async_f64(m_mapa(m_smem_u32(&sm.part2[rank][tid]), 0u), v, m_mapa(m_smem_u32(&sm.p2bar), 0u));
+        }
+        if (rank == 0 && tid == 0) {
+            m_bar_wait_sleep(&sm.p2bar, 0);
+            double kk = 0.0, smm = 0.0;
+            for (int r = 0; r < kC16; ++r) { kk += sm.part2[r][0]; smm += sm.part2[r][1]; }
+            const double mP = tot[S_P] / n, mT = tot[S_T] / n;
+            const double ssP = fmax(tot[S_P2] - tot[S_P] * mP, 0.0), ssT = fmax(tot[S_T2] - tot[S_T] * mT, 0.0);
+            const double sdP = sqrt(ssP / (n - 1.0)), sdT = sqrt(ssT / (n - 1.0));
+            const double cov = tot[S_TP] - tot[S_T] * mP;
+            const double zz = (sdP + kEps) * (sdT + kEps);
+            const double r1 = cov / zz;
+            const double r2 = sqrt((ssP / ((sdP + kEps) * (sdP + kEps))) * (ssT / ((sdT + kEps) * (sdT + kEps))));
+            out[(int64_t)pair * 4 + 0] = (float)(r1 / (r2 + kEps));
+            out[(int64_t)pair * 4 + 1] = (float)(((tot[S_FP] - mP * tot[S_F]) / (sdP + kEps)) / (tot[S_F] + kEps));
+            out[(int64_t)pair * 4 + 2] = (float)kk;
+            out[(int64_t)pair * 4 + 3] = (float)smm;
+        }
+    }
+    // everything sent to this CTA has been awaited above (statistics by warp 0, pass-2 partials by rank 0): it may leave on its own
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (producer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"((uint32_t)kT16Cols) : "memory");
+}
+
+int g_metrics_stream = 1;      // uavsal_set_option key 9: 1 = streaming kernel (pass 2 re-read through L2; default: the fastest measured), 2 = TMEM-resident kernel, one pair per cluster of 16,
+                               // 3 = TMEM-resident persistent kernel (clusters of 8; every byte crosses HBM once),
+                               // 0 = register-batched kernel
 
 }  // namespace uavsal
 
@@ -862,6 +1133,27 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
     // pair / chunk offset.  Anything else takes the register-batched kernel (plain vector loads).
     const bool bulk_ok = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0 && ((int64_t)hw * esz) % 16 == 0 &&
                          hw % 16 == 0;
+    if (g_metrics_stream == 2 && bulk_ok && hw >= kCluster * kStChunkBytes && hw <= kC16 * kT16MaxChunks * kTmChunkPx) {
+        const size_t smem = dtype == 0 ? sizeof(T16Smem<float>) : sizeof(T16Smem<uint8_t>);
+        const void* fn = dtype == 0 ? (const void*)metrics4_tmem16_kernel<float> : (const void*)metrics4_tmem16_kernel<uint8_t>;
+        static bool attr[2] = {false, false};
+        if (!attr[dtype]) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { set_error("metrics4(resident16): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            attr[dtype] = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(kC16 * n)); cfg.blockDim = dim3(kT16Threads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kC16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = dtype == 0 ? cudaLaunchKernelEx(&cfg, metrics4_tmem16_kernel<float>, reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out)
+                                   : cudaLaunchKernelEx(&cfg, metrics4_tmem16_kernel<uint8_t>, reinterpret_cast<const uint8_t*>(pred), reinterpret_cast<const uint8_t*>(truth), hw, out);
+        if (e != cudaSuccess) { set_error("metrics4(resident16): cudaLaunchKernelEx: %s", cudaGetErrorString(e)); return (int)e; }
+        return check_launch("metrics4(resident16)");
+    }
     if (g_metrics_stream >= 2 && bulk_ok && hw >= kCluster * kStChunkBytes && hw <= kCluster * kTmMaxChunks * kTmChunkPx) {
         static int max_clusters[2] = {0, 0};       // co-resident clusters of 8 (one CTA per SM; GPC-limited), per element type
         const size_t smem = kTmGroups * (dtype == 0 ? sizeof(TmSmem<float>) : sizeof(TmSmem<uint8_t>));

@@ -8,8 +8,9 @@ Two stubs are needed:
      the same torchvision architecture with ``weights=None``.
 
 The reference reads its prior ``.mat`` files relative to the CWD (utils_data.py:450-452, 554-557); use
-``reference_cwd()`` around calls to its prior loaders.  This module only works where /root/reference
-exists (the authoring container); GPU-box tests use the committed fixtures instead.
+``reference_cwd()`` around calls to its prior loaders.  The modules come from /root/reference (the authoring container) or,
+where that does not exist (the GPU box), from the copy oracle/stage_ref.py staged under oracle/_ref; GPU-box TESTS use the
+committed fixtures, only bench.py's CPU-baseline legs run the staged reference.
 """
 from __future__ import annotations
 
@@ -19,8 +20,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("UAVSAL_REFERENCE_ROOT", "/root/reference")
 _REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_STAGED = os.path.join(_REPO_ROOT, "oracle", "_ref")          # oracle/stage_ref.py: the same files, staged for the GPU box
+
+
+def _pick_root() -> str:
+    env = os.environ.get("UAVSAL_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if os.path.isfile("/root/reference/model.py") else _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:

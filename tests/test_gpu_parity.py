@@ -268,8 +268,9 @@ def test_pack_weights_kernel_is_bit_exact(cuda):
                           (lively(BasicConv2d(1536, 1536, 3, groups=1536)), [(engine.W_COLS_F32, 1536, 9)]),
                           (lively(BasicConv2d(3, 32, 3, stride=2)), [(engine.W_COLS_F32, 32, 27)]),
                           (lively(BasicConv2d(16, 96, 1)), [(engine.W_ROWS_SPLIT, 128, 16)])):
+        host = copy.deepcopy(conv)
         for lay in layouts:
-            cases.append((copy.deepcopy(conv).wspec(), conv.cuda().wspec(), lay, 1))
+            cases.append((host.wspec(), conv.cuda().wspec(), lay, 1))
     w4, bias = torch.randn(4 * 64, 128, 3, 3) * 0.05, torch.randn(4 * 64)
     cases.append((engine.W(w4, bias=bias), engine.W(w4.cuda(), bias=bias.cuda()), (engine.W_ROWS_SPLIT, 256, 9 * 128), 4))
     cases.append((engine.W(w4), engine.W(w4.cuda()), (engine.W_COLS_F32, 256, 9 * 128), 1))
@@ -303,8 +304,8 @@ def test_convlstm_config3_shape_pair_mode(cuda):
 
 
 def test_metrics_kernel_variants(cuda):
-    """Every kernel behind uavsal_metrics4 against the oracle (1e-4 relative, the north-star band): the TMEM-resident persistent
-    kernel with more pairs than co-resident clusters (each cluster loops over several pairs: ring / barrier phase reuse), real-valued
+    """Every kernel behind uavsal_metrics4 against the oracle (1e-4 relative, the north-star band): the TMEM-resident kernels (one
+    pair per cluster of 16; persistent clusters of 8 with more pairs than co-resident clusters, i.e. ring / barrier phase reuse), real-valued
     (not uint8-valued) maps, uint8 storage, a 720x1280 map (streaming kernel), misaligned views (register kernel: cp.async.bulk
     needs 16-byte aligned planes), and every option value on the same input."""
     from iip_uavsal_saliency_b200 import _ext, utils_score_torch as us
@@ -327,7 +328,7 @@ def test_metrics_kernel_variants(cuda):
     check(noisy_p, noisy_t, "resident fp32, real-valued maps")
     lib = _ext.load()
     try:
-        for opt in (1, 0):                                           # streaming / register-batched kernels on the same pairs
+        for opt in (3, 1, 0):                                        # persistent cluster-of-8 / streaming / register-batched kernels on the same pairs
             lib.uavsal_set_option(9, opt)
             other = us.metrics4(pred[:9].cuda(), true[:9].cuda()).cpu()
             assert ((other - base[:9]).abs() / base[:9].abs().clamp_min(1e-6)).max().item() < 2e-5, opt
