@@ -7,11 +7,14 @@ such a file needs every class it mentions to be importable under its original na
 README.md:27,34) — ``torchvision.models.mobilenet.ConvBNReLU / InvertedResidual / MobileNetV2``, which current
 torchvision no longer has.
 
-``load_reference_state_dict`` therefore unpickles with a remapping ``find_class``: everything under ``torch`` /
-``collections`` / ``numpy`` that a tensor or a stock ``nn`` layer needs resolves normally (allow-list), every class of the
-reference's own modules and of ``torchvision`` is replaced by an empty ``nn.Module`` (or ``nn.Sequential``-like)
-stand-in that only carries ``_parameters / _buffers / _modules`` — which is all ``state_dict()`` walks — and anything
-else is refused.  The result is the plain 685-key state dict of SURVEY App. A, ready for
+``load_reference_state_dict`` therefore unpickles with a remapping ``find_class``: every class of the reference's own
+modules and of ``torchvision`` is replaced by an empty ``nn.Module`` stand-in that only carries ``_parameters / _buffers /
+_modules`` — which is all ``state_dict()`` walks.  Everything else must be on an explicit list of (module, name) pairs:
+the tensor / storage / parameter rebuild helpers, ``torch.Size`` / dtypes / storage classes, ``collections.OrderedDict``,
+classes below ``torch.nn.modules`` that ARE ``nn.Module`` subclasses, numpy's array reconstructors and a handful of plain
+builtins.  Dotted names (pickle protocol 4 resolves ``os.system`` through ``torch`` that way), ``builtins.getattr`` / ``eval``
+and any other callable are refused, so a hostile file cannot reach arbitrary code through this loader (the reference's own
+``torch.load`` executes whatever the pickle says).  The result is the plain 685-key state dict of SURVEY App. A, ready for
 ``UAVSal.load_state_dict(..., strict=True)``.
 
 Files that already hold a state dict (``OrderedDict`` of tensors), or a dict with a ``"state_dict"`` entry, are accepted too.
@@ -30,10 +33,19 @@ from torch import nn
 
 # modules whose classes are replaced by parameter-carrying stand-ins
 _STUB_ROOTS = ("model", "model_feature", "model_convlstm", "torchvision", "__main__")
-# modules that resolve normally (tensors, storages, stock layers, containers, numpy scalars/arrays inside old checkpoints)
-_ALLOW_ROOTS = ("torch", "collections", "numpy", "_codecs", "builtins", "copyreg")
+# exact (module, name) pairs that resolve normally
+_EXACT = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._utils", "_rebuild_qtensor"),
+    ("torch", "Size"), ("torch", "device"), ("torch.serialization", "_get_layout"), ("torch.nn.parameter", "Parameter"),
+    ("torch._tensor", "_rebuild_from_type_v2"), ("torch", "Tensor"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "scalar"), ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+}
 _BUILTINS_OK = {"set", "frozenset", "list", "dict", "tuple", "int", "float", "bool", "str", "bytes", "slice", "range", "complex",
-                "getattr", "object", "bytearray"}
+                "object", "bytearray"}
 
 
 class CheckpointError(ValueError):
@@ -61,16 +73,29 @@ def _stub_for(mod_name: str, name: str) -> type:
 
 class _Unpickler(pickle.Unpickler):
     def find_class(self, mod_name, name):
+        if not name.isidentifier():
+            # protocol 4 resolves dotted names attribute by attribute: ("torch", "os.system") would be arbitrary code
+            raise CheckpointError("checkpoint refers to the dotted name %s.%s" % (mod_name, name))
         root = mod_name.split(".", 1)[0]
         if root in _STUB_ROOTS:
             return _stub_for(mod_name, name)
-        if root == "__builtin__":              # protocol-2 streams (torch.save's default) use the Python 2 module name
-            root = "builtins"
-        if root == "builtins" and name not in _BUILTINS_OK:
-            raise CheckpointError("checkpoint refers to builtins.%s, which a model file has no business doing" % name)
-        if root in _ALLOW_ROOTS:
+        if mod_name in ("__builtin__", "builtins"):   # protocol-2 streams (torch.save's default) use the Python 2 module name
+            if name not in _BUILTINS_OK:
+                raise CheckpointError("checkpoint refers to builtins.%s, which a model file has no business doing" % name)
+            return super().find_class("builtins", name)
+        if (mod_name, name) in _EXACT:
             return super().find_class(mod_name, name)
-        raise CheckpointError("checkpoint refers to %s.%s, which is neither a torch object nor a reference model class" % (mod_name, name))
+        if mod_name == "torch":                        # dtypes and storage classes
+            obj = getattr(torch, name, None)
+            if isinstance(obj, torch.dtype) or (isinstance(obj, type) and name.endswith("Storage")):
+                return obj
+        if mod_name == "torch.storage" and name in ("UntypedStorage", "TypedStorage"):
+            return super().find_class(mod_name, name)
+        if mod_name == "torch.nn.modules" or mod_name.startswith("torch.nn.modules."):
+            obj = super().find_class(mod_name, name)
+            if isinstance(obj, type) and issubclass(obj, nn.Module):
+                return obj
+        raise CheckpointError("checkpoint refers to %s.%s, which is neither a tensor / stock-layer object nor a reference model class" % (mod_name, name))
 
 
 def _pickle_module() -> types.ModuleType:

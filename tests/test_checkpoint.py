@@ -66,3 +66,28 @@ def test_foreign_callables_are_refused(tmp_path):
     torch.save([1, 2, 3], r)
     with pytest.raises(checkpoint.CheckpointError):
         checkpoint.load_reference_state_dict(str(r))
+
+
+def test_unpickler_refuses_code_execution_gadgets(tmp_path):
+    """The loader resolves only an explicit list of globals: dotted names (protocol 4 walks attributes: ("torch", "os.system")),
+    builtins.getattr / eval, and any module outside the list are refused before anything is called."""
+    import pickle
+    import pickletools  # noqa: F401
+    from iip_uavsal_saliency_b200 import checkpoint as ck
+
+    def payload(mod, name, proto):
+        if proto >= 4:      # STACK_GLOBAL resolves dotted names
+            return (b"\x80\x04" + b"\x8c" + bytes([len(mod)]) + mod.encode() + b"\x8c" + bytes([len(name)]) + name.encode() + b"\x93"
+                    + b"\x8c\x04true" + b"\x85R.")
+        return b"\x80\x02c" + mod.encode() + b"\n" + name.encode() + b"\nU\x04true\x85R."
+
+    for mod, name in (("torch", "os.system"), ("builtins", "getattr"), ("builtins", "eval"), ("os", "system"), ("torch.hub", "load"),
+                      ("torch.storage", "_load_from_bytes"), ("numpy", "load"), ("subprocess", "Popen")):
+        for proto in (2, 4):
+            with pytest.raises(ck.CheckpointError):
+                ck._Unpickler(__import__("io").BytesIO(payload(mod, name, proto))).load()
+    # and through the public entry point: a zip-less legacy file that is just such a pickle
+    bad = tmp_path / "evil.pth"
+    bad.write_bytes(payload("torch", "os.system", 4))
+    with pytest.raises(ck.CheckpointError):
+        ck.load_reference_state_dict(str(bad))
