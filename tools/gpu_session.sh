@@ -1,8 +1,10 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-python tools/debug_pack.py > gpurun_out/r02_debug_pack.log 2>&1; cat gpurun_out/r02_debug_pack.log
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_tests_all.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r02_tests_all.log
-tail -6 gpurun_out/r02_tests_all.log
-( time timeout 1200 python bench.py ) > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"; cat gpurun_out/r02_bench_n1.json; tail -8 gpurun_out/r02_bench_n1.err
-( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/r02_bench_ref.json; tail -4 gpurun_out/r02_bench_ref.err
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 ) > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; echo "bench n2 rc=$?"; cut -c1-600 gpurun_out/r02_bench_n2.json; tail -5 gpurun_out/r02_bench_n2.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02_bench_n2.json'))
+print('value',d['value'],'e2e',d['e2e']['value'],'weak',d['weak_scaling']['value'])
+print(json.dumps(d['metrics_config5'])[:900])
+PY
