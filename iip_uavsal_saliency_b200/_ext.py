@@ -46,6 +46,9 @@ _SIGNATURES = {
     "uavsal_dot_sigmoid": ACT + [L, I, P, F, P, P],
     "uavsal_post_u8": [P, I, I, I, I, I, P, P, P],
     "uavsal_post_f32": [P, I, I, I, I, I, P, P, P],
+    "uavsal_conv_first": [P, I, I, I, I, I, I, P, P, I] + ACT + [P],
+    "uavsal_maxpool": ACT + [I, I, I, I, I, I, I] + ACT + [P],
+    "uavsal_add_act": ACT + ACT + [L, I, I] + ACT + [P],
     "uavsal_metrics4": [P, P, I, I, I, I, P, P, P],
     "uavsal_letterbox_u8": [P, I, I, I, P, I, I, I, P],
     "uavsal_auc_judd": [P, P, I, I, I, P, P, L, P],

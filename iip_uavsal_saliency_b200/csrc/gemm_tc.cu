@@ -158,9 +158,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
                 }
             }
             if (EPI == EPI_STD) {
-                if (g.flags & UAVSAL_F_RELU6) {
+                if (g.flags & (UAVSAL_F_RELU6 | UAVSAL_F_RELU)) {
+                    const float cap = (g.flags & UAVSAL_F_RELU6) ? 6.f : 3.0e38f;      // ReLU6 (model.py:71) | ReLU (ResNet / VGG backbones)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = relu6f(v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], 0.f), cap);
                 }
                 if (g.flags & UAVSAL_F_RESIDUAL) {
                     float rr[8];

@@ -14,7 +14,7 @@ import torch
 
 from . import _ext
 
-F_RELU6, F_RESIDUAL, F_SIGMOID, F_OUT_F32 = 1, 2, 4, 8
+F_RELU6, F_RESIDUAL, F_SIGMOID, F_OUT_F32, F_RELU = 1, 2, 4, 8, 16
 TERMS_GEN1 = 0x100        # UAVSAL_TERMS_GEN1
 PLANE_F32 = -1            # UAVSAL_PLANE_F32: the activation is plain fp32 rows, not split-bf16 planes
 BN_EPS = 1e-5
@@ -535,6 +535,19 @@ class Plan:
             self._add("uavsal_conv3x3", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, self.terms_arg, *out.act()), tag)
         else:
             self._add("uavsal_conv3x3_simt", (*x.act(), n, h, w, c, wp.data_ptr(), cout, bp, flags, *out.act()), tag)
+
+    # ---- alternative backbones (ResNet / VGG) ----
+    def conv_first(self, x: torch.Tensor, kind: int, n, h, w, ws: W, stride: int, flags: int, out: Buf, tag=""):
+        """First conv of a ResNet (7x7 s2 + BN) / VGG (3x3 s1 + bias) from the raw frame tensor, 3 -> 64 channels."""
+        assert ws.cin == 3 and ws.cout == 64 and ws.taps in (9, 49)
+        wd, bd = self.packed(ws, W_COLS_F32)
+        self._add("uavsal_conv_first", (x.data_ptr(), kind, n, h, w, 7 if ws.taps == 49 else 3, stride, wd.data_ptr(), bd.data_ptr(), flags, *out.act()), tag)
+
+    def maxpool(self, x: Buf, n, h, w, c, k, stride, pad, out: Buf, tag=""):
+        self._add("uavsal_maxpool", (*x.act(), n, h, w, c, k, stride, pad, *out.act()), tag)
+
+    def add_act(self, a: Buf, b: Buf, rows, c, flags, out: Buf, tag=""):
+        self._add("uavsal_add_act", (*a.act(), *b.act(), rows, c, flags, *out.act()), tag)
 
     def bilinear(self, x: Buf, n_src, hs, ws, c, out: Buf, n_dst, hd, wd, tag="", src_group=0, dst_group=0):
         self._add("uavsal_bilinear_ac", (*x.act(), n_src, hs, ws, c, *out.act(), n_dst, hd, wd, src_group, dst_group), tag)

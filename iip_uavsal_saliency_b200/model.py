@@ -19,12 +19,15 @@ from .blocks import BasicConv2d, dwBlock, init_func, init_weights
 from .engine import F_RELU6, Buf, Plan, out_size
 from .model_convlstm import *            # noqa: F401,F403  (the reference re-exports these, model.py:11)
 from .model_convlstm import ConvLSTM, ConvTWA, emit_twa
-from .model_feature import ReMobileNetV2
+from .model_feature import ReMobileNetV2, ReResNet, ReVGG
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")     # model.py:8
 
-feature_loader = {"mobilenet_v2": ReMobileNetV2}
-feature_inplanes = {"mobilenet_v2": [24, 32, 96, 320]}                    # model.py:25-33 (in-scope backbone)
+feature_loader = {"vgg16": ReVGG, "resnet18": ReResNet, "resnet34": ReResNet, "resnet50": ReResNet, "resnet101": ReResNet,
+                  "resnet152": ReResNet, "mobilenet_v2": ReMobileNetV2}      # model.py:14-22
+feature_inplanes = {"vgg16": [128, 256, 512, 512], "resnet18": [64, 128, 256, 512], "resnet34": [64, 128, 256, 512],
+                    "resnet50": [256, 512, 1024, 2048], "resnet101": [256, 512, 1024, 2048], "resnet152": [256, 512, 1024, 2048],
+                    "mobilenet_v2": [24, 32, 96, 320]}                      # model.py:25-33
 
 
 class uavsal_srfnet_aspp(KernelModule):
@@ -34,8 +37,6 @@ class uavsal_srfnet_aspp(KernelModule):
         super().__init__()
         if last_channel == 128:
             planes = [32, 32, 64, 128]
-        if cnn_type.lower() not in feature_inplanes:
-            raise NotImplementedError("backbone %r is outside the accelerated path (mobilenet_v2 only)" % cnn_type)
         inpl = feature_inplanes[cnn_type.lower()]
         self.conv_lv3 = BasicConv2d(inpl[1], planes[1], 1)
         self.conv_lv4 = BasicConv2d(inpl[2], planes[2], 1)

@@ -119,6 +119,39 @@ def make_state_dict(kind: str = "lively", seed: int = 0, as_torch: bool = True):
     return sd
 
 
+def key_table_of(module):
+    """[(key, shape, dtype)] of a module's state dict, in order (the table make_state_dict_like consumes)."""
+    return [(k, list(v.shape), str(v.dtype)) for k, v in module.state_dict().items()]
+
+
+def make_state_dict_like(table, seed: int = 0, as_torch: bool = True):
+    """'Lively' weights for ANY key table (used for the ResNet / VGG backbone variants, whose state dicts are too large to commit):
+    fan-in scaled conv weights (gain sqrt2 in front of a ReLU, 1 for the linear convs that close a residual block), non-trivial BN
+    statistics, small conv biases.  Depends only on the table's order, shapes and the seed."""
+    rs = np.random.RandomState(6000 + seed)
+    sd = {}
+    for key, shape, dtype in table:
+        if "int64" in dtype:
+            sd[key] = np.zeros(shape, np.int64)
+            continue
+        leaf = key.rsplit(".", 1)[1]
+        if len(shape) == 4:
+            cout, cin_g, kh, kw = shape
+            linear = (key.endswith((".conv.2.weight", ".conv3.weight", ".downsample.0.weight")) or key.endswith("features.1.conv.1.weight")
+                      or "rnn_conv" in key)
+            gain = 1.0 if linear else np.sqrt(2.0)
+            sd[key] = (rs.randn(*shape) * (gain / np.sqrt(cin_g * kh * kw))).astype(np.float32)
+        else:
+            n = shape[0] if shape else 1
+            val = {"weight": rs.uniform(0.8, 1.2, n), "bias": rs.randn(n) * 0.1,
+                   "running_mean": rs.randn(n) * 0.1, "running_var": rs.uniform(0.8, 1.2, n)}[leaf]
+            sd[key] = val.astype(np.float32).reshape(shape)
+    if as_torch:
+        import torch
+        sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    return sd
+
+
 def make_lstm_weight(hidden: int = 256, inp: int = 256, seed: int = 0, bias: bool = False):
     """xavier_uniform (model_convlstm.py:109) for ConvLSTMCell.rnn_conv (4*hidden, inp+hidden, 3, 3)."""
     rs = np.random.RandomState(4000 + seed)

@@ -37,6 +37,7 @@ extern "C" {
 #define UAVSAL_F_RELU6    1    /* clamp to [0,6]            (nn.ReLU6, model.py:71) */
 #define UAVSAL_F_RESIDUAL 2    /* out += res                (model.py:101, 247) */
 #define UAVSAL_F_SIGMOID  4    /* out = sigmoid(out)        (model.py:373) */
+#define UAVSAL_F_RELU     16   /* max(x, 0)                 (nn.ReLU of the ResNet / VGG backbones, model_feature.py:72-128; exclusive with RELU6) */
 #define UAVSAL_F_OUT_F32  8    /* uavsal_pw_gemm only: `out` is a float* to fp32 rows [m][out_ld] (out_plane ignored); used for the
                                   hidden tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92) */
 /* `terms` arguments of the tcgen05 entry points: 1 (bf16 x 1, "fast") or 3 (hi*hi + hi*lo + lo*hi, "exact"), optionally ORed with
@@ -231,6 +232,20 @@ int uavsal_metrics4(const void* pred, const void* truth, int dtype, int n, int h
  *      with cv2.resize's 8-bit INTER_LINEAR arithmetic (bit-exact, incl. its exact-2x INTER_AREA shortcut) keeping the aspect
  *      ratio, centred on a zero canvas; swap_rb = 1 also applies the BGR -> RGB reorder of :270.  dw <= 4096. */
 int uavsal_letterbox_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, void* stream);
+
+/* ---- alternative backbones (model_feature.ReResNet / ReVGG, model_feature.py:72-128; torchvision resnet.py / vgg.py) -------------
+ * uavsal_conv_first: the first conv from the raw frame, 3 -> 64 channels: k = 7, stride 2, pad 3 (ResNet conv1 + bn1 + relu) or k = 3,
+ *   stride 1, pad 1 (VGG features.0 + relu).  x / x_kind as uavsal_stem_conv3x3s2 (uint8 kinds normalise as utils_data.normalize_data);
+ *   wgt fp32 [k*k*3][64] (UAVSAL_W_COLS_F32 of uavsal_pack_weights), bias [64] or NULL; flags: UAVSAL_F_RELU.
+ * uavsal_maxpool: nn.MaxPool2d(k, stride, pad), floor mode (ResNet 3/2/1, VGG 2/2/0); k = 1, stride 2 subsamples rows (in front of a
+ *   stride-2 1x1 conv; behind a stride-1 evaluation of a stride-2 3x3 conv).
+ * uavsal_add_act: out = a + b, then ReLU when flags has UAVSAL_F_RELU (the tail of a ResNet block: relu(conv(x) + identity)). */
+int uavsal_conv_first(const void* x, int x_kind, int n, int h, int w, int k, int stride, const float* wgt, const float* bias, int flags,
+                      uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+int uavsal_maxpool(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, int k, int stride, int pad,
+                   uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+int uavsal_add_act(const uint16_t* a, int64_t a_plane, int a_ld, const uint16_t* b, int64_t b_plane, int b_ld, int64_t rows, int c,
+                   int flags, uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
 /* ---- utils_score_torch.metric_auc_j (53-88), deterministic part: S = min-max normalised pred (fp32, as :83), fixations =
  *      truth channel 1 > 0.5; out[n] = AUC-Judd (NaN when the map has no positive value or the frame no fixation, :54).

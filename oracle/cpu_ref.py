@@ -72,9 +72,71 @@ def mobilenet_v2_features(sd, p, x) -> Tuple[torch.Tensor, ...]:
     return outs[1], outs[3], outs[6], outs[13], outs[17]
 
 
-def srfnet(sd, p, x, trace=None):
+_RESNET_CFG = {"resnet18": ("basic", (2, 2, 2, 2)), "resnet34": ("basic", (3, 4, 6, 3)), "resnet50": ("bottleneck", (3, 4, 6, 3)),
+               "resnet101": ("bottleneck", (3, 4, 23, 3)), "resnet152": ("bottleneck", (3, 8, 36, 3))}
+_VGG16_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
+
+
+def _conv_bn(sd, pc, pb, x, stride=1, relu=True):
+    w = sd[pc + ".weight"]
+    x = _bn(sd, pb, F.conv2d(x, w, None, stride, w.shape[-1] // 2))
+    return F.relu(x) if relu else x
+
+
+def resnet_features(sd, p, x, name="resnet50"):
+    """ReResNet.forward (model_feature.py:92-103) over torchvision's ResNet (resnet.py: BasicBlock / Bottleneck with the stride on
+    the 3x3 conv, downsample = conv1x1(stride) + BN): returns x0 (after the max pool), layer1 .. layer4."""
+    kind, blocks = _RESNET_CFG[name]
+    x = _conv_bn(sd, p + ".conv1", p + ".bn1", x, stride=2)
+    x = F.max_pool2d(x, 3, 2, 1)
+    outs = [x]
+    for li, nb in enumerate(blocks):
+        for bi in range(nb):
+            q = "%s.layer%d.%d" % (p, li + 1, bi)
+            stride = 2 if (bi == 0 and li > 0) else 1
+            idn = x
+            if q + ".downsample.0.weight" in sd:
+                idn = _conv_bn(sd, q + ".downsample.0", q + ".downsample.1", x, stride=stride, relu=False)
+            if kind == "basic":
+                y = _conv_bn(sd, q + ".conv1", q + ".bn1", x, stride=stride)
+                y = _conv_bn(sd, q + ".conv2", q + ".bn2", y, relu=False)
+            else:
+                y = _conv_bn(sd, q + ".conv1", q + ".bn1", x)
+                y = _conv_bn(sd, q + ".conv2", q + ".bn2", y, stride=stride)
+                y = _conv_bn(sd, q + ".conv3", q + ".bn3", y, relu=False)
+            x = F.relu(y + idn)
+        outs.append(x)
+    return tuple(outs)
+
+
+def vgg_features(sd, p, x):
+    """ReVGG.forward (model_feature.py:117-128) over torchvision's vgg16.features.  The reference finds the pooling layers by
+    zipping ``features.modules()`` (whose first element is the Sequential itself) with range(100), so its split points sit one
+    PAST every max pool: each of the five levels ends with its pooling layer (64 @ 1/2, 128 @ 1/4, 256 @ 1/8, 512 @ 1/16, 512 @ 1/32)."""
+    outs = []
+    idx = 0
+    for v in _VGG16_CFG:
+        if v == "M":
+            x = F.max_pool2d(x, 2, 2)
+            outs.append(x)
+            idx += 1
+        else:
+            x = F.relu(F.conv2d(x, sd["%s.%d.weight" % (p, idx)], sd["%s.%d.bias" % (p, idx)], 1, 1))
+            idx += 2
+    return tuple(outs)
+
+
+def backbone_features(sd, p, x, cnn_type="mobilenet_v2"):
+    if cnn_type == "mobilenet_v2":
+        return mobilenet_v2_features(sd, p + ".features", x)
+    if cnn_type == "vgg16":
+        return vgg_features(sd, p + ".features", x)
+    return resnet_features(sd, p, x, cnn_type)
+
+
+def srfnet(sd, p, x, trace=None, cnn_type="mobilenet_v2"):
     """uavsal_srfnet_aspp.forward (model.py:139-158)."""
-    _, _, c3, c4, c5 = mobilenet_v2_features(sd, p + ".features.features", x)
+    _, _, c3, c4, c5 = backbone_features(sd, p + ".features", x, cnn_type)
     if trace is not None:
         trace.update(c3=c3, c4=c4, c5=c5)
     a1 = basic_conv(sd, p + ".lv5_aspp1", c5)
@@ -141,13 +203,13 @@ def lstm_sequence(w, b, x, h, c):
 
 
 def uavsal_forward(sd: Dict[str, torch.Tensor], x, cb, h0, time_dims=5, num_stblock=2,
-                   bias_type=(1, 1, 1), trace: Optional[dict] = None):
+                   bias_type=(1, 1, 1), trace: Optional[dict] = None, cnn_type: str = "mobilenet_v2"):
     """UAVSal.forward (model.py:341-375).  x (N,3,H,W) normalised fp32, cb=[gauss (N,8,h,w), ob (N,20,h,w)],
     h0 (1,256,h,w).  Returns out (N,1,h,w), h_last (1,256,h,w).  ``trace`` collects named intermediates.
     With h0 = (h, c) the recurrence is the ConvLSTM of the UAVSAL_LSTM ablation (model.py:960-1076) and (h, c) is returned."""
     tr = trace if trace is not None else {}
     with torch.no_grad():
-        x = srfnet(sd, "sfnet", x, tr)
+        x = srfnet(sd, "sfnet", x, tr, cnn_type)
         tr["sfnet"] = x
         for i in range(num_stblock):
             x = st_block(sd, "st_layer.%d" % i, x)

@@ -94,6 +94,36 @@ def gen_priors(ref):
                         avs1k_sample_idx=sample_idx(a.size, "avs1k"), avs1k_sample=a.ravel()[sample_idx(a.size, "avs1k")])
 
 
+def gen_backbones(ref):
+    """backbones.npz: UAVSal on the alternative backbones (model_feature.ReResNet / ReVGG, model.py:14-33) - one 5-frame call at
+    96x160 through the unmodified reference; weights from synth.make_state_dict_like over the reference model's own key table."""
+    out = {}
+    clip = synth.make_clip(7, 5, 96, 160)
+    x = torch.tensor(ref.utils_data.normalize_data(clip.transpose(0, 3, 1, 2))).float()
+    g, o = synth.make_priors(5, 12, 20, seed=3)
+    cb = [torch.from_numpy(g), torch.from_numpy(o)]
+    for cnn in ("resnet18", "resnet50", "vgg16"):
+        m = ref.model.UAVSal(cnn_type=cnn, time_dims=5, num_stblock=2, bias_type=[1, 1, 1], iosize=[96, 160, 12, 20], planes=256, pre_model_path="").eval()
+        sd = synth.make_state_dict_like(synth.key_table_of(m), 11)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            levels = m.sfnet.features(x)
+            sf = m.sfnet(x)
+            y, st = m(x, cb, [torch.zeros(1, 256, 12, 20)])
+        out[cnn + "_keys"] = np.array(len(sd))
+        for i, lv in enumerate(levels):
+            a = lv.numpy()
+            out["%s_level%d_shape" % (cnn, i)] = np.array(a.shape)
+            out["%s_level%d" % (cnn, i)] = a.ravel()[sample_idx(a.size, "%s_level%d" % (cnn, i))]
+        a = sf.numpy()
+        out[cnn + "_sfnet"] = a.ravel()[sample_idx(a.size, cnn + "_sfnet")]
+        out[cnn + "_out"] = y.numpy()
+        h = st[0].numpy()
+        out[cnn + "_h"] = h.ravel()[sample_idx(h.size, cnn + "_h")]
+        print(cnn, "out range", float(y.min()), float(y.max()), "levels", [tuple(l.shape) for l in levels])
+    np.savez_compressed(os.path.join(GOLD, "backbones.npz"), **out)
+
+
 def gen_plumbing(ref):
     out = {}
     clip = synth.make_clip(0, 16, 288, 512)
@@ -349,7 +379,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "demo": gen_demo_test, "rnn": gen_rnn_small, "post": gen_post}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "demo": gen_demo_test, "rnn": gen_rnn_small, "post": gen_post, "backbones": gen_backbones}
 
 
 def main():

@@ -71,8 +71,9 @@ def load():
         sys.path.remove(REFERENCE_ROOT)
     import torchvision
 
-    mods["model_feature"].feature_loader["mobilenet_v2"] = (
-        lambda pretrained=True: torchvision.models.mobilenet_v2(weights=None))
+    # every backbone constructor of model_feature.feature_loader downloads ImageNet weights (pretrained=True, :59, :80, :115)
+    for name in list(mods["model_feature"].feature_loader):
+        mods["model_feature"].feature_loader[name] = (lambda ctor: (lambda pretrained=True: ctor(weights=None)))(getattr(torchvision.models, name))
     return types.SimpleNamespace(**mods)
 
 

@@ -249,6 +249,38 @@ def test_post_u8_and_metrics(cuda, gold_dir):
     assert ((mine - ref).abs() / ref.abs()).max() < 1e-4
 
 
+@pytest.mark.parametrize("cnn", ["resnet18", "resnet50", "vgg16"])
+def test_backbone_variants(cuda, gold_dir, cnn):
+    """UAVSal(cnn_type=...) on the ResNet / VGG-16 backbones (model_feature.py:72-128, model.py:14-33) against the unmodified
+    reference's outputs (tests/golden/backbones.npz) and, level by level, against the oracle: 7x7 / 3x3 first conv from the frame,
+    max pools, tcgen05 3x3 and 1x1 convs with the plain-ReLU epilogue, stride-2 convs, residual add + ReLU."""
+    from iip_uavsal_saliency_b200.model import UAVSal
+    g = np.load(os.path.join(gold_dir, "backbones.npz"))
+    clip = synth.make_clip(7, 5, 96, 160)
+    x = torch.from_numpy(cpu_ref.normalize_data(clip.transpose(0, 3, 1, 2)))
+    gp, op = synth.make_priors(5, 12, 20, seed=3)
+    cb = [torch.from_numpy(gp), torch.from_numpy(op)]
+    m = UAVSal(cnn_type=cnn, iosize=[96, 160, 12, 20]).eval()
+    sd = synth.make_state_dict_like(synth.key_table_of(m), 11)
+    assert len(sd) == int(g[cnn + "_keys"])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    levels = m.sfnet.features(x.cuda())
+    with torch.no_grad():
+        ref_levels = cpu_ref.backbone_features(sd, "sfnet.features", x, cnn)
+    for i, (a, r) in enumerate(zip(levels, ref_levels)):
+        assert a.shape == r.shape and _rel(a, r) < 5e-4, (cnn, i, _rel(a, r))
+        got = a.cpu().numpy().ravel()[sample_idx(a.numel(), "%s_level%d" % (cnn, i))]
+        assert np.abs(got - g["%s_level%d" % (cnn, i)]).max() <= 2e-3 * max(1.0, np.abs(g["%s_level%d" % (cnn, i)]).max()), (cnn, i)
+    out, st = m(x.cuda(), [c.cuda() for c in cb], [torch.zeros(1, 256, 12, 20).cuda()])
+    assert np.abs(out.cpu().numpy() - g[cnn + "_out"]).max() < 2e-3                  # the north-star map tolerance
+    h = st[0].cpu().numpy()
+    assert np.abs(h.ravel()[sample_idx(h.size, cnn + "_h")] - g[cnn + "_h"]).max() < 1e-2
+    # uint8 frames in (normalisation fused into the first conv) give the same maps
+    out8, _ = m(torch.from_numpy(clip.transpose(0, 3, 1, 2).copy()).cuda(), [c.cuda() for c in cb], [torch.zeros(1, 256, 12, 20).cuda()])
+    assert (out8 - out).abs().max().item() < 1e-5
+
+
 def test_pack_weights_kernel_is_bit_exact(cuda):
     """uavsal_pack_weights (BN fold + layout + bf16 hi/lo split on the device) against its torch restatement (bit for bit when both
     run on the device):

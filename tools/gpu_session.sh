@@ -1,10 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 ) > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; echo "bench n2 rc=$?"; cut -c1-600 gpurun_out/r02_bench_n2.json; tail -5 gpurun_out/r02_bench_n2.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r02_bench_n2.json'))
-print('value',d['value'],'e2e',d['e2e']['value'],'weak',d['weak_scaling']['value'])
-print(json.dumps(d['metrics_config5'])[:900])
-PY
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_tests_all.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r02_tests_all.log
+tail -25 gpurun_out/r02_tests_all.log | cut -c1-300
+( time timeout 900 python bench.py --steps 6 --warmup 3 --skip-aux --skip-cpu ) > gpurun_out/r02_bench_quick.json 2> gpurun_out/r02_bench_quick.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/r02_bench_quick.json; tail -3 gpurun_out/r02_bench_quick.err
