@@ -509,7 +509,7 @@ static inline bool act_ok16(const void* p, int64_t plane, int ld) {
 
 extern int g_dw_fast;
 namespace uavsal {
-extern int g_twa_resident, g_twa_bn, g_metrics_stream;
+extern int g_twa_resident, g_twa_bn, g_metrics_stream, g_metrics_stages;
 int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, int a_stride, Act x, ActW seq, int out_img, int out_stride, int batch, int H, int W, int c,
                       const uint16_t* wgt, int wk_total, int wk_off, const float* gx, int terms, cudaStream_t s, int dbg);
 }
@@ -526,6 +526,7 @@ int uavsal_set_option(int key, int value) {
     if (key == 7 && value >= 0 && value <= 2) { g_twa_resident = value; return 0; }
     if (key == 8 && (value == 64 || value == 128)) { g_twa_bn = value; return 0; }
     if (key == 9 && value >= 0 && value <= 3) { g_metrics_stream = value; return 0; }
+    if (key == 10 && (value == 3 || value == 4 || value == 5 || value == 7)) { g_metrics_stages = value; return 0; }
     set_error("set_option: unknown key %d / value %d", key, value);
     return UAVSAL_EINVAL;
 }

@@ -244,7 +244,7 @@ metrics4_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw,
 // the cluster barrier (39 % of HBM peak); this one keeps the HBM pipe full.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kStChunkBytes = 4096;            // bytes per plane per stage (1024 fp32 or 4096 uint8 pixels)
-constexpr int kStStages = 3;
+constexpr int kStStages = 3;                   // default ring depth (static-shared-memory sized); deeper rings: see g_metrics_stages
 constexpr int kStConsumers = 256;              // 8 consumer warps + 1 producer warp
 constexpr int kStThreads = kStConsumers + 32;
 
@@ -278,6 +278,37 @@ __device__ __forceinline__ void m_bulk_load_hint(void* dst, const void* src, uin
                  ::"r"(m_smem_u32(dst)), "l"(src), "r"(bytes), "r"(m_smem_u32(bar)), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ uint32_t m_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t m_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// wait with a suspend-time hint: the warp sleeps in hardware (up to ~10 us per try) instead of spinning through issue slots that the
+// CTA's other group needs
+__device__ __forceinline__ void m_bar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; !ok; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity), "r"(10000u) : "memory");
+        if (it > (1u << 21)) __trap();
+    }
+}
+// remote 8-byte store whose completion is counted (complete_tx, 8 bytes) on an mbarrier of the destination CTA
+__device__ __forceinline__ void m_st_async_f64(uint32_t addr_cluster, double v, uint32_t bar_cluster) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(addr_cluster), "l"(__double_as_longlong(v)), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ float st_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <typename T>
 __device__ __forceinline__ void lds4v(const T* p, float v[4]);
 template <>
@@ -291,31 +322,42 @@ __device__ __forceinline__ void lds4v<uint8_t>(const uint8_t* p, float v[4]) {
     v[0] = (float)(q & 0xFF); v[1] = (float)((q >> 8) & 0xFF); v[2] = (float)((q >> 16) & 0xFF); v[3] = (float)(q >> 24);
 }
 
-template <typename T>
+// STAGES = ring depth.  The ring size also sets how many CTAs share an SM, i.e. how many pairs are in flight: 3 stages (36 KiB)
+// -> 4 CTAs per SM -> 74 pairs x 1.84 MB of pred + density = 136 MB waiting for pass 2, more than the 126 MB L2 (ncu, round 1:
+// pass 2 re-reads from DRAM); 5 stages (60 KiB) -> 3 CTAs per SM -> 55 pairs = 102 MB with MORE bytes in flight per SM.
+template <typename T, int STAGES>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kStThreads)
 metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, int hw, float* __restrict__ out) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
+    const int rank = (int)m_cluster_rank();
     const int pair = blockIdx.y;
     const T* P = pred + (int64_t)pair * hw;
     const T* D = truth + (int64_t)pair * 2 * hw;
     const T* Fx = D + hw;
 
     constexpr int kStChunk = kStChunkBytes / (int)sizeof(T);                // pixels per chunk
-    __shared__ __align__(128) T ring[kStStages][3][kStChunk];
-    __shared__ uint64_t full[kStStages], empty[kStStages];
+    constexpr int kStStages = STAGES;                                       // (shadows the namespace default)
+    extern __shared__ __align__(128) uint8_t st_smem_raw[];
+    T (*ring)[3][kStChunk] = reinterpret_cast<T (*)[3][kStChunk]>(st_smem_raw);
+    __shared__ uint64_t full[kStStages], empty[kStStages], statbar, p2bar;
     __shared__ double wpart[kStConsumers / 32][S_COUNT];
-    __shared__ double part1[S_COUNT];
-    __shared__ double part2[2];
+    __shared__ double stats[kCluster][S_COUNT];      // [source rank][item]: every CTA of the cluster st.async's its partials here
+    __shared__ double part2[kCluster][2];            // pass-2 partials, st.async'ed to rank 0
     __shared__ double tot[S_COUNT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == kStConsumers / 32;
     if (tid == 0) {
         for (int s = 0; s < kStStages; ++s) { m_bar_init(full + s, 1); m_bar_init(empty + s, kStConsumers / 32); }
+        m_bar_init(&statbar, 1); m_bar_init(&p2bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        m_bar_expect(&statbar, kCluster * S_COUNT * 8);                       // the 88 remote stores of this pair's pass-1 partials
+        if (rank == 0) m_bar_expect(&p2bar, kCluster * 2 * 8);
     }
     __syncthreads();
+    // the ONE cluster barrier of the kernel: every CTA's mbarriers exist before a peer's st.async can reach them.  The partial
+    // statistics then travel as st.async stores that complete_tx on the receiver's mbarrier: the three cluster.sync() of the first
+    // version (release / acquire fences + an L1 invalidation each) were 22 % of the warps' time (ncu, round 2).
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
     // this CTA's chunks: rank, rank + 8, ... ; the same list is walked twice (pass 1: P, D, F; pass 2: P, D)
     const int nchunks = (hw + kStChunk - 1) / kStChunk;
@@ -351,7 +393,12 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
     for (int i = 0; i < S_COUNT; ++i) s[i] = 0.0;
     float mnP = 3.0e38f, mxP = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
     if (!producer) {
-        float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // packed arithmetic (FADD2 / FFMA2 on pixel pairs, 3-input min / max): the kernel is issue-bound, not DRAM-bound (ncu, round 2:
+        // 1.12x the algorithmic bytes at 4.2 TB/s).  One fp32 accumulator lane sees 2 pixels per 1024-pixel step, <= 64 per pair:
+        // every partial sum of uint8-valued maps is an integer below 2^24, i.e. exact; folded into fp64 once, after the loop.
+        float2 a[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) a[j] = make_float2(0.f, 0.f);
         for (int i = 0; i < mine; ++i) {
             const int st = i % kStStages;
             m_bar_wait(full + st, (i / kStStages) & 1);
@@ -363,21 +410,21 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
                     float p[4], t[4], f[4];
                     lds4v<T>(&ring[st][0][e], p); lds4v<T>(&ring[st][1][e], t); lds4v<T>(&ring[st][2][e], f);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a[0] += p[j]; a[1] = fmaf(p[j], p[j], a[1]); a[2] += t[j]; a[3] = fmaf(t[j], t[j], a[3]);
-                        a[4] = fmaf(t[j], p[j], a[4]); a[5] += f[j]; a[6] = fmaf(f[j], p[j], a[6]);
-                        mnP = fminf(mnP, p[j]); mxP = fmaxf(mxP, p[j]); mnT = fminf(mnT, t[j]); mxT = fmaxf(mxT, t[j]);
+                    for (int j = 0; j < 4; j += 2) {
+                        const float2 pp = make_float2(p[j], p[j + 1]), tt = make_float2(t[j], t[j + 1]), ff = make_float2(f[j], f[j + 1]);
+                        a[0] = __fadd2_rn(a[0], pp); a[1] = __ffma2_rn(pp, pp, a[1]); a[2] = __fadd2_rn(a[2], tt); a[3] = __ffma2_rn(tt, tt, a[3]);
+                        a[4] = __ffma2_rn(tt, pp, a[4]); a[5] = __fadd2_rn(a[5], ff); a[6] = __ffma2_rn(ff, pp, a[6]);
                     }
+                    mnP = fminf(fminf(fminf(p[0], p[1]), fminf(p[2], p[3])), mnP); mxP = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), mxP);
+                    mnT = fminf(fminf(fminf(t[0], t[1]), fminf(t[2], t[3])), mnT); mxT = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), mxT);
                 }
             }
             __syncwarp();
             if (lane == 0) m_bar_arrive(empty + st);
-            if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) {       // fold the fp32 run (<= 32 pixels per thread: exact for uint8-valued maps) into fp64
-                s[S_P] += a[0]; s[S_P2] += a[1]; s[S_T] += a[2]; s[S_T2] += a[3]; s[S_TP] += a[4]; s[S_F] += a[5]; s[S_FP] += a[6];
-#pragma unroll
-                for (int j = 0; j < 7; ++j) a[j] = 0.f;
-            }
         }
+        s[S_P] = (double)a[0].x + (double)a[0].y; s[S_P2] = (double)a[1].x + (double)a[1].y; s[S_T] = (double)a[2].x + (double)a[2].y;
+        s[S_T2] = (double)a[3].x + (double)a[3].y; s[S_TP] = (double)a[4].x + (double)a[4].y; s[S_F] = (double)a[5].x + (double)a[5].y;
+        s[S_FP] = (double)a[6].x + (double)a[6].y;
         s[S_MINP] = mnP; s[S_MAXP] = mxP; s[S_MINT] = mnT; s[S_MAXT] = mxT;
 #pragma unroll
         for (int i = 0; i < S_COUNT; ++i) {
@@ -389,28 +436,29 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
         }
     }
     __syncthreads();
-    if (tid < S_COUNT) {
-        const int i = tid;
-        double v = wpart[0][i];
+    if (tid < kCluster * S_COUNT) {                                           // thread (dest, item): this CTA's partial -> CTA `dest`
+        const int item = tid % S_COUNT, dest = tid / S_COUNT;
+        double v = wpart[0][item];
         for (int w = 1; w < kStConsumers / 32; ++w) {
-            if (i == S_MINP || i == S_MINT) v = fmin(v, wpart[w][i]);
-            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, wpart[w][i]);
-            else v += wpart[w][i];
+            if (item == S_MINP || item == S_MINT) v = fmin(v, wpart[w][item]);
+            else if (item == S_MAXP || item == S_MAXT) v = fmax(v, wpart[w][item]);
+            else v += wpart[w][item];
         }
-        part1[i] = v;
+        m_st_async_f64(m_mapa(m_smem_u32(&stats[rank][item]), (uint32_t)dest), v, m_mapa(m_smem_u32(&statbar), (uint32_t)dest));
     }
-    cluster.sync();
-    if (tid < S_COUNT) {
-        const int i = tid;
-        double v = 0.0;
-        for (int r = 0; r < kCluster; ++r) {
-            const double o = *cluster.map_shared_rank(&part1[i], r);
-            if (r == 0) v = o;
-            else if (i == S_MINP || i == S_MINT) v = fmin(v, o);
-            else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
-            else v += o;
+    if (warp == 0) {                                                          // the other warps sleep in the block barrier below
+        m_bar_wait_sleep(&statbar, 0);
+        if (tid < S_COUNT) {
+            const int i = tid;
+            double v = stats[0][i];
+            for (int r = 1; r < kCluster; ++r) {
+                const double o = stats[r][i];
+                if (i == S_MINP || i == S_MINT) v = fmin(v, o);
+                else if (i == S_MAXP || i == S_MAXT) v = fmax(v, o);
+                else v += o;
+            }
+            tot[i] = v;
         }
-        tot[i] = v;
     }
     __syncthreads();
 
@@ -428,7 +476,12 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
     double kld = 0.0, sim = 0.0;
     if (producer && lane == 0) produce(ahead, 2 * mine);
     if (!producer) {
-        float k = 0.f, sm = 0.f;
+        // th * log(th / (ph + EPS) + EPS) as th * (lg2(th) - lg2(ph + EPS)) * ln 2: the reference's second +EPS (inside the log) only
+        // matters where th / ph < 1e-9, i.e. for < 4e-8 of the sum; th = 0 contributes 0 (the clamp keeps lg2 finite)
+        const float2 rdT2 = make_float2(rdT, rdT), rdP2 = make_float2(rdP, rdP), eps2 = make_float2(kEpsF, kEpsF);
+        const float2 rnT2 = make_float2(rnT, rnT), rnP2 = make_float2(rnP, rnP);
+        const float2 cT2 = make_float2(-minT * rnT, -minT * rnT), cP2 = make_float2(-minP * rnP, -minP * rnP);
+        float2 kf = make_float2(0.f, 0.f), sf = make_float2(0.f, 0.f);
         for (int i = 0; i < mine; ++i) {
             const int ii = mine + i;
             const int st = ii % kStStages;
@@ -441,17 +494,24 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
                     float p[4], t[4];
                     lds4v<T>(&ring[st][0][e], p); lds4v<T>(&ring[st][1][e], t);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float th = t[j] * rdT, ph = p[j] * rdP;
-                        k = fmaf(th, __logf(__fdividef(th, ph + kEpsF) + kEpsF), k);
-                        sm += fminf((t[j] - minT) * rnT, (p[j] - minP) * rnP);
+                    for (int j = 0; j < 4; j += 2) {
+                        const float2 pp = make_float2(p[j], p[j + 1]), tt = make_float2(t[j], t[j + 1]);
+                        const float2 th = __fmul2_rn(tt, rdT2), phe = __ffma2_rn(pp, rdP2, eps2);
+                        const float2 d = make_float2(st_lg2(fmaxf(th.x, 1.2e-38f)) - st_lg2(phe.x), st_lg2(fmaxf(th.y, 1.2e-38f)) - st_lg2(phe.y));
+                        kf = __ffma2_rn(th, d, kf);
+                        const float2 uu = __ffma2_rn(tt, rnT2, cT2), vv = __ffma2_rn(pp, rnP2, cP2);
+                        sf = __fadd2_rn(sf, make_float2(fminf(uu.x, vv.x), fminf(uu.y, vv.y)));
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) m_bar_arrive(empty + st);
-            if (sizeof(T) == 1 || (i & 7) == 7 || i == mine - 1) { kld += k; sim += sm; k = 0.f; sm = 0.f; }
+            if ((i & 7) == 7 || i == mine - 1) {                         // (general floats: keep the fp32 runs of the non-linear terms short)
+                kld += (double)kf.x + (double)kf.y; sim += (double)sf.x + (double)sf.y;
+                kf = make_float2(0.f, 0.f); sf = make_float2(0.f, 0.f);
+            }
         }
+        kld *= 0.6931471805599453;                                        // log2 -> natural log
         kld = warp_sum(kld);
         sim = warp_sum(sim);
         if (lane == 0) { wpart[warp][0] = kld; wpart[warp][1] = sim; }
@@ -460,15 +520,12 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
     if (tid < 2) {
         double v = 0.0;
         for (int w = 0; w < kStConsumers / 32; ++w) v += wpart[w][tid];
-        part2[tid] = v;
+        m_st_async_f64(m_mapa(m_smem_u32(&part2[rank][tid]), 0u), v, m_mapa(m_smem_u32(&p2bar), 0u));
     }
-    cluster.sync();
     if (rank == 0 && tid == 0) {
+        m_bar_wait_sleep(&p2bar, 0);
         double k = 0.0, smm = 0.0;
-        for (int r = 0; r < kCluster; ++r) {
-            k += *cluster.map_shared_rank(&part2[0], r);
-            smm += *cluster.map_shared_rank(&part2[1], r);
-        }
+        for (int r = 0; r < kCluster; ++r) { k += part2[r][0]; smm += part2[r][1]; }
         const double mP = tot[S_P] / n, mT = tot[S_T] / n;
         const double ssP = fmax(tot[S_P2] - tot[S_P] * mP, 0.0), ssT = fmax(tot[S_T2] - tot[S_T] * mT, 0.0);
         const double sdP = sqrt(ssP / (n - 1.0)), sdT = sqrt(ssT / (n - 1.0));
@@ -481,7 +538,8 @@ metrics4_stream_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
         out[pair * 4 + 2] = (float)k;
         out[pair * 4 + 3] = (float)smm;
     }
-    cluster.sync();
+    // everything sent to this CTA has been awaited (the statistics by warp 0 before pass 2, the pass-2 partials by rank 0): no CTA
+    // needs its peers to stay around, so there is no trailing cluster barrier
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -525,31 +583,6 @@ struct TmSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t m_cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t m_mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-// wait with a suspend-time hint: the warp sleeps in hardware (up to ~10 us per try) instead of spinning through issue slots that the
-// CTA's other group needs
-__device__ __forceinline__ void m_bar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t it = 0; !ok; ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(m_smem_u32(bar)), "r"(parity), "r"(10000u) : "memory");
-        if (it > (1u << 21)) __trap();
-    }
-}
-// remote 8-byte store whose completion is counted (complete_tx, 8 bytes) on an mbarrier of the destination CTA
-__device__ __forceinline__ void m_st_async_f64(uint32_t addr_cluster, double v, uint32_t bar_cluster) {
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                 ::"r"(addr_cluster), "l"(__double_as_longlong(v)), "r"(bar_cluster) : "memory");
-}
 __device__ __forceinline__ void m_tmem_st8(uint32_t taddr, const float v[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
@@ -1110,6 +1143,7 @@ metrics4_tmem16_kernel(const T* __restrict__ pred, const T* __restrict__ truth, 
     if (producer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"((uint32_t)kT16Cols) : "memory");
 }
 
+int g_metrics_stages = 4;      // uavsal_set_option key 10: ring depth of the streaming kernel (3 | 5 | 7 -> 4 | 3 | 2 CTAs per SM)
 int g_metrics_stream = 1;      // uavsal_set_option key 9: 1 = streaming kernel (pass 2 re-read through L2; default: the fastest measured), 2 = TMEM-resident kernel, one pair per cluster of 16,
                                // 3 = TMEM-resident persistent kernel (clusters of 8; every byte crosses HBM once),
                                // 0 = register-batched kernel
@@ -1187,12 +1221,25 @@ extern "C" int uavsal_metrics4(const void* pred, const void* truth, int dtype, i
     UAVSAL_REQUIRE(n <= 65535, UAVSAL_ENOTSUP, "metrics4: at most 65535 pairs per call for this map size");
     dim3 grid(kCluster, n);
     if (g_metrics_stream && bulk_ok && hw >= kCluster * kStChunkBytes) {
-        if (dtype == 0)
-            metrics4_stream_kernel<float><<<grid, kStThreads, 0, (cudaStream_t)stream>>>(
-                reinterpret_cast<const float*>(pred), reinterpret_cast<const float*>(truth), hw, out);
-        else
-            metrics4_stream_kernel<uint8_t><<<grid, kStThreads, 0, (cudaStream_t)stream>>>(
-                reinterpret_cast<const uint8_t*>(pred), reinterpret_cast<const uint8_t*>(truth), hw, out);
+        const int st = g_metrics_stages;
+        const size_t smem = (size_t)st * 3 * kStChunkBytes;
+#define UAVSAL_STREAM_LAUNCH(TYPE, ST)                                                                                              \
+        do {                                                                                                                        \
+            static bool attr = false;                                                                                               \
+            if (!attr) {                                                                                                            \
+                cudaError_t e = cudaFuncSetAttribute(metrics4_stream_kernel<TYPE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                if (e != cudaSuccess) { set_error("metrics4(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }       \
+                attr = true;                                                                                                        \
+            }                                                                                                                       \
+            metrics4_stream_kernel<TYPE, ST><<<grid, kStThreads, smem, (cudaStream_t)stream>>>(                                      \
+                reinterpret_cast<const TYPE*>(pred), reinterpret_cast<const TYPE*>(truth), hw, out);                                \
+        } while (0)
+        if (dtype == 0) {
+            if (st == 4) UAVSAL_STREAM_LAUNCH(float, 4); else if (st == 5) UAVSAL_STREAM_LAUNCH(float, 5); else if (st == 7) UAVSAL_STREAM_LAUNCH(float, 7); else UAVSAL_STREAM_LAUNCH(float, 3);
+        } else {
+            if (st == 4) UAVSAL_STREAM_LAUNCH(uint8_t, 4); else if (st == 5) UAVSAL_STREAM_LAUNCH(uint8_t, 5); else if (st == 7) UAVSAL_STREAM_LAUNCH(uint8_t, 7); else UAVSAL_STREAM_LAUNCH(uint8_t, 3);
+        }
+#undef UAVSAL_STREAM_LAUNCH
         return check_launch("metrics4(stream)");
     }
     if (dtype == 0)
