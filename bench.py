@@ -206,7 +206,7 @@ def run_reference_arm(args):
     clip = synth.make_clip(100, 20, H, W)
     for _ in range(max(0, min(args.warmup, 1))):
         arm.uavsal_call(clip)
-    ts = [arm.uavsal_call(clip) for _ in range(max(1, min(args.steps, 12)))]
+    ts = [arm.uavsal_call(clip) for _ in range(max(1, min(args.steps, 30)))]        # ~2 s per step on 16 cores
     total = sum(ts)
     fps = 20 * len(ts) / total
     sample = ("one 20-frame call (batch_size=4 x time_dims=5) of a 64-frame clip per step, incl. normalisation and the CPU post-process "

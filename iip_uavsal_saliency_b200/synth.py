@@ -221,10 +221,11 @@ def make_state_dict_lstm(seed: int = 0):
     return sd
 
 
-def make_eval_dataset(root: str, sal: str, seed: int = 0, method: str = "UAVSal"):
+def make_eval_dataset(root: str, sal: str, seed: int = 0, method: str = "UAVSal", halve_second: bool = True):
     """A tiny evaluation tree in the layout evalscores_vid_torch walks (utils_score_torch.py:473-490): two 5-frame videos at
     36x64 (12 fixations per frame), the second one's saliency maps at half size (the driver's cv2.resize path).  Written with
-    the package's MAT v7.3 writer.  Returns the arrays for reference."""
+    the package's MAT v7.3 writer (halve_second=False keeps both at full size: the `_sum` protocol asserts equal sizes).  Returns
+    the arrays for reference."""
     import os
     from iip_uavsal_saliency_b200 import mat73
     H, W, F = 36, 64, 5
@@ -241,7 +242,7 @@ def make_eval_dataset(root: str, sal: str, seed: int = 0, method: str = "UAVSal"
             idx = rs.choice(H * W, size=12, replace=False, p=p / p.sum())
             fixpts[:, :, 0, f].flat[idx] = 1
         sal_u8 = np.rint(pred[:, 0]).astype(np.uint8)
-        if v == 1:
+        if v == 1 and halve_second:
             sal_u8 = sal_u8[:, ::2, ::2]
         salmap = np.ascontiguousarray(sal_u8.transpose(1, 2, 0)[:, :, None, :])
         mat73.savemat(sal + "Saliency/" + method + "/" + name + ".mat", {"salmap": salmap})

@@ -220,6 +220,44 @@ def getshufmap(ALLFixPts, size=(480, 640), nframes=10):
     return out
 
 
+def _score_frames(salmap, fixmap, nframes, keys_order, batch_size, shuf_of):
+    """The metric loop shared by the two evaluation drivers (utils_score_torch.py:541-572 / 436-466): salmap (F,1,H,W), fixmap
+    (F,2,H,W) numpy -> (F, len(keys_order)) scores, NaN rows for frames without a prediction or without ground truth.
+    ``shuf_of(itrue)`` supplies AUC_shuffled's third argument for a batch."""
+    import math
+    import numpy as np
+    iscores = np.zeros((nframes, len(keys_order)))
+    # CC / NSS / KLD / SIM come out of one fused launch per batch; they draw no random numbers, so computing them ahead of
+    # the reference's metric-major loop (:541-561) leaves the generator order of the sampled AUCs untouched
+    fused = [m for m in ("CC", "NSS", "KLD", "SIM") if m in keys_order]
+    if fused:
+        col = {"CC": 0, "NSS": 1, "KLD": 2, "SIM": 3}
+        for b in range(math.ceil(nframes / batch_size)):
+            ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
+            itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
+            m4 = metrics4(ipred.to(device), itrue.to(device)).cpu()
+            for m in fused:
+                iscores[b * batch_size:(b + 1) * batch_size, keys_order.index(m)] = m4[:, col[m]]
+    for k, metric in enumerate(keys_order):
+        if metric in fused:
+            continue
+        func = metrics[metric]
+        for b in range(math.ceil(nframes / batch_size)):
+            ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
+            itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
+            if metric == "AUC_shuffled":
+                m = func(ipred, itrue, shuf_of(itrue))
+            elif metric == "AUC_Borji":
+                m = func(ipred, itrue)
+            else:
+                m = func(ipred.to(device), itrue.to(device))
+            iscores[b * batch_size:(b + 1) * batch_size, k] = m.data.cpu()[:, 0]
+    for f in range(nframes):
+        if not np.any(salmap[f, 0]) or not np.any(fixmap[f], axis=(1, 2)).all():
+            iscores[f] = np.nan
+    return iscores
+
+
 def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_order, batch_size=64):
     """utils_score_torch.py:473-582: per-video score files ``Scores/<method>/Score_<video>.mat`` ({'iscore': (frames, metrics)})
     from ``Saliency/<method>/<video>.mat`` (salmap), ``maps/<video>_fixMaps.mat`` and ``fixations/maps/<video>_fixPts.mat``.
@@ -260,7 +298,6 @@ def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_
             fixmap = mat73.loadmat(mapsDir + file_name + "_fixMaps.mat")["fixMap"]
             fixpts = mat73.loadmat(fixsDir + file_name + "_fixPts.mat")["fixLoc"]
             nframes = min(salmap.shape[3], min(fixpts.shape[3], fixmap.shape[3]))
-            iscores = np.zeros((nframes, len(keys_order)))
             if salmap.shape[:2] != fixmap.shape[:2]:
                 import cv2
                 rs = np.zeros((nframes, 1, fixmap.shape[0], fixmap.shape[1]))
@@ -270,35 +307,8 @@ def evalscores_vid_torch(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_
             else:
                 salmap = salmap[:, :, :, :nframes].transpose((3, 2, 0, 1))
             fixmap = np.concatenate((fixmap[:, :, :, :nframes], fixpts[:, :, :, :nframes]), axis=2).transpose((3, 2, 0, 1))
-            # CC / NSS / KLD / SIM come out of one fused launch per batch; they draw no random numbers, so computing them ahead of
-            # the reference's metric-major loop (:541-561) leaves the generator order of the sampled AUCs untouched
-            fused = [m for m in ("CC", "NSS", "KLD", "SIM") if m in keys_order]
-            if fused:
-                col = {"CC": 0, "NSS": 1, "KLD": 2, "SIM": 3}
-                for b in range(math.ceil(nframes / batch_size)):
-                    ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
-                    itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
-                    m4 = metrics4(ipred.to(device), itrue.to(device)).cpu()
-                    for m in fused:
-                        iscores[b * batch_size:(b + 1) * batch_size, keys_order.index(m)] = m4[:, col[m]]
-            for k, metric in enumerate(keys_order):
-                if metric in fused:
-                    continue
-                func = metrics[metric]
-                for b in range(math.ceil(nframes / batch_size)):
-                    ipred = torch.tensor(salmap[b * batch_size:(b + 1) * batch_size]).float()
-                    itrue = torch.tensor(fixmap[b * batch_size:(b + 1) * batch_size]).float()
-                    if metric == "AUC_shuffled":
-                        shuf = np.array([getshufmap(all_pts, size=fixmap.shape[2:]) for _ in range(itrue.shape[0])])
-                        m = func(ipred, itrue, torch.tensor(shuf).float().unsqueeze(1))
-                    elif metric == "AUC_Borji":
-                        m = func(ipred, itrue)
-                    else:
-                        m = func(ipred.to(device), itrue.to(device))
-                    iscores[b * batch_size:(b + 1) * batch_size, k] = m.data.cpu()[:, 0]
-            for f in range(nframes):
-                if not np.any(salmap[f, 0]) or not np.any(fixmap[f], axis=(1, 2)).all():
-                    iscores[f] = np.nan
+            shuf_of = lambda itrue: torch.tensor(np.array([getshufmap(all_pts, size=fixmap.shape[2:]) for _ in range(itrue.shape[0])])).float().unsqueeze(1)
+            iscores = _score_frames(salmap, fixmap, nframes, keys_order, batch_size, shuf_of)
             scores[file_name] = iscores
             mat73.savemat(iscore_path, {"iscore": iscores})
         result[method] = scores
@@ -325,3 +335,61 @@ def getSumFix_vid(fixsDir, DataSet="DIEM20", size=None, maxframes=float("inf")):
         shuf += np.sum(fix[:, :, 0, :], axis=2)
         shuf = np.round(shuf)
     return shuf
+
+
+def evalscores_vid_torch_sum(RootDir, SalDir, DataSet, MethodNames, keys_order=keys_order, batch_size=64):
+    """utils_score_torch.py:368-470 (the "STRNN" protocol): as evalscores_vid_torch, but AUC-shuffled uses ONE fixed shuffle map -
+    the dataset's summed fixation map (``getSumFix_vid``, cached as ``RootDir/Shuffle_<DATASET>.mat``, resized with
+    ``resize_fixation`` when its size differs from the fixation maps') - the saliency maps must already have the ground truth's
+    size, and the score files go to ``Scores_sum/``.
+
+    Two behaviours of the reference are kept as they are: (1) its ``shuffle_map != []`` test is meant as "a shuffle map is in use"
+    (numpy < 1.25 answered True for an array; numpy 2 raises, so the reference cannot run this protocol today); (2) the (H, W) map
+    goes to ``metric_auc_s`` unbatched, whose ``flatten(1, -1)`` leaves it (H, W), so frame i of a batch draws its "other" pixels
+    from ROW i of the map (:162-172) - hence batch_size must not exceed H.  Pinned against the unmodified reference run with an
+    ndarray subclass that restores (1) (tests/golden/eval_driver_sum.npz)."""
+    import os
+    import numpy as np
+    from . import mat73
+    mapsDir, fixsDir = RootDir + "maps/", RootDir + "fixations/maps/"
+    salsDir, scoreDir = SalDir + "Saliency/", SalDir + "Scores_sum/"
+    os.makedirs(scoreDir, exist_ok=True)
+    shuffle_map = None
+    if "AUC_shuffled" in keys_order:
+        shuff_path = RootDir + "Shuffle_" + DataSet.upper() + ".mat"
+        if not os.path.exists(shuff_path):
+            shuffle_map = getSumFix_vid(fixsDir, DataSet)
+            mat73.savemat(shuff_path, {"ShufMap": shuffle_map})
+        else:
+            shuffle_map = mat73.loadmat(shuff_path)["ShufMap"]
+    result = {}
+    for method in MethodNames:
+        if os.path.exists(scoreDir + "Score_" + method + ".mat"):
+            continue
+        iscoreDir = scoreDir + method + "/"
+        os.makedirs(iscoreDir, exist_ok=True)
+        salmap_dir = salsDir + method + "/"
+        scores = {}
+        for sal_name in sorted(f for f in os.listdir(salmap_dir) if f.endswith(".mat")):
+            file_name = sal_name[:-4]
+            iscore_path = iscoreDir + "Score_" + file_name + ".mat"
+            if os.path.exists(iscore_path):
+                scores[file_name] = mat73.loadmat(iscore_path)["iscore"]
+                continue
+            salmap = mat73.loadmat(salmap_dir + file_name + ".mat")["salmap"]
+            fixmap = mat73.loadmat(mapsDir + file_name + "_fixMaps.mat")["fixMap"]
+            fixpts = mat73.loadmat(fixsDir + file_name + "_fixPts.mat")["fixLoc"]
+            ishuf = shuffle_map
+            if shuffle_map is not None and shuffle_map.shape != fixpts.shape[:2]:
+                ishuf = resize_fixation(shuffle_map, fixpts.shape[0], fixpts.shape[1])
+            ishuf = torch.tensor(np.asarray(ishuf if ishuf is not None else [])).float()
+            nframes = min(salmap.shape[3], min(fixpts.shape[3], fixmap.shape[3]))
+            salmap = salmap[:, :, :, :nframes].transpose((3, 2, 0, 1))
+            fixmap = np.concatenate((fixmap[:, :, :, :nframes], fixpts[:, :, :, :nframes]), axis=2).transpose((3, 2, 0, 1))
+            if salmap.shape[2:] != fixmap.shape[2:]:
+                raise AssertionError("saliency maps %s and fixation maps %s differ in size (utils_score_torch.py:432)" % (salmap.shape[2:], fixmap.shape[2:]))
+            iscores = _score_frames(salmap, fixmap, nframes, keys_order, batch_size, lambda itrue: ishuf)
+            scores[file_name] = iscores
+            mat73.savemat(iscore_path, {"iscore": iscores})
+        result[method] = scores
+    return result

@@ -296,6 +296,46 @@ def gen_eval_driver(ref):
     print(list(us.keys_order)); print(res["vidA"].round(4)); print(res["vidB"].round(4))
 
 
+def gen_eval_driver_sum(ref):
+    """evalscores_vid_torch_sum (utils_score_torch.py:368-470) of the unmodified reference.  Its `shuffle_map != []` test (:424)
+    raises under numpy 2 ("operands could not be broadcast"); numpy < 1.25 answered True for an array.  That one legacy answer is
+    restored without touching the source: the hdf5storage stub hands ShufMap over as an ndarray subclass whose __ne__ says True
+    to an empty list.  The shuffle map file is written beforehand with the reference's own getSumFix_vid (the branch that
+    computes it in place would compare a plain ndarray)."""
+    import tempfile
+    import hdf5storage as h5
+    from iip_uavsal_saliency_b200 import mat73
+    us = ref.utils_score_torch
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "NaN"):
+        np.NaN = np.nan
+
+    class LegacyNe(np.ndarray):
+        def __ne__(self, other):
+            if isinstance(other, list) and len(other) == 0:
+                return True
+            return np.ndarray.__ne__(self, other)
+
+    orig = h5.loadmat
+    h5.loadmat = lambda path, *a, **k: {kk: (v.view(LegacyNe) if kk == "ShufMap" else v) for kk, v in orig(path).items()}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            root, sal = td + "/data/", td + "/res/"
+            synth.make_eval_dataset(root, sal, 0, halve_second=False)
+            sm = us.getSumFix_vid(root + "fixations/maps/", "UAV2")
+            mat73.savemat(root + "Shuffle_UAV2.mat", {"ShufMap": sm})
+            np.random.seed(12)
+            torch.manual_seed(12)
+            us.evalscores_vid_torch_sum(root, sal, "UAV2", ["UAVSal"], batch_size=3)
+            res = {n: mat73.loadmat(sal + "Scores_sum/UAVSal/Score_%s.mat" % n)["iscore"] for n in ("vidA", "vidB")}
+            res["shufmap_sum"] = np.array(sm.sum())
+    finally:
+        h5.loadmat = orig
+    np.savez_compressed(os.path.join(GOLD, "eval_driver_sum.npz"), keys=np.array(list(us.keys_order)), **res)
+    print(res["vidA"].round(4)); print(res["vidB"].round(4))
+
+
 def gen_demo_test(ref):
     """Demo_Test.test (Demo_Test.py:30-95) of the unmodified reference, end to end on the committed MJPG clip: decode, letterbox
     to 360x640, one 5-frame call with the real UAV2 priors, post-process to the video's size, salmap .mat.  The model file is
@@ -379,7 +419,7 @@ def gen_post(ref):
 
 
 GENS = {"priors": gen_priors, "plumbing": gen_plumbing, "clip64": gen_clip64, "call20": gen_call20_trace,
-        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "demo": gen_demo_test, "rnn": gen_rnn_small, "post": gen_post, "backbones": gen_backbones}
+        "metrics": gen_metrics, "auc": gen_auc, "frontend": gen_frontend, "lstm_model": gen_lstm_model, "eval": gen_eval_driver, "eval_sum": gen_eval_driver_sum, "demo": gen_demo_test, "rnn": gen_rnn_small, "post": gen_post, "backbones": gen_backbones}
 
 
 def main():

@@ -75,6 +75,8 @@ def test_constructor_signatures_and_defaults():
     assert list(inspect.signature(US.metric_auc_j).parameters) == ["y_pred", "y_true", "jitter"]
     assert list(inspect.signature(US.metric_auc_b).parameters) == ["y_pred", "y_true"]
     assert list(inspect.signature(US.metric_auc_s).parameters) == ["y_pred", "y_true", "shuff_map"]
+    for fn in (US.evalscores_vid_torch, US.evalscores_vid_torch_sum):                          # utils_score_torch.py:368, 473
+        assert list(inspect.signature(fn).parameters) == ["RootDir", "SalDir", "DataSet", "MethodNames", "keys_order", "batch_size"]
 
 
 def test_error_behaviour_follows_reference():

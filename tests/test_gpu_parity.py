@@ -714,6 +714,32 @@ def test_metrics_on_successive_equal_shaped_batches(cuda, gold_dir, tmp_path):
             np.testing.assert_allclose(mine[:, k], g[name][:, list(g["keys"]).index(key)], atol=1e-6, rtol=1e-4, err_msg="%s %s" % (name, key))
 
 
+def test_eval_driver_sum_protocol(cuda, gold_dir, tmp_path):
+    """evalscores_vid_torch_sum (utils_score_torch.py:368-470): one fixed shuffle map (the dataset's summed fixations, created and
+    cached by the driver, resized to the fixation maps' size), Scores_sum/ output, the per-row use of the 2-D map kept.  Against
+    the unmodified reference's score files (tests/golden/eval_driver_sum.npz; oracle/make_golden.py gen_eval_driver_sum restores the
+    one legacy-numpy answer the reference needs), generators seeded with 12."""
+    from iip_uavsal_saliency_b200 import mat73
+    from iip_uavsal_saliency_b200 import utils_score_torch as us
+    g = np.load(os.path.join(gold_dir, "eval_driver_sum.npz"))
+    root, sal = str(tmp_path) + "/data/", str(tmp_path) + "/res/"
+    synth.make_eval_dataset(root, sal, 0, halve_second=False)
+    np.random.seed(12)
+    torch.manual_seed(12)
+    res = us.evalscores_vid_torch_sum(root, sal, "UAV2", ["UAVSal"], batch_size=3)          # computes and caches Shuffle_UAV2.mat itself
+    assert abs(float(mat73.loadmat(root + "Shuffle_UAV2.mat")["ShufMap"].sum()) - float(g["shufmap_sum"])) < 1e-9
+    for name in ("vidA", "vidB"):
+        mine = mat73.loadmat(sal + "Scores_sum/UAVSal/Score_%s.mat" % name)["iscore"]
+        assert mine.shape == g[name].shape == (5, 7) and np.array_equal(mine, res["UAVSal"][name])
+        for k, key in enumerate(us.keys_order):
+            tol = dict(atol=2e-5, rtol=0) if key.startswith("AUC") else dict(atol=1e-6, rtol=1e-4)
+            np.testing.assert_allclose(mine[:, k], g[name][:, k], err_msg="%s %s" % (name, key), **tol)
+    # maps of another size than the ground truth are an error in this protocol (:432), not a silent resize
+    synth.make_eval_dataset(root, str(tmp_path) + "/res2/", 0, halve_second=True)
+    with pytest.raises(AssertionError):
+        us.evalscores_vid_torch_sum(root, str(tmp_path) + "/res2/", "UAV2", ["UAVSal"], keys_order=["CC"], batch_size=3)
+
+
 def test_frontend_and_auc_edge_cases(cuda):
     """Limits and degenerate inputs of the widened-path kernels: tiny sources, extreme aspect ratios, unsupported widths
     (error, not a wrong answer), degenerate AUC inputs."""
