@@ -136,6 +136,13 @@ class ClipRunner:
         F_ = frames.shape[0]
         H, W = (frames.shape[1], frames.shape[2]) if self.kind == 2 else (frames.shape[2], frames.shape[3])
         keep = (F_ // self.T) * self.T
+        if keep == 0:
+            # fewer frames than one chunk: Demo_Test's loop body never runs (count_bs = 0, Demo_Test.py:68-76) and the video gets
+            # an empty salmap
+            mh, mw = self.model._iosize[2], self.model._iosize[3]
+            oh, ow = self.out_hw or (H, W)
+            m = torch.empty((0, 1, mh, mw), device=self.dev) if want_maps else None
+            return m, (out[:0] if out is not None else torch.empty((0, oh, ow), dtype=torch.uint8, device=self.dev))
         if self.whole_clip:
             return self._run_whole(frames, keep, H, W, want_maps, out, sync)
         ncalls = math.ceil(keep / self.per_call)

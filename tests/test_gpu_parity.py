@@ -464,6 +464,12 @@ def test_clip_runner_config2_and_config1(cuda, gold_dir):
     assert np.abs(u8[g["u8_frame_idx"]].astype(int) - g["u8_frames"].astype(int)).max() <= 1
     # size-independent properties at full size: maps in (0,1), every uint8 frame peaks at 255
     assert maps.min() > 0 and maps.max() < 1 and (u8.reshape(60, -1).max(1) == 255).all()
+    # ragged / empty clips: 3 frames < time_dims -> no call at all (Demo_Test.py:68-76), 27 frames -> calls of 20 and 5, 2 dropped
+    m0, u0 = r.run_clip(torch.from_numpy(synth.make_clip(2, 3, 360, 640)).cuda())
+    assert m0.shape == (0, 1, 45, 80) and u0.shape == (0, 360, 640)
+    m27, u27 = r.run_clip(torch.from_numpy(synth.make_clip(2, 64, 360, 640)[:27]).cuda())
+    assert m27.shape == (25, 1, 45, 80) and u27.shape == (25, 360, 640)
+    assert np.abs(m27[:20].cpu().numpy() - maps[:20]).max() < 1e-5              # the first call is the first call of the long clip
     # host-pinned input gives identical output (the e2e path of bench.py)
     _, u8b = r.run_clip(torch.from_numpy(synth.make_clip(2, 64, 360, 640)).pin_memory(), want_maps=False)
     assert np.array_equal(u8b.cpu().numpy(), u8)
