@@ -1,14 +1,13 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_tests_all.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r02_tests_all.log
-tail -6 gpurun_out/r02_tests_all.log | cut -c1-300
-( time timeout 600 python __graft_entry__.py --smoke ) > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/r02_smoke.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_smoke_launches.csv python __graft_entry__.py --smoke > gpurun_out/r02_smoke_ncu.log 2>&1; echo "smoke ncu rc=$?"
-python - <<'PY'
-import csv, collections
-rows=[r for r in csv.reader(open('gpurun_out/r02_smoke_launches.csv', errors='replace')) if len(r)>10]
-h=rows[0]; ik=h.index('Kernel Name')
-c=collections.Counter(r[ik].split('(')[0][:60] for r in rows[1:])
-print(len(rows)-1, 'launches in the first 400:'); [print('  %4d %s'%(v,k)) for k,v in c.most_common(25)]
+for n in 8 4; do
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 ) > gpurun_out/r02_bench_n$n.json 2> gpurun_out/r02_bench_n$n.err; echo "bench n$n rc=$?"
+python - <<PY
+import json
+lines=[l for l in open('gpurun_out/r02_bench_n$n.json') if l.startswith('{')]
+d=json.loads(lines[-1])
+print('N=$n value',round(d['value']),'e2e',round(d['e2e']['value']),'weak',round(d['weak_scaling']['value']),'timed',d['timed_region_s'],'clock samples',d['clocks']['samples'])
+m=d['metrics_config5']; print('  metrics5',round(m['pairs_per_s']),m['ms'],m['allreduce'],m['allreduce_ms'],m['frac'],m['means_vs_single_rank_rel_err'])
 PY
+done
