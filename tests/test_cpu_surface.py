@@ -292,3 +292,36 @@ def test_pack_reference_matches_the_module_level_folding():
     dw = BasicConv2d(16, 16, 3, groups=16)
     wd, bd = dw.wspec().pack_reference(engine.W_COLS_F32, 16, 9)
     assert torch.equal(wd, engine.pack_dw(dw.folded()[0])) and torch.equal(bd, dw.folded()[1])
+
+
+def test_backbone_wrappers_surface():
+    """ReResNet / ReVGG (model_feature.py:72-128): error behaviour of the name checks, torchvision's state-dict layout (without
+    the classification head the reference discards), the reference's feature_loader / feature_inplanes tables (model.py:14-33),
+    and the plan structure of a ResNet-50 UAVSal."""
+    import torchvision
+    with pytest.raises(ValueError):
+        MF.ReResNet("mobilenet_v2")                      # not a resnet name (:75-76)
+    with pytest.raises(NotImplementedError):
+        MF.ReResNet("resnext50_32x4d")                   # a torchvision resnet the reference has no loader for (:77-78)
+    with pytest.raises(ValueError):
+        MF.ReVGG("resnet18")
+    with pytest.raises(NotImplementedError):
+        MF.ReVGG("vgg11")
+    assert sorted(M.feature_loader) == sorted(["vgg16", "resnet18", "resnet34", "resnet50", "resnet101", "resnet152", "mobilenet_v2"])
+    assert M.feature_inplanes["resnet50"] == [256, 512, 1024, 2048] and M.feature_inplanes["vgg16"] == [128, 256, 512, 512]
+    for name in ("resnet18", "resnet34", "resnet50", "vgg16"):
+        mine = (MF.ReVGG if name == "vgg16" else MF.ReResNet)(name)
+        tv = getattr(torchvision.models, name)(weights=None)
+        ref = {("features." + k): v for k, v in tv.features.state_dict().items()} if name == "vgg16" else \
+            {k: v for k, v in tv.state_dict().items() if not k.startswith("fc.")}
+        got = mine.state_dict()
+        assert list(got) == list(ref), name
+        assert all(got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype for k in ref), name
+    m = M.UAVSal(cnn_type="resnet50", iosize=[96, 160, 12, 20])
+    plan = engine.Plan("cpu", 3, "tc")
+    m.build_plan(plan, 5, 96, 160, x_kind=1)
+    names = [o.name for o in plan.ops]
+    assert names[0] == "uavsal_conv_first" and names[1] == "uavsal_maxpool"
+    assert names.count("uavsal_add_act") == 16 and names.count("uavsal_conv3x3") == 16 + 1        # 16 bottlenecks + conv_last
+    assert names.count("uavsal_maxpool") == 1 + 2 * 3                                           # stem pool + (conv2, shortcut) subsampling of layer2-4
+    assert plan.named["out"].shape == (5, 1, 12, 20)
