@@ -325,3 +325,39 @@ def test_backbone_wrappers_surface():
     assert names.count("uavsal_add_act") == 16 and names.count("uavsal_conv3x3") == 16 + 1        # 16 bottlenecks + conv_last
     assert names.count("uavsal_maxpool") == 1 + 2 * 3                                           # stem pool + (conv2, shortcut) subsampling of layer2-4
     assert plan.named["out"].shape == (5, 1, 12, 20)
+
+
+def test_plan_cache_keys_and_eviction(monkeypatch):
+    """_kernel_module: plans are keyed on one (data_ptr, _version) pair per parameter / buffer (a tracked in-place update or a
+    re-allocation of ANY tensor gives a new plan), evicted least-recently-used by arena bytes, and dropped by invalidate()."""
+    from iip_uavsal_saliency_b200.blocks import dwBlock
+    torch.manual_seed(0)
+    blk = dwBlock(16, 16).eval()
+    built = []
+
+    def builder(plan):
+        built.append(plan)
+        plan.alloc(1000, 64)                                       # 256 000 bytes of arena
+
+    dev = torch.device("cpu")
+    p1 = blk._cached_plan((dev, "a"), builder)
+    assert blk._cached_plan((dev, "a"), builder) is p1 and len(built) == 1
+    sig = blk._weights_signature()
+    assert len(sig) == len(list(blk.parameters())) + len(list(blk.buffers())) and all(len(t) == 2 for t in sig)
+    with torch.no_grad():
+        blk.conv[1][1].running_var.mul_(1.5)                        # a tracked in-place update of one buffer
+    assert blk._weights_signature() != sig
+    p2 = blk._cached_plan((dev, "a"), builder)
+    assert p2 is not p1 and len(built) == 2
+    # swapping two equally shaped parameters' storage changes the signature (the XOR of pointers the first version used did not)
+    a, b = blk.conv[0][1].weight, blk.conv[0][1].bias
+    sig = blk._weights_signature()
+    a.data, b.data = b.data, a.data
+    assert blk._weights_signature() != sig
+    # eviction by bytes: with a 0 GB budget every new plan displaces the others
+    monkeypatch.setenv("UAVSAL_PLAN_CACHE_GB", "0")
+    blk._cached_plan((dev, "b"), builder)
+    blk._cached_plan((dev, "c"), builder)
+    assert len(blk._plan_cache()) == 1
+    blk.invalidate()
+    assert len(blk._plan_cache()) == 0
