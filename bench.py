@@ -413,11 +413,11 @@ def run_product_arm(args):
     sampler.start()
     runner.warm(FRAMES, H, W)
 
-    # this rank's share of a step's clips: clip c -> rank c % world.  Distinct clips (44 MB each, generated once per distinct seed)
-    # so a step's inputs exceed the 126 MB L2 as long as the rank holds >= 3; the arena traffic of a clip (GBs) exceeds it by far anyway
+    # this rank's share of a step's clips: clip c -> rank c % world.  The clips of a step are drawn in rotation from a pool of
+    # distinct synthetic clips (44 MB each) larger than the 126 MB L2; the arena traffic of a clip (GBs) exceeds it by far anyway
     my_ids = [c for c in range(args.clips) if c % world == rank]
-    n_distinct = max(1, min(len(my_ids), 8))
-    host_pool = [torch.from_numpy(synth.make_clip(100 + my_ids[i % max(1, len(my_ids))] if my_ids else 100, FRAMES, H, W)).pin_memory() for i in range(n_distinct)]
+    n_distinct = max(4, min(len(my_ids), 8))                           # >= 4 x 44 MB: more than the 126 MB L2 at every N
+    host_pool = [torch.from_numpy(synth.make_clip(100 + 16 * rank + i, FRAMES, H, W)).pin_memory() for i in range(n_distinct)]
     dev_pool = [c.to(dev) for c in host_pool]
     n_mine = len(my_ids)
     host_out = [torch.empty((OUT_PER_CLIP, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
