@@ -1,13 +1,8 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_tests_all.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r02_tests_all.log
-tail -4 gpurun_out/r02_tests_all.log | cut -c1-300
-for d in 1 3; do
-( timeout 600 python bench.py --steps 8 --warmup 3 --skip-aux --skip-cpu --depth $d ) > gpurun_out/r02_bench_depth$d.json 2> gpurun_out/r02_bench_depth$d.err; echo "depth $d rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_depth$d.json')); print(round(d['value']), round(d['e2e']['value']))"
-done
-( timeout 600 python bench.py --steps 8 --warmup 3 --skip-aux --skip-cpu --clips-per-plan 1 ) > gpurun_out/r02_bench_cpp1.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_cpp1.json')); print('cpp1', round(d['value']), round(d['e2e']['value']))"
-( timeout 600 python bench.py --steps 8 --warmup 3 --skip-aux --skip-cpu --precision fast ) > gpurun_out/r02_bench_fast.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_fast.json')); print('fast', round(d['value']), round(d['e2e']['value']))"
+timeout 900 python -m pytest tests -m gpu -q -k "pointwise or hidden or block_modules or conv3x3 or uavsal_call or recurrences or convlstm" > gpurun_out/r02_tests_gemm.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02_tests_gemm.log
+echo "--- bias hoisted"; python tools/microbench.py f32set 2>&1 | tail -9
+python tools/microbench.py r2 2>&1 | grep "pw\[" | head -12
+( timeout 600 python bench.py --steps 6 --warmup 3 --skip-aux --skip-cpu ) > gpurun_out/r02_bench_biashoist.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_biashoist.json')); print('bench', round(d['value']), round(d['e2e']['value']), d['breakdown_per_plan']['uavsal_pw_gemm'], d['breakdown_per_plan']['uavsal_conv3x3'], d['breakdown_per_plan']['uavsal_twa_sequence'])"

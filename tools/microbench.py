@@ -150,6 +150,10 @@ def main():
         gemm("tc", 432000, 32, 256, res=True); gemm("tc", 432000, 256, 256, res=True); gemm("tc", 110400, 384, 64, res=True)
         gemm("tc", 1728000, 144, 24, res=True); gemm("tc", M, 1536, 256, res=True)
       lib.uavsal_set_option(3, 0)
+    if what == "f32set":       # the expand GEMMs of a 120-frame plan (fp32 hidden rows out)
+        for (m, k, n) in ((432000, 256, 1536), (432000, 320, 1920), (432000, 192, 1152), (432000, 32, 192), (432000, 64, 384), (1728000, 24, 144),
+                          (110400, 64, 384), (110400, 96, 576), (28800, 160, 960)):
+            gemm("tc", m, k, n, f32=True)
     if what == "pairbig":
         gemm("tc", 432000, 256, 1536, f32=True)
     if what == "wr":
