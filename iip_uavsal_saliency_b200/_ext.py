@@ -40,7 +40,7 @@ _SIGNATURES = {
     "uavsal_tdiff_cat": ACT + [I, I, I] + ACT + [I, P],
     "uavsal_ctx_sum": ACT + [I, I, I, I] + ACT + [P],
     "uavsal_add": ACT + ACT + [L, I] + ACT + [P],
-    "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [I, P],
+    "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [I, P, P],
     "uavsal_convlstm_sequence": ACT + ACT + [P, I, I, I, I, I, I, P, P, P, I] + ACT + [P],
     "uavsal_dw3x3_dot_sigmoid": [P, I, I, I, I, I, P, P, P, F, P, P, P],
     "uavsal_dot_sigmoid": ACT + [L, I, P, F, P, P],
@@ -55,7 +55,7 @@ _SIGNATURES = {
     "uavsal_auc_sampled": [P, P, I, I, I, P, P, I, I, c_double, P, P],
 }
 
-EXPORTS = ["uavsal_version", "uavsal_arch", "uavsal_last_error", "uavsal_auc_judd_workspace"] + list(_SIGNATURES)
+EXPORTS = ["uavsal_version", "uavsal_arch", "uavsal_last_error", "uavsal_auc_judd_workspace", "uavsal_twa_sync_bytes"] + list(_SIGNATURES)
 
 
 class UavsalError(RuntimeError):
@@ -83,6 +83,8 @@ def load():
     lib.uavsal_last_error.restype = c_char_p
     lib.uavsal_auc_judd_workspace.argtypes = [I, I, I]
     lib.uavsal_auc_judd_workspace.restype = c_int64
+    lib.uavsal_twa_sync_bytes.argtypes = [I, I, I]
+    lib.uavsal_twa_sync_bytes.restype = ctypes.c_size_t
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

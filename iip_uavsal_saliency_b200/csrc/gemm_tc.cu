@@ -510,6 +510,9 @@ static inline bool act_ok16(const void* p, int64_t plane, int ld) {
 extern int g_dw_fast;
 namespace uavsal {
 extern int g_twa_resident, g_twa_bn, g_metrics_stream, g_metrics_stages;
+size_t twa_sync_bytes(int batch, int H, int W);
+int twa_sequence_persistent(Act x, Act h0, ActW seq, int batch, int t_steps, int H, int W, int c, const uint16_t* wgt, int wk_total, int wk_off,
+                            const float* gx, int terms, int* ready, cudaStream_t s, int dbg);
 int twa_step_resident(Act hsrc, int hsrc_nimg, int a_img, int a_stride, Act x, ActW seq, int out_img, int out_stride, int batch, int H, int W, int c,
                       const uint16_t* wgt, int wk_total, int wk_off, const float* gx, int terms, cudaStream_t s, int dbg);
 }
@@ -519,11 +522,11 @@ extern "C" {
 int uavsal_set_option(int key, int value) {
     if (key == 1 && (value == 1 || value == 2)) { g_tc_version = value; return 0; }
     if (key == 2 && value >= 0 && value <= 2) { g_dw_fast = value; return 0; }
-    if (key == 3) { g_tc_debug = value & 0x1F0000; return 0; }
+    if (key == 3) { g_tc_debug = value & 0x5F0000; return 0; }
     if (key == 4 && (value == 1 || value == 2)) { g_tc_cluster = value; return 0; }
     if (key == 5 && value >= 1 && value <= 8) { g_tc_max_stages = value; return 0; }
     if (key == 6 && (value == 0 || value == 1)) { g_pdl = value; return 0; }
-    if (key == 7 && value >= 0 && value <= 2) { g_twa_resident = value; return 0; }
+    if (key == 7 && value >= 0 && value <= 3) { g_twa_resident = value; return 0; }
     if (key == 8 && (value == 64 || value == 128)) { g_twa_bn = value; return 0; }
     if (key == 9 && value >= 0 && value <= 3) { g_metrics_stream = value; return 0; }
     if (key == 10 && (value == 3 || value == 4 || value == 5 || value == 7)) { g_metrics_stages = value; return 0; }
@@ -619,7 +622,8 @@ static int twa_sequence_one(Act X, Act H0, ActW S, int t_steps, int h, int w, in
 
 int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane, int h0_ld,
                         int t_steps, int h, int w, int c, const uint16_t* wgt, const float* wgt_f32, int terms,
-                        float* gx_workspace, uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* stream) {
+                        float* gx_workspace, uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* sync_workspace,
+                        void* stream) {
     UAVSAL_REQUIRE(act_ok16(x, x_plane, x_ld) && act_ok16(h0, h0_plane, h0_ld) && act_ok16(seq_out, seq_plane, seq_ld) &&
                        t_steps > 0 && batch > 0 && c % 8 == 0 && x_ld >= c && h0_ld >= c && seq_ld >= c,
                    UAVSAL_EINVAL, "twa_sequence: bad arguments");
@@ -638,6 +642,12 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
         int rc = conv_tc(X, nimg, 1, 0, c, X, nimg, 1, 0, 0, nimg, h, w, wgt, c, nullptr, 0, terms, EPI_RAW, Act{}, Act{},
                          nullptr, ActW{}, nimg, 1, 0, s, "twa_sequence(x half)", 2 * c, 0, nullptr, gx_workspace);
         if (rc) return rc;
+        if (sync_workspace && g_twa_resident == 3 && !(reinterpret_cast<uintptr_t>(sync_workspace) & 3)) {
+            // the recurrence as ONE launch whenever the step grid fits the SMs (twa_seq_kernel); otherwise one launch per step
+            rc = twa_sequence_persistent(X, H0, S, batch, t_steps, h, w, c, wgt, 2 * c, c, gx_workspace, terms & 0xFF,
+                                         static_cast<int*>(sync_workspace), s, g_tc_debug);
+            if (rc != UAVSAL_ENOTSUP) return rc;
+        }
         for (int t = 0; t < t_steps; ++t) {
             rc = t == 0 ? twa_step_resident(H0, batch, 0, 1, X, S, 0, t_steps, batch, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug)
                         : twa_step_resident(SA, nimg, t - 1, t_steps, X, S, t, t_steps, batch, h, w, c, wgt, 2 * c, c, gx_workspace, terms, s, g_tc_debug);
@@ -653,6 +663,10 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint
         if (rc) return rc;
     }
     return 0;
+}
+
+size_t uavsal_twa_sync_bytes(int batch, int h, int w) {
+    return batch > 0 && h > 0 && w > 0 ? twa_sync_bytes(batch, h, w) : 0;
 }
 
 int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld, const uint16_t* h0, int64_t h0_plane,

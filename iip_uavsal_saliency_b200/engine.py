@@ -565,10 +565,12 @@ class Plan:
         wp, _ = self._conv_weights(w4d, None)
         if self.engine != "simt":
             gx = self.tensor((batch * t_steps * h * w, c)) if (self.engine == "tc" and c % 64 == 0) else None     # hoisted W_x*x_t workspace
+            sync = self.tensor((max(1, batch * ((h + 15) // 16) * ((w + 7) // 8)),), dtype=torch.int32) if gx is not None else None
             self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, wp.data_ptr(), 0, self.terms_arg,
-                                              gx.data_ptr() if gx is not None else 0, *seq.act(), batch), tag)
+                                              gx.data_ptr() if gx is not None else 0, *seq.act(), batch,
+                                              sync.data_ptr() if sync is not None else 0), tag)
         else:
-            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, 0, wp.data_ptr(), self.terms, 0, *seq.act(), batch), tag)
+            self._add("uavsal_twa_sequence", (*x.act(), *h0.act(), t_steps, h, w, c, 0, wp.data_ptr(), self.terms, 0, *seq.act(), batch, 0), tag)
 
     def lstm(self, x: Buf, h0: Buf, c_state: torch.Tensor, b, t_steps, h, w, cin, ch, w4d, bias, seq: Buf, tag=""):
         """w4d: W (weight + optional conv bias) or the (4ch, cin+ch, 3, 3) tensor + bias; rows are re-ordered gate-interleaved."""

@@ -184,10 +184,15 @@ int uavsal_twa_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
                         const uint16_t* h0, int64_t h0_plane, int h0_ld,
                         int t_steps, int h, int w, int c,
                         const uint16_t* wgt, const float* wgt_f32, int terms, float* gx_workspace,
-                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* stream);
+                        uint16_t* seq_out, int64_t seq_plane, int seq_ld, int batch, void* sync_workspace, void* stream);
 /*      batch independent sequences advance together (x, seq: batch*t_steps images, sequence-major; h0: batch images).
  *      gx_workspace (optional, batch*t_steps*h*w*c floats): when given, the input half W_x*x_t of the gate conv is hoisted out
- *      of the recurrence into one batched implicit GEMM and only W_h*h_{t-1} (K = 9c) runs per step. */
+ *      of the recurrence into one batched implicit GEMM and only W_h*h_{t-1} (K = 9c) runs per step.
+ *      sync_workspace (optional, with gx_workspace; uavsal_twa_sync_bytes(batch, h, w) bytes of device memory, 4-byte aligned,
+ *      zeroed by the call): when given and one step's grid fits the SMs, the whole `for t` loop (model_convlstm.py:364-377) is
+ *      ONE launch whose CTAs hand h_{t-1} tiles to their neighbours through per-tile counters; otherwise one launch per step.
+ *      Same results bit for bit. */
+size_t uavsal_twa_sync_bytes(int batch, int h, int w);
 
 /* ---- K9: ConvLSTM sequence, one layer, batch_first (model_convlstm.py:111-126 cell, 199-212 loop).
  *      x: act (b, t, h, w, cin) ; h state act (b,h,w,ch) updated in place through seq_out; c state fp32

@@ -544,6 +544,38 @@ def test_batched_twa_sequences(cuda):
         assert torch.equal(outs[0], outs[1])
 
 
+def test_twa_one_launch_equals_per_step(cuda):
+    """The whole ConvTWA recurrence as ONE launch (twa_seq_kernel, uavsal_set_option(7, 3): CTAs hand h_{t-1} tiles to their neighbours
+    through per-tile counters) == one launch per step (the default), bit for bit; a batch whose step grid does not fit the SMs falls
+    back to per-step launches."""
+    from iip_uavsal_saliency_b200 import _ext
+    lib = _ext.load()
+    assert lib.uavsal_twa_sync_bytes(2, 45, 80) == 2 * 3 * 10 * 4
+    torch.manual_seed(17)
+    try:
+        for (b, t, h, w, c) in [(2, 7, 45, 80, 256), (1, 5, 45, 80, 256), (3, 4, 20, 24, 128), (1, 3, 9, 7, 64), (8, 2, 45, 80, 256)]:
+            wgt = torch.randn(c, 2 * c, 3, 3, device="cuda") * 0.02
+            x, h0 = torch.randn(b * t * h * w, c, device="cuda"), torch.randn(b * h * w, c, device="cuda") * 0.5
+            outs = []
+            for opt in (3, 1, 3):
+                lib.uavsal_set_option(7, opt)
+                p = _plan()
+                xb, hb, seq = p.alloc(b * t * h * w, c), p.alloc(b * h * w, c), p.alloc(b * t * h * w, c)
+                for buf, src in ((xb, x), (hb, h0)):
+                    hi = src.to(torch.bfloat16)
+                    buf.t[0].copy_(hi)
+                    buf.t[1].copy_((src - hi.float()).to(torch.bfloat16))
+                p.twa(xb, hb, t, h, w, c, wgt, seq, batch=b)
+                p.run()
+                p.run()                                  # a replay must zero its counters again
+                torch.cuda.synchronize()
+                outs.append(seq.to_float().clone())
+            assert all(torch.equal(outs[0], o) for o in outs[1:]), (b, t, h, w, c)
+            assert float(outs[0].abs().max()) > 0.1
+    finally:
+        lib.uavsal_set_option(7, 1)
+
+
 def test_fast_mode_is_reported_not_claimed(cuda, gold_dir):
     """bf16x1 'fast' mode: runs, stays highly correlated, but is NOT held to the 2e-3 bar."""
     from iip_uavsal_saliency_b200.model import UAVSal

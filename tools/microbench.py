@@ -87,14 +87,14 @@ def conv(engine, n, h, w, c, co, terms=3):
     print("conv3x3[%s,t%d] n=%d %dx%d c=%d co=%d: %.1f us  %.1f TF/s(alg)" % (engine, terms, n, h, w, c, co, ms * 1e3, fl / ms / 1e9), flush=True)
 
 
-def twa(engine, t, h, w, c, terms=3):
+def twa(engine, t, h, w, c, terms=3, batch=1):
     p = Plan(dev, terms, engine)
-    x = p.alloc(t * h * w, c); x.t.normal_()
-    h0 = p.alloc(h * w, c)
-    seq = p.alloc(t * h * w, c)
-    p.twa(x, h0, t, h, w, c, torch.randn(c, 2 * c, 3, 3, device=dev) * 0.01, seq)
+    x = p.alloc(batch * t * h * w, c); x.t.normal_()
+    h0 = p.alloc(batch * h * w, c)
+    seq = p.alloc(batch * t * h * w, c)
+    p.twa(x, h0, t, h, w, c, torch.randn(c, 2 * c, 3, 3, device=dev) * 0.01, seq, batch=batch)
     ms = timeit(p)
-    print("twa[%s] t=%d %dx%d c=%d: %.1f us total, %.1f us/step, %.1f TF/s(alg)" % (engine, t, h, w, c, ms * 1e3, ms * 1e3 / t, 2.0 * t * h * w * 9 * 2 * c * c / ms / 1e9), flush=True)
+    print("twa[%s] batch=%d t=%d %dx%d c=%d: %.1f us total, %.1f us/step (incl. the hoisted x half), %.1f TF/s(alg)" % (engine, batch, t, h, w, c, ms * 1e3, ms * 1e3 / t, 2.0 * batch * t * h * w * 9 * 2 * c * c / ms / 1e9), flush=True)
 
 
 def lstm(b, t, h, w, c, terms=3):
@@ -179,6 +179,26 @@ def main():
             lib.uavsal_set_option(7, mode)
             print("--- twa step kernel mode", mode)
             twa("tc", 20, 45, 80, 256); twa("tc", 60, 45, 80, 256)
+        lib.uavsal_set_option(7, 1)
+    if what == "twa3":
+        lib = _ext.load()
+        for mode in (1, 3):
+            lib.uavsal_set_option(7, mode)
+            print("--- twa mode", mode, "(1 = one launch per step, 3 = one launch per sequence)")
+            for batch in (1, 2, 4):
+                twa("tc", 60, 45, 80, 256, batch=batch)
+        lib.uavsal_set_option(7, 1)
+    if what == "twa_trace":
+        lib = _ext.load()
+        lib.uavsal_set_option(3, 1 << 22)
+        lib.uavsal_set_option(7, 3)
+        p = Plan(dev, 3, "tc")
+        t, h, w, c, batch = 12, 45, 80, 256, 2
+        x = p.alloc(batch * t * h * w, c); x.t.normal_()
+        h0 = p.alloc(batch * h * w, c); seq = p.alloc(batch * t * h * w, c)
+        p.twa(x, h0, t, h, w, c, torch.randn(c, 2 * c, 3, 3, device=dev) * 0.01, seq, batch=batch)
+        p.run(); torch.cuda.synchronize()
+        lib.uavsal_set_option(3, 0)
         lib.uavsal_set_option(7, 1)
     if what == "twa_ablate":
         lib = _ext.load()
