@@ -31,6 +31,7 @@ _SIGNATURES = {
     "uavsal_dw3x3": ACT + [I, I, I, I, I, I, P, P, I] + ACT + [P],
     "uavsal_expand_dw3x3": ACT + [I, I, I, I, P, I, P, I, I, P, P] + ACT + [P],
     "uavsal_dw_project": [P, I, I, I, I, I, P, P, P, I, I, P, I, I] + ACT + ACT + [P],
+    "uavsal_mbconv_fused": ACT + [I, I, I, I, P, I, P, I, P, P, P, I, P, I, I] + ACT + ACT + [P],
     "uavsal_dw_project32_hw": [P, I, I, I, I, P, P, P, P] + ACT + [P],
     "uavsal_pw_gemm": ACT + [I, I, P, I, I, P, I, I] + ACT + ACT + [P],
     "uavsal_pw_gemm_simt": ACT + [I, I, P, I, P, I] + ACT + ACT + [P],

@@ -120,6 +120,14 @@ class dwBlock(KernelModule):
         inp, oup, hidden, stride, dil, has_expand = self.geom
         cur = x
         i = 0
+        fuse_all = getattr(plan, "fuse_mbconv", True)
+        if (fuse_all and has_expand and plan.engine == "tc" and stride == 1 and dil == 1 and not x.f32 and x.c <= 64 and hidden % 64 == 0
+                and oup % 16 == 0 and oup <= 64):
+            # narrow stride-1 block: expand -> depthwise -> project (+ x) in ONE kernel, the 6x hidden tensor stays on the SM (mbconv.cu)
+            out = out if out is not None else plan.alloc(n * h * w, oup)
+            plan.mbconv(x, n, h, w, self.conv[0].wspec(), self.conv[1].wspec(), self.project_wspec(), out,
+                        res=x if self.use_res_connect else None, tag=tag + ".expand+dw+project")
+            return out, h, w
         fuse = getattr(plan, "fuse_expand_dw", "auto")
         if fuse == "auto":       # measured (profiles/r01_microbench_expdw.txt): the fused kernel wins on the stride-2 high-resolution blocks
             fuse = stride == 2 and h * w >= 10000       # per-frame size: the choice must not depend on how many frames are batched

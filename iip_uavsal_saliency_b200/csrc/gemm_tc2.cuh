@@ -260,6 +260,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             mbar_wait(acc_full + buf, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * g.bn);
+            // the TMEM read of piece ch+1 is issued as soon as piece ch's values have left `raw` and waited for one piece later, so its
+            // latency hides under the copy-out
+            // (not in the residual instantiation: its prefetched residual cells already fill the register budget)
+            constexpr bool kPipe = EPI != EPI_RES;
+            uint32_t raw[16];
+            if (kPipe && sub < min(64, g.bn)) { __syncwarp(); tmem_ld16_issue(trow + sub, raw); }
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int ncols = min(64, g.bn - ch * 64);                    // multiple of 16
                 if (kRes) {
@@ -279,12 +285,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                         bv[0] = __ldg(bp); bv[1] = __ldg(bp + 1);
                         if (second) { bv[2] = __ldg(bp + 2); bv[3] = __ldg(bp + 3); }
                     }
-                    uint32_t raw[16];
-                    __syncwarp();
-                    tmem_ld16(trow + ch * 64 + sub, raw);
+                    if (!kPipe) { __syncwarp(); tmem_ld16_issue(trow + ch * 64 + sub, raw); }
+                    tmem_ld16_wait(raw);
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    if (kPipe && ch + 1 < nchunks && sub < min(64, g.bn - (ch + 1) * 64)) { __syncwarp(); tmem_ld16_issue(trow + (ch + 1) * 64 + sub, raw); }
                     if (EPI == EPI_RAW) {
                         if (live) {
                             float4* o = reinterpret_cast<float4*>(g.raw_out + orow * g.N + n);
@@ -385,13 +391,20 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                                        __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                             __syncwarp();
                             float* outf = reinterpret_cast<float*>(g.out.p);
+                            // all four reads first, into registers of their own: with one register quad per read -> store pair the
+                            // compiler chained them (ncu: LDS waiting for the previous STG to release its source, 22 % of the samples)
+                            uint4 val[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {                     // 8 rows x 64 contiguous bytes per instruction
                                 const int row = 8 * i + (lane >> 2), c = lane & 3;
-                                const uint4 val = lds128(wst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+                                val[i] = lds128(wst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int row = 8 * i + (lane >> 2), c = lane & 3;
                                 const int64_t gr = grow_of(q * 32 + row);
                                 const int col = n + c * 4;
-                                if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<uint4*>(outf + gr * g.out.ld + col) = val;
+                                if (gr >= 0 && col < g.N && do_store) *reinterpret_cast<uint4*>(outf + gr * g.out.ld + col) = val[i];
                             }
                         } else if (kRes) {
                             // stage fp32 (layout as above); each lane then owns 8 columns of two rows: residual hi/lo arrive as
@@ -443,18 +456,23 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                                 sts128(wst + 1024 + off, l[0], l[1], l[2], l[3]);
                             }
                             __syncwarp();
+                            uint4 hv4[2], lv4[2];
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {                     // 16 rows x 32 contiguous bytes per plane per instruction
                                 const int row = 16 * i + (lane >> 1), c = lane & 1;
                                 const int off = row * 32 + ((c ^ ((row >> 2) & 1)) << 4);
-                                const uint4 hv4 = lds128(wst + off);
-                                const uint4 lv4 = lds128(wst + 1024 + off);
+                                hv4[i] = lds128(wst + off);
+                                lv4[i] = lds128(wst + 1024 + off);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int row = 16 * i + (lane >> 1), c = lane & 1;
                                 const int64_t gr = grow_of(q * 32 + row);
                                 const int col = n + c * 8;
                                 if (gr >= 0 && col < g.N && do_store) {
                                     uint16_t* dst = g.out.p + gr * g.out.ld + col;
-                                    *reinterpret_cast<uint4*>(dst) = hv4;
-                                    if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = lv4;
+                                    *reinterpret_cast<uint4*>(dst) = hv4[i];
+                                    if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = lv4[i];
                                 }
                             }
                         }

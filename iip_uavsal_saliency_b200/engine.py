@@ -487,6 +487,20 @@ class Plan:
                                         wp.data_ptr(), hidden, cout, b.data_ptr(), F_RESIDUAL if res is not None else 0, self.terms,
                                         *r, *out.act()), tag)
 
+    def mbconv(self, x: Buf, n, h, w, w1: W, wd: W, w2: W, out: Buf, res: Optional[Buf] = None, tag=""):
+        """Whole stride-1 inverted-residual block in one kernel (mbconv.cu): expand + BN + ReLU6 -> depthwise 3x3 + BN + ReLU6 ->
+        project + BN (+ residual); the hidden tensor never reaches HBM.  cin <= 64, hidden % 64 == 0, cout % 16 == 0 and <= 64."""
+        hidden, cin, cout = w1.cout, w1.cin, w2.cout
+        kp1 = _pad8(cin)
+        assert self.engine == "tc" and not x.f32 and x.c in (cin, kp1) and w2.cin == hidden and wd.cout == hidden
+        assert kp1 <= 64 and hidden % 64 == 0 and cout % 16 == 0 and cout <= 64 and out.c >= cout and (res is None or not res.f32)
+        w1p, b1 = self.packed(w1, W_ROWS_SPLIT, hidden, kp1)
+        wdd, bdd = self._dw_weights(wd, None)
+        w2p, b2 = self.packed(w2, W_ROWS_SPLIT, cout, hidden)
+        r = res.act() if res is not None else NULL_ACT
+        self._add("uavsal_mbconv_fused", (*x.act(), n, h, w, kp1, w1p.data_ptr(), kp1, b1.data_ptr(), hidden, wdd.data_ptr(), bdd.data_ptr(),
+                                          w2p.data_ptr(), cout, b2.data_ptr(), F_RESIDUAL if res is not None else 0, self.terms, *r, *out.act()), tag)
+
     def pw(self, x: Buf, m: int, w2d, bias, flags: int, out: Buf, res: Optional[Buf] = None, tag=""):
         """Pointwise conv as GEMM.  w2d: W, or folded fp32 (N, K_logical) + bias; x.c may be padded beyond K_logical."""
         n, k = (w2d.cout, w2d.cin) if isinstance(w2d, W) else w2d.shape

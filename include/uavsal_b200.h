@@ -127,6 +127,19 @@ int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hid
                       const uint16_t* res, int64_t res_plane, int res_ld,
                       uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
+/* Whole dwBlock / InvertedResidual (model.py:74-103; stride 1, dilation 1) in one launch: 1x1 expand + BN + ReLU6 -> depthwise 3x3
+ * + BN + ReLU6 -> 1x1 project + BN (+ residual x); the 6x hidden tensor lives in TMEM / shared memory only.
+ * x act (n, h, w, cin), cin % 8 == 0, cin <= 64; w1: bf16 planes [2][hidden][kp1] (K-major, kp1 >= cin), b1 [hidden];
+ * hidden % 64 == 0; wd [9][hidden], bd [hidden] as uavsal_dw3x3; w2: bf16 planes [2][cout][hidden], b2 [cout], cout % 16 == 0,
+ * cout <= 64; flags: UAVSAL_F_RESIDUAL only; res / out as uavsal_pw_gemm.  Results equal uavsal_pw_gemm(F_OUT_F32) ->
+ * uavsal_dw3x3 -> uavsal_pw_gemm bit for bit. */
+int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld, int n, int h, int w, int cin,
+                        const uint16_t* w1, int kp1, const float* b1, int hidden,
+                        const float* wd, const float* bd,
+                        const uint16_t* w2, int cout, const float* b2, int flags, int terms,
+                        const uint16_t* res, int64_t res_plane, int res_ld,
+                        uint16_t* out, int64_t out_plane, int out_ld, void* stream);
+
 /* The 32 -> 16 block (torchvision features[1]) with its weights as HOST arrays: wd [9][32], bd [32], wp [16][32] (cout, hidden)
  * fp32 and bias [16] are copied into the kernel's parameter block at launch and read as constant-bank operands. */
 int uavsal_dw_project32_hw(const float* hid, int hid_ld, int n, int h, int w, const float* wd_host, const float* bd_host,

@@ -107,13 +107,22 @@ def test_plan_structure_of_one_call():
     # ... and the seven large stride-1 blocks whose project conv has 64..256 outputs (st0/st1.sp, fust, gauss1, ob1, fucb, fucbst)
     # run depthwise + project fused
     # ... plus features.1 (32 -> 16, no expand conv), whose depthwise + project run as one fp32 FFMA kernel behind the same entry
-    assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7 and names.count("uavsal_dw_project32_hw") == 1
+    # ... and the nine narrow stride-1 blocks (cin <= 64, cout <= 64, hidden % 64 == 0: features.5/6/8/9/10, both ST blocks' te.sub, gauss1,
+    # ob1) run as ONE kernel each (uavsal_mbconv_fused)
+    assert names.count("uavsal_mbconv_fused") == 9
+    assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7 - 2 and names.count("uavsal_dw_project32_hw") == 1
     # ... and the readout's depthwise conv is folded into its 1-output project (dw3x3_dot_sigmoid)
-    assert names.count("uavsal_pw_gemm") == 76 - 2 - 8 and names.count("uavsal_dw3x3") == 34 - 2 - 8 - 1
+    assert names.count("uavsal_pw_gemm") == 76 - 2 - 8 - 16 and names.count("uavsal_dw3x3") == 34 - 2 - 8 - 1 - 7
+    pu = engine.Plan("cpu", 3, "tc")
+    pu.fuse_mbconv = False
+    m.build_plan(pu, 20, 360, 640, x_kind=1, post_hw=(360, 640))
+    nu = [o.name for o in pu.ops]
+    assert nu.count("uavsal_mbconv_fused") == 0 and nu.count("uavsal_dw_project") == 7 and nu.count("uavsal_pw_gemm") == 76 - 2 - 8
     assert names.count("uavsal_dw3x3_dot_sigmoid") == 1 and names.count("uavsal_dot_sigmoid") == 0
     pf = engine.Plan("cpu", 3, "tc")
     pf.fuse_expand_dw = True
     pf.fuse_dw_project = False
+    pf.fuse_mbconv = False
     m.build_plan(pf, 20, 360, 640, x_kind=1, post_hw=(360, 640))
     assert [o.name for o in pf.ops].count("uavsal_expand_dw3x3") == 8
     ps = engine.Plan("cpu", 3, "simt")                                 # the SIMT cross-check engine keeps every conv separate

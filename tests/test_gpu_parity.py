@@ -412,6 +412,37 @@ def test_block_modules_against_oracle(cuda):
         assert _rel(o, r) < 5e-4
 
 
+@pytest.mark.parametrize("inp,oup,n,h,w", [(64, 64, 3, 23, 40), (32, 32, 2, 45, 80), (64, 32, 5, 45, 80), (64, 64, 1, 7, 5), (32, 16, 2, 33, 47),
+                                           (64, 48, 170, 12, 20)])
+def test_mbconv_fused_block(cuda, inp, oup, n, h, w):
+    """Whole inverted-residual block in one kernel (uavsal_mbconv_fused: the hidden tensor never leaves the SM) vs the oracle, and
+    bit for bit vs the three separate kernels (expand GEMM -> depthwise -> project GEMM); ragged maps, more tiles than SMs."""
+    from iip_uavsal_saliency_b200 import model as M
+    torch.manual_seed(inp * 131 + oup)
+    blk = M.dwBlock(inp, oup).eval()
+    for mod in blk.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.8, 1.2); mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    x = torch.randn(n, inp, h, w)
+    sd = {"b." + k: v for k, v in blk.state_dict().items()}
+    blk = blk.cuda()
+    outs = []
+    for fused in (True, False):
+        p = _plan()
+        p.fuse_mbconv = fused
+        xb = _upload(p, x.cuda())
+        ob, ho, wo = blk._emit(p, xb, n, h, w)
+        names = [o.name for o in p.ops]
+        assert ("uavsal_mbconv_fused" in names) == fused
+        out = _download(p, ob, n, oup, ho, wo)
+        p.run()
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
+    if n <= 5:
+        assert _rel(outs[0], cpu_ref.dw_block(sd, "b", x)) < KERNEL_TOL
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 def test_uavsal_call_of_20_frames_vs_reference_golden(cuda, gold_dir, engine):
     """One Demo_Test-sized call (B=4,T=5) at 360x640 with per-stage taps (quirks Q2/Q3 included)."""

@@ -65,6 +65,20 @@ def expdw(n, h, w, cin, hidden, stride):
     print("expand+dw n=%d %dx%d cin=%d hidden=%d s=%d: %.1f us  %.0f GB/s (in+out)" % (n, h, w, cin, hidden, stride, ms * 1e3, by / ms / 1e6), flush=True)
 
 
+def mbblock(n, h, w, inp, oup, fused):
+    """a dwBlock (stride 1) as one kernel (uavsal_mbconv_fused) or as expand GEMM -> depthwise -> project GEMM"""
+    from iip_uavsal_saliency_b200 import model as M
+    blk = M.dwBlock(inp, oup).eval().cuda()
+    p = Plan(dev, 3, "tc")
+    p.fuse_mbconv = fused
+    x = p.alloc(n * h * w, inp); x.t.normal_()
+    blk._emit(p, x, n, h, w)
+    ms = timeit(p)
+    by = 4.0 * n * h * w * (inp + oup + (inp if inp == oup else 0))
+    print("dwBlock %d->%d->%d n=%d %dx%d %s: %.1f us  %.0f GB/s (block in+out)  [%s]" % (inp, 6 * inp, oup, n, h, w, "fused" if fused else "3 kernels",
+          ms * 1e3, by / ms / 1e6, ", ".join(o.name.replace("uavsal_", "") for o in p.ops)), flush=True)
+
+
 def dwproj(n, h, w, hidden, co, res=False, terms=3):
     p = Plan(dev, terms, "tc")
     hb = p.alloc_f32(n * h * w, hidden); hb.t.uniform_(0, 6)
@@ -154,6 +168,11 @@ def main():
         for (m, k, n) in ((432000, 256, 1536), (432000, 320, 1920), (432000, 192, 1152), (432000, 32, 192), (432000, 64, 384), (1728000, 24, 144),
                           (110400, 64, 384), (110400, 96, 576), (28800, 160, 960)):
             gemm("tc", m, k, n, f32=True)
+    if what == "smallk":       # HBM-bound expand GEMMs: the epilogue's store rate is what matters
+        gemm("tc", 1728000, 24, 144, f32=True); gemm("tc", 432000, 32, 192, f32=True); gemm("tc", 432000, 32, 256, res=True)
+    if what == "mbconv":
+        for fused in (False, True):
+            mbblock(120, 45, 80, 64, 32, fused); mbblock(120, 45, 80, 32, 32, fused); mbblock(120, 23, 40, 64, 64, fused)
     if what == "pairbig":
         gemm("tc", 432000, 256, 1536, f32=True)
     if what == "wr":
