@@ -337,7 +337,7 @@ static int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
 
 // ---- version 2: persistent kernel (gemm_tc2.cuh) ------------------------------------------------------
 static int g_tc_version = 2;
-static int g_tc_debug = 0;     // DBG_* ablation bits ORed into the kernel flags
+int g_tc_debug = 0;     // DBG_* ablation bits ORed into the kernel flags
 
 static int num_sms() {
     static int n = 0;

@@ -16,10 +16,14 @@
 //   * drains acc2: + bias (+ residual) -> hi/lo split -> coalesced stores.
 // The halo recompute costs 180/128 of a K <= 64 expand GEMM - a few percent of the tile's time.  Arithmetic and accumulation
 // order are those of the separate kernels (gemm_tc2 -> dw3x3_tma -> gemm_tc2), so results are bit-identical to them.
+#include <cstdio>
+
 #include "tc_common.cuh"
 #include "gemm_tc2.cuh"
 
 namespace uavsal {
+
+extern int g_tc_debug;
 
 struct MbArgs {
     int n, H, W, cin, hidden, N;     // images, map size, channels in / hidden / out
@@ -32,7 +36,14 @@ struct MbArgs {
     int flags;                       // UAVSAL_F_RESIDUAL
     Act res;
     ActW out;
+    int dbg;                         // 1 << 22: CTA 0 prints a per-chunk phase trace of its third tile (development)
 };
+
+__device__ __forceinline__ unsigned long long mb_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int kMbTW = 16, kMbTH = 8, kMbIW = kMbTW + 2, kMbIH = kMbTH + 2, kMbPix = kMbIW * kMbIH;   // 180 haloed pixels
 constexpr uint32_t kMbXPlane = 24 * 1024;                  // 192 rows x 128 B (the second M tile's rows 192..255 read whatever follows)
@@ -61,21 +72,30 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(hid + kMbHid);
     uint64_t* x_full = bars;            // TMA -> issuer
     uint64_t* x_empty = bars + 1;       // expand MMAs of the tile retired -> producer
-    uint64_t* w_full = bars + 2;        // [2] TMA -> issuer
-    uint64_t* w_empty = bars + 4;       // [2] project MMAs of the chunk retired -> producer
+    // The two weight operands of a chunk have rings of their own: W1(c) is released by the expand MMAs of chunk c, W2(c) only by its
+    // project MMAs a chunk and a half later.  (With one ring of [W1|W2] stages W1(c) could not be fetched before project(c-2) had
+    // retired, and the expand of chunk c - TMA latency + 24 MMAs - no longer fitted under the depthwise stage of chunk c-1.)
+    uint64_t* w1_full = bars + 2;       // [2] TMA -> issuer
+    uint64_t* w1_empty = bars + 4;      // [2] expand MMAs of the chunk retired -> producer
     uint64_t* acc1_full = bars + 6;     // [2] expand MMAs retired -> workers
     uint64_t* acc1_empty = bars + 8;    // [2] workers (16 warps) -> issuer
     uint64_t* a2_full = bars + 10;      // [2] workers (one arrive after the CTA-wide barrier) -> issuer
     uint64_t* a2_empty = bars + 12;     // [2] project MMAs retired -> workers
     uint64_t* acc2_full = bars + 14;
     uint64_t* acc2_empty = bars + 15;   // workers (16 warps) -> issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* w2_full = bars + 16;      // [2] TMA -> issuer
+    uint64_t* w2_empty = bars + 18;     // [2] project MMAs of the chunk retired -> producer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    unsigned long long* trace = reinterpret_cast<unsigned long long*>(bars + 22);           // [8 chunks][8]
+    const bool tracing = (g.dbg & (1 << 22)) && blockIdx.x == 0;
+#define MB_TRACE(itv, c, slot) do { if (tracing && (itv) == 2 && (c) < 8) trace[(c) * 8 + (slot)] = mb_gtime(); } while (0)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1);
+            mbar_init(w1_full + s, 1); mbar_init(w1_empty + s, 1);
+            mbar_init(w2_full + s, 1); mbar_init(w2_empty + s, 1);
             mbar_init(acc1_full + s, 1); mbar_init(acc1_empty + s, kEpiWarps);
             mbar_init(a2_full + s, 1); mbar_init(a2_empty + s, 1);
         }
@@ -116,14 +136,16 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                 for (int p = 0; p < NPL; ++p) tma_load_5d(&tmX, x_full, xbuf + p * kMbXPlane, 0, x0 - 1, y0 - 1, img, p);
                 for (int c = 0; c < g.nchunks; ++c, ++wc) {
                     const int s = wc & 1;
-                    mbar_wait(w_empty + s, ((wc >> 1) & 1) ^ 1);
-                    mbar_expect_tx(w_full + s, w_stage);
+                    const uint32_t par = ((wc >> 1) & 1) ^ 1;
                     uint8_t* ws = wbuf + s * w_stage;
+                    mbar_wait(w1_empty + s, par);
+                    mbar_expect_tx(w1_full + s, NPL * kMbW1Plane);
 #pragma unroll
-                    for (int p = 0; p < NPL; ++p) {
-                        tma_load_3d(&tmW1, w_full + s, ws + p * kMbW1Plane, 0, c * 64, p);
-                        tma_load_3d(&tmW2, w_full + s, ws + NPL * kMbW1Plane + p * w2_plane, c * 64, 0, p);
-                    }
+                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmW1, w1_full + s, ws + p * kMbW1Plane, 0, c * 64, p);
+                    mbar_wait(w2_empty + s, par);
+                    mbar_expect_tx(w2_full + s, NPL * w2_plane);
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) tma_load_3d(&tmW2, w2_full + s, ws + NPL * kMbW1Plane + p * w2_plane, c * 64, 0, p);
                 }
             }
         }
@@ -134,6 +156,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
         int it = 0;
         auto project = [&](uint32_t pc, bool first, bool last) {              // chunk counter pc: A2[pc & 1] x W2 of stage pc & 1
             const int s = pc & 1;
+            mbar_wait(w2_full + s, (pc >> 1) & 1);
             mbar_wait(a2_full + s, (pc >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                     }
                 }
                 umma_commit(a2_empty + s);
-                umma_commit(w_empty + s);
+                umma_commit(w2_empty + s);
                 if (last) umma_commit(acc2_full);
             }
             __syncwarp();
@@ -161,10 +184,11 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
             mbar_wait(x_full, it & 1);
             for (int c = 0; c < g.nchunks; ++c, ++wc) {
                 const int s = wc & 1;
-                mbar_wait(w_full + s, (wc >> 1) & 1);
+                mbar_wait(w1_full + s, (wc >> 1) & 1);
                 mbar_wait(acc1_empty + s, ((wc >> 1) & 1) ^ 1);               // epi 1 of two chunks ago has drained this buffer
                 tc_fence_after();
                 if (lane == 0) {
+                    MB_TRACE(it, c, 6);
                     const uint32_t x_hi = smem_u32(xbuf);
                     const uint32_t b_hi = smem_u32(wbuf + s * w_stage);
 #pragma unroll
@@ -183,6 +207,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                         }
                     }
                     umma_commit(acc1_full + s);
+                    umma_commit(w1_empty + s);
                     if (c == g.nchunks - 1) umma_commit(x_empty);
                 }
                 __syncwarp();
@@ -231,24 +256,33 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                         b1v[4 * i] = b4.x; b1v[4 * i + 1] = b4.y; b1v[4 * i + 2] = b4.z; b1v[4 * i + 3] = b4.w;
                     }
                 }
+                if (et == 0) MB_TRACE(it, c, 0);
                 mbar_wait(acc1_full + s, par);
                 tc_fence_after();
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    if (mt == 1 && q >= 2) break;                             // rows 192..255 of the second M tile do not exist
-                    uint32_t raw[16];
+                if (et == 0) MB_TRACE(it, c, 1);
+                {
+                    // both M tiles' TMEM reads are issued before the first is waited for (rows 192..255 of the second do not exist)
+                    uint32_t raw[2][16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + j16 * 16);
                     __syncwarp();
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + mt * 64 + j16 * 16), raw);
-                    const int p = mt ? p1 : p0;
-                    const bool inside = mt ? in1 : in0;
-                    if (p < kMbPix) {
+                    tmem_ld16_issue(taddr, raw[0]);
+                    if (q < 2) tmem_ld16_issue(taddr + 64, raw[1]);
+                    tmem_ld16_wait(raw[0]);
+                    if (q < 2) tmem_ld16_wait(raw[1]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float v[4];
+                    for (int mt = 0; mt < 2; ++mt) {
+                        if (mt == 1 && q >= 2) break;
+                        const int p = mt ? p1 : p0;
+                        const bool inside = mt ? in1 : in0;
+                        if (p < kMbPix) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) v[k] = inside ? relu6f(__uint_as_float(raw[4 * i + k]) + b1v[4 * i + k]) : 0.f;
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hid_s + mb_hid_off(p, j16 * 4 + i)), "f"(v[0]), "f"(v[1]),
-                                         "f"(v[2]), "f"(v[3]) : "memory");
+                            for (int i = 0; i < 4; ++i) {
+                                float v[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) v[k] = inside ? relu6f(__uint_as_float(raw[mt][4 * i + k]) + b1v[4 * i + k]) : 0.f;
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hid_s + mb_hid_off(p, j16 * 4 + i)), "f"(v[0]), "f"(v[1]),
+                                             "f"(v[2]), "f"(v[3]) : "memory");
+                            }
                         }
                     }
                 }
@@ -257,27 +291,30 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(acc1_empty + s);
                 // depthwise taps / bias of this thread's 4 channels
                 const int c0 = c * 64 + quad * 4;
-                float wr[9][4], br[4];
+                // (channel pairs: the 9-tap dot products run as packed fma.rn.f32x2 - the same IEEE fma per lane, half the instructions)
+                float2 wr[9][2], br[2];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wd + k * g.hidden + c0));
-                    wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
+                    wr[k][0] = make_float2(w4.x, w4.y); wr[k][1] = make_float2(w4.z, w4.w);
                 }
                 {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bd + c0));
-                    br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
+                    br[0] = make_float2(b4.x, b4.y); br[1] = make_float2(b4.z, b4.w);
                 }
+                if (et == 0) MB_TRACE(it, c, 2);
                 named_bar_sync(1, kEpiThreads);                               // hidden tile complete
                 mbar_wait(a2_empty + s, par ^ 1);                             // the project MMAs that read A2[s] two chunks ago retired
+                if (et == 0) MB_TRACE(it, c, 3);
                 // ---- depthwise 3x3 + bias + ReLU6 -> A2[s] (K-major, 128-B swizzle) ----
                 {
                     const uint32_t a_hi = smem_u32(a2buf + s * NPL * kMbA2Plane);
-                    float win[3][4][4];                                       // [row slot][column 2cp-1 .. 2cp+2][channel]
+                    float2 win[3][4][2];                                      // [row slot][column 2cp-1 .. 2cp+2][channel pair]
                     auto load_row = [&](int slot, int iy) {
 #pragma unroll
                         for (int d = 0; d < 4; ++d) {
-                            float* v = win[slot][d];
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                            float2* v = win[slot][d];
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y)
                                          : "r"(hid_s + mb_hid_off(iy * kMbIW + 2 * cp + d, quad)));
                         }
                     };
@@ -290,21 +327,19 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                         const int slots[3] = {s0, s1, s2};
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
-                            float acc[4] = {br[0], br[1], br[2], br[3]};
+                            float2 acc[2] = {br[0], br[1]};
 #pragma unroll
                             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                                 for (int kx = 0; kx < 3; ++kx) {
-                                    const float* v = win[slots[ky]][cc + kx];
+                                    const float2* v = win[slots[ky]][cc + kx];
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[k] = fmaf(v[k], wr[ky * 3 + kx][k], acc[k]);
+                                    for (int k = 0; k < 2; ++k) acc[k] = __ffma2_rn(v[k], wr[ky * 3 + kx][k], acc[k]);
                                 }
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[k] = relu6f(acc[k]);
                             const int r = (oyl0 + i) * kMbTW + 2 * cp + cc;   // A row = pixel index inside the tile
                             uint32_t h0, h1, l0, l1;
-                            split2(acc[0], acc[1], h0, l0);
-                            split2(acc[2], acc[3], h1, l1);
+                            split2(relu6f(acc[0].x), relu6f(acc[0].y), h0, l0);
+                            split2(relu6f(acc[1].x), relu6f(acc[1].y), h1, l1);
                             const uint32_t off = r * 128 + ((((uint32_t)quad >> 1) ^ (r & 7)) << 4) + (quad & 1) * 8;
                             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
                             if (TERMS == 3) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + kMbA2Plane + off), "r"(l0), "r"(l1) : "memory");
@@ -312,8 +347,9 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                     }
                 }
                 fence_async_smem();                                           // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                if (et == 0) MB_TRACE(it, c, 4);
                 named_bar_sync(1, kEpiThreads);                               // A2[s] complete; the hidden tile may be overwritten
-                if (et == 0) mbar_arrive(a2_full + s);
+                if (et == 0) { mbar_arrive(a2_full + s); MB_TRACE(it, c, 5); }
             }
 
             // ---- epilogue of the tile: acc2 -> + bias (+ residual) -> split -> staging -> coalesced stores ----
@@ -394,6 +430,14 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
     __syncthreads();
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (tracing && threadIdx.x == 0) {
+        const unsigned long long b = trace[0];
+        for (int c = 0; c < min(g.nchunks, 8); ++c)
+            printf("chunk %d: start %6lld | acc1 ready %6lld | epi1 done %6lld | hidden barrier + A2 free %6lld | dw done %6lld | A2 published %6lld | expand issued %6lld ns\n",
+                   c, (long long)(trace[c * 8 + 0] - b), (long long)(trace[c * 8 + 1] - b), (long long)(trace[c * 8 + 2] - b), (long long)(trace[c * 8 + 3] - b),
+                   (long long)(trace[c * 8 + 4] - b), (long long)(trace[c * 8 + 5] - b), (long long)(trace[c * 8 + 6] - b));
+    }
+#undef MB_TRACE
 }
 
 }  // namespace uavsal
@@ -422,7 +466,7 @@ extern "C" int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld,
     g.tiles_x = div_up(w, kMbTW); g.tiles_y = div_up(h, kMbTH);
     g.num_tiles = n * g.tiles_x * g.tiles_y;
     g.nchunks = hidden / 64;
-    g.b1 = b1; g.wd = wd; g.bd = bd; g.b2 = b2; g.flags = flags;
+    g.b1 = b1; g.wd = wd; g.bd = bd; g.b2 = b2; g.flags = flags; g.dbg = g_tc_debug;
     g.res = Act{res, res_plane, res_ld};
     g.out = ActW{out, out_plane, out_ld};
     const uint32_t npl = terms == 3 ? 2 : 1;
@@ -449,7 +493,7 @@ extern "C" int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld,
         int rc = tc_encode(&tW2, w2, 3, dims, str, box, "mbconv_fused project weights", 1);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)npl * kMbXPlane + 2 * (size_t)npl * kMbA2Plane + 2 * (size_t)npl * (kMbW1Plane + (size_t)cout * 128) + kMbHid + 256 + 1024;
+    const size_t smem = (size_t)npl * kMbXPlane + 2 * (size_t)npl * kMbA2Plane + 2 * (size_t)npl * (kMbW1Plane + (size_t)cout * 128) + kMbHid + 256 + 512 + 1024;
     UAVSAL_REQUIRE(smem <= 227 * 1024, UAVSAL_ENOTSUP, "mbconv_fused: tile does not fit shared memory");
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }

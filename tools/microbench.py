@@ -170,6 +170,16 @@ def main():
             gemm("tc", m, k, n, f32=True)
     if what == "smallk":       # HBM-bound expand GEMMs: the epilogue's store rate is what matters
         gemm("tc", 1728000, 24, 144, f32=True); gemm("tc", 432000, 32, 192, f32=True); gemm("tc", 432000, 32, 256, res=True)
+    if what == "mbconv_trace":
+        lib = _ext.load()
+        lib.uavsal_set_option(3, 1 << 22)
+        from iip_uavsal_saliency_b200 import model as M
+        blk = M.dwBlock(64, 32).eval().cuda()
+        p = Plan(dev, 3, "tc")
+        x = p.alloc(120 * 45 * 80, 64); x.t.normal_()
+        blk._emit(p, x, 120, 45, 80)
+        p.run(); torch.cuda.synchronize()
+        lib.uavsal_set_option(3, 0)
     if what == "mbconv":
         for fused in (False, True):
             mbblock(120, 45, 80, 64, 32, fused); mbblock(120, 45, 80, 32, 32, fused); mbblock(120, 23, 40, 64, 64, fused)
