@@ -256,7 +256,7 @@ def time_op_classes(plan, torch, detail=None):
         if op.name == "uavsal_pw_gemm":
             m, k, n = a[3], a[4], a[7]
             fl = 2.0 * m * k * n
-            by = 4.0 * m * (k + n) + 4.0 * n * k
+            by = 4.0 * m * k + (2.0 if a[9] & 32 else 4.0) * m * n + 4.0 * n * k          # UAVSAL_F_OUT_Q16: 16-bit hidden rows
             if _pw_is_pair(m, k, n) and not ((a[9] & 2) and n >= 64):      # the launcher's rule (gemm_tc.cu want_cluster), not EPI_RES
                 r = res.setdefault("uavsal_pw_gemm/pair", [0.0, 0.0, 0.0, 0])
                 r[0] += ms; r[1] += fl; r[2] += by; r[3] += 1
@@ -271,7 +271,7 @@ def time_op_classes(plan, torch, detail=None):
         elif op.name == "uavsal_dw_project":
             nimg, hh, ww, hidden, cout = a[2], a[3], a[4], a[5], a[10]
             fl = 2.0 * nimg * hh * ww * hidden * cout + 18.0 * nimg * hh * ww * hidden
-            by = 4.0 * nimg * hh * ww * (hidden + cout)
+            by = nimg * hh * ww * ((2.0 if a[12] & 64 else 4.0) * hidden + 4.0 * cout)     # UAVSAL_F_HID_Q16
         elif op.name == "uavsal_expand_dw3x3":
             nimg, hh, ww, cin, hidden, stride = a[3], a[4], a[5], a[6], a[10], a[11]
             ho, wo = (hh if stride == 1 else (hh - 1) // 2 + 1), (ww if stride == 1 else (ww - 1) // 2 + 1)
@@ -281,7 +281,7 @@ def time_op_classes(plan, torch, detail=None):
             nimg, hh, ww, c, stride = a[3], a[4], a[5], a[6], a[7]
             ho, wo = (hh if stride == 1 else (hh - 1) // 2 + 1), (ww if stride == 1 else (ww - 1) // 2 + 1)
             fl = 18.0 * nimg * ho * wo * c
-            by = 4.0 * nimg * c * (hh * ww + ho * wo)
+            by = nimg * c * ((2.0 if a[1] == -2 else 4.0) * hh * ww + 4.0 * ho * wo)          # UAVSAL_PLANE_Q16 input
         r = res.setdefault(op.name, [0.0, 0.0, 0.0, 0])
         r[0] += ms; r[1] += fl; r[2] += by; r[3] += 1
         if detail is not None:

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "uavsal_twa_sequence": ACT + ACT + [I, I, I, I, P, P, I, P] + ACT + [I, P, P],
     "uavsal_convlstm_sequence": ACT + ACT + [P, I, I, I, I, I, I, P, P, P, I] + ACT + [P],
     "uavsal_dw3x3_dot_sigmoid": [P, I, I, I, I, I, P, P, P, F, P, P, P],
+    "uavsal_dw3x3_dot_sigmoid_q16": [P, I, I, I, I, I, P, P, P, F, P, P, P],
     "uavsal_dot_sigmoid": ACT + [L, I, P, F, P, P],
     "uavsal_post_u8": [P, I, I, I, I, I, P, P, P],
     "uavsal_post_f32": [P, I, I, I, I, I, P, P, P],

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from ._kernel_module import KernelModule
-from .engine import F_RELU6, Buf, Plan, W, fold_bn, out_size, pack_dw
+from .engine import F_RELU6, FMT_SPLIT, Buf, Plan, W, fold_bn, out_size, pack_dw
 
 __all__ = ["BasicConv2d", "dwBlock", "init_weights", "emit_stem"]
 
@@ -55,13 +55,13 @@ class BasicConv2d(nn.Sequential):
         """This layer's parameters for ``Plan.packed`` (BN fold + layout + hi/lo split happen in uavsal_pack_weights)."""
         return W(self[0].weight, bn=self[1], owner=self[0])
 
-    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag="", f32_out: bool = False):
+    def _emit(self, plan: Plan, x: Buf, n, h, w, out: Buf = None, res: Buf = None, tag="", out_fmt: int = FMT_SPLIT):
         cin, cout, k, stride, dil, groups = self.spec
         ws = self.wspec()
         if k == 1:
             assert stride == 1 and groups == 1
             if out is None:
-                out = plan.alloc_f32(n * h * w, cout) if f32_out else plan.alloc(n * h * w, cout)
+                out = plan.alloc_hidden(n * h * w, cout, out_fmt)
             plan.pw(x, n * h * w, ws, None, F_RELU6, out, res=res, tag=tag)
             return out, h, w
         if groups == cin and groups == cout:
@@ -121,7 +121,7 @@ class dwBlock(KernelModule):
         cur = x
         i = 0
         fuse_all = getattr(plan, "fuse_mbconv", True)
-        if (fuse_all and has_expand and plan.engine == "tc" and stride == 1 and dil == 1 and not x.f32 and x.c <= 64 and hidden % 64 == 0
+        if (fuse_all and has_expand and plan.engine == "tc" and stride == 1 and dil == 1 and not x.plain and x.c <= 64 and hidden % 64 == 0
                 and oup % 16 == 0 and oup <= 64):
             # narrow stride-1 block: expand -> depthwise -> project (+ x) in ONE kernel, the 6x hidden tensor stays on the SM (mbconv.cu)
             out = out if out is not None else plan.alloc(n * h * w, oup)
@@ -131,7 +131,7 @@ class dwBlock(KernelModule):
         fuse = getattr(plan, "fuse_expand_dw", "auto")
         if fuse == "auto":       # measured (profiles/r01_microbench_expdw.txt): the fused kernel wins on the stride-2 high-resolution blocks
             fuse = stride == 2 and h * w >= 10000       # per-frame size: the choice must not depend on how many frames are batched
-        if has_expand and plan.engine == "tc" and dil == 1 and x.c <= 32 and not x.f32 and fuse:
+        if has_expand and plan.engine == "tc" and dil == 1 and x.c <= 32 and not x.plain and fuse:
             # few input channels: expand + depthwise in one kernel, the 6x hidden tensor never reaches HBM
             ho, wo = out_size(h, stride), out_size(w, stride)
             cur = plan.alloc(n * ho * wo, hidden)
@@ -142,15 +142,16 @@ class dwBlock(KernelModule):
             plan.pw(cur, n * ho * wo, self.project_wspec(), None, 0, out, res=x if self.use_res_connect else None, tag=tag + ".project")
             return out, ho, wo
         if has_expand:
-            # the 6x hidden tensor stays fp32 between the expand GEMM and the TMA depthwise kernel (dilation 1 only)
-            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", f32_out=plan.f32_hidden and dil == 1)
+            # the 6x hidden tensor travels as plain rows between the expand GEMM and the TMA depthwise kernels (dilation 1 only):
+            # fp32, or 16-bit fixed point for the widest blocks (Plan.hidden_fmt)
+            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", out_fmt=plan.hidden_fmt(hidden, dil))
             i = 1
         fuse_dp = getattr(plan, "fuse_dw_project", "auto")
         if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
             fuse_dp = h * w >= 3600 and n * h * w >= 32768
         wide = has_expand and hidden % 128 == 0 and oup % 64 == 0 and oup <= 256          # tcgen05 pair kernel (dwproj.cu)
         narrow = (hidden, oup) == (32, 16) and not self.use_res_connect                    # features.1: fp32 FFMA kernel (dwproj32.cu)
-        if fuse_dp and cur.f32 and plan.engine == "tc" and stride == 1 and dil == 1 and (wide or narrow):
+        if fuse_dp and cur.plain and plan.engine == "tc" and stride == 1 and dil == 1 and (wide or narrow):
             out = out if out is not None else plan.alloc(n * h * w, oup)
             plan.dwproj(cur, n, h, w, self.conv[i].wspec(), None, self.project_wspec(), None, out, res=x if self.use_res_connect else None,
                         tag=tag + ".dw+project")

@@ -133,6 +133,20 @@ __device__ __forceinline__ void store1(uint16_t* hi, int64_t plane, float v) {
     if (plane) hi[plane] = (uint16_t)l;
 }
 
+// ---- "q16" rows: the ReLU6 output of a wide expand conv as 16-bit fixed point ------------------------------------------
+// A value v in [0, 6] is stored as q = rne(v * 65535 / 6) (uint16) and read back as fp32(q * 6 / 65535): absolute error
+// <= 4.6e-5, half the bytes of the fp32 rows.  Both directions avoid the conversion unit: adding 2^23 leaves rne(v * s) in the
+// low mantissa bits, and fma(2^23 + q, 6/65535, -2^23 * 6/65535) is the single correctly rounded product q * 6/65535.
+constexpr float kQ16Enc = 10922.5f;               // 65535 / 6 (exact)
+constexpr float kQ16Dec = 6.0f / 65535.0f;
+__device__ __forceinline__ uint32_t q16_pack2(float a, float b) {     // a, b already clamped to [0, 6]
+    return __byte_perm(__float_as_uint(fmaf(a, kQ16Enc, 8388608.f)), __float_as_uint(fmaf(b, kQ16Enc, 8388608.f)), 0x5410);
+}
+__device__ __forceinline__ float2 q16_unpack2(uint32_t w) {
+    const float2 f = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)));
+    return __ffma2_rn(f, make_float2(kQ16Dec, kQ16Dec), make_float2(-8388608.f * kQ16Dec, -8388608.f * kQ16Dec));
+}
+
 __device__ __forceinline__ float relu6f(float x) { return fminf(fmaxf(x, 0.f), 6.f); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 // accurate variants used where the reference's sigmoid/tanh feed a recurrence

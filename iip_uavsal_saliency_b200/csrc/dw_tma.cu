@@ -7,8 +7,9 @@
 // nine times.  Threads slide a 3x3 register window down their column of the tile (3 shared-memory reads per output),
 // apply the folded BN bias + ReLU6 and write both bf16 planes of the output with 128-byte-contiguous stores.
 //
-// Input formats: the arena's split-bf16 planes (two boxes per tile) or plain fp32 rows (F32IN — the "hidden" tensor
-// between an expand GEMM and its depthwise conv is kept in fp32: same bytes, no unpack/re-split work on either side).
+// Input formats (FMT): 0 = the arena's split-bf16 planes (two boxes per tile); 1 = plain fp32 rows (the "hidden" tensor
+// between an expand GEMM and its depthwise conv is kept in fp32: same bytes, no unpack/re-split work on either side);
+// 2 = q16 rows (16-bit fixed point of a ReLU6 output, common.cuh: half the bytes, used for the widest hidden tensors).
 #include "tc_common.cuh"
 
 namespace uavsal {
@@ -34,13 +35,19 @@ struct DwGeom {
     static constexpr int RGRPS = 256 / (16 * TW);         // row groups: 1 (stride 1) or 2 (stride 2)
     static constexpr int RPT = TH / RGRPS;                // output rows per thread: 8 (stride 1) or 2 (stride 2)
     static constexpr uint32_t TILE_BYTES = PIX * 256;     // 64 channels x (2 bf16 planes | fp32)
+    static constexpr uint32_t TILE_BYTES_Q16 = PIX * 128; // 64 channels x uint16
 };
 
 // 4 channels from the staged tile -> fp32 (explicit shared-space loads: `tile` is a 32-bit shared address)
-template <bool F32IN>
+template <int FMT>
 __device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pix, int quad, float v[4]) {
-    if (F32IN) {
+    if (FMT == 1) {
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(tile + pix * 256 + quad * 16));
+    } else if (FMT == 2) {
+        uint2 a;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(tile + pix * 128 + quad * 8));
+        const float2 lo = q16_unpack2(a.x), hi = q16_unpack2(a.y);
+        v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
     } else {
         uint2 a, b;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(tile + pix * 128 + quad * 8));
@@ -58,12 +65,13 @@ __device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pi
 // DOT: instead of storing the depthwise output, every thread folds its 4 channels into the dot product with `wproj` (the
 // dwBlock's project conv when it has ONE output channel: the readout, model.py:372), the 16 threads sharing a pixel reduce by
 // shuffles and one partial per (pixel, channel block) is written; dot_finish_kernel adds the blocks in a fixed order.
-template <int STRIDE, bool F32IN, bool DOT>
+template <int STRIDE, int FMT, bool DOT>
 __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs g) {
     using G = DwGeom<STRIDE>;
+    constexpr uint32_t kTile = FMT == 2 ? G::TILE_BYTES_Q16 : G::TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * G::TILE_BYTES);      // [2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kTile);              // [2]
 
     const int tid = threadIdx.x;
     pdl_trigger();
@@ -81,17 +89,17 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     auto issue = [&](int t, int b) {                                           // one thread
         int cblk, x0, y0, img;
         decode(t, cblk, x0, y0, img);
-        uint8_t* dst = smem + b * G::TILE_BYTES;
+        uint8_t* dst = smem + b * kTile;
         fence_async_smem();                                                    // order the buffer's generic reads before the async overwrite
-        mbar_expect_tx(bar + b, G::TILE_BYTES);
-        if (F32IN) {
+        mbar_expect_tx(bar + b, kTile);
+        if (FMT != 0) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                 ::"r"(smem_u32(dst)), "l"(&tmIn), "r"(smem_u32(bar + b)), "r"(cblk * 64), "r"(x0 * STRIDE - 1), "r"(y0 * STRIDE - 1), "r"(img)
                 : "memory");
         } else {
             tma_load_5d(&tmIn, bar + b, dst, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 0);
-            tma_load_5d(&tmIn, bar + b, dst + G::TILE_BYTES / 2, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 1);
+            tma_load_5d(&tmIn, bar + b, dst + kTile / 2, cblk * 64, x0 * STRIDE - 1, y0 * STRIDE - 1, img, 1);
         }
     };
 
@@ -129,11 +137,11 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
 
         const int ox = x0 + col;
         if (DOT || (cvalid && ox < g.wo)) {                                    // DOT: all lanes stay for the shuffles
-            const uint32_t tile = smem_u32(smem) + b * G::TILE_BYTES;
+            const uint32_t tile = smem_u32(smem) + b * kTile;
             float win[3][3][4];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
 #pragma unroll
-                for (int d = 0; d < 3; ++d) lds4<F32IN>(tile, G::TILE_BYTES / 2, iy * G::IW + col * STRIDE + d, quad, win[slot][d]);
+                for (int d = 0; d < 3; ++d) lds4<FMT>(tile, kTile / 2, iy * G::IW + col * STRIDE + d, quad, win[slot][d]);
             };
             const int oyl0 = rgrp * G::RPT;
             if (STRIDE == 1) { load_row(0, oyl0); load_row(1, oyl0 + 1); }
@@ -181,29 +189,29 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     }
 }
 
-template <int STRIDE, bool F32IN, bool DOT = false>
+template <int STRIDE, int FMT, bool DOT = false>
 static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     using G = DwGeom<STRIDE>;
     g.tiles_x = div_up(g.wo, G::TW);
     g.tiles_y = div_up(g.ho, G::TH);
     g.cblocks = div_up(g.c, 64);
     g.num_tiles = g.n * g.tiles_x * g.tiles_y * g.cblocks;
-    const size_t smem = 2 * G::TILE_BYTES + 64 + 128;
+    const size_t smem = 2 * (FMT == 2 ? G::TILE_BYTES_Q16 : G::TILE_BYTES) + 64 + 128;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE, F32IN, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dw3x3_tma_kernel<STRIDE, FMT, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("dw3x3(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = g.num_tiles < sms * 2 ? g.num_tiles : sms * 2;           // 2 resident CTAs per SM (registers, 2 x 92 KiB smem)
-    cudaError_t e = launch_k(dw3x3_tma_kernel<STRIDE, F32IN, DOT>, dim3(grid), dim3(256), smem, s, 1, tm, g);
+    cudaError_t e = launch_k(dw3x3_tma_kernel<STRIDE, FMT, DOT>, dim3(grid), dim3(256), smem, s, 1, tm, g);
     if (e != cudaSuccess) { set_error("dw3x3(tma): launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("dw3x3(tma)");
 }
 
-// in.plane == UAVSAL_PLANE_F32: `in.p` is a float* to fp32 rows [n*h*w][in.ld]
+// in.plane == UAVSAL_PLANE_F32: `in.p` is a float* to fp32 rows [n*h*w][in.ld]; UAVSAL_PLANE_Q16: uint16 fixed-point rows
 int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, const float* bias, int relu6, ActW out,
               cudaStream_t s) {
     DwArgs g{};
@@ -213,20 +221,21 @@ int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, 
     g.wgt = wgt; g.bias = bias; g.relu6 = relu6; g.out = out;
     CUtensorMap tm;
     int rc;
-    if (in.plane == UAVSAL_PLANE_F32) {
+    if (in.plane == UAVSAL_PLANE_F32 || in.plane == UAVSAL_PLANE_Q16) {
+        const bool q16 = in.plane == UAVSAL_PLANE_Q16;
         const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        const uint64_t row = (uint64_t)in.ld * 4;
+        const uint64_t row = (uint64_t)in.ld * (q16 ? 2 : 4);
         const uint64_t str[3] = {row, row * w, row * w * h};
         if (stride == 1) {
             const uint32_t box[4] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1};
-            rc = tc_encode(&tm, in.p, 4, dims, str, box, "dw input (f32)", 2);
+            rc = tc_encode(&tm, in.p, 4, dims, str, box, q16 ? "dw input (q16)" : "dw input (f32)", q16 ? 0 : 2);
             if (rc) return rc;
-            return launch_dw_tma<1, true>(tm, g, s);
+            return q16 ? launch_dw_tma<1, 2>(tm, g, s) : launch_dw_tma<1, 1>(tm, g, s);
         }
         const uint32_t box[4] = {64, (uint32_t)DwGeom<2>::IW, (uint32_t)DwGeom<2>::IH, 1};
-        rc = tc_encode(&tm, in.p, 4, dims, str, box, "dw input (f32)", 2);
+        rc = tc_encode(&tm, in.p, 4, dims, str, box, q16 ? "dw input (q16)" : "dw input (f32)", q16 ? 0 : 2);
         if (rc) return rc;
-        return launch_dw_tma<2, true>(tm, g, s);
+        return q16 ? launch_dw_tma<2, 2>(tm, g, s) : launch_dw_tma<2, 1>(tm, g, s);
     }
     const uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n, in.plane ? 2u : 1u};
     const uint64_t row = (uint64_t)in.ld * 2;
@@ -235,12 +244,12 @@ int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, 
         const uint32_t box[5] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1, 1};
         rc = tc_encode(&tm, in.p, 5, dims, str, box, "dw input", 0);
         if (rc) return rc;
-        return launch_dw_tma<1, false>(tm, g, s);
+        return launch_dw_tma<1, 0>(tm, g, s);
     }
     const uint32_t box[5] = {64, (uint32_t)DwGeom<2>::IW, (uint32_t)DwGeom<2>::IH, 1, 1};
     rc = tc_encode(&tm, in.p, 5, dims, str, box, "dw input", 0);
     if (rc) return rc;
-    return launch_dw_tma<2, false>(tm, g, s);
+    return launch_dw_tma<2, 0>(tm, g, s);
 }
 
 // readout tail: sum the channel-block partials of a pixel in a fixed order, add the folded BN bias, sigmoid (model.py:373)
@@ -255,19 +264,19 @@ __global__ void __launch_bounds__(256) dot_finish_kernel(const float* __restrict
     out[r] = 1.f / (1.f + expf(-(s + bias)));
 }
 
-int dw3x3_dot_tma(const float* in, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
+int dw3x3_dot_tma(const void* in, bool q16, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
                   float bias_proj, float* partial, float* out, cudaStream_t s) {
     DwArgs g{};
     g.n = n; g.h = h; g.w = w; g.c = c; g.ho = h; g.wo = w;
     g.wgt = wgt; g.bias = bias; g.relu6 = 1; g.wproj = wproj; g.partial = partial;
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t row = (uint64_t)in_ld * 4;
+    const uint64_t row = (uint64_t)in_ld * (q16 ? 2 : 4);
     const uint64_t str[3] = {row, row * w, row * w * h};
     const uint32_t box[4] = {64, (uint32_t)DwGeom<1>::IW, (uint32_t)DwGeom<1>::IH, 1};
     CUtensorMap tm;
-    int rc = tc_encode(&tm, in, 4, dims, str, box, "dw_dot input (f32)", 2);
+    int rc = tc_encode(&tm, in, 4, dims, str, box, q16 ? "dw_dot input (q16)" : "dw_dot input (f32)", q16 ? 0 : 2);
     if (rc) return rc;
-    rc = launch_dw_tma<1, true, true>(tm, g, s);
+    rc = q16 ? launch_dw_tma<1, 2, true>(tm, g, s) : launch_dw_tma<1, 1, true>(tm, g, s);
     if (rc) return rc;
     const int64_t rows = (int64_t)n * h * w;
     cudaError_t e = launch_k(dot_finish_kernel, dim3(div_up(rows, 256)), dim3(256), 0, s, 1, (const float*)partial, rows, g.cblocks, bias_proj, out);

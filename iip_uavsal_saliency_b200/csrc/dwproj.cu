@@ -3,8 +3,8 @@
 // The depthwise output of the 45x80 blocks (72 000 x 1536 x 4 B = 442 MB per 20-frame call) was written by one kernel and
 // read back by the project GEMM; here it only ever exists as the A operand tile of a tcgen05 GEMM in shared memory:
 //
-//   warp 0        TMA producer : haloed fp32 hidden tile (18 x 10 pixels x 64 channels, OOB zero fill = conv padding) of
-//                                k-block kb+1 and this CTA's half of the project-weight k-block (bf16 hi/lo, 128-B swizzle)
+//   warp 0        TMA producer : haloed hidden tile (18 x 10 pixels x 64 channels, fp32 or q16; OOB zero fill = conv padding)
+//                                of k-block kb+1 and this CTA's half of the project-weight k-block (bf16 hi/lo, 128-B swizzle)
 //   warps 2..17   depthwise    : sliding 3x3 window over the hidden tile -> bias -> ReLU6 -> hi/lo split -> A tile
 //                                [128 pixels x 64 channels] written in the K-major 128-B-swizzled layout UMMA expects
 //   warp 1        MMA issuer   : cta_group::2 MMAs (M = 256: the 16x8-pixel tiles of BOTH CTAs of the pair), fp32 in TMEM
@@ -13,6 +13,9 @@
 //
 // Per k-block a CTA ingests 46 KB (hidden) + 32 KB (weights) instead of the GEMM's 64 KB, and the 2 x 442 MB round trip of
 // the depthwise output through HBM plus the separate depthwise launch disappear.
+//
+// Q16 (UAVSAL_F_HID_Q16): the hidden tensor arrives as 16-bit fixed point rows (common.cuh) - 23 KB per k-block, one LDS.64
+// instead of one LDS.128 per 4 channels (the kernel is bound by the shared-memory data path) and half the HBM read.
 #include "tc_common.cuh"
 #include "gemm_tc2.cuh"
 
@@ -31,15 +34,18 @@ struct DwProjArgs {
 };
 
 constexpr int kDpTW = 16, kDpTH = 8, kDpIW = kDpTW + 2, kDpIH = kDpTH + 2;
-constexpr uint32_t kDpHBytes = kDpIW * kDpIH * 256;        // 46 080: haloed tile, 64 fp32 channels per pixel
+constexpr uint32_t kDpHBytesF32 = kDpIW * kDpIH * 256;     // 46 080: haloed tile, 64 fp32 channels per pixel
+constexpr uint32_t kDpHBytesQ16 = kDpIW * kDpIH * 128;     // 23 040: 64 q16 channels per pixel
 constexpr uint32_t kDpAPlane = 128 * 128;                  // 16 KiB: 128 rows x 64 bf16
 
-template <int TERMS>
+template <int TERMS, bool Q16>
 __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_constant__ CUtensorMap tmH,
                                                              const __grid_constant__ CUtensorMap tmB, const DwProjArgs g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NPL = TERMS == 3 ? 2 : 1;
+    constexpr uint32_t kDpHBytes = Q16 ? kDpHBytesQ16 : kDpHBytesF32;
+    constexpr uint32_t kPixB = Q16 ? 128 : 256;                               // bytes per pixel of the staged hidden tile
     const uint32_t b_plane = (uint32_t)(g.N / 2) * 128;                       // this CTA's half of the weight k-block, one plane
     const uint32_t a_stage = NPL * kDpAPlane, b_stage = NPL * b_plane;
     uint8_t* abuf = smem;                                                     // [2][a_stage]   (1024-aligned)
@@ -176,27 +182,35 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
                 const int s = gsel;
                 const uint32_t par = (uint32_t)((it * (g.num_kb >> 1) + (kb >> 1)) & 1);   // use count of buffer s so far
                 const int c0 = kb * 64 + quad * 4;
-                float wr[9][4], br[4];
+                // (channel pairs: the 9-tap dot products run as packed fma.rn.f32x2 - the same IEEE fma per lane, half the instructions)
+                float2 wr[9][2], br[2];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wd + k * g.hidden + c0));
-                    wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
+                    wr[k][0] = make_float2(w4.x, w4.y); wr[k][1] = make_float2(w4.z, w4.w);
                 }
                 {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bd + c0));
-                    br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
+                    br[0] = make_float2(b4.x, b4.y); br[1] = make_float2(b4.z, b4.w);
                 }
                 mbar_wait(h_full + s, par);                                   // hidden tile landed
                 mbar_wait(ab_empty + s, par ^ 1);                             // the MMAs that read this A buffer two k-blocks ago retired
                 const uint32_t tile = smem_u32(hbuf + s * kDpHBytes);
                 const uint32_t a_hi = smem_u32(abuf + s * a_stage);
-                float win[3][4][4];                                           // [row slot][column 2cp-1 .. 2cp+2][channel]
+                float2 win[3][4][2];                                          // [row slot][column 2cp-1 .. 2cp+2][channel pair]
                 auto load_row = [&](int slot, int iy) {
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
-                        float* v = win[slot][d];
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-                                     : "r"(tile + (iy * kDpIW + 2 * cp + d) * 256 + quad * 16));
+                        float2* v = win[slot][d];
+                        if (Q16) {
+                            uint32_t w0, w1;
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1)
+                                         : "r"(tile + (iy * kDpIW + 2 * cp + d) * kPixB + quad * 8));
+                            v[0] = q16_unpack2(w0); v[1] = q16_unpack2(w1);
+                        } else {
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y)
+                                         : "r"(tile + (iy * kDpIW + 2 * cp + d) * kPixB + quad * 16));
+                        }
                     }
                 };
                 const int oyl0 = rgrp * 4;
@@ -208,22 +222,20 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
                     const int slots[3] = {s0, s1, s2};
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        float acc[4] = {br[0], br[1], br[2], br[3]};
+                        float2 acc[2] = {br[0], br[1]};
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
-                                const float* v = win[slots[ky]][c + kx];
+                                const float2* v = win[slots[ky]][c + kx];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
+                                for (int j = 0; j < 2; ++j) acc[j] = __ffma2_rn(v[j], wr[ky * 3 + kx][j], acc[j]);
                             }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
                         // A row = pixel index inside the tile; 16-byte chunk (quad >> 1) of the 128-byte row sits at chunk ^ (row & 7)
                         const int r = (oyl0 + i) * kDpTW + 2 * cp + c;
                         uint32_t h0, h1, l0, l1;
-                        split2(acc[0], acc[1], h0, l0);
-                        split2(acc[2], acc[3], h1, l1);
+                        split2(relu6f(acc[0].x), relu6f(acc[0].y), h0, l0);
+                        split2(relu6f(acc[1].x), relu6f(acc[1].y), h1, l1);
                         const uint32_t off = r * 128 + ((((uint32_t)quad >> 1) ^ (r & 7)) << 4) + (quad & 1) * 8;
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
                         if (TERMS == 3) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + kDpAPlane + off), "r"(l0), "r"(l1) : "memory");
@@ -314,13 +326,13 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
 }
 
-template <int TERMS>
+template <int TERMS, bool Q16>
 static int launch_dwproj(const CUtensorMap& tH, const CUtensorMap& tB, DwProjArgs& g, cudaStream_t s) {
     const uint32_t npl = TERMS == 3 ? 2 : 1;
-    const size_t smem = 2 * (size_t)npl * kDpAPlane + 2 * (size_t)npl * (g.N / 2) * 128 + 2 * (size_t)kDpHBytes + 256 + 1024;
+    const size_t smem = 2 * (size_t)npl * kDpAPlane + 2 * (size_t)npl * (g.N / 2) * 128 + 2 * (size_t)(Q16 ? kDpHBytesQ16 : kDpHBytesF32) + 256 + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dwproj_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dwproj_kernel<TERMS, Q16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("dw_project: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
@@ -335,12 +347,12 @@ static int launch_dwproj(const CUtensorMap& tH, const CUtensorMap& tB, DwProjArg
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         q.attrs = at; q.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, dwproj_kernel<TERMS>, &q) != cudaSuccess || n <= 0) { n = sms / 2 - 2; cudaGetLastError(); }
+        if (cudaOccupancyMaxActiveClusters(&n, dwproj_kernel<TERMS, Q16>, &q) != cudaSuccess || n <= 0) { n = sms / 2 - 2; cudaGetLastError(); }
         max_clusters = n;
     }
     const int pairs = (g.num_tiles + 1) / 2;
     const int grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
-    cudaError_t e = launch_k(dwproj_kernel<TERMS>, dim3(grid), dim3(kThreads2), smem, s, 2, tH, tB, g);
+    cudaError_t e = launch_k(dwproj_kernel<TERMS, Q16>, dim3(grid), dim3(kThreads2), smem, s, 2, tH, tB, g);
     if (e != cudaSuccess) { set_error("dw_project: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("dw_project");
 }
@@ -359,12 +371,14 @@ extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int
                                  const uint16_t* res, int64_t res_plane, int res_ld, uint16_t* out, int64_t out_plane, int out_ld,
                                  void* stream) {
     auto al16 = [](const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool q16 = flags & UAVSAL_F_HID_Q16;                    // `hid` holds uint16 fixed-point rows (uavsal_pw_gemm with UAVSAL_F_OUT_Q16)
+    flags &= ~UAVSAL_F_HID_Q16;
     UAVSAL_REQUIRE(al16(hid) && al16(wd) && al16(bd) && al16(wgt) && al16(bias) && al16(out) && n > 0 && h > 0 && w > 0 &&
-                       hid_ld % 4 == 0 && hid_ld >= hidden && out_ld % 8 == 0 && out_ld >= cout && out_plane > 0 && out_plane % 8 == 0 &&
+                       hid_ld % (q16 ? 8 : 4) == 0 && hid_ld >= hidden && out_ld % 8 == 0 && out_ld >= cout && out_plane > 0 && out_plane % 8 == 0 &&
                        kpad >= hidden && kpad % 8 == 0,
                    UAVSAL_EINVAL, "dw_project: bad arguments");
     if (hidden == 32 && cout == 16) {                             // features.1: fp32 FFMA kernel (dwproj32.cu), exact in both precision modes
-        UAVSAL_REQUIRE(!flags, UAVSAL_ENOTSUP, "dw_project: the 32 -> 16 kernel has no residual input");
+        UAVSAL_REQUIRE(!flags && !q16, UAVSAL_ENOTSUP, "dw_project: the 32 -> 16 kernel takes fp32 rows and has no residual input");
         return dw_project32(hid, hid_ld, n, h, w, wd, bd, wgt, kpad, bias, ActW{out, out_plane, out_ld}, (cudaStream_t)stream);
     }
     UAVSAL_REQUIRE(hidden % 128 == 0 && cout % 64 == 0 && cout <= 256 && (terms == 1 || terms == 3), UAVSAL_ENOTSUP,
@@ -386,10 +400,11 @@ extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int
     CUtensorMap tH, tB;
     {
         const uint64_t dims[4] = {(uint64_t)hidden, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        const uint64_t row = (uint64_t)hid_ld * 4;
+        const uint64_t row = (uint64_t)hid_ld * (q16 ? 2 : 4);
         const uint64_t str[3] = {row, row * w, row * w * h};
         const uint32_t box[4] = {64, (uint32_t)kDpIW, (uint32_t)kDpIH, 1};
-        int rc = tc_encode(&tH, hid, 4, dims, str, box, "dw_project hidden (f32)", 2);
+        int rc = q16 ? tc_encode(&tH, hid, 4, dims, str, box, "dw_project hidden (q16)", 0)      // 2-byte elements, zero fill decodes to 0.0
+                     : tc_encode(&tH, hid, 4, dims, str, box, "dw_project hidden (f32)", 2);
         if (rc) return rc;
     }
     {
@@ -399,6 +414,10 @@ extern "C" int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int
         int rc = tc_encode(&tB, wgt, 3, dims, str, box, "dw_project weights", 1);
         if (rc) return rc;
     }
-    if (terms == 3) return launch_dwproj<3>(tH, tB, g, (cudaStream_t)stream);
-    return launch_dwproj<1>(tH, tB, g, (cudaStream_t)stream);
+    if (q16) {
+        if (terms == 3) return launch_dwproj<3, true>(tH, tB, g, (cudaStream_t)stream);
+        return launch_dwproj<1, true>(tH, tB, g, (cudaStream_t)stream);
+    }
+    if (terms == 3) return launch_dwproj<3, false>(tH, tB, g, (cudaStream_t)stream);
+    return launch_dwproj<1, false>(tH, tB, g, (cudaStream_t)stream);
 }

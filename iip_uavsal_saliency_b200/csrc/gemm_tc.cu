@@ -538,10 +538,14 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
                    const float* bias, int flags, int terms, const uint16_t* res, int64_t res_plane, int res_ld,
                    uint16_t* out, int64_t out_plane, int out_ld, void* stream) {
     const bool f32out = flags & UAVSAL_F_OUT_F32;
+    const bool q16out = flags & UAVSAL_F_OUT_Q16;
     const bool v2 = !(terms & UAVSAL_TERMS_GEN1) && g_tc_version == 2;
     terms &= 0xFF;
     UAVSAL_REQUIRE(!f32out || (v2 && !(flags & UAVSAL_F_SIGMOID)), UAVSAL_ENOTSUP, "pw_gemm: fp32 output needs the persistent kernel");
-    UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && (f32out ? (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_ld % 4 == 0) : act_ok16(out, out_plane, out_ld)) && wgt &&
+    UAVSAL_REQUIRE(!q16out || (v2 && flags == (UAVSAL_F_OUT_Q16 | UAVSAL_F_RELU6)), UAVSAL_ENOTSUP,
+                   "pw_gemm: q16 output is the ReLU6 output of the persistent kernel (flags = RELU6 | OUT_Q16 only)");
+    UAVSAL_REQUIRE(act_ok16(a, a_plane, a_ld) && (f32out ? (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_ld % 4 == 0) :
+                                                  q16out ? act_ok16(out, 0, out_ld) : act_ok16(out, out_plane, out_ld)) && wgt &&
                        (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 && m > 0 && k > 0 && n > 0 && k % 8 == 0 &&
                        kpad % 8 == 0 && kpad >= k && n % 8 == 0 && a_ld >= k && out_ld >= n,
                    UAVSAL_EINVAL, "pw_gemm: bad arguments (m=%d k=%d kpad=%d n=%d)", m, k, kpad, n);
@@ -562,8 +566,9 @@ int uavsal_pw_gemm(const uint16_t* a, int64_t a_plane, int a_ld, int m, int k, c
     if (rc) return rc;
     if (v2) {
         CUtensorMap tO = tA;                                   // (the copy-out uses the LSU path; the map is kept for TMA-store experiments)
-        if (!f32out) rc = map_out_pw(&tO, g.out, m, n);
+        if (!f32out && !q16out) rc = map_out_pw(&tO, g.out, m, n);
         if (rc) return rc;
+        if (q16out) return launch_tc2<MODE_PW, EPI_Q16>(tA, tA, tB, tO, g, terms, div_up(m, kBM), cl, (cudaStream_t)stream, "pw_gemm");
         // residual blocks with wide outputs: the residual is added in the coalesced copy-out phase (measured 318 -> 272 us for
         // 432000 x 32 -> 256); narrow outputs (N < 64) keep the row-strided loads, which are as fast there
         const bool res_coal = (flags & UAVSAL_F_RESIDUAL) && !(flags & UAVSAL_F_SIGMOID) && !f32out && n >= 64 && !(g_tc_debug & DBG_ROW_RES);

@@ -640,7 +640,7 @@ static inline bool act_ok(const void* p, int64_t plane, int ld) {
 }
 
 namespace uavsal {
-int dw3x3_dot_tma(const float* in, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
+int dw3x3_dot_tma(const void* in, bool q16, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
                   float bias_proj, float* partial, float* out, cudaStream_t s);
 }
 
@@ -724,8 +724,9 @@ int uavsal_stem_conv3x3s2_hw(const void* x, int x_kind, int n, int h, int w, con
 int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c, int stride, int dilation,
                  const float* wgt, const float* bias, int relu6, uint16_t* out, int64_t out_plane, int out_ld,
                  void* stream) {
-    const bool f32in = in_plane == UAVSAL_PLANE_F32;
-    UAVSAL_REQUIRE((f32in ? (in && aligned16(in) && in_ld % 4 == 0) : act_ok(in, in_plane, in_ld)) && act_ok(out, out_plane, out_ld) &&
+    const bool q16in = in_plane == UAVSAL_PLANE_Q16;
+    const bool f32in = in_plane == UAVSAL_PLANE_F32 || q16in;              // plain rows (fp32 | q16): TMA kernel only
+    UAVSAL_REQUIRE((f32in ? (in && aligned16(in) && in_ld % (q16in ? 8 : 4) == 0) : act_ok(in, in_plane, in_ld)) && act_ok(out, out_plane, out_ld) &&
                        wgt && bias && aligned16(wgt) && aligned16(bias) && c % 8 == 0 && c > 0 && in_ld >= c && out_ld >= c && n > 0,
                    UAVSAL_EINVAL, "dw3x3: bad arguments (c=%d)", c);
     UAVSAL_REQUIRE((stride == 1 || stride == 2) && dilation >= 1 && (stride == 1 || dilation == 1), UAVSAL_ENOTSUP,
@@ -735,7 +736,7 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
         return dw3x3_tma(Act{in, in_plane, in_ld}, n, h, w, c, stride, wgt, bias, relu6, ActW{out, out_plane, out_ld},
                          (cudaStream_t)stream);
     }
-    UAVSAL_REQUIRE(!f32in, UAVSAL_ENOTSUP, "dw3x3: fp32 input is only implemented by the TMA kernel (dilation 1)");
+    UAVSAL_REQUIRE(!f32in, UAVSAL_ENOTSUP, "dw3x3: fp32 / q16 row input is only implemented by the TMA kernel (dilation 1)");
     if (dilation == 1 && g_dw_fast == 1) {
         const int strips = div_up(ho, kDwRB);
         const dim3 grid(div_up(c, 64), div_up(wo, 32), strips * n);
@@ -812,7 +813,16 @@ int uavsal_dw3x3_dot_sigmoid(const float* in, int in_ld, int n, int h, int w, in
                        n > 0 && h > 0 && w > 0 && c > 0 && in_ld % 4 == 0 && in_ld >= c,
                    UAVSAL_EINVAL, "dw3x3_dot_sigmoid: bad arguments");
     UAVSAL_REQUIRE(c % 4 == 0, UAVSAL_ENOTSUP, "dw3x3_dot_sigmoid: channels must be a multiple of 4");
-    return dw3x3_dot_tma(in, in_ld, n, h, w, c, wd, bd, wproj, bias_proj, partial_ws, out_f32, (cudaStream_t)stream);
+    return dw3x3_dot_tma(in, false, in_ld, n, h, w, c, wd, bd, wproj, bias_proj, partial_ws, out_f32, (cudaStream_t)stream);
+}
+
+int uavsal_dw3x3_dot_sigmoid_q16(const uint16_t* in, int in_ld, int n, int h, int w, int c, const float* wd, const float* bd,
+                                 const float* wproj, float bias_proj, float* partial_ws, float* out_f32, void* stream) {
+    UAVSAL_REQUIRE(in && wd && bd && wproj && partial_ws && out_f32 && aligned16(in) && aligned16(wd) && aligned16(bd) && aligned16(wproj) &&
+                       n > 0 && h > 0 && w > 0 && c > 0 && in_ld % 8 == 0 && in_ld >= c,
+                   UAVSAL_EINVAL, "dw3x3_dot_sigmoid_q16: bad arguments");
+    UAVSAL_REQUIRE(c % 4 == 0, UAVSAL_ENOTSUP, "dw3x3_dot_sigmoid_q16: channels must be a multiple of 4");
+    return dw3x3_dot_tma(in, true, in_ld, n, h, w, c, wd, bd, wproj, bias_proj, partial_ws, out_f32, (cudaStream_t)stream);
 }
 
 int uavsal_dot_sigmoid(const uint16_t* a, int64_t a_plane, int a_ld, int64_t rows, int k, const float* wgt, float bias,

@@ -7,7 +7,7 @@
 namespace uavsal {
 
 enum { MODE_PW = 0, MODE_CONV = 1 };
-enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3, EPI_RES = 4 };   // EPI_RES: EPI_STD + residual added in the coalesced copy-out phase
+enum { EPI_STD = 0, EPI_TWA = 1, EPI_LSTM = 2, EPI_RAW = 3, EPI_RES = 4, EPI_Q16 = 5 };   // EPI_RES: EPI_STD + residual added in the coalesced copy-out phase; EPI_Q16: EPI_STD (bias + ReLU6) writing q16 rows
 // timing-ablation switches (uavsal_set_option key 3; results are garbage, never set on the product path)
 enum { DBG_NO_MMA = 1 << 16, DBG_NO_STORE = 1 << 17, DBG_NO_B = 1 << 18, DBG_NO_A = 1 << 19, DBG_ROW_RES = 1 << 20 };
 

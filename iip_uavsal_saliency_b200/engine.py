@@ -14,9 +14,12 @@ import torch
 
 from . import _ext
 
-F_RELU6, F_RESIDUAL, F_SIGMOID, F_OUT_F32, F_RELU = 1, 2, 4, 8, 16
+F_RELU6, F_RESIDUAL, F_SIGMOID, F_OUT_F32, F_RELU, F_OUT_Q16, F_HID_Q16 = 1, 2, 4, 8, 16, 32, 64
 TERMS_GEN1 = 0x100        # UAVSAL_TERMS_GEN1
 PLANE_F32 = -1            # UAVSAL_PLANE_F32: the activation is plain fp32 rows, not split-bf16 planes
+PLANE_Q16 = -2            # UAVSAL_PLANE_Q16: uint16 fixed-point rows of a ReLU6 output, q = rne(v * 65535 / 6)
+FMT_SPLIT, FMT_F32, FMT_Q16 = 0, 1, 2
+Q16_HIDDEN_MIN = 1152     # hidden tensors at least this wide travel as q16 rows (see Plan.hidden_fmt)
 BN_EPS = 1e-5
 
 
@@ -38,15 +41,29 @@ class _Alloc:
 
 
 class Buf:
-    """A (rows x c) activation living in a (2, rows, ld) bf16 tensor at channel offset ``off`` — or, when ``f32``, in a
-    plain (rows, ld) fp32 tensor (the hidden tensor between an expand conv and its depthwise conv).  ``root`` ties every
-    slot / row view to the arena allocation it lives in (liveness tracking of two-pass plans)."""
+    """A (rows x c) activation living in a (2, rows, ld) bf16 tensor at channel offset ``off`` (``fmt`` FMT_SPLIT) — or in
+    plain rows: a (rows, ld) fp32 tensor (FMT_F32) or uint16 fixed point (FMT_Q16), the two forms of the hidden tensor between
+    an expand conv and its depthwise conv.  ``root`` ties every slot / row view to the arena allocation it lives in
+    (liveness tracking of two-pass plans)."""
 
-    __slots__ = ("t", "rows", "c", "ld", "off", "f32", "root", "plan", "base")
+    __slots__ = ("t", "rows", "c", "ld", "off", "fmt", "root", "plan", "base")
 
-    def __init__(self, t, rows: int, c: int, ld: int, off: int = 0, f32: bool = False, root=None, plan=None, base: int = 0):
-        self.t, self.rows, self.c, self.ld, self.off, self.f32 = t, rows, c, ld, off, f32
+    def __init__(self, t, rows: int, c: int, ld: int, off: int = 0, fmt: int = FMT_SPLIT, root=None, plan=None, base: int = 0):
+        self.t, self.rows, self.c, self.ld, self.off, self.fmt = t, rows, c, ld, off, int(fmt)
         self.root, self.plan, self.base = root, plan, base
+
+    @property
+    def f32(self) -> bool:
+        return self.fmt == FMT_F32
+
+    @property
+    def q16(self) -> bool:
+        return self.fmt == FMT_Q16
+
+    @property
+    def plain(self) -> bool:
+        """Plain rows (fp32 | q16): written by the expand GEMM, read by the depthwise kernels only."""
+        return self.fmt != FMT_SPLIT
 
     def _touch(self):
         if self.root is not None:
@@ -60,22 +77,25 @@ class Buf:
 
     @property
     def plane(self) -> int:
-        return PLANE_F32 if self.f32 else self.rows * self.ld
+        return PLANE_F32 if self.f32 else PLANE_Q16 if self.q16 else self.rows * self.ld
 
     def act(self) -> Tuple[int, int, int]:
         return (self.ptr, self.plane, self.ld)
 
     def slot(self, off: int, c: int) -> "Buf":
         assert off % 8 == 0 and off + c <= self.ld
-        return Buf(self.t, self.rows, c, self.ld, self.off + off, self.f32, self.root, self.plan, self.base)
+        return Buf(self.t, self.rows, c, self.ld, self.off + off, self.fmt, self.root, self.plan, self.base)
 
     def at_row(self, row: int) -> "Buf":
         """The same buffer seen from row ``row`` on (same plane distance and pitch: used for the last frame of a sequence)."""
-        return Buf(self.t, self.rows, self.c, self.ld, self.off + row * self.ld, self.f32, self.root, self.plan, self.base)
+        return Buf(self.t, self.rows, self.c, self.ld, self.off + row * self.ld, self.fmt, self.root, self.plan, self.base)
 
     def to_float(self) -> torch.Tensor:
         """fp32 (rows, c) reconstruction hi + lo (debug / tests)."""
-        v = self.t if self.f32 else self.t[0].float() + self.t[1].float()
+        if self.q16:
+            v = self.t.view(torch.int16).to(torch.int32).bitwise_and(0xFFFF).float() * (6.0 / 65535.0)
+        else:
+            v = self.t if self.f32 else self.t[0].float() + self.t[1].float()
         return v[:, self.off:self.off + self.c]
 
 
@@ -322,14 +342,42 @@ class Plan:
             t = torch.zeros((rows, ld), dtype=torch.float32, device=self.device)
             self.arena_bytes += t.numel() * 4
             self.keep.append(t)
-            return Buf(t, rows, c, ld, 0, True)
+            return Buf(t, rows, c, ld, 0, FMT_F32)
         a = self._new(rows * ld * 4)
         t = self._carve(a, torch.float32, (rows, ld)) if self.mode == "arena" else None
-        return Buf(t, rows, c, ld, 0, True, a, self, 4096 * (a.idx + 1))
+        return Buf(t, rows, c, ld, 0, FMT_F32, a, self, 4096 * (a.idx + 1))
+
+    def alloc_q16(self, rows: int, c: int) -> Buf:
+        """uint16 fixed-point rows (q = rne(v * 65535 / 6) of a ReLU6 output; only the persistent tcgen05 GEMM writes them, only
+        the depthwise kernels read them).  Held as an int16 tensor (same bits)."""
+        ld = _pad8(c)
+        if self.mode == "direct":
+            t = torch.zeros((rows, ld), dtype=torch.int16, device=self.device)
+            self.arena_bytes += t.numel() * 2
+            self.keep.append(t)
+            return Buf(t, rows, c, ld, 0, FMT_Q16)
+        a = self._new(rows * ld * 2)
+        t = self._carve(a, torch.int16, (rows, ld)) if self.mode == "arena" else None
+        return Buf(t, rows, c, ld, 0, FMT_Q16, a, self, 4096 * (a.idx + 1))
+
+    def alloc_hidden(self, rows: int, c: int, fmt: int) -> Buf:
+        return self.alloc_q16(rows, c) if fmt == FMT_Q16 else self.alloc_f32(rows, c) if fmt == FMT_F32 else self.alloc(rows, c)
 
     @property
     def f32_hidden(self) -> bool:
         return self.engine == "tc"
+
+    def hidden_fmt(self, hidden: int, dilation: int = 1) -> int:
+        """Storage of the tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92).  The tcgen05 engine
+        keeps it in plain rows for the TMA depthwise kernels (dilation 1): fp32, or - for the widest blocks (hidden >=
+        Q16_HIDDEN_MIN: the 256 -> 1536 class, whose 2.65 GB hidden tensors dominate the plan's HBM traffic) - 16-bit fixed point
+        of the ReLU6 output (|error| <= 4.6e-5; measured on config #2: +3.6e-5 max-abs on the saliency map).  ``hidden_q16 = False``
+        on the plan keeps everything in fp32."""
+        if not self.f32_hidden or dilation != 1:
+            return FMT_SPLIT
+        if hidden >= Q16_HIDDEN_MIN and getattr(self, "hidden_q16", True):
+            return FMT_Q16
+        return FMT_F32
 
     def tensor(self, shape, dtype=torch.float32) -> torch.Tensor:
         """A module-boundary tensor / workspace: persistent (never shares memory), zero-initialised."""
@@ -442,7 +490,7 @@ class Plan:
             hidden, k = w1.cout, w1.cin
         else:
             hidden, k = w1.shape
-        assert not x.f32 and cin % 8 == 0 and k <= cin <= 32 and hidden % 8 == 0
+        assert not x.plain and cin % 8 == 0 and k <= cin <= 32 and hidden % 8 == 0
         kp = (cin + 15) // 16 * 16
         hp = (hidden + 63) // 64 * 64
         if isinstance(w1, W):
@@ -458,10 +506,11 @@ class Plan:
                                           wdd.data_ptr(), bdd.data_ptr(), *out.act()), tag)
 
     def dwproj(self, hid: Buf, n, h, w, wd, bd, w2d, bias, out: Buf, res: Optional[Buf] = None, tag=""):
-        """Fused depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (+ residual) from the fp32 hidden tensor (stride 1).
+        """Fused depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (+ residual) from the fp32 / q16 hidden tensor (stride 1).
         wd / w2d: W specs, or folded tensors ([9][hidden], bd) / ((cout, hidden), bias)."""
         cout, hidden = (w2d.cout, w2d.cin) if isinstance(w2d, W) else w2d.shape
-        assert hid.f32 and hid.c == hidden and self.engine == "tc"
+        assert hid.plain and hid.c == hidden and self.engine == "tc"
+        assert not hid.q16 or hidden % 128 == 0, "q16 rows feed the tensor-core kernel only"
         assert (hidden % 128 == 0 and cout % 64 == 0 and cout <= 256) or ((hidden, cout) == (32, 16) and res is None)
         if (hidden, cout) == (32, 16) and getattr(self, "dwproj32_params", True):
             # features.1: all 848 weights go into the kernel's parameter block as HOST arrays (constant-bank FFMA operands)
@@ -484,7 +533,8 @@ class Plan:
             wp, b = self.hold(pack_pw_tc(w2d, hidden)), self.hold(bias.float())
         r = res.act() if res is not None else NULL_ACT
         self._add("uavsal_dw_project", (hid.ptr, hid.ld, n, h, w, hidden, wdd.data_ptr(), bdd.data_ptr(),
-                                        wp.data_ptr(), hidden, cout, b.data_ptr(), F_RESIDUAL if res is not None else 0, self.terms,
+                                        wp.data_ptr(), hidden, cout, b.data_ptr(),
+                                        (F_RESIDUAL if res is not None else 0) | (F_HID_Q16 if hid.q16 else 0), self.terms,
                                         *r, *out.act()), tag)
 
     def mbconv(self, x: Buf, n, h, w, w1: W, wd: W, w2: W, out: Buf, res: Optional[Buf] = None, tag=""):
@@ -492,8 +542,8 @@ class Plan:
         project + BN (+ residual); the hidden tensor never reaches HBM.  cin <= 64, hidden % 64 == 0, cout % 16 == 0 and <= 64."""
         hidden, cin, cout = w1.cout, w1.cin, w2.cout
         kp1 = _pad8(cin)
-        assert self.engine == "tc" and not x.f32 and x.c in (cin, kp1) and w2.cin == hidden and wd.cout == hidden
-        assert kp1 <= 64 and hidden % 64 == 0 and cout % 16 == 0 and cout <= 64 and out.c >= cout and (res is None or not res.f32)
+        assert self.engine == "tc" and not x.plain and x.c in (cin, kp1) and w2.cin == hidden and wd.cout == hidden
+        assert kp1 <= 64 and hidden % 64 == 0 and cout % 16 == 0 and cout <= 64 and out.c >= cout and (res is None or not res.plain)
         w1p, b1 = self.packed(w1, W_ROWS_SPLIT, hidden, kp1)
         wdd, bdd = self._dw_weights(wd, None)
         w2p, b2 = self.packed(w2, W_ROWS_SPLIT, cout, hidden)
@@ -509,10 +559,13 @@ class Plan:
         r = res.act() if res is not None else NULL_ACT
         if res is not None:
             flags |= F_RESIDUAL
-        assert not x.f32 and (res is None or not res.f32), "fp32 rows are only consumed by the depthwise kernel"
+        assert not x.plain and (res is None or not res.plain), "fp32 / q16 rows are only consumed by the depthwise kernels"
         if out.f32:
             assert self.engine == "tc"
             flags |= F_OUT_F32
+        elif out.q16:
+            assert self.engine == "tc" and flags == F_RELU6 and res is None, "q16 rows hold a ReLU6 output"
+            flags |= F_OUT_Q16
         tc = self.engine != "simt"
         if isinstance(w2d, W):
             wp, b = self.packed(w2d, W_ROWS_SPLIT if tc else W_COLS_F32, n, kpad)
@@ -596,13 +649,13 @@ class Plan:
         self._add("uavsal_convlstm_sequence", args, tag)
 
     def dw_dot_sigmoid(self, hid: Buf, n, h, w, c, wd, bd, wproj, bias, out: torch.Tensor, tag=""):
-        """Readout tail fused: depthwise 3x3 + BN + ReLU6 on the fp32 hidden tensor -> 1-output project + BN + sigmoid.
+        """Readout tail fused: depthwise 3x3 + BN + ReLU6 on the fp32 / q16 hidden tensor -> 1-output project + BN + sigmoid.
         wd: W or [9][C] + bd; wproj: W (1 x C project + BN) or the folded (C,) vector + the folded scalar bias."""
-        assert hid.f32 and hid.c == c
+        assert hid.plain and hid.c == c
         ws = self.tensor((n * h * w, (c + 63) // 64))
         wdd, bdd = self._dw_weights(wd, bd)
         wv, bias = self._dot_weights(wproj, bias)
-        self._add("uavsal_dw3x3_dot_sigmoid", (hid.ptr, hid.ld, n, h, w, c, wdd.data_ptr(), bdd.data_ptr(),
+        self._add("uavsal_dw3x3_dot_sigmoid_q16" if hid.q16 else "uavsal_dw3x3_dot_sigmoid", (hid.ptr, hid.ld, n, h, w, c, wdd.data_ptr(), bdd.data_ptr(),
                                                wv.data_ptr(), float(bias), ws.data_ptr(), out.data_ptr()), tag)
 
     def _dot_weights(self, wproj, bias):
@@ -675,7 +728,7 @@ class Plan:
                 n += op.args[6] * (1 if op.args[13] else op.args[17]) + (1 if op.args[13] else 0)
             elif op.name == "uavsal_convlstm_sequence":
                 n += op.args[8] * (1 if self.engine != "simt" else op.args[7])
-            elif op.name in ("uavsal_post_u8", "uavsal_dw3x3_dot_sigmoid"):
+            elif op.name in ("uavsal_post_u8", "uavsal_dw3x3_dot_sigmoid", "uavsal_dw3x3_dot_sigmoid_q16"):
                 n += 2
             else:
                 n += 1

@@ -324,9 +324,9 @@ class UAVSal(KernelModule):
             plan.unpack_nchw(last, 1, planes, mh, mw, h_out[ci:ci + 1], tag="state.unpack")
         # readout: expand + dw (dwBlock 256->1), then the 1536->1 project + BN + sigmoid as a dot product (model.py:372-373)
         ro = self.conv_out_st
-        e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", f32_out=plan.f32_hidden)
+        e, _, _ = ro.conv[0]._emit(plan, seq, n, mh, mw, tag="readout.expand", out_fmt=plan.hidden_fmt(ro.geom[2]))
         out = plan.tensor((n, 1, mh, mw))
-        if e.f32 and getattr(plan, "fuse_readout", True):
+        if e.plain and getattr(plan, "fuse_readout", True):
             plan.dw_dot_sigmoid(e, n, mh, mw, e.c, ro.conv[1].wspec(), None, ro.project_wspec(), None, out, tag="readout.dw+dot")
         else:
             d, _, _ = ro.conv[1]._emit(plan, e, n, mh, mw, tag="readout.dw")

@@ -40,12 +40,18 @@ extern "C" {
 #define UAVSAL_F_RELU     16   /* max(x, 0)                 (nn.ReLU of the ResNet / VGG backbones, model_feature.py:72-128; exclusive with RELU6) */
 #define UAVSAL_F_OUT_F32  8    /* uavsal_pw_gemm only: `out` is a float* to fp32 rows [m][out_ld] (out_plane ignored); used for the
                                   hidden tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92) */
+#define UAVSAL_F_OUT_Q16  32   /* uavsal_pw_gemm only, with UAVSAL_F_RELU6: `out` is a uint16_t* to "q16" rows [m][out_ld] (out_plane ignored),
+                                  q = rne(relu6(v) * 65535 / 6), read back as q * 6 / 65535 (|error| <= 4.6e-5): half the bytes of the fp32 rows
+                                  for the widest hidden tensors (the 256 -> 1536 class of dwBlocks, model.py:90-92) */
+#define UAVSAL_F_HID_Q16  64   /* uavsal_dw_project only: `hid` points to q16 rows (uint16_t, hid_ld in elements) instead of fp32 rows */
 /* `terms` arguments of the tcgen05 entry points: 1 (bf16 x 1, "fast") or 3 (hi*hi + hi*lo + lo*hi, "exact"), optionally ORed with
    UAVSAL_TERMS_GEN1 to run the first-generation one-tile-per-CTA tcgen05 kernel instead of the persistent one (an independent
    cross-check engine for the tests; per call, so two callers on concurrent streams cannot disturb each other) */
 #define UAVSAL_TERMS_GEN1 0x100
 /* plane value marking an activation argument as plain fp32 rows (uavsal_dw3x3 input) instead of split-bf16 planes */
 #define UAVSAL_PLANE_F32  (-1)
+/* plane value marking an activation argument as q16 rows (uint16_t fixed point of a ReLU6 output, see UAVSAL_F_OUT_Q16) */
+#define UAVSAL_PLANE_Q16  (-2)
 
 int         uavsal_version(void);                 /* ABI version, currently 1 */
 const char* uavsal_arch(void);                    /* "sm_100a" */
@@ -120,7 +126,8 @@ int uavsal_expand_dw3x3(const uint16_t* x, int64_t x_plane, int x_ld, int n, int
  * tensor `hid` (n, h, w, hidden) [rows of hid_ld floats], immediately consumed as the A operand of the 1x1 project conv + BN
  * (+ residual) on the tensor cores - the depthwise output never reaches HBM.  hidden % 128 == 0, cout % 64 == 0, cout <= 256;
  * also hidden == 32 with cout == 16 and no residual (torchvision features[1]): an fp32 FFMA kernel, `terms` ignored.
- * wd [9][hidden], bd [hidden] as uavsal_dw3x3; wgt/kpad/bias/res/out as uavsal_pw_gemm (flags: UAVSAL_F_RESIDUAL only). */
+ * wd [9][hidden], bd [hidden] as uavsal_dw3x3; wgt/kpad/bias/res/out as uavsal_pw_gemm (flags: UAVSAL_F_RESIDUAL, and
+ * UAVSAL_F_HID_Q16 when `hid` holds q16 rows - tensor-core kernel only). */
 int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hidden,
                       const float* wd, const float* bd,
                       const uint16_t* wgt, int kpad, int cout, const float* bias, int flags, int terms,
@@ -223,6 +230,9 @@ int uavsal_convlstm_sequence(const uint16_t* x, int64_t x_plane, int x_ld,
  *      output is never written.  partial_ws: n*h*w*ceil(c/64) floats of workspace. */
 int uavsal_dw3x3_dot_sigmoid(const float* in, int in_ld, int n, int h, int w, int c, const float* wd, const float* bd,
                              const float* wproj, float bias_proj, float* partial_ws, float* out_f32, void* stream);
+/*      the same on q16 rows (the hidden tensor written by uavsal_pw_gemm with UAVSAL_F_OUT_Q16), in_ld in elements */
+int uavsal_dw3x3_dot_sigmoid_q16(const uint16_t* in, int in_ld, int n, int h, int w, int c, const float* wd, const float* bd,
+                                 const float* wproj, float bias_proj, float* partial_ws, float* out_f32, void* stream);
 
 /* ---- K10a: readout project conv 1536->1 + BN + sigmoid (conv_out_st.conv.2/.3 + model.py:373):
  *      out_f32[row] = sigmoid( dot(A[row][:k], wgt[:k]) + bias ). */

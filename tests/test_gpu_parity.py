@@ -129,6 +129,96 @@ def test_fused_depthwise_project(cuda, ch, co, n, h, w, res):
     assert _rel(y, F.conv2d(d, w2.reshape(co, ch, 1, 1), b2) + (r if res else 0)) < KERNEL_TOL
 
 
+def _q16(x):
+    """The oracle side of a q16 hidden tensor: q = rne(relu6(x) * 65535 / 6) as the kernels store it, and its read-back value."""
+    q = torch.round(x.clamp(0, 6).double() * (65535.0 / 6.0))
+    return q, (q.float() * np.float32(6.0 / 65535.0))
+
+
+@pytest.mark.parametrize("cin,ch,s,n,h,w", [(256, 1536, 1, 2, 45, 80), (256, 1536, 2, 1, 45, 80), (320, 1920, 1, 1, 12, 20), (24, 120, 1, 1, 37, 41),
+                                             (192, 1152, 2, 1, 23, 40)])
+def test_q16_hidden_expand_then_depthwise(cuda, cin, ch, s, n, h, w):
+    """The widest hidden tensors travel as 16-bit fixed-point rows: the expand GEMM's epilogue writes q = rne(relu6(v) * 65535 / 6)
+    (within one step of the fp32 oracle's q, the step being the GEMM's own rounding), the TMA depthwise kernel (stride 1 | 2,
+    ragged channel blocks) reads q * 6 / 65535 back: its output matches the oracle run on exactly those read-back values."""
+    from iip_uavsal_saliency_b200.engine import out_size, pack_dw
+    torch.manual_seed(17)
+    p = _plan()
+    x = torch.randn(n, cin, h, w)
+    w1, b1 = torch.randn(ch, cin) / cin ** 0.5 * 2, torch.randn(ch) * 0.1 + 1.0          # values spread over and beyond [0, 6]
+    wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+    hid = p.alloc_q16(n * h * w, ch)
+    p.pw(_upload(p, x), n * h * w, w1.cuda(), b1.cuda(), 1, hid)
+    ho, wo = out_size(h, s), out_size(w, s)
+    ob = p.alloc(n * ho * wo, ch)
+    p.dw(hid, n, h, w, ch, s, 1, p.hold(pack_dw(wd)), p.hold(bd), True, ob)
+    y = _download(p, ob, n, ch, ho, wo)
+    p.run()
+    q_ref, _ = _q16(F.conv2d(x, w1.reshape(ch, cin, 1, 1), b1))
+    q_gpu = hid.t.cpu().view(torch.int16).to(torch.int32).bitwise_and(0xFFFF)[:, :ch].reshape(n, h, w, ch).permute(0, 3, 1, 2)
+    dq = (q_gpu.double() - q_ref).abs()
+    assert dq.max().item() <= 2 and (dq > 0).float().mean().item() < 0.25, (dq.max().item(), (dq > 0).float().mean().item())
+    assert (q_gpu == 0).any() and (q_gpu == 65535).any()                                   # both clamps exercised
+    back = hid.to_float().cpu().reshape(n, h, w, ch).permute(0, 3, 1, 2)
+    assert torch.equal(back, q_gpu.float() * np.float32(6.0 / 65535.0))
+    assert _rel(y, F.hardtanh(F.conv2d(back, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
+
+
+@pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
+                                              (1152, 64, 1, 45, 80, False), (384, 256, 1, 9, 40, True), (1920, 256, 1, 45, 80, True)])
+def test_fused_depthwise_project_q16(cuda, ch, co, n, h, w, res):
+    """dw_project reading the hidden tensor as q16 rows (UAVSAL_F_HID_Q16): same result as the fp32-row kernel fed the read-back
+    values (bit for bit: the decode is exact and the arithmetic after it is the same), and within the kernel tolerance of the oracle."""
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(13)
+    q, hid = _q16(torch.rand(n, ch, h, w) * 7 - 0.5)
+    wd, bd = torch.randn(ch, 1, 3, 3) * 0.3, torch.randn(ch) * 0.1
+    w2, b2 = torch.randn(co, ch) / ch ** 0.5, torch.randn(co) * 0.1
+    r = torch.randn(n, co, h, w)
+    ys = []
+    for fmt in ("q16", "f32"):
+        p = _plan()
+        if fmt == "q16":
+            hb = p.alloc_q16(n * h * w, ch)
+            hb.t.copy_(q.permute(0, 2, 3, 1).reshape(-1, ch).to(torch.int32).to(torch.int16))     # 0..65535 -> the same 16 bits
+        else:
+            hb = p.alloc_f32(n * h * w, ch)
+            hb.t.copy_(hid.permute(0, 2, 3, 1).reshape(-1, ch))
+        ob = p.alloc(n * h * w, co)
+        p.dwproj(hb, n, h, w, pack_dw(wd), bd, w2.cuda(), b2.cuda(), ob, res=_upload(p, r) if res else None)
+        y = _download(p, ob, n, co, h, w)
+        p.run()
+        ys.append(y.cpu())
+    assert torch.equal(ys[0], ys[1])
+    d = F.hardtanh(F.conv2d(hid, wd, bd, 1, 1, 1, ch), 0, 6)
+    assert _rel(ys[0], F.conv2d(d, w2.reshape(co, ch, 1, 1), b2) + (r if res else 0)) < KERNEL_TOL
+
+
+@pytest.mark.parametrize("fmt", ["f32", "q16"])
+@pytest.mark.parametrize("c,n,h,w", [(1536, 2, 45, 80), (192, 1, 13, 21), (100, 1, 9, 17)])
+def test_readout_depthwise_dot_sigmoid(cuda, fmt, c, n, h, w):
+    """Readout tail (model.py:372-373): depthwise 3x3 + BN + ReLU6 folded into the 1-output project + BN + sigmoid, from fp32 or
+    q16 rows of the hidden tensor; ragged tiles and a channel count that is not a multiple of 64."""
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(19)
+    p = _plan()
+    q, hid = _q16(torch.rand(n, c, h, w) * 7 - 0.5)
+    wd, bd = torch.randn(c, 1, 3, 3) * 0.3, torch.randn(c) * 0.1
+    wp, bp = torch.randn(c) / c ** 0.5, 0.3
+    if fmt == "q16":
+        hb = p.alloc_q16(n * h * w, c)
+        hb.t[:, :c].copy_(q.permute(0, 2, 3, 1).reshape(-1, c).to(torch.int32).to(torch.int16))
+    else:
+        hb = p.alloc_f32(n * h * w, c)
+        hb.t[:, :c].copy_(hid.permute(0, 2, 3, 1).reshape(-1, c))
+    out = p.tensor((n, 1, h, w))
+    p.dw_dot_sigmoid(hb, n, h, w, c, pack_dw(wd).cuda(), bd.cuda(), wp.cuda(), bp, out)
+    p.run()
+    d = F.hardtanh(F.conv2d(hid, wd, bd, 1, 1, 1, c), 0, 6)
+    ref = torch.sigmoid(F.conv2d(d, wp.reshape(1, c, 1, 1)) + bp)
+    assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 @pytest.mark.parametrize("m,k,n,relu,res", [(300, 32, 16, 0, 0), (777, 20, 120, 1, 0), (3600, 256, 1536, 1, 0), (3600, 1536, 256, 0, 1),
                                             (500, 8, 48, 1, 0), (129, 320, 1920, 1, 0), (4000, 144, 24, 0, 1), (1, 64, 64, 0, 0)])

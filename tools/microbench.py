@@ -27,29 +27,30 @@ def timeit(plan, reps=5):
     return ts[len(ts) // 2]
 
 
-def gemm(engine, m, k, n, res=False, terms=3, f32=False):
+def gemm(engine, m, k, n, res=False, terms=3, f32=False, q16=False):
     p = Plan(dev, terms, engine)
     a = p.alloc(m, k); a.t.normal_()
-    o = p.alloc_f32(m, n) if f32 else p.alloc(m, n)
+    o = p.alloc_q16(m, n) if q16 else p.alloc_f32(m, n) if f32 else p.alloc(m, n)
     r = p.alloc(m, n) if res else None
     w = torch.randn(n, k, device=dev) / k ** 0.5
     p.pw(a, m, w, torch.zeros(n, device=dev), 1, o, res=r)
     ms = timeit(p)
     fl = 2.0 * m * k * n
-    by = 4.0 * m * (k + n * (2 if res else 1))
-    print("pw[%s,t%d%s] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, ",f32out" if f32 else "", m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
+    by = 4.0 * m * (k + n * (2 if res else 1)) - (2.0 * m * n if q16 else 0)
+    print("pw[%s,t%d%s] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, ",q16out" if q16 else ",f32out" if f32 else "", m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
 
 
-def dw(fast, n, h, w, c, stride, f32=False):
+def dw(fast, n, h, w, c, stride, f32=False, q16=False):
     _ext.load().uavsal_set_option(2, fast)
     p = Plan(dev, 3, "tc")
-    x = p.alloc_f32(n * h * w, c) if f32 else p.alloc(n * h * w, c); x.t.normal_()
+    x = p.alloc_q16(n * h * w, c) if q16 else p.alloc_f32(n * h * w, c) if f32 else p.alloc(n * h * w, c)
+    x.t.random_(-32768, 32767) if q16 else x.t.normal_()
     ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
     o = p.alloc(n * ho * wo, c)
     p.dw(x, n, h, w, c, stride, 1, p.hold(pack_dw(torch.randn(c, 1, 3, 3))), p.hold(torch.zeros(c)), True, o)
     ms = timeit(p)
-    by = 4.0 * n * c * (h * w + ho * wo)
-    print("dw[fast=%d%s] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, ",f32in" if f32 else "", n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
+    by = 4.0 * n * c * (h * w + ho * wo) - (2.0 * n * c * h * w if q16 else 0)
+    print("dw[fast=%d%s] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, ",q16in" if q16 else ",f32in" if f32 else "", n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
     _ext.load().uavsal_set_option(2, 1)
 
 
@@ -79,16 +80,31 @@ def mbblock(n, h, w, inp, oup, fused):
           ms * 1e3, by / ms / 1e6, ", ".join(o.name.replace("uavsal_", "") for o in p.ops)), flush=True)
 
 
-def dwproj(n, h, w, hidden, co, res=False, terms=3):
+def dwproj(n, h, w, hidden, co, res=False, terms=3, q16=False):
     p = Plan(dev, terms, "tc")
-    hb = p.alloc_f32(n * h * w, hidden); hb.t.uniform_(0, 6)
+    if q16:
+        hb = p.alloc_q16(n * h * w, hidden); hb.t.random_(-32768, 32767)
+    else:
+        hb = p.alloc_f32(n * h * w, hidden); hb.t.uniform_(0, 6)
     o = p.alloc(n * h * w, co)
     r = p.alloc(n * h * w, co) if res else None
     p.dwproj(hb, n, h, w, pack_dw(torch.randn(hidden, 1, 3, 3)), torch.zeros(hidden), torch.randn(co, hidden, device=dev) / hidden ** 0.5,
              torch.zeros(co, device=dev), o, res=r)
     ms = timeit(p)
-    print("dw+project[t%d] n=%d %dx%d hidden=%d co=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s(hidden read)" %
-          (terms, n, h, w, hidden, co, ms * 1e3, 2.0 * n * h * w * hidden * co / ms / 1e9, 4.0 * n * h * w * hidden / ms / 1e6), flush=True)
+    print("dw+project[t%d%s] n=%d %dx%d hidden=%d co=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s(hidden read)" %
+          (terms, ",q16" if q16 else "", n, h, w, hidden, co, ms * 1e3, 2.0 * n * h * w * hidden * co / ms / 1e9, (2.0 if q16 else 4.0) * n * h * w * hidden / ms / 1e6), flush=True)
+
+
+def readout(n, h, w, c, q16=False):
+    p = Plan(dev, 3, "tc")
+    if q16:
+        hb = p.alloc_q16(n * h * w, c); hb.t.random_(-32768, 32767)
+    else:
+        hb = p.alloc_f32(n * h * w, c); hb.t.uniform_(0, 6)
+    out = p.tensor((n, 1, h, w))
+    p.dw_dot_sigmoid(hb, n, h, w, c, pack_dw(torch.randn(c, 1, 3, 3)).to(dev), torch.zeros(c, device=dev), torch.randn(c, device=dev) / c ** 0.5, 0.0, out)
+    ms = timeit(p)
+    print("readout dw+dot[%s] n=%d %dx%d c=%d: %.1f us  %.0f GB/s(hidden read)" % ("q16" if q16 else "f32", n, h, w, c, ms * 1e3, (2.0 if q16 else 4.0) * n * h * w * c / ms / 1e6), flush=True)
 
 
 def conv(engine, n, h, w, c, co, terms=3):
@@ -133,6 +149,14 @@ def lstm(b, t, h, w, c, terms=3):
 
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "q16":           # fp32 rows vs 16-bit fixed-point rows for the widest hidden tensors (120 frames of 45x80)
+        M = 120 * 3600
+        for q in (False, True):
+            gemm("tc", M, 256, 1536, f32=not q, q16=q); gemm("tc", M, 320, 1920, f32=not q, q16=q); gemm("tc", M, 192, 1152, f32=not q, q16=q)
+            dwproj(120, 45, 80, 1536, 256, res=True, q16=q); dwproj(120, 45, 80, 1920, 256, q16=q); dwproj(120, 45, 80, 1152, 64, q16=q)
+            readout(120, 45, 80, 1536, q16=q)
+            dw(2, 24, 45, 80, 1536, 2, f32=not q, q16=q)
+        return
     M = 72000
     if what in ("gemm", "all"):
         for eng in ("tc1", "tc"):
