@@ -22,7 +22,8 @@ struct DwArgs {
     int relu6;
     ActW out;
     const float* wproj;    // DOT mode: weights of a following 1-output pointwise conv [c]
-    float* partial;        // DOT mode: per-(pixel, 64-channel block) partial dot products [n*ho*wo][cblocks]
+    float* partial;        // DOT mode: per-(pixel, part) partial dot products [n*ho*wo][parts]
+    int parts, cpp;        // work unit = (spatial tile, part); a unit covers cpp consecutive 64-channel blocks (1 unless DOT)
 };
 
 template <int STRIDE>
@@ -39,32 +40,33 @@ struct DwGeom {
 };
 
 // 4 channels from the staged tile -> fp32 (explicit shared-space loads: `tile` is a 32-bit shared address)
+// (as two channel pairs: the 9-tap dot products run as packed fma.rn.f32x2 - the same IEEE fma per lane, half the instructions)
 template <int FMT>
-__device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pix, int quad, float v[4]) {
+__device__ __forceinline__ void lds4(uint32_t tile, uint32_t plane_bytes, int pix, int quad, float2 v[2]) {
     if (FMT == 1) {
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(tile + pix * 256 + quad * 16));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y) : "r"(tile + pix * 256 + quad * 16));
     } else if (FMT == 2) {
         uint2 a;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(tile + pix * 128 + quad * 8));
-        const float2 lo = q16_unpack2(a.x), hi = q16_unpack2(a.y);
-        v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+        v[0] = q16_unpack2(a.x); v[1] = q16_unpack2(a.y);
     } else {
         uint2 a, b;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(tile + pix * 128 + quad * 8));
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(tile + plane_bytes + pix * 128 + quad * 8));
-        float t[4];
-        unpack2(a.x, v[0], v[1]); unpack2(a.y, v[2], v[3]);
-        unpack2(b.x, t[0], t[1]); unpack2(b.y, t[2], t[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] += t[i];
+        float2 t[2];
+        unpack2(a.x, v[0].x, v[0].y); unpack2(a.y, v[1].x, v[1].y);
+        unpack2(b.x, t[0].x, t[0].y); unpack2(b.y, t[1].x, t[1].y);
+        v[0] = __fadd2_rn(v[0], t[0]); v[1] = __fadd2_rn(v[1], t[1]);
     }
 }
 
 // thread = (4-channel quad, output column[, row group]); it keeps its 36 folded weights in registers for the tile and
 // slides a 3x3x4 register window down RPT output rows.
 // DOT: instead of storing the depthwise output, every thread folds its 4 channels into the dot product with `wproj` (the
-// dwBlock's project conv when it has ONE output channel: the readout, model.py:372), the 16 threads sharing a pixel reduce by
-// shuffles and one partial per (pixel, channel block) is written; dot_finish_kernel adds the blocks in a fixed order.
+// dwBlock's project conv when it has ONE output channel: the readout, model.py:372).  A CTA walks the cpp channel blocks of a
+// (spatial tile, part) unit back to back and keeps the per-row sums in registers; after the unit's last block the 16 threads
+// sharing a pixel reduce by shuffles and one partial per (pixel, part) is written (until round 2: shuffles + a store per channel
+// block - the kernel is instruction-issue bound); dot_finish_kernel adds the parts in a fixed order.
 template <int STRIDE, int FMT, bool DOT>
 __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs g) {
     using G = DwGeom<STRIDE>;
@@ -79,16 +81,18 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     __syncthreads();
     pdl_wait();                                                                // the input tensor is the previous kernel's output
 
-    auto decode = [&](int t, int& cblk, int& x0, int& y0, int& img) {
-        int r = t;
-        cblk = r % g.cblocks; r /= g.cblocks;
+    // iteration j of this CTA: channel block j % cpp of its (j / cpp)-th unit; unit = (image, tile y, tile x, part), part fastest
+    auto decode = [&](int j, int& cblk, int& x0, int& y0, int& img) {
+        const int cb = DOT ? j % g.cpp : 0;
+        int r = (int)blockIdx.x + (DOT ? j / g.cpp : j) * (int)gridDim.x;
+        cblk = (r % g.parts) * g.cpp + cb; r /= g.parts;
         x0 = (r % g.tiles_x) * G::TW; r /= g.tiles_x;
         y0 = (r % g.tiles_y) * G::TH;
         img = r / g.tiles_y;
     };
-    auto issue = [&](int t, int b) {                                           // one thread
+    auto issue = [&](int j, int b) {                                           // one thread
         int cblk, x0, y0, img;
-        decode(t, cblk, x0, y0, img);
+        decode(j, cblk, x0, y0, img);
         uint8_t* dst = smem + b * kTile;
         fence_async_smem();                                                    // order the buffer's generic reads before the async overwrite
         mbar_expect_tx(bar + b, kTile);
@@ -106,39 +110,46 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     const int quad = tid & 15;                                                 // 4-channel quad inside the 64-channel block
     const int col = (tid >> 4) % G::TW;
     const int rgrp = (tid >> 4) / G::TW;
-    if (tid == 0 && (int)blockIdx.x < g.num_tiles) issue(blockIdx.x, 0);
-    int it = 0;
-    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x, ++it) {
+    const int units_mine = (int)blockIdx.x < g.num_tiles ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int iters = units_mine * (DOT ? g.cpp : 1);
+    if (tid == 0 && iters > 0) issue(0, 0);
+    float dsum[DOT ? G::RPT : 1];                                              // DOT: this thread's 4-channel share of the row sums of the unit
+    for (int it = 0; it < iters; ++it) {
         const int b = it & 1;
-        if (tid == 0 && t + (int)gridDim.x < g.num_tiles) issue(t + gridDim.x, b ^ 1);   // prefetch the next tile
+        if (tid == 0 && it + 1 < iters) issue(it + 1, b ^ 1);                  // prefetch the next tile
         int cblk, x0, y0, img;
-        decode(t, cblk, x0, y0, img);
+        decode(it, cblk, x0, y0, img);
+        const int cb = DOT ? it % g.cpp : 0;
         const int c0 = cblk * 64 + quad * 4;
         const bool cvalid = c0 < g.c;
-        float wr[9][4], br[4], wp[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 wr[9][2], br[2], wp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         if (cvalid) {                                                          // overlaps the TMA flight time (L1/L2 hits)
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wgt + k * g.c + c0));
-                wr[k][0] = w4.x; wr[k][1] = w4.y; wr[k][2] = w4.z; wr[k][3] = w4.w;
+                wr[k][0] = make_float2(w4.x, w4.y); wr[k][1] = make_float2(w4.z, w4.w);
             }
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
-            br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
+            br[0] = make_float2(b4.x, b4.y); br[1] = make_float2(b4.z, b4.w);
             if (DOT) {
                 const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.wproj + c0));
-                wp[0] = p4.x; wp[1] = p4.y; wp[2] = p4.z; wp[3] = p4.w;
+                wp[0] = make_float2(p4.x, p4.y); wp[1] = make_float2(p4.z, p4.w);
             }
         } else if (DOT) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { wr[k][0] = wr[k][1] = wr[k][2] = wr[k][3] = 0.f; }
-            br[0] = br[1] = br[2] = br[3] = 0.f;
+            for (int k = 0; k < 9; ++k) { wr[k][0] = wr[k][1] = make_float2(0.f, 0.f); }
+            br[0] = br[1] = make_float2(0.f, 0.f);
+        }
+        if (DOT && cb == 0) {
+#pragma unroll
+            for (int i = 0; i < (DOT ? G::RPT : 1); ++i) dsum[i] = 0.f;
         }
         mbar_wait(bar + b, (it >> 1) & 1);
 
         const int ox = x0 + col;
         if (DOT || (cvalid && ox < g.wo)) {                                    // DOT: all lanes stay for the shuffles
             const uint32_t tile = smem_u32(smem) + b * kTile;
-            float win[3][3][4];
+            float2 win[3][3][2];
             auto load_row = [&](int slot, int iy) {                            // iy: row inside the input box
 #pragma unroll
                 for (int d = 0; d < 3; ++d) lds4<FMT>(tile, kTile / 2, iy * G::IW + col * STRIDE + d, quad, win[slot][d]);
@@ -160,29 +171,38 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
                 }
                 const int oy = y0 + oyl;
                 if (oy >= g.ho) break;
-                float acc[4] = {br[0], br[1], br[2], br[3]};
+                float2 a2[2] = {br[0], br[1]};
                 const int slots[3] = {s0, s1, s2};
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        const float* v = win[slots[ky]][kx];
+                        const float2* v = win[slots[ky]][kx];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
+                        for (int j = 0; j < 2; ++j) a2[j] = __ffma2_rn(v[j], wr[ky * 3 + kx][j], a2[j]);
                     }
+                float acc[4] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y};
                 if (g.relu6) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
                 }
                 if (DOT) {
-                    float d = acc[0] * wp[0] + acc[1] * wp[1] + acc[2] * wp[2] + acc[3] * wp[3];
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);      // the 16 quads of this pixel
-                    if (quad == 0 && ox < g.wo)
-                        g.partial[(((int64_t)img * g.ho + oy) * g.wo + ox) * g.cblocks + cblk] = d;
+                    dsum[i] += acc[0] * wp[0].x + acc[1] * wp[0].y + acc[2] * wp[1].x + acc[3] * wp[1].y;
                     continue;
                 }
                 store4(g.out.p + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.out.ld + c0, g.out.plane, acc);
+            }
+            if (DOT && cb == g.cpp - 1) {                                      // unit complete: one partial per (pixel, part)
+                const int part = cblk / g.cpp;
+#pragma unroll
+                for (int i = 0; i < (DOT ? G::RPT : 1); ++i) {
+                    float d = dsum[i];
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);      // the 16 quads of this pixel
+                    const int oy = y0 + oyl0 + i;
+                    if (quad == 0 && ox < g.wo && oy < g.ho)
+                        g.partial[(((int64_t)img * g.ho + oy) * g.wo + ox) * g.parts + part] = d;
+                }
             }
         }
         __syncthreads();                                                       // tile consumed: its buffer may be refilled
@@ -195,7 +215,10 @@ static int launch_dw_tma(const CUtensorMap& tm, DwArgs& g, cudaStream_t s) {
     g.tiles_x = div_up(g.wo, G::TW);
     g.tiles_y = div_up(g.ho, G::TH);
     g.cblocks = div_up(g.c, 64);
-    g.num_tiles = g.n * g.tiles_x * g.tiles_y * g.cblocks;
+    // DOT: two parts per spatial tile when there are enough channel blocks (units / CTA slots stays fine-grained enough), else one
+    g.parts = DOT ? ((g.cblocks % 2 == 0 && g.cblocks >= 8) ? 2 : 1) : g.cblocks;
+    g.cpp = g.cblocks / g.parts;
+    g.num_tiles = g.n * g.tiles_x * g.tiles_y * g.parts;                       // work units
     const size_t smem = 2 * (FMT == 2 ? G::TILE_BYTES_Q16 : G::TILE_BYTES) + 64 + 128;
     static bool attr = false;
     if (!attr) {
@@ -279,7 +302,7 @@ int dw3x3_dot_tma(const void* in, bool q16, int in_ld, int n, int h, int w, int 
     rc = q16 ? launch_dw_tma<1, 2, true>(tm, g, s) : launch_dw_tma<1, 1, true>(tm, g, s);
     if (rc) return rc;
     const int64_t rows = (int64_t)n * h * w;
-    cudaError_t e = launch_k(dot_finish_kernel, dim3(div_up(rows, 256)), dim3(256), 0, s, 1, (const float*)partial, rows, g.cblocks, bias_proj, out);
+    cudaError_t e = launch_k(dot_finish_kernel, dim3(div_up(rows, 256)), dim3(256), 0, s, 1, (const float*)partial, rows, g.parts, bias_proj, out);
     if (e != cudaSuccess) { set_error("dw_dot: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return check_launch("dw_dot(finish)");
 }

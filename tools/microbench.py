@@ -149,6 +149,13 @@ def lstm(b, t, h, w, c, terms=3):
 
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "dwproj_q16":
+        dwproj(120, 45, 80, 1536, 256, res=True, q16=True); dwproj(120, 45, 80, 1920, 256, q16=True); dwproj(120, 45, 80, 1152, 64, q16=True)
+        dwproj(120, 45, 80, 1536, 256, res=True)
+        return
+    if what == "q16prof":       # one launch each for ncu (after a warm-up launch)
+        dwproj(120, 45, 80, 1536, 256, res=True, q16=True); readout(120, 45, 80, 1536, q16=True)
+        return
     if what == "q16":           # fp32 rows vs 16-bit fixed-point rows for the widest hidden tensors (120 frames of 45x80)
         M = 120 * 3600
         for q in (False, True):
