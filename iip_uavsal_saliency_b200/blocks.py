@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from ._kernel_module import KernelModule
-from .engine import F_RELU6, FMT_SPLIT, Buf, Plan, W, fold_bn, out_size, pack_dw
+from .engine import F_RELU6, FMT_F32, FMT_Q16, FMT_SPLIT, Buf, Plan, W, fold_bn, out_size, pack_dw
 
 __all__ = ["BasicConv2d", "dwBlock", "init_weights", "emit_stem"]
 
@@ -144,7 +144,12 @@ class dwBlock(KernelModule):
         if has_expand:
             # the 6x hidden tensor travels as plain rows between the expand GEMM and the TMA depthwise kernels (dilation 1 only):
             # fp32, or 16-bit fixed point for the widest blocks (Plan.hidden_fmt)
-            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", out_fmt=plan.hidden_fmt(hidden, dil))
+            fmt = plan.hidden_fmt(hidden, dil)
+            if fmt == FMT_Q16 and stride == 1 and 8 <= oup < 128:
+                # dw_project with a narrow N tile is bound by its depthwise stage, where the q16 decode costs more than the bytes
+                # save (1152 -> 64 @ 432 000 px: 779 vs 693 us; the expand GEMM only gains 60 us): fp32 rows
+                fmt = FMT_F32
+            cur, _, _ = self.conv[0]._emit(plan, cur, n, h, w, tag=tag + ".expand", out_fmt=fmt)
             i = 1
         fuse_dp = getattr(plan, "fuse_dw_project", "auto")
         if fuse_dp == "auto":    # big stride-1 blocks: the depthwise output is the project GEMM's A operand, built in shared memory
