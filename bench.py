@@ -258,7 +258,8 @@ def time_op_classes(plan, torch, detail=None):
             fl = 2.0 * m * k * n
             by = 4.0 * m * k + (2.0 if a[9] & 32 else 4.0) * m * n + 4.0 * n * k          # UAVSAL_F_OUT_Q16: 16-bit hidden rows
             if _pw_is_pair(m, k, n) and not ((a[9] & 2) and n >= 64):      # the launcher's rule (gemm_tc.cu want_cluster), not EPI_RES
-                r = res.setdefault("uavsal_pw_gemm/pair", [0.0, 0.0, 0.0, 0])
+                # two instantiations: EPI_Q16 (the 256 -> 1536 class of expand convs, 16-bit hidden rows out) and EPI_STD
+                r = res.setdefault("uavsal_pw_gemm/pair_q16" if a[9] & 32 else "uavsal_pw_gemm/pair", [0.0, 0.0, 0.0, 0])
                 r[0] += ms; r[1] += fl; r[2] += by; r[3] += 1
         elif op.name == "uavsal_conv3x3":
             nimg, hh, ww, c, cout = a[3], a[4], a[5], a[6], a[8]
@@ -519,11 +520,14 @@ def run_product_arm(args):
         return t.get("dram_bytes_per_launch") if t else None
 
     terms = 3 if args.precision == "exact" else 1
-    # dominant kernel = the top entry of the ncu launch list: gemm_tc2_kernel<MODE_PW, EPI_STD, TERMS, CL=2> (the cta_group::2
-    # pointwise GEMM of the wide layers); the whole pointwise-GEMM family, small HBM-bound layers included, is reported next to it
-    dom = "uavsal_pw_gemm/pair" if cls.get("uavsal_pw_gemm/pair", [0])[0] > 0 else "uavsal_pw_gemm"
+    # dominant kernel = the top entry of the ncu launch list: gemm_tc2_kernel<MODE_PW, EPI_Q16 | EPI_STD, TERMS, CL=2> (the cta_group::2
+    # pointwise GEMM of the wide layers; the instantiation writing 16-bit hidden rows carries the 256 -> 1536 class of expand convs);
+    # the whole pointwise-GEMM family, small HBM-bound layers included, is reported next to it
+    pairs = [k for k in ("uavsal_pw_gemm/pair_q16", "uavsal_pw_gemm/pair") if cls.get(k, [0])[0] > 0]
+    dom = max(pairs, key=lambda k: cls[k][0]) if pairs else "uavsal_pw_gemm"
+    epi = "EPI_Q16" if dom.endswith("q16") else "EPI_STD"
     ach = cls[dom][1] / cls[dom][0] / 1e9
-    roofline = {"kernel": "gemm_tc2_kernel<MODE_PW,EPI_STD,TERMS=%d,CL=2> (cta_group::2 tcgen05 pointwise-conv GEMM, %d launches per %d-frame plan)" % (terms, cls[dom][3], prof_frames),
+    roofline = {"kernel": "gemm_tc2_kernel<MODE_PW,%s,TERMS=%d,CL=2> (cta_group::2 tcgen05 pointwise-conv GEMM, %d launches per %d-frame plan)" % (epi, terms, cls[dom][3], prof_frames),
                 "bound": "tensor", "achieved": round(ach, 2), "peak": tens_peak, "unit": "TFLOP/s", "frac": round(ach / tens_peak, 4),
                 "traffic": per_launch_traffic(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src,
                 "algorithmic_flops_per_launch": round(cls[dom][1] / cls[dom][3]), "avg_launch_us": round(1e3 * cls[dom][0] / cls[dom][3], 2),
@@ -532,7 +536,7 @@ def run_product_arm(args):
                         "bf16x3 split issues 3x that on the tensor pipe (issued_frac); traffic = ncu dram bytes per launch from this round's capture"}
     allpw = "uavsal_pw_gemm"
     ach_a = cls[allpw][1] / cls[allpw][0] / 1e9
-    roofline_all_pw = {"kernel": "every pointwise-conv GEMM launch (CL=1|2, EPI_STD|EPI_RES; %d launches, the small-K backbone layers are HBM-bound)" % cls[allpw][3],
+    roofline_all_pw = {"kernel": "every pointwise-conv GEMM launch (CL=1|2, EPI_STD|EPI_RES|EPI_Q16; %d launches, the small-K backbone layers are HBM-bound)" % cls[allpw][3],
                        "bound": "tensor", "achieved": round(ach_a, 2), "peak": tens_peak, "unit": "TFLOP/s", "frac": round(ach_a / tens_peak, 4),
                        "issued_frac": round(terms * ach_a / tens_peak, 4), "gbs": round(cls[allpw][2] / cls[allpw][0] / 1e6, 1)}
     hb = "uavsal_dw3x3"

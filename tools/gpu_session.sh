@@ -1,17 +1,16 @@
 #!/bin/bash
+# round-2 evidence at HEAD: full GPU test suite, default bench line, ncu launch list of the 120-frame plan, ncu --set full of the top kernel
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "depthwise or readout or q16 or hidden or uavsal_call or config2" > gpurun_out/r02f_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/r02f_tests.log | cut -c1-300
-python - <<'PY' 2>&1 | tee gpurun_out/r02f_microbench.txt
-import sys; sys.argv=['x','none']; sys.path.insert(0,'tools')
-import microbench as mb
-mb.readout(120,45,80,1536,q16=True); mb.readout(120,45,80,1536,q16=False)
-mb.dw(2,24,45,80,1536,2,q16=True); mb.dw(2,24,45,80,1536,2,f32=True)
-mb.dw(2,120,90,160,144,1,f32=True); mb.dw(2,120,23,40,576,1,f32=True); mb.dw(2,120,45,80,192,2,f32=True); mb.dw(2,20,45,80,1536,1,f32=True); mb.dw(2,20,45,80,1536,1)
-PY
-( timeout 600 python bench.py --steps 8 --warmup 3 --skip-aux --skip-cpu --dump-ops gpurun_out/r02f_ops.txt ) > gpurun_out/r02f_bench.json 2> gpurun_out/r02f_bench.err; echo "bench rc=$?"
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r02i_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r02i_tests.log | cut -c1-200
+( timeout 900 python bench.py --dump-ops gpurun_out/r02i_ops.txt ) > gpurun_out/r02i_bench_n1.json 2> gpurun_out/r02i_bench_n1.err; echo "bench rc=$?"
 python - <<'PY'
-import json; d=json.load(open('gpurun_out/r02f_bench.json'))
-print(round(d['value']), round(d['e2e']['value']), d['clocks'], d['roofline']['frac'])
-for k,v in d['breakdown_per_plan'].items(): print(k, v)
+import json; d=json.load(open('gpurun_out/r02i_bench_n1.json'))
+print(round(d['value']), round(d['e2e']['value']), d['clocks'], d['roofline'], d['wall_s'])
 PY
+( timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/r02i_bench_ref.json 2> gpurun_out/r02i_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/r02i_bench_ref.json
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none --csv --log-file gpurun_out/r02i_clip120_kernels.csv python tools/profile_call.py exact 120 > gpurun_out/r02i_ncu.log 2>&1; echo "ncu rc=$?"
+python tools/summarize_ncu.py gpurun_out/r02i_clip120_kernels.csv gpurun_out/r02i_clip120 | tail -3
+python tools/microbench.py pairq16prof
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel --launch-skip 2 -c 1 -f -o gpurun_out/r02i_gemm_pair_q16 python tools/microbench.py pairq16prof > gpurun_out/r02i_ncu2.log 2>&1; echo "ncu2 rc=$?"

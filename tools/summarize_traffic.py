@@ -25,6 +25,8 @@ def main():
             keys.append("uavsal_pw_gemm")
             if name.startswith("gemm_tc2_kernel<0,0,") and name.endswith(",2>"):
                 keys.append("uavsal_pw_gemm/pair")
+            if name.startswith("gemm_tc2_kernel<0,5,") and name.endswith(",2>"):
+                keys.append("uavsal_pw_gemm/pair_q16")
         elif name.startswith("dw3x3"):
             keys.append("uavsal_dw3x3")
         elif name.startswith("dwproj_kernel"):
