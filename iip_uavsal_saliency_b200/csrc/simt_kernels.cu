@@ -335,39 +335,69 @@ __global__ void __launch_bounds__(256, 2) dw3x3_rows_kernel(Act in, int h, int w
 // [model.py:152-153, 360-361; ATen upsample_bilinear2d: ratio=(in-1)/(out-1), src=ratio*dst, l1=src-floor]
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(Act in, int n_src, int hs, int ws, int c, ActW out,
-                                                          int n_dst, int hd, int wd, float ry, float rx, int src_group, int dst_group) {
+                                                          int n_dst, int hd, int wd, float ry, float rx, int src_group, int dst_group,
+                                                          int rows_per_cta) {
     pdl_trigger();
     pdl_wait();
-    // grid: x covers (output column, 8-channel group) pairs of one output row, y = output row, z = output frame
-    // (no 64-bit index arithmetic: the first version spent most of its instructions on four int64 div/mod pairs)
+    // thread = (output column, 8-channel group) of one output frame (blockIdx.z); it walks down rows_per_cta output rows.  The
+    // horizontal interpolation of a source row (lx0*a + lx1*b) is computed once and reused by every output row between two
+    // source rows (3.75 of them when 12x20 maps go to 45x80); the first version recomputed all four taps per output pixel and
+    // spent ~200 instructions per 8 outputs, which - not memory - was what the kernel was bound by.
     const unsigned groups = (unsigned)c >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)wd * groups) return;
     const int ox = (int)(idx / groups);
     const int g = (int)(idx - (unsigned)ox * groups);
-    const int oy = blockIdx.y, img = blockIdx.z;
-    const int64_t pix = ((int64_t)img * hd + oy) * wd + ox;
+    const int img = blockIdx.z;
+    const int oy_begin = blockIdx.y * rows_per_cta, oy_end = min(hd, oy_begin + rows_per_cta);
     // output frame i = (call g, local j) reads source frame g*src_group + j % (sources of call g): with one group this is the
     // reference's repeat(T) interleave i % n_src (quirk Q3); several groups = several reference calls batched in one launch
     const int grp = img / dst_group, j = img - grp * dst_group;
     const int nsg = min(src_group, n_src - grp * src_group);
     const int simg = grp * src_group + j % nsg;
-    const float sy = __fmul_rn(ry, (float)oy);
     const float sx = __fmul_rn(rx, (float)ox);
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
-    const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
-    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const int x0 = (int)sx;
+    const int x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
     const uint16_t* base = in.p + (int64_t)simg * hs * ws * in.ld + g * 8;
-    float a[8], b[8], cc[8], d[8], r[8];
-    load8(base + ((int64_t)y0 * ws + x0) * in.ld, in.plane, a);
-    load8(base + ((int64_t)y0 * ws + x1) * in.ld, in.plane, b);
-    load8(base + ((int64_t)y1 * ws + x0) * in.ld, in.plane, cc);
-    load8(base + ((int64_t)y1 * ws + x1) * in.ld, in.plane, d);
+    float h0[8], h1[8];
+    int cy0 = -1, cy1 = -1;                                                    // source rows held in h0 / h1
+    auto hrow = [&](int y, float (&h)[8]) {
+        float a[8], b[8];
+        load8(base + ((int64_t)y * ws + x0) * in.ld, in.plane, a);
+        load8(base + ((int64_t)y * ws + x1) * in.ld, in.plane, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        r[j] = ly0 * (lx0 * a[j] + lx1 * b[j]) + ly1 * (lx0 * cc[j] + lx1 * d[j]);
-    store8(out.p + pix * out.ld + g * 8, out.plane, r);
+        for (int k = 0; k < 8; ++k) h[k] = lx0 * a[k] + lx1 * b[k];
+    };
+    uint16_t* dst = out.p + (((int64_t)img * hd + oy_begin) * wd + ox) * out.ld + g * 8;
+    for (int oy = oy_begin; oy < oy_end; ++oy, dst += (int64_t)wd * out.ld) {
+        const float sy = __fmul_rn(ry, (float)oy);
+        const int y0 = (int)sy;
+        const int y1 = y0 + (y0 < hs - 1 ? 1 : 0);
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+        if (y0 != cy0) {
+            if (y0 == cy1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) h0[k] = h1[k];
+            } else {
+                hrow(y0, h0);
+            }
+            cy0 = y0;
+        }
+        if (y1 != cy1) {
+            if (y1 == y0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) h1[k] = h0[k];
+            } else {
+                hrow(y1, h1);
+            }
+            cy1 = y1;
+        }
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = ly0 * h0[k] + ly1 * h1[k];
+        store8(dst, out.plane, r);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -768,9 +798,15 @@ int uavsal_bilinear_ac(const uint16_t* in, int64_t in_plane, int in_ld, int n_sr
     UAVSAL_REQUIRE((int64_t)div_up(n_dst, dst_group) * src_group >= n_src && div_up(n_dst, dst_group) == div_up(n_src, src_group), UAVSAL_EINVAL,
                    "bilinear_ac: %d sources in groups of %d do not match %d outputs in groups of %d", n_src, src_group, n_dst, dst_group);
     UAVSAL_REQUIRE(hd <= 65535 && n_dst <= 65535, UAVSAL_ENOTSUP, "bilinear_ac: more than 65535 output rows / frames");
-    launch_k(bilinear_ac_kernel, dim3(div_up((int64_t)wd * (c / 8), 256), hd, n_dst), dim3(256), 0, (cudaStream_t)stream, 1, Act{in, in_plane, in_ld}, n_src, hs, ws, c,
-                                                                            ActW{out, out_plane, out_ld}, n_dst, hd, wd,
-                                                                            ry, rx, src_group, dst_group);
+    // a thread walks down a strip of output rows (the source-row interpolation is reused); the strips are as long as still leaves
+    // about four CTAs per SM
+    const int64_t ctas_full = (int64_t)div_up((int64_t)wd * (c / 8), 256) * n_dst;
+    int chunks = (int)((4LL * 148 + ctas_full - 1) / ctas_full);
+    if (chunks < 1) chunks = 1;
+    if (chunks > hd) chunks = hd;
+    const int rows_per_cta = div_up(hd, chunks);
+    launch_k(bilinear_ac_kernel, dim3(div_up((int64_t)wd * (c / 8), 256), div_up(hd, rows_per_cta), n_dst), dim3(256), 0, (cudaStream_t)stream, 1,
+             Act{in, in_plane, in_ld}, n_src, hs, ws, c, ActW{out, out_plane, out_ld}, n_dst, hd, wd, ry, rx, src_group, dst_group, rows_per_cta);
     return check_launch("bilinear_ac");
 }
 

@@ -107,6 +107,15 @@ def readout(n, h, w, c, q16=False):
     print("readout dw+dot[%s] n=%d %dx%d c=%d: %.1f us  %.0f GB/s(hidden read)" % ("q16" if q16 else "f32", n, h, w, c, ms * 1e3, (2.0 if q16 else 4.0) * n * h * w * c / ms / 1e6), flush=True)
 
 
+def bilinear(n_src, hs, ws, c, n_dst, hd, wd, src_group=0, dst_group=0):
+    p = Plan(dev, 3, "tc")
+    x = p.alloc(n_src * hs * ws, c); x.t.normal_()
+    o = p.alloc(n_dst * hd * wd, c)
+    p.bilinear(x, n_src, hs, ws, c, o, n_dst, hd, wd, src_group=src_group, dst_group=dst_group)
+    ms = timeit(p)
+    print("bilinear %dx%dx%d (%d) -> %dx%d (%d): %.1f us  %.0f GB/s (written)" % (hs, ws, c, n_src, hd, wd, n_dst, ms * 1e3, 4.0 * n_dst * hd * wd * c / ms / 1e6), flush=True)
+
+
 def conv(engine, n, h, w, c, co, terms=3):
     p = Plan(dev, terms, engine)
     x = p.alloc(n * h * w, c); x.t.normal_()
@@ -152,6 +161,10 @@ def main():
     if what == "dwproj_q16":
         dwproj(120, 45, 80, 1536, 256, res=True, q16=True); dwproj(120, 45, 80, 1920, 256, q16=True); dwproj(120, 45, 80, 1152, 64, q16=True)
         dwproj(120, 45, 80, 1536, 256, res=True)
+        return
+    if what == "bilinear":      # the five upsample / broadcast launches of a 120-frame plan
+        bilinear(120, 12, 20, 256, 120, 45, 80); bilinear(120, 23, 40, 128, 120, 45, 80)
+        bilinear(1, 45, 80, 64, 120, 45, 80); bilinear(24, 12, 20, 64, 120, 45, 80, src_group=4, dst_group=20)
         return
     if what == "pairq16prof":   # the plan's top kernel (256 -> 1536 expand conv, q16 rows out) for an ncu --set full capture
         gemm("tc", 120 * 3600, 256, 1536, q16=True)
