@@ -144,7 +144,7 @@ class dwBlock(KernelModule):
         if has_expand:
             # the 6x hidden tensor travels as plain rows between the expand GEMM and the TMA depthwise kernels (dilation 1 only):
             # fp32, or 16-bit fixed point for the widest blocks (Plan.hidden_fmt)
-            fmt = plan.hidden_fmt(hidden, dil)
+            fmt = plan.hidden_fmt(hidden, dil, h * w)
             if fmt == FMT_Q16 and stride == 1 and 8 <= oup < 128:
                 # dw_project with a narrow N tile is bound by its depthwise stage, where the q16 decode costs more than the bytes
                 # save (1152 -> 64 @ 432 000 px: 779 vs 693 us; the expand GEMM only gains 60 us): fp32 rows

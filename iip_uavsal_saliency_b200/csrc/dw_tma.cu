@@ -275,6 +275,141 @@ int dw3x3_tma(Act in, int n, int h, int w, int c, int stride, const float* wgt, 
     return launch_dw_tma<2, 0>(tm, g, s);
 }
 
+// ---- small maps, any dilation (the ASPP branches: 12x20 maps, dilation 6 / 12 / 18, model.py:117-128) ------------------------
+// A CTA stages the WHOLE image of one 64-channel block by TMA (double-buffered across work items), so every input byte crosses
+// HBM once whatever the dilation, and out-of-image taps are skipped.  thread = (4-channel quad, every 16th pixel).
+struct DwImgArgs {
+    int n, h, w, c, dil, cblocks, num_items;
+    const float* wgt;      // [9][c]
+    const float* bias;     // [c]
+    int relu6;
+    ActW out;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) dw3x3_img_kernel(const __grid_constant__ CUtensorMap tmIn, const DwImgArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int hw = g.h * g.w;
+    const uint32_t tile_bytes = (uint32_t)hw * (FMT == 2 ? 128u : 256u);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * tile_bytes);         // [2]
+    const int tid = threadIdx.x;
+    pdl_trigger();
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
+    __syncthreads();
+    pdl_wait();
+    auto issue = [&](int t, int b) {                                           // one thread; item t = (image, channel block), block fastest
+        const int cblk = t % g.cblocks, img = t / g.cblocks;
+        uint8_t* dst = smem + b * tile_bytes;
+        fence_async_smem();
+        mbar_expect_tx(bar + b, tile_bytes);
+        if (FMT != 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(dst)), "l"(&tmIn), "r"(smem_u32(bar + b)), "r"(cblk * 64), "r"(0), "r"(0), "r"(img)
+                : "memory");
+        } else {
+            tma_load_5d(&tmIn, bar + b, dst, cblk * 64, 0, 0, img, 0);
+            tma_load_5d(&tmIn, bar + b, dst + tile_bytes / 2, cblk * 64, 0, 0, img, 1);
+        }
+    };
+    const int quad = tid & 15, pl = tid >> 4;
+    if (tid == 0 && (int)blockIdx.x < g.num_items) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < g.num_items; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < g.num_items) issue(t + gridDim.x, b ^ 1);
+        const int cblk = t % g.cblocks, img = t / g.cblocks;
+        const int c0 = cblk * 64 + quad * 4;
+        const bool cvalid = c0 < g.c;
+        float2 wr[9][2], br[2];
+        if (cvalid) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wgt + k * g.c + c0));
+                wr[k][0] = make_float2(w4.x, w4.y); wr[k][1] = make_float2(w4.z, w4.w);
+            }
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0));
+            br[0] = make_float2(b4.x, b4.y); br[1] = make_float2(b4.z, b4.w);
+        }
+        mbar_wait(bar + b, (it >> 1) & 1);
+        if (cvalid) {
+            const uint32_t tile = smem_u32(smem) + b * tile_bytes;
+            for (int p = pl; p < hw; p += 16) {
+                const int y = p / g.w, x = p - y * g.w;
+                float2 a2[2] = {br[0], br[1]};
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int yy = y + (ky - 1) * g.dil;
+                    if (yy < 0 || yy >= g.h) continue;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xx = x + (kx - 1) * g.dil;
+                        if (xx < 0 || xx >= g.w) continue;
+                        float2 v[2];
+                        lds4<FMT>(tile, tile_bytes / 2, yy * g.w + xx, quad, v);
+                        a2[0] = __ffma2_rn(v[0], wr[ky * 3 + kx][0], a2[0]);
+                        a2[1] = __ffma2_rn(v[1], wr[ky * 3 + kx][1], a2[1]);
+                    }
+                }
+                float acc[4] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y};
+                if (g.relu6) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = relu6f(acc[j]);
+                }
+                store4(g.out.p + ((int64_t)img * hw + p) * g.out.ld + c0, g.out.plane, acc);
+            }
+        }
+        __syncthreads();                                                       // image consumed: its buffer may be refilled
+    }
+}
+
+template <int FMT>
+static int launch_dw_img(const CUtensorMap& tm, DwImgArgs& g, cudaStream_t s) {
+    const size_t smem = 2 * (size_t)g.h * g.w * (FMT == 2 ? 128 : 256) + 64 + 128;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(dw3x3_img_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("dw3x3(img): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = smem;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = g.num_items < sms * per_sm ? g.num_items : sms * per_sm;
+    cudaError_t e = launch_k(dw3x3_img_kernel<FMT>, dim3(grid), dim3(256), smem, s, 1, tm, g);
+    if (e != cudaSuccess) { set_error("dw3x3(img): launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return check_launch("dw3x3(img)");
+}
+
+// whole-image staging fits: 2 buffers of h*w pixels x 64 channels (256 B per pixel split-bf16 / fp32, 128 B q16)
+bool dw3x3_img_fits(int64_t in_plane, int h, int w) {
+    const int64_t px = (int64_t)h * w;
+    return w <= 256 && h <= 256 && 2 * px * (in_plane == UAVSAL_PLANE_Q16 ? 128 : 256) + 192 <= 200 * 1024;
+}
+
+// stride 1, dilation >= 1 (padding = dilation) on small maps; in.plane as dw3x3_tma
+int dw3x3_img(Act in, int n, int h, int w, int c, int dil, const float* wgt, const float* bias, int relu6, ActW out, cudaStream_t s) {
+    DwImgArgs g{};
+    g.n = n; g.h = h; g.w = w; g.c = c; g.dil = dil; g.cblocks = div_up(c, 64); g.num_items = n * g.cblocks;
+    g.wgt = wgt; g.bias = bias; g.relu6 = relu6; g.out = out;
+    CUtensorMap tm;
+    if (in.plane == UAVSAL_PLANE_F32 || in.plane == UAVSAL_PLANE_Q16) {
+        const bool q16 = in.plane == UAVSAL_PLANE_Q16;
+        const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t row = (uint64_t)in.ld * (q16 ? 2 : 4);
+        const uint64_t str[3] = {row, row * w, row * w * h};
+        const uint32_t box[4] = {64, (uint32_t)w, (uint32_t)h, 1};
+        int rc = tc_encode(&tm, in.p, 4, dims, str, box, q16 ? "dw(img) input (q16)" : "dw(img) input (f32)", q16 ? 0 : 2);
+        if (rc) return rc;
+        return q16 ? launch_dw_img<2>(tm, g, s) : launch_dw_img<1>(tm, g, s);
+    }
+    set_error("dw3x3(img): plain-row input (fp32 / q16) only");
+    return UAVSAL_ENOTSUP;
+}
+
 // readout tail: sum the channel-block partials of a pixel in a fixed order, add the folded BN bias, sigmoid (model.py:373)
 __global__ void __launch_bounds__(256) dot_finish_kernel(const float* __restrict__ partial, int64_t rows, int cblocks, float bias,
                                                          float* __restrict__ out) {

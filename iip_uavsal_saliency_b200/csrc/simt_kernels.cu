@@ -670,6 +670,8 @@ static inline bool act_ok(const void* p, int64_t plane, int ld) {
 }
 
 namespace uavsal {
+bool dw3x3_img_fits(int64_t in_plane, int h, int w);
+int dw3x3_img(Act in, int n, int h, int w, int c, int dil, const float* wgt, const float* bias, int relu6, ActW out, cudaStream_t s);
 int dw3x3_dot_tma(const void* in, bool q16, int in_ld, int n, int h, int w, int c, const float* wgt, const float* bias, const float* wproj,
                   float bias_proj, float* partial, float* out, cudaStream_t s);
 }
@@ -766,7 +768,12 @@ int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, 
         return dw3x3_tma(Act{in, in_plane, in_ld}, n, h, w, c, stride, wgt, bias, relu6, ActW{out, out_plane, out_ld},
                          (cudaStream_t)stream);
     }
-    UAVSAL_REQUIRE(!f32in, UAVSAL_ENOTSUP, "dw3x3: fp32 / q16 row input is only implemented by the TMA kernel (dilation 1)");
+    if (dilation > 1 && stride == 1 && f32in && out_plane != 0 && dw3x3_img_fits(in_plane, h, w)) {
+        // small maps with dilation (the ASPP branches at 12x20), plain-row input: the whole image of a channel block staged by TMA
+        // (split-bf16 input stays with the generic kernel below: two 61 KB images per CTA leave one CTA per SM - measured slower)
+        return dw3x3_img(Act{in, in_plane, in_ld}, n, h, w, c, dilation, wgt, bias, relu6, ActW{out, out_plane, out_ld}, (cudaStream_t)stream);
+    }
+    UAVSAL_REQUIRE(!f32in, UAVSAL_ENOTSUP, "dw3x3: fp32 / q16 row input is only implemented by the TMA kernels (dilation 1, or small maps)");
     if (dilation == 1 && g_dw_fast == 1) {
         const int strips = div_up(ho, kDwRB);
         const dim3 grid(div_up(c, 64), div_up(wo, 32), strips * n);

@@ -367,14 +367,18 @@ class Plan:
     def f32_hidden(self) -> bool:
         return self.engine == "tc"
 
-    def hidden_fmt(self, hidden: int, dilation: int = 1) -> int:
+    def hidden_fmt(self, hidden: int, dilation: int = 1, hw: int = 0) -> int:
         """Storage of the tensor between a dwBlock's expand conv and its depthwise conv (model.py:90-92).  The tcgen05 engine
         keeps it in plain rows for the TMA depthwise kernels (dilation 1): fp32, or - for the widest blocks (hidden >=
         Q16_HIDDEN_MIN: the 256 -> 1536 class, whose 2.65 GB hidden tensors dominate the plan's HBM traffic) - 16-bit fixed point
         of the ReLU6 output (|error| <= 4.6e-5; measured on config #2: +3.6e-5 max-abs on the saliency map).  ``hidden_q16 = False``
         on the plan keeps everything in fp32."""
-        if not self.f32_hidden or dilation != 1:
+        if not self.f32_hidden:
             return FMT_SPLIT
+        if dilation != 1:
+            # dilated depthwise convs (the ASPP branches) read plain rows only through the whole-image kernel for small maps
+            # (dw_tma.cu dw3x3_img_kernel: two q16 images of 64 channels in shared memory)
+            return FMT_Q16 if (hidden >= Q16_HIDDEN_MIN and getattr(self, "hidden_q16", True) and 0 < hw <= 768) else FMT_SPLIT
         if hidden >= Q16_HIDDEN_MIN and getattr(self, "hidden_q16", True):
             return FMT_Q16
         return FMT_F32

@@ -118,14 +118,14 @@ def test_plan_structure_of_one_call():
     m.build_plan(pu, 20, 360, 640, x_kind=1, post_hw=(360, 640))
     nu = [o.name for o in pu.ops]
     assert nu.count("uavsal_mbconv_fused") == 0 and nu.count("uavsal_dw_project") == 7 and nu.count("uavsal_pw_gemm") == 76 - 2 - 8
-    # the hidden tensors of the widest blocks (>= 1152 channels, dilation 1: st0/st1.sp, fust, cxt0, fucbst, the readout; not fucb, whose
-    # 64-output dw_project is bound by its depthwise stage) travel as 16-bit fixed-point rows: the expand GEMM writes them
+    # the hidden tensors of the widest blocks (>= 1152 channels: st0/st1.sp, fust, cxt0, fucbst, the readout and the three dilated ASPP
+    # branches at 12x20; not fucb, whose 64-output dw_project is bound by its depthwise stage) travel as 16-bit fixed-point rows: the expand GEMM writes them
     # (F_OUT_Q16), dw_project / dw3x3 / the readout's dw+dot read them
     assert names.count("uavsal_dw3x3_dot_sigmoid_q16") == 1 and names.count("uavsal_dw3x3_dot_sigmoid") == 0 and names.count("uavsal_dot_sigmoid") == 0
     q16_out = [o for o in plan.ops if o.name == "uavsal_pw_gemm" and o.args[9] & engine.F_OUT_Q16]
-    assert len(q16_out) == 6 and all(o.args[9] == engine.F_OUT_Q16 | engine.F_RELU6 and o.args[7] >= engine.Q16_HIDDEN_MIN for o in q16_out)
+    assert len(q16_out) == 9 and all(o.args[9] == engine.F_OUT_Q16 | engine.F_RELU6 and o.args[7] >= engine.Q16_HIDDEN_MIN for o in q16_out)
     assert sum(1 for o in plan.ops if o.name == "uavsal_dw_project" and o.args[12] & engine.F_HID_Q16) == 4
-    assert sum(1 for o in plan.ops if o.name == "uavsal_dw3x3" and o.args[1] == engine.PLANE_Q16) == 1          # cxt0 (stride 2)
+    assert sum(1 for o in plan.ops if o.name == "uavsal_dw3x3" and o.args[1] == engine.PLANE_Q16) == 4          # cxt0 (stride 2) + aspp2..4 (dilation 6 / 12 / 18)
     pq = engine.Plan("cpu", 3, "tc")
     pq.hidden_q16 = False                                               # everything in fp32 rows
     m.build_plan(pq, 20, 360, 640, x_kind=1, post_hw=(360, 640))

@@ -164,6 +164,35 @@ def test_q16_hidden_expand_then_depthwise(cuda, cin, ch, s, n, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(back, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("fmt", ["split", "f32", "q16"])
+@pytest.mark.parametrize("c,d,n,h,w", [(1920, 6, 3, 12, 20), (1920, 18, 2, 12, 20), (104, 2, 2, 9, 17), (64, 12, 1, 12, 20), (192, 3, 1, 23, 32)])
+def test_dilated_depthwise_small_maps(cuda, fmt, c, d, n, h, w):
+    """The ASPP branches' dilated depthwise convs (model.py:117-128; 12x20 maps, dilation 6 / 12 / 18): the whole image of a
+    64-channel block is staged by TMA (plain-row input: fp32 or q16), out-of-image taps are skipped; split-bf16 input runs the generic kernel."""
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(23)
+    p = _plan()
+    q, xq = _q16(torch.rand(n, c, h, w) * 7 - 0.5)
+    wt, b = torch.randn(c, 1, 3, 3) * 0.3, torch.randn(c) * 0.1
+    if fmt == "q16":
+        xb = p.alloc_q16(n * h * w, c)
+        xb.t[:, :c].copy_(q.permute(0, 2, 3, 1).reshape(-1, c).to(torch.int32).to(torch.int16))
+    elif fmt == "f32":
+        xb = p.alloc_f32(n * h * w, c)
+        xb.t[:, :c].copy_(xq.permute(0, 2, 3, 1).reshape(-1, c))
+    else:
+        xb = _upload(p, xq)
+    ob = p.alloc(n * h * w, c)
+    p.dw(xb, n, h, w, c, 1, d, p.hold(pack_dw(wt)), p.hold(b), True, ob)
+    y = _download(p, ob, n, c, h, w)
+    if fmt == "f32" and 2 * h * w * 256 + 192 > 200 * 1024:
+        with pytest.raises(ValueError):                      # two fp32 images of a channel block do not fit shared memory: refused, not silently slow
+            p.run()
+        return
+    p.run()
+    assert _rel(y, F.hardtanh(F.conv2d(xq, wt, b, 1, d, d, c), 0, 6)) < KERNEL_TOL
+
+
 @pytest.mark.parametrize("ch,co,n,h,w,res", [(128, 64, 1, 8, 16, False), (256, 64, 3, 13, 21, False), (1536, 256, 2, 45, 80, True),
                                               (1152, 64, 1, 45, 80, False), (384, 256, 1, 9, 40, True), (1920, 256, 1, 45, 80, True)])
 def test_fused_depthwise_project_q16(cuda, ch, co, n, h, w, res):

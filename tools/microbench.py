@@ -40,17 +40,17 @@ def gemm(engine, m, k, n, res=False, terms=3, f32=False, q16=False):
     print("pw[%s,t%d%s] m=%d k=%d n=%d res=%d: %.1f us  %.1f TF/s(alg)  %.0f GB/s" % (engine, terms, ",q16out" if q16 else ",f32out" if f32 else "", m, k, n, res, ms * 1e3, fl / ms / 1e9, by / ms / 1e6), flush=True)
 
 
-def dw(fast, n, h, w, c, stride, f32=False, q16=False):
+def dw(fast, n, h, w, c, stride, f32=False, q16=False, dil=1):
     _ext.load().uavsal_set_option(2, fast)
     p = Plan(dev, 3, "tc")
     x = p.alloc_q16(n * h * w, c) if q16 else p.alloc_f32(n * h * w, c) if f32 else p.alloc(n * h * w, c)
     x.t.random_(-32768, 32767) if q16 else x.t.normal_()
     ho, wo = (h, w) if stride == 1 else ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
     o = p.alloc(n * ho * wo, c)
-    p.dw(x, n, h, w, c, stride, 1, p.hold(pack_dw(torch.randn(c, 1, 3, 3))), p.hold(torch.zeros(c)), True, o)
+    p.dw(x, n, h, w, c, stride, dil, p.hold(pack_dw(torch.randn(c, 1, 3, 3))), p.hold(torch.zeros(c)), True, o)
     ms = timeit(p)
     by = 4.0 * n * c * (h * w + ho * wo) - (2.0 * n * c * h * w if q16 else 0)
-    print("dw[fast=%d%s] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, ",q16in" if q16 else ",f32in" if f32 else "", n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
+    print("dw[fast=%d%s%s] n=%d %dx%d c=%d s=%d: %.1f us  %.0f GB/s" % (fast, ",q16in" if q16 else ",f32in" if f32 else "", ",dil=%d" % dil if dil > 1 else "", n, h, w, c, stride, ms * 1e3, by / ms / 1e6), flush=True)
     _ext.load().uavsal_set_option(2, 1)
 
 
@@ -161,6 +161,11 @@ def main():
     if what == "dwproj_q16":
         dwproj(120, 45, 80, 1536, 256, res=True, q16=True); dwproj(120, 45, 80, 1920, 256, q16=True); dwproj(120, 45, 80, 1152, 64, q16=True)
         dwproj(120, 45, 80, 1536, 256, res=True)
+        return
+    if what == "aspp":          # dilated depthwise convs of the ASPP branches (120 frames of 12x20 x 1920 channels)
+        for d in (6, 12, 18):
+            dw(0, 120, 12, 20, 1920, 1, dil=d); dw(2, 120, 12, 20, 1920, 1, dil=d); dw(2, 120, 12, 20, 1920, 1, q16=True, dil=d)
+        gemm("tc", 28800, 320, 1920); gemm("tc", 28800, 320, 1920, q16=True)
         return
     if what == "bilinear":      # the five upsample / broadcast launches of a 120-frame plan
         bilinear(120, 12, 20, 256, 120, 45, 80); bilinear(120, 23, 40, 128, 120, 45, 80)
