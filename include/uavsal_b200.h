@@ -108,7 +108,10 @@ int uavsal_stem_conv3x3s2_hw(const void* x, int x_kind, int n, int h, int w, con
                              uint16_t* out, int64_t out_plane, int out_ld, void* stream);
 
 /* ---- K2: depthwise 3x3 + BN + ReLU6 (model.py:92 BasicConv2d(groups=hidden); torchvision InvertedResidual dw)
- *      stride 1|2, dilation >= 1, padding = dilation.  wgt: [9][c] fp32 BN-folded, bias[c]. */
+ *      stride 1|2, dilation >= 1, padding = dilation.  wgt: [9][c] fp32 BN-folded, bias[c].
+ *      in_plane == UAVSAL_PLANE_F32 / UAVSAL_PLANE_Q16: `in` points to plain fp32 / q16 rows [n*h*w][in_ld] (the hidden tensor written by
+ *      uavsal_pw_gemm with UAVSAL_F_OUT_F32 / UAVSAL_F_OUT_Q16); accepted for dilation 1, and for dilation > 1 (stride 1) on maps small
+ *      enough for two whole images of a 64-channel block to fit shared memory (h*w <= 799 for q16, 399 for fp32), else UAVSAL_ENOTSUP. */
 int uavsal_dw3x3(const uint16_t* in, int64_t in_plane, int in_ld, int n, int h, int w, int c,
                  int stride, int dilation, const float* wgt, const float* bias, int relu6,
                  uint16_t* out, int64_t out_plane, int out_ld, void* stream);
