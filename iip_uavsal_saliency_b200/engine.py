@@ -7,6 +7,7 @@ packing and the op list that way) but ``Plan.run`` requires CUDA tensors and the
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -372,9 +373,11 @@ class Plan:
         keeps it in plain rows for the TMA depthwise kernels (dilation 1): fp32, or - for the widest blocks (hidden >=
         Q16_HIDDEN_MIN: the 256 -> 1536 class, whose 2.65 GB hidden tensors dominate the plan's HBM traffic) - 16-bit fixed point
         of the ReLU6 output (|error| <= 4.6e-5; measured on config #2: +3.6e-5 max-abs on the saliency map).  ``hidden_q16 = False``
-        on the plan keeps everything in fp32."""
+        on the plan (or UAVSAL_HIDDEN_Q16=0 in the environment, for A/B runs) keeps everything in fp32."""
         if not self.f32_hidden:
             return FMT_SPLIT
+        if not hasattr(self, "hidden_q16"):
+            self.hidden_q16 = os.environ.get("UAVSAL_HIDDEN_Q16", "1") != "0"
         if dilation != 1:
             # dilated depthwise convs (the ASPP branches) read plain rows only through the whole-image kernel for small maps
             # (dw_tma.cu dw3x3_img_kernel: two q16 images of 64 channels in shared memory)

@@ -562,6 +562,37 @@ def test_mbconv_fused_block(cuda, inp, oup, n, h, w):
         assert _rel(outs[0], cpu_ref.dw_block(sd, "b", x)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("inp,oup,stride,dil,n,h,w", [(256, 256, 1, 1, 10, 45, 80), (320, 256, 1, 1, 10, 45, 80), (256, 64, 2, 1, 10, 45, 80),
+                                                      (320, 256, 1, 12, 6, 12, 20), (256, 256, 1, 1, 2, 36, 64)])
+def test_wide_block_q16_vs_fp32_hidden_rows(cuda, inp, oup, stride, dil, n, h, w):
+    """The 256 -> 1536 class of dwBlocks (model.py:74-103) with the hidden tensor as q16 rows (default) and as fp32 rows
+    (plan.hidden_q16 = False): both within the kernel tolerance of the oracle, and within 1e-4 relative of each other.  Covers the
+    dw_project path, the stride-2 TMA depthwise kernel, the dilated whole-image kernel and the small-map fallback (dw3x3 + GEMM)."""
+    from iip_uavsal_saliency_b200 import engine as E, model as M
+    torch.manual_seed(inp + 7 * oup + dil)
+    blk = M.dwBlock(inp, oup, stride=stride, dilation=dil).eval()
+    for mod in blk.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.8, 1.2); mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    x = torch.randn(n, inp, h, w)
+    sd = {"b." + k: v for k, v in blk.state_dict().items()}
+    blk = blk.cuda()
+    outs = []
+    for q16 in (True, False):
+        p = _plan()
+        p.hidden_q16 = q16
+        ob, ho, wo = blk._emit(p, _upload(p, x.cuda()), n, h, w)
+        has_q16 = any((o.name == "uavsal_pw_gemm" and o.args[9] & E.F_OUT_Q16) for o in p.ops)
+        assert has_q16 == q16
+        out = _download(p, ob, n, oup, ho, wo)
+        p.run()
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    ref = cpu_ref.dw_block(sd, "b", x, stride=stride, dilation=dil)
+    assert _rel(outs[0], ref) < KERNEL_TOL and _rel(outs[1], ref) < KERNEL_TOL
+    assert _rel(outs[0], outs[1]) < 1e-4
+
+
 @pytest.mark.parametrize("engine", ["tc", "simt"])
 def test_uavsal_call_of_20_frames_vs_reference_golden(cuda, gold_dir, engine):
     """One Demo_Test-sized call (B=4,T=5) at 360x640 with per-stage taps (quirks Q2/Q3 included)."""
