@@ -114,8 +114,13 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
             const int img = (int)(row / (unsigned)ho);
             const int oy = (int)(row - (unsigned)img * (unsigned)ho);
             float acc[32];
+            float2 acc2[PW ? 16 : 1];                                          // PW: channel pairs (packed fma.rn.f32x2, weights through uniform registers)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = PW ? cw.w[27 * 32 + j] : sb[j];
+            for (int j = 0; j < 32; ++j) acc[j] = PW ? 0.f : sb[j];
+            if (PW) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc2[j] = make_float2(cw.w[27 * 32 + 2 * j], cw.w[27 * 32 + 2 * j + 1]);
+            }
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int y = oy * 2 - 1 + ky;
@@ -131,8 +136,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
                         else if (KIND == 1) v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * 3 + ch) * h + y) * w + xx)];
                         else v = lut[ch][__ldg(reinterpret_cast<const uint8_t*>(x) + (((int64_t)img * h + y) * w + xx) * 3 + ch)];
                         if (PW) {
+                            const float* wk = cw.w + ((ky * 3 + kx) * 3 + ch) * 32;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) acc[j] = fmaf(v, cw.w[((ky * 3 + kx) * 3 + ch) * 32 + j], acc[j]);
+                            for (int j = 0; j < 16; ++j) acc2[j] = __ffma2_rn(make_float2(v, v), make_float2(wk[2 * j], wk[2 * j + 1]), acc2[j]);
                             continue;
                         }
                         const float4* wr = sw + ((ky * 3 + kx) * 3 + ch) * 8;
@@ -146,6 +152,10 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ x, i
                         }
                     }
                 }
+            }
+            if (PW) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) st[threadIdx.x * 33 + j] = relu6f(acc[j]);

@@ -116,6 +116,16 @@ def bilinear(n_src, hs, ws, c, n_dst, hd, wd, src_group=0, dst_group=0):
     print("bilinear %dx%dx%d (%d) -> %dx%d (%d): %.1f us  %.0f GB/s (written)" % (hs, ws, c, n_src, hd, wd, n_dst, ms * 1e3, 4.0 * n_dst * hd * wd * c / ms / 1e6), flush=True)
 
 
+def stem(n, h, w):
+    p = Plan(dev, 3, "tc")
+    x = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    o = p.alloc_f32(n * ho * wo, 32)
+    p.stem(p.hold(x), 2, n, h, w, torch.randn(3, 3, 3, 32) * 0.3, torch.zeros(32), o)
+    ms = timeit(p)
+    print("stem n=%d %dx%d: %.1f us  %.0f GB/s (written)" % (n, h, w, ms * 1e3, 4.0 * n * ho * wo * 32 / ms / 1e6), flush=True)
+
+
 def conv(engine, n, h, w, c, co, terms=3):
     p = Plan(dev, terms, engine)
     x = p.alloc(n * h * w, c); x.t.normal_()
@@ -166,6 +176,9 @@ def main():
         for d in (6, 12, 18):
             dw(0, 120, 12, 20, 1920, 1, dil=d); dw(2, 120, 12, 20, 1920, 1, dil=d); dw(2, 120, 12, 20, 1920, 1, q16=True, dil=d)
         gemm("tc", 28800, 320, 1920); gemm("tc", 28800, 320, 1920, q16=True)
+        return
+    if what == "stem":
+        stem(120, 360, 640); dwproj(120, 180, 320, 32, 16)
         return
     if what == "bilinear":      # the five upsample / broadcast launches of a 120-frame plan
         bilinear(120, 12, 20, 256, 120, 45, 80); bilinear(120, 23, 40, 128, 120, 45, 80)
