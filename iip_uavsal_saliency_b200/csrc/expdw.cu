@@ -238,24 +238,25 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
             // depthwise taps / bias of this thread's 4 channels
             const int c0 = cblk * 64 + quad * 4;
             const bool cvalid = c0 < g.hidden;
-            float wr[9][4], br[4];
+            // (channel pairs: the 9-tap dot products run as packed fma.rn.f32x2 - the same IEEE fma per lane, half the instructions)
+            float2 wr[9][2], br[2];
 #pragma unroll
             for (int k = 0; k < 9; ++k)
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wr[k][0]), "=f"(wr[k][1]), "=f"(wr[k][2]), "=f"(wr[k][3])
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wr[k][0].x), "=f"(wr[k][0].y), "=f"(wr[k][1].x), "=f"(wr[k][1].y)
                              : "r"(wds + (k * cb64 + c0) * 4));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(br[0]), "=f"(br[1]), "=f"(br[2]), "=f"(br[3]) : "r"(bds + c0 * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(br[0].x), "=f"(br[0].y), "=f"(br[1].x), "=f"(br[1].y) : "r"(bds + c0 * 4));
             __syncthreads();                                                   // hidden tile complete; the x tile is dead
             if (cblk == cb_end - 1 && tn < g.num_tiles) issue_x(nimg, ny0, nx0);
 
             // ---- depthwise 3x3 + bias + ReLU6 from the hidden tile (sliding 3x3x4 register window, as dw_tma.cu) ----
             const int ox = x0 + col;
             if (cvalid && ox < g.wo) {
-                float win[3][3][4];
+                float2 win[3][3][2];
                 auto load_row = [&](int slot, int iy) {
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        float* v = win[slot][d];
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                        float2* v = win[slot][d];
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y)
                                      : "r"(hid + (iy * G::IW + col * STRIDE + d) * G::HPITCH + quad * 16));
                     }
                 };
@@ -276,19 +277,19 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                         load_row(s2, oyl * 2 + 2);
                     }
                     if (y0 + oyl >= g.ho) break;
-                    float acc[4] = {br[0], br[1], br[2], br[3]};
+                    float2 acc[2] = {br[0], br[1]};
                     const int slots[3] = {s0, s1, s2};
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const float* v = win[slots[ky]][kx];
+                            const float2* v = win[slots[ky]][kx];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[j] = fmaf(v[j], wr[ky * 3 + kx][j], acc[j]);
+                            for (int j = 0; j < 2; ++j) acc[j] = __ffma2_rn(v[j], wr[ky * 3 + kx][j], acc[j]);
                         }
                     uint32_t h0, l0, h1, l1;
-                    split2(relu6f(acc[0]), relu6f(acc[1]), h0, l0);
-                    split2(relu6f(acc[2]), relu6f(acc[3]), h1, l1);
+                    split2(relu6f(acc[0].x), relu6f(acc[0].y), h0, l0);
+                    split2(relu6f(acc[1].x), relu6f(acc[1].y), h1, l1);
                     uint16_t* dst = orow + (int64_t)i * g.wo * g.out.ld;
                     *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
                     if (g.out.plane) *reinterpret_cast<uint2*>(dst + g.out.plane) = make_uint2(l0, l1);

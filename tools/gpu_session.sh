@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "stem or config1 or backbone_levels or block_modules or fused_depthwise_project" > gpurun_out/r02r_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02r_tests.log | cut -c1-300
-timeout 300 python tools/microbench.py stem 2>&1 | tail -2 | tee gpurun_out/r02r_stem.txt
+timeout 900 python -m pytest tests -m gpu -q -x -k "fused_expand or config1 or backbone_levels or block_modules" > gpurun_out/r02s_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02s_tests.log | cut -c1-300
+python - <<'PY' 2>&1 | tee gpurun_out/r02s_expdw.txt
+import sys; sys.argv=['x','none']; sys.path.insert(0,'tools')
+import microbench as mb
+mb.expdw(120, 180, 320, 16, 96, 2); mb.expdw(120, 90, 160, 24, 144, 2)
+PY
