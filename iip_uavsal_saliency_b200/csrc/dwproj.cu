@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
             }
 
             // ---- epilogue of this tile (same warps): TMEM -> bias (+ residual) -> split -> staging -> coalesced stores ----
+            mbar_wait(acc_full, it & 1);
+            tc_fence_after();
             auto grow_of = [&](int rr) -> int64_t {
                 const int y = y0 + rr / kDpTW, x = x0 + rr % kDpTW;
                 if (!tvalid || y >= g.H || x >= g.W) return -1;
@@ -257,31 +259,10 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
             };
             const int r = q * 32 + lane;
             const int64_t orow = grow_of(r);
-            const int nchunks = g.N >> 6;
-            // the residual cells of chunk ch + 1 are requested before chunk ch is processed, those of chunk 0 before the accumulator is
-            // waited for (ncu: the row-strided residual loads, issued where they were needed, were 16 % of all warp samples)
-            const bool has_res = (g.flags & UAVSAL_F_RESIDUAL) && orow >= 0;
-            uint4 rq[4], nrq[4];                                              // raw residual cells: hi[0..7], hi[8..15], lo[0..7], lo[8..15]
-            auto issue_res = [&](int ch, uint4 (&d)[4]) {
-                if (has_res) {
-                    const uint16_t* a = g.res.p + orow * g.res.ld + ch * 64 + sub;
-                    d[0] = __ldg(reinterpret_cast<const uint4*>(a));
-                    d[1] = __ldg(reinterpret_cast<const uint4*>(a + 8));
-                    if (g.res.plane) {
-                        d[2] = __ldg(reinterpret_cast<const uint4*>(a + g.res.plane));
-                        d[3] = __ldg(reinterpret_cast<const uint4*>(a + g.res.plane + 8));
-                    }
-                }
-            };
-            issue_res(0, nrq);
-            mbar_wait(acc_full, it & 1);
-            tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int nchunks = g.N >> 6;
             for (int ch = 0; ch < nchunks; ++ch) {
                 uint32_t raw[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rq[i] = nrq[i];
-                if (ch + 1 < nchunks) issue_res(ch + 1, nrq);
                 __syncwarp();
                 tmem_ld16(trow + ch * 64 + sub, raw);
                 const int n = ch * 64 + sub;
@@ -294,22 +275,14 @@ __global__ void __launch_bounds__(kThreads2, 1) dwproj_kernel(const __grid_const
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j4);
                         v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
                     }
-                    if (has_res) {
+                    if (g.flags & UAVSAL_F_RESIDUAL) {
+                        float rr[8];
+                        load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            float rr[8];
-                            unpack2(rq[hf].x, rr[0], rr[1]); unpack2(rq[hf].y, rr[2], rr[3]);
-                            unpack2(rq[hf].z, rr[4], rr[5]); unpack2(rq[hf].w, rr[6], rr[7]);
-                            if (g.res.plane) {
-                                float rl[8];
-                                unpack2(rq[2 + hf].x, rl[0], rl[1]); unpack2(rq[2 + hf].y, rl[2], rl[3]);
-                                unpack2(rq[2 + hf].z, rl[4], rl[5]); unpack2(rq[2 + hf].w, rl[6], rl[7]);
+                        for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                        load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) rr[j] += rl[j];
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[hf * 8 + j] += rr[j];
-                        }
+                        for (int j = 0; j < 8; ++j) v[8 + j] += rr[j];
                     }
                 }
                 if (ch == nchunks - 1) {                                      // accumulator fully read by this warp
