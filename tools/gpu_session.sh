@@ -1,23 +1,15 @@
 #!/bin/bash
+# round-2 evidence at HEAD: full GPU suite, default bench line (+ reference arm), ncu launch list of the 120-frame plan, smoke() launch list
 set -u
 mkdir -p gpurun_out
-for lib in base mr base mr; do
-  if [ $lib = mr ]; then export UAVSAL_LIB=$PWD/gpurun_aux/libuavsal_b200_mr.so; else unset UAVSAL_LIB; fi
-  echo "=== $lib"
-  python - <<'PY' 2>&1 | grep -v "^$"
-import sys; sys.argv=['x','none']; sys.path.insert(0,'tools')
-import microbench as mb
-M=432000
-mb.gemm("tc", M, 256, 1536, q16=True); mb.gemm("tc", M, 320, 1920, q16=True); mb.gemm("tc", M, 256, 256, res=True); mb.gemm("tc", M, 32, 256, res=True)
-mb.gemm("tc", 1728000, 24, 144, f32=True); mb.gemm("tc", 110400, 96, 576, f32=True); mb.gemm("tc", 28800, 1920, 256)
-mb.dwproj(120, 45, 80, 1536, 256, res=True, q16=True); mb.dwproj(120, 45, 80, 1920, 256, q16=True); mb.dwproj(120, 45, 80, 1152, 64)
-mb.mbblock(120, 45, 80, 64, 32, True); mb.mbblock(120, 45, 80, 32, 32, True); mb.mbblock(120, 23, 40, 64, 64, True)
-mb.twa("tc", 60, 45, 80, 256, batch=2); mb.conv("tc", 120, 45, 80, 448, 256)
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r02v_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02v_tests.log | cut -c1-200
+( timeout 900 python bench.py --dump-ops gpurun_out/r02v_ops.txt ) > gpurun_out/r02v_bench_n1.json 2> gpurun_out/r02v_bench_n1.err; echo "bench rc=$?"
+python - <<'PY'
+import json; d=json.load(open('gpurun_out/r02v_bench_n1.json'))
+print(round(d['value']), round(d['e2e']['value']), d['clocks'], d['roofline']['frac'], d['roofline']['issued_frac'], d['wall_s'])
 PY
-done 2>&1 | tee gpurun_out/r02u_maxnreg.txt
-for lib in base mr base mr; do
-  if [ $lib = mr ]; then export UAVSAL_LIB=$PWD/gpurun_aux/libuavsal_b200_mr.so; else unset UAVSAL_LIB; fi
-  ( timeout 600 python bench.py --steps 8 --warmup 3 --skip-aux --skip-cpu ) > gpurun_out/r02u_bench_$lib.json 2>/dev/null
-  python -c "
-import json; d=json.load(open('gpurun_out/r02u_bench_$lib.json')); print('$lib', round(d['value']), round(d['e2e']['value']), d['clocks']['sm_mhz'], d['whole_network']['sum_of_kernel_ms_per_plan'])"
-done
+( timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/r02v_bench_ref.json 2> gpurun_out/r02v_bench_ref.err; echo "ref rc=$?"
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none --csv --log-file gpurun_out/r02v_clip120_kernels.csv python tools/profile_call.py exact 120 > gpurun_out/r02v_ncu.log 2>&1; echo "ncu rc=$?"
+python tools/summarize_ncu.py gpurun_out/r02v_clip120_kernels.csv gpurun_out/r02v_clip120 | tail -2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02v_smoke_kernels.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02v_smoke.log 2>&1; echo "smoke-ncu rc=$?"; tail -1 gpurun_out/r02v_smoke.log
