@@ -164,6 +164,43 @@ def test_q16_hidden_expand_then_depthwise(cuda, cin, ch, s, n, h, w):
     assert _rel(y, F.hardtanh(F.conv2d(back, wd, bd, s, 1, 1, ch), 0, 6)) < KERNEL_TOL
 
 
+def test_q16_producers_and_consumers_stay_inside_their_slot(cuda):
+    """Canary check (no compute-sanitizer on the pool): the q16 GEMM epilogue, the whole-image dilated depthwise kernel and the
+    strip-walking bilinear kernel write a channel slot of a wider, sentinel-filled buffer and a row count that is not a multiple of
+    any tile; every byte outside the slot / beyond the last row must keep the sentinel."""
+    from iip_uavsal_saliency_b200.engine import pack_dw
+    torch.manual_seed(29)
+    p = _plan()
+    m, k, n = 1000, 64, 1160                                   # rows: 7.8 tiles of 128; N: 4.5 tiles of 256, not a multiple of 16
+    x = torch.randn(1, k, 25, 40)
+    wide = p.alloc_q16(m + 200, 2 * n + 8)
+    wide.t.fill_(0x5A5A - 0x10000 if 0x5A5A > 0x7FFF else 0x5A5A)
+    slot = wide.slot(n // 2 + 4, n)                            # channel offset 584 (a multiple of 8)
+    p.pw(_upload(p, x), m, (torch.randn(n, k) / 8).cuda(), torch.zeros(n).cuda(), 1, slot)
+    c, hh, ww = 104, 9, 17
+    q, xq = _q16(torch.rand(2, c, hh, ww) * 7 - 0.5)
+    xin = p.alloc_q16(2 * hh * ww, c)
+    xin.t[:, :c].copy_(q.permute(0, 2, 3, 1).reshape(-1, c).to(torch.int32).to(torch.int16))
+    owide = p.alloc(2 * hh * ww + 50, 3 * 104)
+    owide.t.fill_(7.0)
+    oslot = owide.slot(104, c)
+    p.dw(xin, 2, hh, ww, c, 1, 3, p.hold(pack_dw(torch.randn(c, 1, 3, 3) * 0.3)), p.hold(torch.zeros(c)), True, oslot)
+    bwide = p.alloc(6 * 45 * 80 + 77, 3 * 64)
+    bwide.t.fill_(7.0)
+    bslot = bwide.slot(64, 64)
+    p.bilinear(_upload(p, torch.randn(2, 64, 12, 20)), 2, 12, 20, 64, bslot, 6, 45, 80)
+    p.run()
+    torch.cuda.synchronize()
+    w16 = wide.t.cpu()
+    off = n // 2 + 4
+    assert (w16[:m, off:off + n] != 0x5A5A).any()
+    assert (w16[:, :off] == 0x5A5A).all() and (w16[:, off + n:] == 0x5A5A).all() and (w16[m:] == 0x5A5A).all()
+    for t, rows, lo, hi in ((owide.t, 2 * hh * ww, 104, 104 + c), (bwide.t, 6 * 45 * 80, 64, 128)):
+        tt = t.float().cpu()
+        assert (tt[:, :rows, lo:hi] != 7.0).any()
+        assert (tt[:, :, :lo] == 7.0).all() and (tt[:, :, hi:] == 7.0).all() and (tt[:, rows:] == 7.0).all()
+
+
 @pytest.mark.parametrize("fmt", ["split", "f32", "q16"])
 @pytest.mark.parametrize("c,d,n,h,w", [(1920, 6, 3, 12, 20), (1920, 18, 2, 12, 20), (104, 2, 2, 9, 17), (64, 12, 1, 12, 20), (192, 3, 1, 23, 32)])
 def test_dilated_depthwise_small_maps(cuda, fmt, c, d, n, h, w):
