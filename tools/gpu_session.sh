@@ -1,4 +1,5 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "stay_inside" > gpurun_out/r02w_tests.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/r02w_tests.log | cut -c1-250
+timeout 900 python -m pytest tests -m gpu -q -x -k "mbconv or block_modules or uavsal_call" > gpurun_out/r02x_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02x_tests.log | cut -c1-300
+timeout 300 python tools/microbench.py mbconv 2>&1 | tail -6 | tee gpurun_out/r02x_mbconv.txt
