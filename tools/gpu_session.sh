@@ -1,5 +1,4 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "mbconv or block_modules or uavsal_call" > gpurun_out/r02x_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02x_tests.log | cut -c1-300
-timeout 300 python tools/microbench.py mbconv 2>&1 | tail -6 | tee gpurun_out/r02x_mbconv.txt
+python tools/parity_report.py 2>&1 | tee gpurun_out/r02_parity_report.txt
