@@ -26,7 +26,8 @@ namespace uavsal {
 extern int g_tc_debug;
 
 struct MbArgs {
-    int n, H, W, cin, hidden, N;     // images, map size, channels in / hidden / out
+    int n, H, W, cin, hidden, N;     // images, map size, channels in / hidden / out (N: cout rounded up to 16, the UMMA N)
+    int Nv;                          // valid output channels (a multiple of 8, <= N): stores and residual loads stop there
     int ksteps1;                     // expand k-steps of 16 (K padded)
     int tiles_x, tiles_y, num_tiles, nchunks;
     const float* b1;                 // expand bias [hidden]
@@ -383,9 +384,11 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                             load8(g.res.p + orow * g.res.ld + n, g.res.plane, rr);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) v[k] += rr[k];
-                            load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
+                            if (n + 8 < g.Nv) {
+                                load8(g.res.p + orow * g.res.ld + n + 8, g.res.plane, rr);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) v[8 + k] += rr[k];
+                                for (int k = 0; k < 8; ++k) v[8 + k] += rr[k];
+                            }
                         }
                     }
                     __syncwarp();
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kThreads2, 1) mbconv_kernel(const __grid_const
                     for (int i = 0; i < 2; ++i) {
                         const int row = 16 * i + (lane >> 1), cc = lane & 1;
                         const int64_t gr = grow_of(q * 32 + row);
-                        if (gr >= 0) {
+                        if (gr >= 0 && n + cc * 8 < g.Nv) {
                             uint16_t* dst = g.out.p + gr * g.out.ld + n + cc * 8;
                             *reinterpret_cast<uint4*>(dst) = hv4[i];
                             if (g.out.plane) *reinterpret_cast<uint4*>(dst + g.out.plane) = lv4[i];
@@ -453,15 +456,16 @@ extern "C" int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld,
                        x_ld % 8 == 0 && x_ld >= cin && x_plane % 8 == 0 && out_ld % 8 == 0 && out_ld >= cout && out_plane > 0 &&
                        out_plane % 8 == 0 && kp1 % 8 == 0 && kp1 >= cin,
                    UAVSAL_EINVAL, "mbconv_fused: bad arguments");
-    UAVSAL_REQUIRE(cin % 8 == 0 && cin <= 64 && hidden % 64 == 0 && hidden >= 64 && cout % 16 == 0 && cout <= 64 && (terms == 1 || terms == 3),
-                   UAVSAL_ENOTSUP, "mbconv_fused: cin %d (<= 64), hidden %d (multiple of 64), cout %d (multiple of 16, <= 64)", cin, hidden, cout);
+    UAVSAL_REQUIRE(cin % 8 == 0 && cin <= 64 && hidden % 64 == 0 && hidden >= 64 && cout % 8 == 0 && cout > 0 && cout <= 64 && (terms == 1 || terms == 3),
+                   UAVSAL_ENOTSUP, "mbconv_fused: cin %d (<= 64), hidden %d (multiple of 64), cout %d (multiple of 8, <= 64)", cin, hidden, cout);
+    const int cout16 = (cout + 15) & ~15;                         // the project MMA's N; w2 / b2 carry cout16 rows (zero beyond cout)
     UAVSAL_REQUIRE(terms == 1 || x_plane > 0, UAVSAL_EINVAL, "mbconv_fused: terms = 3 needs the lo plane of x");
     UAVSAL_REQUIRE(!(flags & UAVSAL_F_RESIDUAL) || (al16(res) && res_ld % 8 == 0 && res_plane % 8 == 0 && res_plane > 0), UAVSAL_EINVAL,
                    "mbconv_fused: residual requested without a residual tensor");
     UAVSAL_REQUIRE(!(flags & ~UAVSAL_F_RESIDUAL), UAVSAL_ENOTSUP, "mbconv_fused: only the residual flag is supported (the project conv is linear)");
     cudaStream_t s = (cudaStream_t)stream;
     MbArgs g{};
-    g.n = n; g.H = h; g.W = w; g.cin = cin; g.hidden = hidden; g.N = cout;
+    g.n = n; g.H = h; g.W = w; g.cin = cin; g.hidden = hidden; g.N = cout16; g.Nv = cout;
     g.ksteps1 = (cin + 15) / 16;
     g.tiles_x = div_up(w, kMbTW); g.tiles_y = div_up(h, kMbTH);
     g.num_tiles = n * g.tiles_x * g.tiles_y;
@@ -487,13 +491,13 @@ extern "C" int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld,
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)hidden, (uint64_t)cout, 2};
-        const uint64_t str[2] = {(uint64_t)hidden * 2, (uint64_t)hidden * 2 * (uint64_t)cout};
-        const uint32_t box[3] = {kBK, (uint32_t)cout, 1};
+        const uint64_t dims[3] = {(uint64_t)hidden, (uint64_t)cout16, 2};
+        const uint64_t str[2] = {(uint64_t)hidden * 2, (uint64_t)hidden * 2 * (uint64_t)cout16};
+        const uint32_t box[3] = {kBK, (uint32_t)cout16, 1};
         int rc = tc_encode(&tW2, w2, 3, dims, str, box, "mbconv_fused project weights", 1);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)npl * kMbXPlane + 2 * (size_t)npl * kMbA2Plane + 2 * (size_t)npl * (kMbW1Plane + (size_t)cout * 128) + kMbHid + 256 + 512 + 1024;
+    const size_t smem = (size_t)npl * kMbXPlane + 2 * (size_t)npl * kMbA2Plane + 2 * (size_t)npl * (kMbW1Plane + (size_t)cout16 * 128) + kMbHid + 256 + 512 + 1024;
     UAVSAL_REQUIRE(smem <= 227 * 1024, UAVSAL_ENOTSUP, "mbconv_fused: tile does not fit shared memory");
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }

@@ -546,14 +546,17 @@ class Plan:
 
     def mbconv(self, x: Buf, n, h, w, w1: W, wd: W, w2: W, out: Buf, res: Optional[Buf] = None, tag=""):
         """Whole stride-1 inverted-residual block in one kernel (mbconv.cu): expand + BN + ReLU6 -> depthwise 3x3 + BN + ReLU6 ->
-        project + BN (+ residual); the hidden tensor never reaches HBM.  cin <= 64, hidden % 64 == 0, cout % 16 == 0 and <= 64."""
-        hidden, cin, cout = w1.cout, w1.cin, w2.cout
+        project + BN (+ residual); the hidden tensor never reaches HBM.  cin <= 64, cout % 8 == 0 and <= 64.  The kernel works on
+        64-channel chunks of the hidden tensor and a project N that is a multiple of 16: other widths are passed zero-padded (padded
+        hidden channels are exactly 0 through both ReLU6s and meet zero project weights; padded outputs are never stored)."""
+        hid_true, cin, cout = w1.cout, w1.cin, w2.cout
         kp1 = _pad8(cin)
-        assert self.engine == "tc" and not x.plain and x.c in (cin, kp1) and w2.cin == hidden and wd.cout == hidden
-        assert kp1 <= 64 and hidden % 64 == 0 and cout % 16 == 0 and cout <= 64 and out.c >= cout and (res is None or not res.plain)
+        hidden, cout16 = (hid_true + 63) // 64 * 64, (cout + 15) // 16 * 16
+        assert self.engine == "tc" and not x.plain and x.c in (cin, kp1) and w2.cin == hid_true and wd.cout == hid_true
+        assert kp1 <= 64 and cout % 8 == 0 and cout <= 64 and out.c >= cout and (res is None or not res.plain)
         w1p, b1 = self.packed(w1, W_ROWS_SPLIT, hidden, kp1)
-        wdd, bdd = self._dw_weights(wd, None)
-        w2p, b2 = self.packed(w2, W_ROWS_SPLIT, cout, hidden)
+        wdd, bdd = self.packed(wd, W_COLS_F32, hidden)
+        w2p, b2 = self.packed(w2, W_ROWS_SPLIT, cout16, hidden)
         r = res.act() if res is not None else NULL_ACT
         self._add("uavsal_mbconv_fused", (*x.act(), n, h, w, kp1, w1p.data_ptr(), kp1, b1.data_ptr(), hidden, wdd.data_ptr(), bdd.data_ptr(),
                                           w2p.data_ptr(), cout, b2.data_ptr(), F_RESIDUAL if res is not None else 0, self.terms, *r, *out.act()), tag)

@@ -140,7 +140,9 @@ int uavsal_dw_project(const float* hid, int hid_ld, int n, int h, int w, int hid
 /* Whole dwBlock / InvertedResidual (model.py:74-103; stride 1, dilation 1) in one launch: 1x1 expand + BN + ReLU6 -> depthwise 3x3
  * + BN + ReLU6 -> 1x1 project + BN (+ residual x); the 6x hidden tensor lives in TMEM / shared memory only.
  * x act (n, h, w, cin), cin % 8 == 0, cin <= 64; w1: bf16 planes [2][hidden][kp1] (K-major, kp1 >= cin), b1 [hidden];
- * hidden % 64 == 0; wd [9][hidden], bd [hidden] as uavsal_dw3x3; w2: bf16 planes [2][cout][hidden], b2 [cout], cout % 16 == 0,
+ * hidden % 64 == 0 (a block whose hidden width is not a multiple of 64 is passed with its weights zero-padded: padded hidden
+ * channels are exactly 0 through both ReLU6s and meet zero project weights); wd [9][hidden], bd [hidden] as uavsal_dw3x3;
+ * w2: bf16 planes [2][cout16][hidden], b2 [cout16] with cout16 = cout rounded up to 16 (rows >= cout zero), cout % 8 == 0,
  * cout <= 64; flags: UAVSAL_F_RESIDUAL only; res / out as uavsal_pw_gemm.  Results equal uavsal_pw_gemm(F_OUT_F32) ->
  * uavsal_dw3x3 -> uavsal_pw_gemm bit for bit. */
 int uavsal_mbconv_fused(const uint16_t* x, int64_t x_plane, int x_ld, int n, int h, int w, int cin,

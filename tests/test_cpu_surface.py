@@ -107,12 +107,12 @@ def test_plan_structure_of_one_call():
     # ... and the seven large stride-1 blocks whose project conv has 64..256 outputs (st0/st1.sp, fust, gauss1, ob1, fucb, fucbst)
     # run depthwise + project fused
     # ... plus features.1 (32 -> 16, no expand conv), whose depthwise + project run as one fp32 FFMA kernel behind the same entry
-    # ... and the nine narrow stride-1 blocks (cin <= 64, cout <= 64, hidden % 64 == 0: features.5/6/8/9/10, both ST blocks' te.sub, gauss1,
-    # ob1) run as ONE kernel each (uavsal_mbconv_fused)
-    assert names.count("uavsal_mbconv_fused") == 9
+    # ... and the twelve narrow stride-1 blocks (cin <= 64, cout <= 64: features.3/5/6/8/9/10, both ST blocks' te.sub, gauss0/1, ob0/1;
+    # hidden widths that are not multiples of 64 - 144, 48, 120 - are zero-padded) run as ONE kernel each (uavsal_mbconv_fused)
+    assert names.count("uavsal_mbconv_fused") == 12
     assert names.count("uavsal_expand_dw3x3") == 2 and names.count("uavsal_dw_project") == 7 - 2 and names.count("uavsal_dw_project32_hw") == 1
     # ... and the readout's depthwise conv is folded into its 1-output project (dw3x3_dot_sigmoid)
-    assert names.count("uavsal_pw_gemm") == 76 - 2 - 8 - 16 and names.count("uavsal_dw3x3") == 34 - 2 - 8 - 1 - 7
+    assert names.count("uavsal_pw_gemm") == 76 - 2 - 8 - 16 - 6 and names.count("uavsal_dw3x3") == 34 - 2 - 8 - 1 - 7 - 3
     pu = engine.Plan("cpu", 3, "tc")
     pu.fuse_mbconv = False
     m.build_plan(pu, 20, 360, 640, x_kind=1, post_hw=(360, 640))

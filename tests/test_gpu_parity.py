@@ -569,10 +569,11 @@ def test_block_modules_against_oracle(cuda):
 
 
 @pytest.mark.parametrize("inp,oup,n,h,w", [(64, 64, 3, 23, 40), (32, 32, 2, 45, 80), (64, 32, 5, 45, 80), (64, 64, 1, 7, 5), (32, 16, 2, 33, 47),
-                                           (64, 48, 170, 12, 20)])
+                                           (64, 48, 170, 12, 20), (24, 24, 2, 90, 160), (8, 64, 1, 45, 80), (24, 40, 3, 19, 27), (24, 8, 1, 13, 9)])
 def test_mbconv_fused_block(cuda, inp, oup, n, h, w):
     """Whole inverted-residual block in one kernel (uavsal_mbconv_fused: the hidden tensor never leaves the SM) vs the oracle, and
-    bit for bit vs the three separate kernels (expand GEMM -> depthwise -> project GEMM); ragged maps, more tiles than SMs."""
+    bit for bit vs the three separate kernels (expand GEMM -> depthwise -> project GEMM); ragged maps, more tiles than SMs, hidden
+    widths that are not multiples of 64 (144, 48: zero-padded chunks) and output widths that are not multiples of 16 (24, 40, 8)."""
     from iip_uavsal_saliency_b200 import model as M
     torch.manual_seed(inp * 131 + oup)
     blk = M.dwBlock(inp, oup).eval()

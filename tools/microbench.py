@@ -248,6 +248,7 @@ def main():
     if what == "mbconv":
         for fused in (False, True):
             mbblock(120, 45, 80, 64, 32, fused); mbblock(120, 45, 80, 32, 32, fused); mbblock(120, 23, 40, 64, 64, fused)
+            mbblock(120, 90, 160, 24, 24, fused)
     if what == "pairbig":
         gemm("tc", 432000, 256, 1536, f32=True)
     if what == "wr":
