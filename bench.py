@@ -575,6 +575,8 @@ def run_product_arm(args):
             "config": {"workload": WORKLOAD, "clips_per_step": args.clips, "partition": "clip c -> rank c % world", "frames_in_per_clip": FRAMES,
                        "maps_out_per_clip": OUT_PER_CLIP, "precision": args.precision, "cuda_graph": not args.no_graph, "calls_in_flight": args.depth,
                        "clips_per_plan": args.clips_per_plan,
+                       "hidden_rows": "16-bit fixed point of the ReLU6 output (|err| <= 4.6e-5) for hidden tensors >= 1152 channels, fp32 otherwise"
+                                      if os.environ.get("UAVSAL_HIDDEN_Q16", "1") != "0" else "fp32",
                        "plan": "one per %d clip(s) (60 frames each, call size 20 passed to the call-granular kernels)" % cpp if not args.per_call else "one per 20-frame call",
                        "l2": "inputs larger than L2: %d distinct 44 MB clips per rank rotated, and ~4 GB of arena traffic per clip" % n_distinct},
             "timed_region_s": round(t_res, 3),
