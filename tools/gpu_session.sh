@@ -1,13 +1,10 @@
 #!/bin/bash
-# round-2 evidence at HEAD: full GPU suite, default bench line (+ reference arm), ncu launch list of the 120-frame plan, smoke() launch list
+# round-2 evidence at HEAD (what profiles/r02_* were produced with): full GPU suite, default bench line (+ reference arm), ncu launch
+# list of the 120-frame plan, smoke() launch list, parity-margin report.  Run through gpurun; tools/gpu_session_n.sh N for N > 1.
 set -u
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r02z_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02z_tests.log | cut -c1-200
 ( timeout 900 python bench.py --dump-ops gpurun_out/r02z_ops.txt ) > gpurun_out/r02z_bench_n1.json 2> gpurun_out/r02z_bench_n1.err; echo "bench rc=$?"
-python - <<'PY'
-import json; d=json.load(open('gpurun_out/r02z_bench_n1.json'))
-print(round(d['value']), round(d['e2e']['value']), d['clocks'], d['roofline']['frac'], d['roofline']['issued_frac'], d['wall_s'])
-PY
 ( timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/r02z_bench_ref.json 2> gpurun_out/r02z_bench_ref.err; echo "ref rc=$?"
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file gpurun_out/r02z_clip120_kernels.csv python tools/profile_call.py exact 120 > gpurun_out/r02z_ncu.log 2>&1; echo "ncu rc=$?"
