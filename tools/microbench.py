@@ -184,6 +184,10 @@ def main():
         bilinear(120, 12, 20, 256, 120, 45, 80); bilinear(120, 23, 40, 128, 120, 45, 80)
         bilinear(1, 45, 80, 64, 120, 45, 80); bilinear(24, 12, 20, 64, 120, 45, 80, src_group=4, dst_group=20)
         return
+    if what == "glueprof":      # one launch each of the kernels reworked late in round 2, for an ncu --set full capture
+        readout(120, 45, 80, 1536, q16=True); stem(120, 360, 640); bilinear(120, 12, 20, 256, 120, 45, 80)
+        dw(2, 120, 12, 20, 1920, 1, q16=True, dil=6); mbblock(120, 90, 160, 24, 24, True)
+        return
     if what == "pairq16prof":   # the plan's top kernel (256 -> 1536 expand conv, q16 rows out) for an ncu --set full capture
         gemm("tc", 120 * 3600, 256, 1536, q16=True)
         return
