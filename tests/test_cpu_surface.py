@@ -383,3 +383,26 @@ def test_plan_cache_keys_and_eviction(monkeypatch):
     assert len(blk._plan_cache()) == 1
     blk.invalidate()
     assert len(blk._plan_cache()) == 0
+
+
+def test_hidden_row_format_rules_and_q16_view(monkeypatch):
+    """Plan.hidden_fmt: which storage the tensor between a dwBlock's expand conv and its depthwise conv gets (model.py:90-92), and the
+    host-side view of q16 rows (q * 6 / 65535, the value the kernels read back)."""
+    p = engine.Plan("cpu", 3, "tc")
+    assert p.hidden_fmt(1536) == engine.FMT_Q16 and p.hidden_fmt(1152) == engine.FMT_Q16 and p.hidden_fmt(960) == engine.FMT_F32
+    assert p.hidden_fmt(1920, 6, 12 * 20) == engine.FMT_Q16           # dilated: whole-image kernel, small maps only
+    assert p.hidden_fmt(1920, 6, 45 * 80) == engine.FMT_SPLIT and p.hidden_fmt(960, 6, 240) == engine.FMT_SPLIT
+    p.hidden_q16 = False
+    assert p.hidden_fmt(1536) == engine.FMT_F32 and p.hidden_fmt(1920, 6, 240) == engine.FMT_SPLIT
+    assert engine.Plan("cpu", 3, "simt").hidden_fmt(1536) == engine.FMT_SPLIT      # the cross-check engines keep split-bf16 everywhere
+    monkeypatch.setenv("UAVSAL_HIDDEN_Q16", "0")
+    assert engine.Plan("cpu", 3, "tc").hidden_fmt(1536) == engine.FMT_F32
+    monkeypatch.delenv("UAVSAL_HIDDEN_Q16")
+    b = engine.Plan("cpu", 3, "tc").alloc_q16(4, 16)
+    assert b.q16 and b.plain and not b.f32 and b.plane == engine.PLANE_Q16 and b.t.dtype == torch.int16
+    q = torch.tensor([0, 1, 32767, 32768, 65535, 10922], dtype=torch.int32)
+    b.t[0, :6] = q.to(torch.int16)                                     # the same 16 bits
+    v = b.to_float()[0, :6]
+    assert torch.equal(v, q.float() * np.float32(6.0 / 65535.0)) and v[4].item() == pytest.approx(6.0, abs=1e-6) and v[0].item() == 0.0
+    s = b.slot(8, 8)
+    assert s.ptr == b.ptr + 16 and s.fmt == engine.FMT_Q16            # 2 bytes per element
