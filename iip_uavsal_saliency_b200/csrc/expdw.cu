@@ -140,9 +140,6 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
         cp_async_commit();
     };
 
-    const int quad = tid & 15;
-    const int col = (tid >> 4) % G::TW;
-    const int rgrp = (tid >> 4) / G::TW;
     int img, y0, x0, cg;
     decode(blockIdx.x, img, y0, x0, cg);
     pdl_wait();
@@ -235,6 +232,14 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                     }
                 }
             }
+            // depthwise stage mapping: thread = (4-channel quad, output column, row group).  A last block with at most 32 valid channels
+            // (hidden = 96: features.2) has only 8 quads: the threads are dealt over twice as many row groups instead of leaving half
+            // of them idle, and the stage takes half as long
+            const bool half = g.hidden - cblk * 64 <= 32;                      // warp-uniform
+            const int quad = half ? (tid & 7) : (tid & 15);
+            const int pcol = half ? (tid >> 3) : (tid >> 4);
+            const int col = pcol % G::TW, rgrp = pcol / G::TW;
+            const int rpt = half ? G::RPT / 2 : G::RPT;
             // depthwise taps / bias of this thread's 4 channels
             const int c0 = cblk * 64 + quad * 4;
             const bool cvalid = c0 < g.hidden;
@@ -260,12 +265,13 @@ __global__ void __launch_bounds__(256, 2) expdw_kernel(const ExpDwArgs g) {
                                      : "r"(hid + (iy * G::IW + col * STRIDE + d) * G::HPITCH + quad * 16));
                     }
                 };
-                const int oyl0 = rgrp * G::RPT;
+                const int oyl0 = rgrp * rpt;
                 if (STRIDE == 1) { load_row(0, oyl0); load_row(1, oyl0 + 1); }
                 else             { load_row(0, oyl0 * 2); }
                 uint16_t* orow = g.out.p + (((int64_t)img * g.ho + y0 + oyl0) * g.wo + ox) * g.out.ld + c0;
 #pragma unroll
                 for (int i = 0; i < G::RPT; ++i) {
+                    if (i >= rpt) break;
                     const int oyl = oyl0 + i;
                     int s0, s1, s2;
                     if (STRIDE == 1) {

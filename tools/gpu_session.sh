@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-python tools/microbench.py glueprof || exit 1
-timeout 900 ncu --set full --clock-control none -k regex:"dw3x3_tma_kernel|stem_kernel|bilinear_ac_kernel|dw3x3_img_kernel|mbconv_kernel" --launch-skip 5 --launch-count 5 -f -o gpurun_out/r02_glue python tools/microbench.py glueprof > gpurun_out/r02_glue_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 900 python -m pytest tests -m gpu -q -x -k "fused_expand or block_modules or backbone_levels or uavsal_call" > gpurun_out/r02_expdw_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r02_expdw_tests.log | cut -c1-300
+python - <<'PY' 2>&1 | tee gpurun_out/r02_expdw_remap.txt
+import sys; sys.argv=['x','none']; sys.path.insert(0,'tools')
+import microbench as mb
+mb.expdw(120, 180, 320, 16, 96, 2); mb.expdw(120, 90, 160, 24, 144, 2)
+PY
