@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(256, 3) dwproj32_kernel(const __grid_constant_
 
 // ---------------------------------------------------------------------------------------------------
 // Parameter-block variant (uavsal_dw_project32_hw, the engine's default): the block's 848 weights (taps, both biases, project
-// matrix) are HOST arrays copied into the kernel parameters, so every FFMA reads its weight as a warp-uniform constant-bank
-// operand and shared memory only carries the activations.  Thread = one output pixel with all 32 channels (no exchange
+// matrix) are HOST arrays copied into the kernel parameters (constant bank), so the weights reach the FMAs as warp-uniform operands
+// (pairs of them through uniform registers, feeding packed fma.rn.f32x2) and shared memory only carries the activations.  Thread = one output pixel with all 32 channels (no exchange
 // between threads); tile 16 x 16 output pixels, 18 x 18 haloed box (1.27x re-read instead of 1.41x).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kP3T = 16, kP3I = kP3T + 2;

@@ -74,8 +74,9 @@ __device__ __forceinline__ float stem_fetch(const void* x, int img, int ch, int 
     }
 }
 
-// PW = true: weights [27][32] + bias [32] travel in the kernel parameters (constant bank): every FFMA takes its weight as a
-// warp-uniform constant operand instead of 216 shared-memory loads per pixel (uavsal_stem_conv3x3s2_hw: host weight pointers)
+// PW = true: weights [27][32] + bias [32] travel in the kernel parameters (constant bank): the FMAs take their weights as
+// warp-uniform operands (pairs through uniform registers, packed fma.rn.f32x2) instead of 216 shared-memory loads per pixel
+// (uavsal_stem_conv3x3s2_hw: host weight pointers)
 struct StemW {
     float w[27 * 32 + 32];
 };

@@ -466,7 +466,7 @@ class Plan:
 
     def stem(self, x: torch.Tensor, kind: int, n, h, w, wgt, bias, out: Buf, tag=""):
         """wgt: W (3->32, 3x3, BN) or folded fp32 [3][3][3][32] (ky, kx, cin, cout) + bias [32].  The tcgen05 engines hand the 3.5 KB
-        of weights over as HOST arrays: they travel in the kernel parameters and every FFMA reads its weight from the constant bank."""
+        of weights over as HOST arrays: they travel in the kernel parameters and reach the FMAs as warp-uniform constant-bank operands."""
         host = self.engine != "simt" and ((isinstance(wgt, W) and (wgt.cout, wgt.cin, wgt.taps) == (32, 3, 9)) or
                                           (not isinstance(wgt, W) and tuple(wgt.shape) == (3, 3, 3, 32)))
         if isinstance(wgt, W):
